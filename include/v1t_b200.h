@@ -1,0 +1,175 @@
+/* v1t_b200 — C-ABI of the B200-native V1T hot path (ViT core + Gaussian2d readout + Poisson loss).
+ *
+ * The reference (bryanlimy/V1T) is pure Python/PyTorch and has no FFI; these entry points are what a
+ * binding for the hot path replaces (file:line relative to /root/reference/):
+ *
+ *   v1t_core_forward / v1t_core_backward      ViTCore.forward + its autograd   src/v1t/models/core/vit.py:423-436
+ *        (Image2Patches vit.py:122-129, BehaviorMLP :200-202, Attention.mha :267-275,
+ *         scaled_dot_product_attention :253-265, MLP :153-154, Transformer.forward :348-362)
+ *   v1t_readout_forward / v1t_readout_backward  Gaussian2DReadout.forward + autograd
+ *                                                              src/v1t/models/readout/gaussian2d.py:195-278
+ *   v1t_elu1_poisson_forward / _backward      ELU1 (src/v1t/models/utils.py:109-118) + PoissonLoss.forward
+ *                                                              (src/v1t/losses.py:114-119,153-166)
+ *   v1t_attention_probs                       what attention_rollout.Recorder's hook on Attention.attend
+ *                                             observes (src/v1t/utils/attention_rollout.py:31-36)
+ *
+ * Conventions: every function returns 0 on success or a negative V1T_ERR_* code; v1t_last_error() gives the
+ * message (thread-local).  All tensor pointers are DEVICE pointers owned by the caller (PyTorch), fp32 unless
+ * stated, never allocated or freed here; workspaces are passed in and sized by the *_bytes queries.  Launches
+ * go to the given cudaStream_t (passed as void*); nothing synchronises.  One host thread per device.
+ */
+#ifndef V1T_B200_H
+#define V1T_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V1T_MAX_BLOCKS 16
+
+#define V1T_OK 0
+#define V1T_ERR_INVALID (-1)   /* bad shape / null pointer / unsupported flag */
+#define V1T_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed */
+#define V1T_ERR_WORKSPACE (-3) /* workspace too small */
+
+/* arithmetic used for the GEMM/attention contractions */
+#define V1T_IMPL_FP32 0   /* fp32 CUDA-core kernels (also: materialised attention probabilities) */
+#define V1T_IMPL_BF16X3 1 /* tcgen05 tensor cores, bf16 hi+lo split operands, fp32 accumulate ("exact") */
+#define V1T_IMPL_BF16 2   /* tcgen05 tensor cores, plain bf16 operands, fp32 accumulate ("fast") */
+
+typedef struct v1t_core_shape {
+  int32_t batch;                 /* B */
+  int32_t in_ch, in_h, in_w;     /* image C,H,W after the cropper (1|2, 36, 64) */
+  int32_t patch, stride;         /* nn.Unfold kernel/stride (vit.py:68) */
+  int32_t emb;                   /* E = emb_dim = head_dim (vit.py:218) */
+  int32_t heads;                 /* H */
+  int32_t mlp;                   /* M = mlp_dim */
+  int32_t blocks;                /* num_blocks <= V1T_MAX_BLOCKS */
+  int32_t bdim;                  /* BehaviorMLP input width: 0 (behavior_mode 0/1), 3 (mode 2), 5 (mode 3/4) */
+  int32_t impl;                  /* V1T_IMPL_* */
+  float p_drop_tokens;           /* Image2Patches dropout p (vit.py:106); 0 in eval */
+  float p_drop_block;            /* Transformer dropout p: attention probs, proj out, MLP x2 (vit.py:148-150,227,231) */
+  uint64_t seed;                 /* counter-based RNG seed for the dropout masks (replayed in backward) */
+} v1t_core_shape;
+
+typedef struct v1t_core_dims { /* derived sizes, see v1t_core_dims_of() */
+  int32_t gh, gw;   /* patch grid (29,57) */
+  int32_t tokens;   /* T = gh*gw + 1 */
+  int32_t emb_ld;   /* row stride (floats) of the token buffers: E rounded up to 32 (155 -> 160) */
+  int32_t inner;    /* I = H*E */
+  int32_t mlp_ld;   /* row stride of the MLP hidden buffer (M rounded up to 32) */
+  int32_t patch_dim;/* C*patch*patch */
+  int32_t hid;      /* BehaviorMLP hidden = E/2 */
+} v1t_core_dims;
+
+/* per-block parameter pointers, reference state-dict layouts; NULL = absent bias */
+typedef struct v1t_block_ptrs {
+  float *ln1_w, *ln1_b;   /* mha.layer_norm.{weight,bias}        [E]            */
+  float *wqkv;            /* mha.to_qkv.weight                   [3*H*E, E]     */
+  float *wproj, *bproj;   /* mha.projection.0.{weight,bias}      [E, H*E], [E]  */
+  float *ln2_w, *ln2_b;   /* mlp.model.0.{weight,bias}           [E]            */
+  float *w1, *b1;         /* mlp.model.1.{weight,bias}           [M, E], [M]    */
+  float *w2, *b2;         /* mlp.model.4.{weight,bias}           [E, M], [E]    */
+  float *bw0, *bb0;       /* b-mlp.models.<k>.0.{weight,bias}    [E/2, bdim], [E/2] */
+  float *bw3, *bb3;       /* b-mlp.models.<k>.3.{weight,bias}    [E, E/2], [E]  */
+} v1t_block_ptrs;
+
+typedef struct v1t_core_ptrs { /* used both for parameters (read) and for their gradients (written) */
+  float *cls;  /* patch_embedding.cls_token      [1,1,E]      */
+  float *pos;  /* patch_embedding.pos_embedding  [T,E]        */
+  float *wpe;  /* patch_embedding.projection.2.weight [E, C*p*p] */
+  float *bpe;  /* patch_embedding.projection.2.bias   [E]     */
+  v1t_block_ptrs blk[V1T_MAX_BLOCKS];
+} v1t_core_ptrs;
+
+const char* v1t_last_error(void);
+int v1t_version(void);
+
+int v1t_core_dims_of(const v1t_core_shape* shape, v1t_core_dims* out);
+
+/* bytes of the activations kept between forward and backward, and of the transient scratch */
+size_t v1t_core_saved_bytes(const v1t_core_shape* shape);
+size_t v1t_core_scratch_bytes(const v1t_core_shape* shape);
+
+/* ViTCore.forward.  images [B,C,H,W]; behaviors [B,bdim] (= cat(behaviors,pupil_centers) for mode 3/4) or NULL.
+ * tokens_out [B, T, emb_ld]: final residual stream; the core output map is rows 1.. (CLS dropped), cols 0..E-1.
+ * saved: v1t_core_saved_bytes (only written when keep_for_backward != 0); scratch: v1t_core_scratch_bytes. */
+int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs* params, const float* images,
+                     const float* behaviors, float* tokens_out, void* saved, void* scratch,
+                     int keep_for_backward, void* stream);
+
+/* autograd of v1t_core_forward.  d_tokens [B,T,emb_ld] is dL/d(tokens_out) and is CLOBBERED.
+ * grads: every non-NULL pointer is overwritten with that parameter's gradient.  d_images may be NULL. */
+int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptrs* params, const float* images,
+                      const float* behaviors, float* d_tokens, const void* saved, void* scratch,
+                      const v1t_core_ptrs* grads, float* d_images, void* stream);
+
+/* softmax(QK^T * E^-0.5) of block `block` for the given input: probs [B,H,T,T] (the tensor the reference's
+ * Attention.attend emits); uses the fp32 kernels.  Needs the `saved` buffer of a keep_for_backward forward. */
+int v1t_attention_probs(const v1t_core_shape* shape, const void* saved, int block, float* probs, void* stream);
+
+/* ---- Gaussian2d readout ------------------------------------------------------------------------------ */
+typedef struct v1t_readout_shape {
+  int32_t batch;        /* B */
+  int32_t neurons;      /* N */
+  int32_t channels;     /* C = core emb dim */
+  int32_t gh, gw;       /* feature-map height, width (29, 57) */
+  int64_t fs_b, fs_y, fs_x; /* fmap element strides for batch / row / col; channel stride must be 1 */
+} v1t_readout_shape;
+
+size_t v1t_readout_scratch_bytes(const v1t_readout_shape* s);
+
+/* z[b,n] = sum_c bilinear(fmap[b,:,:,c]; grid[b,n]) * features[c,n] + bias[n]
+ * grid = clamp(mu[n] + sigma[n] @ noise[b,n], -1, 1) + shifts[b]      (gaussian2d.py:219-235,267-270)
+ * mu [N,2]; sigma [N,2,2]; noise [B,N,2] or NULL (eval); shifts [B,2] or NULL; features [C,N]; bias [N] or NULL.
+ * y_true [B,N] or NULL.  Outputs: z [B,N] (pre-activation); if y_out != NULL: y = elu(z)+1;
+ * if loss_out != NULL (needs y_true): loss = loss_scale * sum((y+eps) - (y_true+eps) log(y+eps)). */
+int v1t_readout_forward(const v1t_readout_shape* s, const float* fmap, const float* mu, const float* sigma,
+                        const float* noise, const float* shifts, const float* features, const float* bias,
+                        const float* y_true, float loss_scale, float* z, float* y_out, float* loss_out,
+                        void* scratch, void* stream);
+
+/* backward.  dz [B,N] = dL/dz, or NULL with y_true given: then dz = dloss * loss_scale * dPoisson/dz (fused).
+ * Outputs (any may be NULL): d_fmap (same strides as fmap, ACCUMULATED into: caller zero-fills),
+ * d_mu [N,2], d_sigma [N,2,2], d_shifts [B,2], d_features [C,N], d_bias [N]. */
+int v1t_readout_backward(const v1t_readout_shape* s, const float* fmap, const float* mu, const float* sigma,
+                         const float* noise, const float* shifts, const float* features, const float* z,
+                         const float* dz, const float* y_true, float loss_scale, float dloss, float* d_fmap,
+                         float* d_mu, float* d_sigma, float* d_shifts, float* d_features, float* d_bias,
+                         void* scratch, void* stream);
+
+/* standalone ELU1 + Poisson (strict drop-in mode: Model owns ELU1, train_step owns the criterion) */
+int v1t_elu1_forward(const float* z, float* y, int64_t n, void* stream);
+int v1t_elu1_backward(const float* z, const float* dy, float* dz, int64_t n, void* stream);
+size_t v1t_poisson_scratch_bytes(int64_t n);
+int v1t_poisson_forward(const float* y_pred, const float* y_true, int64_t n, float eps, float loss_scale,
+                        float* loss_out, void* scratch, void* stream);
+int v1t_poisson_backward(const float* y_pred, const float* y_true, int64_t n, float eps, float loss_scale,
+                         const float* dloss, float* dy, void* stream);
+
+/* ---- building blocks, exported for unit tests -------------------------------------------------------- */
+/* C[b][m,n] = alpha * sum_k A[b][m,k] * B[b][k,n] (+ bias[n]) (+ R[b][m,n]); arbitrary element strides */
+typedef struct v1t_gemm_desc {
+  int32_t m, n, k, batch1, batch2;
+  int64_t a_m, a_k, a_b1, a_b2;
+  int64_t b_k, b_n, b_b1, b_b2;
+  int64_t c_m, c_b1, c_b2;      /* C column stride is 1 */
+  int64_t r_m, r_b1, r_b2;      /* residual operand (optional) */
+  float alpha;
+  int32_t accumulate;           /* C += ... instead of C = ... */
+} v1t_gemm_desc;
+int v1t_gemm_fp32(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
+                  const float* R, void* stream);
+
+/* the inverted-dropout multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` =
+ * block*8 + {0 tokens, 1 attention probs, 2 proj out, 3 MLP hidden, 4 MLP out}; element index = row-major
+ * index in the logical tensor ([B,T,E], [B,H,T,T], [B,T,M]).  Lets tests replay the exact masks. */
+int v1t_dropout_mask(float* out, int64_t n, uint64_t seed, uint32_t site, float p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V1T_B200_H */

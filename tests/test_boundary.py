@@ -1,0 +1,129 @@
+"""Host-side checks that run without a GPU: the C-ABI library loads and exports every declared symbol, the
+nn.Module boundary has the reference's state-dict layout, and CUDA-only ops fail loudly on CPU tensors."""
+import ctypes
+import os
+import re
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import v1t_b200
+from v1t_b200 import _lib
+from golden_util import Golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "v1t_b200.h")).read()
+    declared = set(re.findall(r"\b(v1t_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/v1t_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.v1t_version() >= 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # 12 int32 + 2 float + uint64 -> 64 bytes; pointers struct = (4 + 16*15) * 8
+    assert ctypes.sizeof(_lib.CoreShape) == 64
+    assert ctypes.sizeof(_lib.CorePtrs) == (4 + 16 * 15) * 8
+    assert ctypes.sizeof(_lib.ReadoutShape) == 48
+    assert ctypes.sizeof(_lib.GemmDesc) == 5 * 4 + 4 + 14 * 8 + 8
+
+
+def test_dims_and_workspace_queries_default_config():
+    lib = _lib.load()
+    s = _lib.CoreShape(batch=16, in_ch=1, in_h=36, in_w=64, patch=8, stride=1, emb=155, heads=4, mlp=488,
+                       blocks=4, bdim=5, impl=0)
+    d = _lib.CoreDims()
+    assert lib.v1t_core_dims_of(ctypes.byref(s), ctypes.byref(d)) == 0
+    assert (d.gh, d.gw, d.tokens, d.emb_ld, d.inner, d.patch_dim, d.hid) == (29, 57, 1654, 160, 620, 64, 77)
+    assert lib.v1t_core_saved_bytes(ctypes.byref(s)) > 0
+    bad = _lib.CoreShape(batch=0)
+    assert lib.v1t_core_dims_of(ctypes.byref(bad), ctypes.byref(d)) < 0
+    assert b"core" in lib.v1t_last_error()
+
+
+def _args(g: Golden, **over):
+    a = dict(g.args)
+    a.update(input_shape=tuple(g.meta["in_shape"]), output_shapes={k: (n,) for k, n in g.meta["neurons"].items()},
+             device=torch.device("cpu"))
+    a.update(over)
+    return SimpleNamespace(**a)
+
+
+class _DS:
+    def __init__(self, n):
+        self.coordinates = np.random.default_rng(0).standard_normal((n, 3)).astype(np.float32)
+        self.response_stats = {"mean": np.ones(n, np.float32), "std": np.ones(n, np.float32)}
+
+    def __len__(self):
+        return 4500
+
+
+def make_ds(neurons):
+    return {k: SimpleNamespace(dataset=_DS(n)) for k, n in neurons.items()}
+
+
+@pytest.mark.parametrize("case", ["tiny_train", "color_mode4", "nobias_mu_param", "nobehav", "default_dims"])
+def test_state_dict_layout_matches_reference(case):
+    """Every reference key exists with the same shape/dtype, no extra persistent keys -> strict load both ways."""
+    g = Golden(case)
+    args = _args(g)
+    model = v1t_b200.Model(args, ds=make_ds(g.meta["neurons"]))
+    sd = model.state_dict()
+    assert set(sd) == set(g.sd), set(sd) ^ set(g.sd)
+    for k, v in g.sd.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+        assert sd[k].dtype == torch.from_numpy(np.asarray(v)).dtype, k
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in g.sd.items()}, strict=True)
+
+
+def test_out_of_scope_flags_raise():
+    g = Golden("tiny_train")
+    for over in (dict(patch_mode=1), dict(use_lsa=True), dict(drop_path=0.1)):
+        with pytest.raises(NotImplementedError):
+            v1t_b200.Model(_args(g, **over), ds=make_ds(g.meta["neurons"]))
+
+
+def test_cpu_tensors_fail_loudly():
+    g = Golden("tiny_train")
+    model = v1t_b200.Model(_args(g), ds=make_ds(g.meta["neurons"]))
+    d = g.mice["A"]
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        model(torch.from_numpy(d["images"]), mouse_id="A", behaviors=torch.from_numpy(d["behaviors"]),
+              pupil_centers=torch.from_numpy(d["pupil_centers"]))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        v1t_b200.functional.poisson_loss(torch.ones(2, 3), torch.ones(2, 3))
+
+
+def test_dropin_install_overwrites_reference_registries():
+    from oracle import ref_harness as rh
+
+    if not rh.reference_available():
+        pytest.skip("reference checkout not present (GPU box)")
+    rh.import_reference()
+    import v1t.models.core.core as ref_core
+    import v1t.models.readout.readout as ref_readout
+    import v1t.losses as ref_losses
+    import v1t.models.model as ref_model
+    keep = (ref_core._CORES["vit"], ref_readout._READOUTS["gaussian2d"], ref_losses._CRITERION["poisson"],
+            ref_model.ELU1, ref_model.get_model_info)
+    try:
+        from v1t_b200 import dropin
+        dropin.install()
+        g = Golden("tiny_train")
+        model = ref_model.Model(_args(g), ds=make_ds(g.meta["neurons"]))  # the REFERENCE's Model class
+        assert isinstance(model.core, v1t_b200.ViTCore)
+        assert isinstance(model.readouts["A"], v1t_b200.Gaussian2DReadout)
+        assert isinstance(model.elu1, v1t_b200.ELU1)
+        assert set(model.state_dict()) == set(g.sd)
+        crit = ref_losses.get_criterion(_args(g), ds=make_ds(g.meta["neurons"]))
+        assert isinstance(crit, v1t_b200.PoissonLoss)
+    finally:
+        (ref_core._CORES["vit"], ref_readout._READOUTS["gaussian2d"], ref_losses._CRITERION["poisson"],
+         ref_model.ELU1, ref_model.get_model_info) = keep

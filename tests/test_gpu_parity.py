@@ -1,0 +1,286 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C-ABI library.
+
+Tolerance (BASELINE.json north_star): <= 1e-3 relative on responses / loss; measured as
+max|a-b| / max|b| per tensor (golden_util.rel_err).  The fp32 implementation is held to 2e-4 on forward
+quantities and 1e-3 on gradients against the reference's own fp32 outputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import v1t_b200
+from v1t_b200 import functional as VF
+from oracle import v1t_oracle as O
+from golden_util import CASES, Golden, rel_err
+from test_boundary import _args, make_ds
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_FWD, TOL_GRAD = 2e-4, 1e-3
+
+
+def cu(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float32, device=DEV)
+
+
+def build(g: Golden, **over):
+    model = v1t_b200.Model(_args(g, device=torch.device(DEV), **over), ds=make_ds(g.meta["neurons"]))
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in g.sd.items()}, strict=True)
+    crit = v1t_b200.get_criterion(_args(g, device=torch.device(DEV)), ds=make_ds(g.meta["neurons"]))
+    return model.to(DEV), crit
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_model_matches_reference_golden(case):
+    g = Golden(case)
+    model, crit = build(g)
+    model.train(g.meta["mode"] == "train")
+    for mouse_id, d in g.mice.items():
+        model.zero_grad(set_to_none=True)
+        images = cu(d["images"]).requires_grad_(True)
+        noise = cu(d["noise"]) if "noise" in d else None
+        fmap = model.core(images, mouse_id=mouse_id, behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]))
+        assert tuple(fmap.shape) == (d["fmap"].shape[0], d["fmap"].shape[3], d["fmap"].shape[1], d["fmap"].shape[2])
+        assert fmap.stride(1) == 1  # channel-last view
+        assert rel_err(fmap.detach().permute(0, 2, 3, 1).cpu().numpy(), d["fmap"]) < TOL_FWD
+        y, _, _ = model(images, mouse_id=mouse_id, behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]),
+                        noise=noise)
+        assert rel_err(y.detach().cpu().numpy(), d["y"]) < TOL_FWD
+        loss = crit(y_true=cu(d["y_true"]), y_pred=y, mouse_id=mouse_id, batch_size=y.shape[0])
+        assert abs(loss.item() - float(d["loss"])) / abs(float(d["loss"])) < TOL_FWD
+        loss.backward()
+        assert rel_err(images.grad.cpu().numpy(), d["dimages"]) < TOL_GRAD
+        named = dict(model.named_parameters())
+        for k, ref in d["grads"].items():
+            got = named[k].grad
+            if np.abs(ref).max() == 0:
+                assert got is None or float(got.abs().max()) < 1e-6, k
+                continue
+            assert got is not None, k
+            assert rel_err(got.cpu().numpy(), ref) < TOL_GRAD, (k, rel_err(got.cpu().numpy(), ref))
+
+
+def _random_state(cfg: O.CoreConfig, n, rng, mouse="A"):
+    """Seeded synthetic weights with the reference's state-dict keys (no reference needed on the GPU box)."""
+    E, H, M, T = cfg.emb_dim, cfg.num_heads, cfg.mlp_dim, cfg.num_tokens
+    pd = cfg.in_ch * cfg.patch_size ** 2
+    r = lambda *s, sc=0.02: (rng.standard_normal(s) * sc).astype(np.float32)
+    sd = {"core.patch_embedding.cls_token": r(1, 1, E, sc=1.0), "core.patch_embedding.pos_embedding": r(T, E, sc=1.0),
+          "core.patch_embedding.projection.2.weight": r(E, pd, sc=0.1), "core.patch_embedding.projection.2.bias": r(E, sc=0.1)}
+    for i in range(cfg.num_blocks):
+        p = f"core.transformer.blocks.{i}."
+        sd.update({p + "mha.layer_norm.weight": 1 + r(E, sc=0.1), p + "mha.layer_norm.bias": r(E, sc=0.1),
+                   p + "mha.to_qkv.weight": r(3 * H * E, E, sc=0.06), p + "mha.projection.0.weight": r(E, H * E),
+                   p + "mha.projection.0.bias": r(E, sc=0.05), p + "mlp.model.0.weight": 1 + r(E, sc=0.1),
+                   p + "mlp.model.0.bias": r(E, sc=0.1), p + "mlp.model.1.weight": r(M, E, sc=0.05),
+                   p + "mlp.model.1.bias": r(M, sc=0.05), p + "mlp.model.4.weight": r(E, M, sc=0.05),
+                   p + "mlp.model.4.bias": r(E, sc=0.05),
+                   p + "b-mlp.models.share.0.weight": r(E // 2, 5, sc=0.5), p + "b-mlp.models.share.0.bias": r(E // 2, sc=0.1),
+                   p + "b-mlp.models.share.3.weight": r(E, E // 2, sc=0.2), p + "b-mlp.models.share.3.bias": r(E, sc=0.1)})
+    q = f"readouts.{mouse}."
+    sd.update({q + "sigma": (rng.uniform(-0.3, 0.3, (1, n, 2, 2))).astype(np.float32),
+               q + "features": (1.0 / E + r(1, E, 1, n, sc=0.05)), q + "bias": r(n, sc=0.3),
+               q + "mu_transform.0.weight": r(30, 2, sc=1.0), q + "mu_transform.0.bias": r(30, sc=0.3),
+               q + "mu_transform.2.weight": r(2, 30, sc=0.5), q + "mu_transform.2.bias": r(2, sc=0.1)})
+    s = f"core_shifter.{mouse}."
+    sd.update({s + "mlp.0.weight": r(5, 2, sc=0.5), s + "mlp.0.bias": r(5, sc=0.2), s + "mlp.2.weight": r(5, 5, sc=0.5),
+               s + "mlp.2.bias": r(5, sc=0.2), s + "mlp.4.weight": r(2, 5, sc=0.5), s + "mlp.4.bias": r(2, sc=0.2)})
+    return sd
+
+
+def _default_model(n, blocks, rng, **over):
+    from types import SimpleNamespace
+    a = dict(input_shape=(1, 36, 64), output_shapes={"A": (n,)}, device=torch.device(DEV), core="vit",
+             readout="gaussian2d", behavior_mode=3, shift_mode=2, center_crop=1.0, resize_image=0, ds_name="sensorium",
+             patch_mode=0, patch_size=8, patch_stride=1, emb_dim=155, num_blocks=blocks, num_heads=4, mlp_dim=488,
+             p_dropout=0.0, t_dropout=0.0, drop_path=0.0, use_lsa=False, disable_bias=False, grad_checkpointing=0,
+             core_reg_scale=0.5379, readout_reg_scale=0.0076, disable_grid_predictor=False, grid_predictor_dim=2,
+             bias_mode=0, shifter_reg_scale=0.0, cropper_reg_scale=0.0, criterion="poisson", ds_scale=1, verbose=0)
+    a.update(over)
+    args = SimpleNamespace(**a)
+    ds = make_ds({"A": n})
+    model = v1t_b200.Model(args, ds=ds)
+    cfg = O.CoreConfig(num_blocks=blocks)
+    sd = _random_state(cfg, n, rng)
+    full = {k: v.clone() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        assert tuple(full[k].shape) == v.shape, k
+        full[k] = torch.from_numpy(v)
+    model.load_state_dict(full, strict=True)
+    sd["readouts.A.source_grid"] = model.readouts["A"].source_grid.numpy()
+    crit = v1t_b200.get_criterion(args, ds=ds)
+    return model.to(DEV), crit, cfg, sd
+
+
+def test_full_default_shape_matches_oracle():
+    """Default V1T widths and the full 1654-token sequence (1x36x64, patch 8 stride 1), B=2, 2 blocks, N=1000:
+    CUDA path vs the numpy fp64 oracle, forward + every gradient."""
+    rng = np.random.default_rng(7)
+    n, B = 1000, 2
+    model, crit, cfg, sd = _default_model(n, 2, rng)
+    model.train(True)
+    images = rng.standard_normal((B, 1, 36, 64)).astype(np.float32)
+    beh, pup = rng.uniform(size=(B, 3)).astype(np.float32), rng.uniform(size=(B, 2)).astype(np.float32)
+    y_true = rng.uniform(0, 2, size=(B, n)).astype(np.float32)
+    noise = rng.standard_normal((B, n, 2)).astype(np.float32)
+    ref = O.path_forward_backward(sd, cfg, "A", images, beh, pup, y_true, ds_size=4500, noise=noise)
+    im = cu(images).requires_grad_(True)
+    y, _, _ = model(im, mouse_id="A", behaviors=cu(beh), pupil_centers=cu(pup), noise=cu(noise))
+    loss = crit(y_true=cu(y_true), y_pred=y, mouse_id="A", batch_size=B)
+    loss.backward()
+    assert rel_err(y.detach().cpu().numpy(), ref["y"]) < TOL_FWD
+    assert abs(loss.item() - ref["loss"]) / abs(ref["loss"]) < TOL_FWD
+    assert rel_err(im.grad.cpu().numpy(), ref["dimages"]) < TOL_GRAD
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), ref["grads"][k]) < TOL_GRAD, (k, rel_err(p.grad.cpu().numpy(), ref["grads"][k]))
+
+
+def test_dropout_masks_replay_exactly_against_oracle():
+    """Train mode WITH dropout: fetch the kernels' own masks through v1t_dropout_mask and hand them to the
+    oracle -> forward and gradients must still agree (validates in-kernel RNG replay in backward)."""
+    g = Golden("tiny_train")
+    p_tok, p_blk, seed = 0.1, 0.25, 12345
+    model, crit = build(g, p_dropout=p_tok, t_dropout=p_blk)
+    model.train(True)
+    model.core.dropout_seed = seed
+    d = g.mice["A"]
+    cfg = g.core_config()
+    B, T, E, H, M = d["images"].shape[0], cfg.num_tokens, cfg.emb_dim, cfg.num_heads, cfg.mlp_dim
+    mk = lambda site, shape, p: VF.dropout_mask(int(np.prod(shape)), seed, site, p, DEV).cpu().numpy().reshape(shape).astype(np.float64)
+    masks = {"tokens": mk(0, (B, T, E), p_tok)}
+    for i in range(cfg.num_blocks):
+        masks[(i, "attn")] = mk(i * 8 + 1, (B, H, T, T), p_blk)
+        masks[(i, "proj")] = mk(i * 8 + 2, (B, T, E), p_blk)
+        masks[(i, "mlp1")] = mk(i * 8 + 3, (B, T, M), p_blk)
+        masks[(i, "mlp2")] = mk(i * 8 + 4, (B, T, E), p_blk)
+    keep = masks[(0, "attn")] != 0
+    assert abs(keep.mean() - (1 - p_blk)) < 0.03 and np.allclose(masks[(0, "attn")][keep], 1 / (1 - p_blk))
+    ref = O.path_forward_backward(g.sd, cfg, "A", d["images"], d["behaviors"], d["pupil_centers"], d["y_true"],
+                                  ds_size=4500, noise=d["noise"], masks=masks)
+    y, _, _ = model(cu(d["images"]), mouse_id="A", behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]),
+                    noise=cu(d["noise"]))
+    loss = crit(y_true=cu(d["y_true"]), y_pred=y, mouse_id="A", batch_size=B)
+    loss.backward()
+    assert rel_err(y.detach().cpu().numpy(), ref["y"]) < TOL_FWD
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), ref["grads"][k]) < TOL_GRAD, k
+
+
+def test_readout_edge_cases_against_oracle():
+    """Clamped positions, shifts pushing corners out of the map (zero padding), ragged N (not a multiple of the
+    32-neuron CTA tile), batch larger than one batch tile, strided channel-last input with padded rows."""
+    rng = np.random.default_rng(3)
+    B, gh, gw, C, N = 37, 5, 7, 19, 45
+    base = torch.zeros(B, gh * gw + 1, 32, device=DEV)
+    fm = rng.standard_normal((B, gh, gw, C)).astype(np.float32)
+    base[:, 1:, :C] = cu(fm).reshape(B, gh * gw, C)
+    fmap = base[:, 1:, :C].unflatten(1, (gh, gw)).permute(0, 3, 1, 2).requires_grad_(True)
+    mu = rng.uniform(-1.4, 1.4, (N, 2)).astype(np.float32)
+    mu[:4] = [[-1, -1], [1, 1], [0, 0], [3, -3]]
+    sigma = rng.uniform(-0.4, 0.4, (N, 2, 2)).astype(np.float32)
+    noise = rng.standard_normal((B, N, 2)).astype(np.float32)
+    shifts = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+    shifts[0] = [2.5, -2.5]
+    feats = rng.standard_normal((C, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    dz = rng.standard_normal((B, N)).astype(np.float32)
+    t = [cu(a).requires_grad_(True) for a in (mu, sigma, shifts, feats, bias)]
+    z = VF.readout_forward(fmap, t[0], t[1], cu(noise), t[2], t[3], t[4])
+    zr, cache = O.readout_forward(fm, mu.astype(np.float64), sigma.astype(np.float64), feats.astype(np.float64),
+                                  bias.astype(np.float64), noise=noise, shifts=shifts)
+    assert rel_err(z.detach().cpu().numpy(), zr) < 1e-5
+    assert np.all(z.detach().cpu().numpy()[0] == bias)  # sample 0 is shifted fully out of the map
+    z.backward(cu(dz))
+    G, dfm = O.readout_backward(cache, sigma.astype(np.float64), feats.astype(np.float64), dz.astype(np.float64))
+    got_dfm = fmap.grad.permute(0, 2, 3, 1).cpu().numpy()
+    assert rel_err(got_dfm, dfm) < 1e-4
+    for name, tt in zip(("mu", "sigma", "shifts", "features", "bias"), t):
+        assert rel_err(tt.grad.cpu().numpy(), G[name]) < 1e-4, name
+    # eval mode (no noise, no shifts, no bias)
+    z2 = VF.readout_forward(fmap.detach(), cu(mu), cu(sigma), None, None, cu(feats), None)
+    zr2, _ = O.readout_forward(fm, mu.astype(np.float64), sigma.astype(np.float64), feats.astype(np.float64), None)
+    assert rel_err(z2.cpu().numpy(), zr2) < 1e-5
+
+
+def test_gemm_fp32_strided_batched_vs_torch():
+    import ctypes as C
+    from v1t_b200 import _lib
+    lib = _lib.load()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rng = torch.Generator(device=DEV).manual_seed(0)
+    for (m, n, k, b1, b2, ta, tb) in [(130, 70, 33, 1, 1, False, False), (64, 155, 155, 2, 3, False, True),
+                                      (155, 64, 1000, 1, 1, True, False), (1, 1, 1, 1, 1, False, False),
+                                      (257, 129, 17, 3, 1, True, True)]:
+        A = torch.randn((b1, b2, k, m) if ta else (b1, b2, m, k), device=DEV, generator=rng)
+        Bm = torch.randn((b1, b2, n, k) if tb else (b1, b2, k, n), device=DEV, generator=rng)
+        bias = torch.randn(n, device=DEV, generator=rng)
+        R = torch.randn(b1, b2, m, n, device=DEV, generator=rng)
+        Cm = torch.empty(b1, b2, m, n, device=DEV)
+        d = _lib.GemmDesc(m=m, n=n, k=k, batch1=b1, batch2=b2, alpha=0.5, accumulate=0)
+        d.a_m, d.a_k = (1, m) if ta else (k, 1)
+        d.a_b1, d.a_b2 = b2 * m * k, m * k
+        d.b_k, d.b_n = (1, k) if tb else (n, 1)
+        d.b_b1, d.b_b2 = b2 * n * k, n * k
+        d.c_m, d.c_b1, d.c_b2 = n, b2 * m * n, m * n
+        d.r_m, d.r_b1, d.r_b2 = n, b2 * m * n, m * n
+        rc = lib.v1t_gemm_fp32(C.byref(d), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), bias.data_ptr(), R.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _lib.last_error()
+        Am = A.transpose(-1, -2) if ta else A
+        Bn = Bm.transpose(-1, -2) if tb else Bm
+        ref = 0.5 * (Am.double() @ Bn.double()) + bias.double() + R.double()
+        assert rel_err(Cm.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+def test_attention_probs_hook_matches_oracle():
+    """Forward hooks on ``mha.attend`` (what attention_rollout.Recorder registers) receive softmax(QK^T/sqrt(E))."""
+    g = Golden("tiny_eval")
+    model, _ = build(g)
+    model.eval()
+    got = []
+    hooks = [blk["mha"].attend.register_forward_hook(lambda m, i, o: got.append(o.detach().clone()))
+             for blk in model.core.transformer.blocks]
+    d = g.mice["A"]
+    with torch.no_grad():
+        model.core(cu(d["images"]), mouse_id="A", behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]))
+    for h in hooks:
+        h.remove()
+    P = O.params_to_f64(g.sd, "core.")
+    _, cache = O.core_forward(P, g.core_config(), d["images"], d["behaviors"], d["pupil_centers"])
+    assert len(got) == len(cache["blocks"])
+    for a, c in zip(got, cache["blocks"]):
+        assert rel_err(a.cpu().numpy(), c["p"]) < 1e-4
+        assert np.allclose(a.sum(-1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+def test_full_size_properties_baseline_config():
+    """BASELINE configs[0] size (B=16, 4 blocks, T=1654, N=8000): size-independent properties — run-to-run
+    determinism of everything except the atomically-scattered map gradient, batch-split invariance, loss equal to
+    the sum of per-sample losses, finite gradients."""
+    rng = np.random.default_rng(11)
+    n, B = 8000, 16
+    model, crit, cfg, _ = _default_model(n, 4, rng)
+    model.train(True)
+    images, beh, pup = cu(rng.standard_normal((B, 1, 36, 64))), cu(rng.uniform(size=(B, 3))), cu(rng.uniform(size=(B, 2)))
+    y_true, noise = cu(rng.uniform(0, 2, size=(B, n))), cu(rng.standard_normal((B, n, 2)))
+
+    def run(sl):
+        model.zero_grad(set_to_none=True)
+        y, _, _ = model(images[sl], mouse_id="A", behaviors=beh[sl], pupil_centers=pup[sl], noise=noise[sl])
+        loss = crit(y_true=y_true[sl], y_pred=y, mouse_id="A", batch_size=B)
+        loss.backward()
+        return y.detach().clone(), loss.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    y_a, l_a, g_a = run(slice(0, B))
+    y_b, l_b, g_b = run(slice(0, B))
+    assert torch.equal(y_a, y_b) and torch.equal(l_a, l_b)
+    assert all(torch.isfinite(v).all() for v in g_a.values())
+    for k in ("readouts.A.features", "readouts.A.bias", "readouts.A.sigma"):
+        assert torch.equal(g_a[k], g_b[k]), k  # atomic-free reductions are bitwise reproducible
+    y_1, l_1, g_1 = run(slice(0, B // 2))
+    y_2, l_2, g_2 = run(slice(B // 2, B))
+    assert rel_err(torch.cat([y_1, y_2]).cpu().numpy(), y_a.cpu().numpy()) < 1e-5
+    assert abs((l_1 + l_2).item() - l_a.item()) / abs(l_a.item()) < 1e-5
+    for k in g_a:
+        s = (g_1[k] + g_2[k]).cpu().numpy()
+        assert rel_err(s, g_a[k].cpu().numpy()) < 1e-3, k

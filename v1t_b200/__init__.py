@@ -1,0 +1,11 @@
+"""v1t_b200 — B200-native (sm_100a) implementation of the V1T hot path: ViT core + Gaussian2d readout +
+Poisson loss, forward and backward, behind the reference's nn.Module / registry API."""
+from . import _lib  # noqa: F401
+from .modules import (  # noqa: F401
+    Attention, BehaviorMLP, Core, CoreShifter, CoreShifters, ELU1, Gaussian2DReadout, Image2Patches, ImageCropper,
+    Loss, MLP, Model, PoissonLoss, Readout, Readouts, Transformer, ViTCore, get_core, get_criterion,
+)
+from . import functional  # noqa: F401
+
+__all__ = ["ViTCore", "Gaussian2DReadout", "PoissonLoss", "ELU1", "Model", "Readouts", "get_core", "get_criterion",
+           "functional"]

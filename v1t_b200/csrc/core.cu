@@ -1,0 +1,452 @@
+// Host-side orchestration of the ViT core forward / backward (the launch sequence lives in native code, the
+// Python boundary only hands over pointers).  Reference: ViTCore.forward vit.py:423-436 and everything it
+// calls (Image2Patches :122-129, Transformer.forward :348-362, Attention.mha :267-275, MLP :153-154), plus
+// the autograd of that graph.  This file implements V1T_IMPL_FP32 (CUDA-core GEMMs, materialised attention
+// probabilities per batch chunk); the tcgen05 paths plug into the same save/scratch layout.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace v1t {
+namespace {
+
+enum Site { kSiteTokens = 0, kSiteAttn = 1, kSiteProj = 2, kSiteMlp1 = 3, kSiteMlp2 = 4 };
+inline DropSpec site_drop(const v1t_core_shape& s, int block, Site site) {
+  const float p = site == kSiteTokens ? s.p_drop_tokens : s.p_drop_block;
+  return DropSpec{s.seed, (uint32_t)(block * 8 + site), p};
+}
+
+struct Dims {
+  int B, C, H, W, p, s, gh, gw, L, T, E, Ep, heads, I, M, Mp, pd, hid, bdim, blocks;
+  int64_t R;  // B*T rows
+};
+
+int make_dims(const v1t_core_shape* sh, Dims& d) {
+  V1T_CHECK_ARG(sh, "core: null shape");
+  V1T_CHECK_ARG(sh->batch > 0 && sh->in_ch > 0 && sh->in_h > 0 && sh->in_w > 0, "core: bad image shape");
+  V1T_CHECK_ARG(sh->patch > 0 && sh->stride >= 1 && sh->stride <= sh->patch, "core: need 1 <= stride <= patch");
+  V1T_CHECK_ARG(sh->in_h >= sh->patch && sh->in_w >= sh->patch, "core: image smaller than a patch");
+  V1T_CHECK_ARG(sh->emb > 0 && sh->emb <= 512 && sh->heads > 0 && sh->mlp > 0, "core: bad widths (emb <= 512)");
+  V1T_CHECK_ARG(sh->blocks > 0 && sh->blocks <= V1T_MAX_BLOCKS, "core: 1..%d blocks", V1T_MAX_BLOCKS);
+  V1T_CHECK_ARG(sh->bdim == 0 || sh->bdim == 3 || sh->bdim == 5, "core: bdim must be 0, 3 or 5");
+  V1T_CHECK_ARG(sh->p_drop_tokens >= 0.f && sh->p_drop_tokens < 1.f && sh->p_drop_block >= 0.f &&
+                    sh->p_drop_block < 1.f, "core: dropout p must be in [0,1)");
+  V1T_CHECK_ARG(sh->impl == V1T_IMPL_FP32, "core: impl %d not available in this build", sh->impl);
+  d.B = sh->batch; d.C = sh->in_ch; d.H = sh->in_h; d.W = sh->in_w; d.p = sh->patch; d.s = sh->stride;
+  d.gh = (d.H - d.p) / d.s + 1;
+  d.gw = (d.W - d.p) / d.s + 1;
+  d.L = d.gh * d.gw;
+  d.T = d.L + 1;
+  d.E = sh->emb;
+  d.Ep = (int)round_up(d.E, 32);
+  d.heads = sh->heads;
+  d.I = d.heads * d.E;
+  d.M = sh->mlp;
+  d.Mp = (int)round_up(d.M, 32);
+  d.pd = d.C * d.p * d.p;
+  d.hid = d.E / 2;
+  d.bdim = sh->bdim;
+  d.blocks = sh->blocks;
+  d.R = (int64_t)d.B * d.T;
+  return V1T_OK;
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  float* take(int64_t floats) {
+    float* p = base ? (float*)(base + off) : nullptr;
+    off += (size_t)round_up(floats * (int64_t)sizeof(float), 256);
+    return p;
+  }
+};
+
+struct BlockSaved {
+  float *x1, *st1, *qkv, *o, *x2, *st2, *u, *bhid, *blat;
+};
+struct Saved {
+  BlockSaved blk[V1T_MAX_BLOCKS];
+  size_t total;
+};
+void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
+  b.x1 = c.take(d.R * d.Ep);
+  b.st1 = c.take(d.R * 2);
+  b.qkv = c.take(d.R * 3 * d.I);
+  b.o = c.take(d.R * d.I);
+  b.x2 = c.take(d.R * d.Ep);
+  b.st2 = c.take(d.R * 2);
+  b.u = c.take(d.R * d.Mp);
+  b.bhid = c.take((int64_t)d.B * d.hid + 1);
+  b.blat = c.take((int64_t)d.B * d.E);
+}
+Saved carve_saved(const Dims& d, void* base) {
+  Carver c(base);
+  Saved s;
+  for (int i = 0; i < d.blocks; ++i) carve_block(c, d, s.blk[i]);
+  s.total = c.off;
+  return s;
+}
+
+constexpr size_t kPartialBytes = 64u << 20;
+
+struct Scratch {
+  BlockSaved tmp;    // one block of "saved" space for inference (keep_for_backward == 0)
+  float *h, *dh, *g, *dqkv, *dO, *patches, *P1, *P2, *partials, *dlat, *dz3, *dhid, *dpos;
+  int chunk;         // attention batch chunk
+  size_t total;
+};
+int attn_chunk(const Dims& d) {
+  const int64_t per = (int64_t)d.heads * d.T * d.T * (int64_t)sizeof(float);
+  int64_t c = (1ll << 30) / std::max<int64_t>(per, 1);
+  c = std::max<int64_t>(1, std::min<int64_t>(c, d.B));
+  // keep grid.z = chunk*heads within limits
+  while (c * d.heads > 65535) --c;
+  return (int)c;
+}
+Scratch carve_scratch(const Dims& d, void* base) {
+  Carver c(base);
+  Scratch s;
+  carve_block(c, d, s.tmp);
+  s.chunk = attn_chunk(d);
+  s.h = c.take(d.R * d.Ep);
+  s.dh = c.take(d.R * d.Ep);
+  s.g = c.take(d.R * d.Mp);
+  s.dqkv = c.take(d.R * 3 * d.I);
+  s.dO = c.take(d.R * d.I);
+  s.patches = c.take((int64_t)d.B * d.L * d.pd);
+  s.P1 = c.take((int64_t)s.chunk * d.heads * d.T * d.T);
+  s.P2 = c.take((int64_t)s.chunk * d.heads * d.T * d.T);
+  s.partials = c.take(kPartialBytes / sizeof(float));
+  s.dlat = c.take((int64_t)d.B * d.E);
+  s.dz3 = c.take((int64_t)d.B * d.E);
+  s.dhid = c.take((int64_t)d.B * d.hid + 1);
+  s.dpos = c.take((int64_t)d.T * d.E);
+  s.total = c.off;
+  return s;
+}
+
+v1t_gemm_desc gd(int m, int n, int k) {
+  v1t_gemm_desc g{};
+  g.m = m; g.n = n; g.k = k; g.batch1 = 1; g.batch2 = 1; g.alpha = 1.f;
+  return g;
+}
+
+// P[b,h] = softmax(scale * Q K^T) (optionally with dropout) for samples [b0, b0+bc) into P1
+int attention_probs(const Dims& d, const float* qkv, int b0, int bc, float* P, DropSpec dr, cudaStream_t st) {
+  const int64_t ld = 3 * d.I;
+  v1t_gemm_desc g = gd(d.T, d.T, d.E);
+  g.batch1 = bc; g.batch2 = d.heads;
+  g.a_m = ld; g.a_k = 1; g.a_b1 = d.T * ld; g.a_b2 = d.E;
+  g.b_k = 1; g.b_n = ld; g.b_b1 = d.T * ld; g.b_b2 = d.E;
+  g.c_m = d.T; g.c_b1 = (int64_t)d.heads * d.T * d.T; g.c_b2 = (int64_t)d.T * d.T;
+  g.alpha = 1.0f / sqrtf((float)d.E);  // emb_dim ** -0.5 (vit.py:234)
+  const float* q = qkv + (int64_t)b0 * d.T * ld;
+  V1T_TRY(gemm_fp32(g, q, q + d.I, P, nullptr, nullptr, st));
+  return softmax_rows(P, (int64_t)bc * d.heads * d.T, d.T, d.T, dr, (int64_t)b0 * d.heads * d.T, st);
+}
+
+}  // namespace
+}  // namespace v1t
+
+using namespace v1t;
+
+extern "C" int v1t_core_dims_of(const v1t_core_shape* shape, v1t_core_dims* out) {
+  Dims d;
+  V1T_TRY(make_dims(shape, d));
+  V1T_CHECK_ARG(out, "core_dims_of: null out");
+  out->gh = d.gh; out->gw = d.gw; out->tokens = d.T; out->emb_ld = d.Ep; out->inner = d.I; out->mlp_ld = d.Mp;
+  out->patch_dim = d.pd; out->hid = d.hid;
+  return V1T_OK;
+}
+
+extern "C" size_t v1t_core_saved_bytes(const v1t_core_shape* shape) {
+  Dims d;
+  if (make_dims(shape, d) != V1T_OK) return 0;
+  return carve_saved(d, nullptr).total;
+}
+extern "C" size_t v1t_core_scratch_bytes(const v1t_core_shape* shape) {
+  Dims d;
+  if (make_dims(shape, d) != V1T_OK) return 0;
+  return carve_scratch(d, nullptr).total;
+}
+
+extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs* P, const float* images,
+                                const float* behaviors, float* x, void* saved_mem, void* scratch_mem,
+                                int keep, void* stream) {
+  Dims d;
+  V1T_TRY(make_dims(shape, d));
+  V1T_CHECK_ARG(P && images && x && scratch_mem, "core_forward: null argument");
+  V1T_CHECK_ARG(!keep || saved_mem, "core_forward: keep_for_backward needs the saved buffer");
+  V1T_CHECK_ARG(d.bdim == 0 || behaviors, "core_forward: behaviors missing");
+  V1T_CHECK_ARG(P->cls && P->pos && P->wpe && P->bpe, "core_forward: patch-embedding parameter missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved sv = carve_saved(d, keep ? saved_mem : nullptr);
+  Scratch sc = carve_scratch(d, scratch_mem);
+
+  // ---- Image2Patches (vit.py:122-129): unfold -> Linear -> [CLS; tokens] + pos -> dropout
+  V1T_CUDA(cudaMemsetAsync(x, 0, sizeof(float) * d.R * d.Ep, st));
+  V1T_TRY(im2col(images, sc.patches, d.B, d.C, d.H, d.W, d.p, d.s, d.gh, d.gw, st));
+  {
+    v1t_gemm_desc g = gd(d.L, d.E, d.pd);
+    g.batch1 = d.B;
+    g.a_m = d.pd; g.a_k = 1; g.a_b1 = (int64_t)d.L * d.pd;
+    g.b_k = 1; g.b_n = d.pd;                       // Wpe [E, pd]
+    g.c_m = d.Ep; g.c_b1 = (int64_t)d.T * d.Ep;
+    g.r_m = d.E; g.r_b1 = 0;                       // + pos[1 + l]
+    V1T_TRY(gemm_fp32(g, sc.patches, P->wpe, x + d.Ep, P->bpe, P->pos + d.E, st));
+  }
+  V1T_TRY(cls_rows(P->cls, P->pos, x, d.B, d.T, d.E, d.Ep, st));
+  if (shape->p_drop_tokens > 0.f) V1T_TRY(dropout_rows(x, x, d.R, d.E, d.Ep, site_drop(*shape, 0, kSiteTokens), st));
+
+  for (int i = 0; i < d.blocks; ++i) {
+    const v1t_block_ptrs& W = P->blk[i];
+    const BlockSaved& S = keep ? sv.blk[i] : sc.tmp;
+    V1T_CHECK_ARG(W.ln1_w && W.ln1_b && W.wqkv && W.wproj && W.ln2_w && W.ln2_b && W.w1 && W.w2,
+                  "core_forward: block %d parameter missing", i);
+    // ---- behaviour latent added to every token, persists in the residual stream (vit.py:355-359)
+    const float* lat = nullptr;
+    if (d.bdim > 0) {
+      V1T_CHECK_ARG(W.bw0 && W.bw3, "core_forward: block %d b-mlp weights missing", i);
+      V1T_TRY(bmlp_forward(behaviors, W.bw0, W.bb0, W.bw3, W.bb3, S.bhid, S.blat, d.B, d.bdim, d.hid, d.E, st));
+      lat = S.blat;
+    }
+    // ---- Attention.mha (vit.py:267-275)
+    V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st));
+    {
+      v1t_gemm_desc g = gd((int)d.R, 3 * d.I, d.E);
+      V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
+      g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = 3 * d.I;
+      V1T_TRY(gemm_fp32(g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st));
+    }
+    for (int b0 = 0; b0 < d.B; b0 += sc.chunk) {
+      const int bc = std::min(sc.chunk, d.B - b0);
+      V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, site_drop(*shape, i, kSiteAttn), st));
+      v1t_gemm_desc g = gd(d.T, d.E, d.T);  // O = P V
+      g.batch1 = bc; g.batch2 = d.heads;
+      g.a_m = d.T; g.a_k = 1; g.a_b1 = (int64_t)d.heads * d.T * d.T; g.a_b2 = (int64_t)d.T * d.T;
+      g.b_k = 3 * d.I; g.b_n = 1; g.b_b1 = (int64_t)d.T * 3 * d.I; g.b_b2 = d.E;
+      g.c_m = d.I; g.c_b1 = (int64_t)d.T * d.I; g.c_b2 = d.E;
+      V1T_TRY(gemm_fp32(g, sc.P1, S.qkv + (int64_t)b0 * d.T * 3 * d.I + 2 * d.I, S.o + (int64_t)b0 * d.T * d.I,
+                        nullptr, nullptr, st));
+    }
+    {  // x2 = x1 + dropout(o Wproj^T + b)
+      v1t_gemm_desc g = gd((int)d.R, d.E, d.I);
+      g.a_m = d.I; g.a_k = 1; g.b_k = 1; g.b_n = d.I; g.c_m = d.Ep; g.r_m = d.Ep;
+      V1T_TRY(gemm_fp32(g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj)));
+    }
+    // ---- MLP (vit.py:143-150)
+    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, S.st2, d.R, d.E, d.Ep, st));
+    {
+      v1t_gemm_desc g = gd((int)d.R, d.M, d.E);
+      g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = d.Mp;
+      V1T_TRY(gemm_fp32(g, sc.h, W.w1, S.u, W.b1, nullptr, st));
+    }
+    V1T_TRY(gelu_forward(S.u, sc.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));
+    {
+      v1t_gemm_desc g = gd((int)d.R, d.E, d.M);
+      g.a_m = d.Mp; g.a_k = 1; g.b_k = 1; g.b_n = d.M; g.c_m = d.Ep; g.r_m = d.Ep;
+      V1T_TRY(gemm_fp32(g, sc.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2)));
+    }
+  }
+  return V1T_OK;
+}
+
+extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptrs* P, const float* images,
+                                 const float* behaviors, float* dx, const void* saved_mem, void* scratch_mem,
+                                 const v1t_core_ptrs* G, float* d_images, void* stream) {
+  Dims d;
+  V1T_TRY(make_dims(shape, d));
+  V1T_CHECK_ARG(P && images && dx && saved_mem && scratch_mem && G, "core_backward: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved sv = carve_saved(d, const_cast<void*>(saved_mem));
+  Scratch sc = carve_scratch(d, scratch_mem);
+  const float scale = 1.0f / sqrtf((float)d.E);
+  const int R = (int)d.R;
+  const bool drop = shape->p_drop_block > 0.f;
+
+  for (int i = d.blocks - 1; i >= 0; --i) {
+    const v1t_block_ptrs& W = P->blk[i];
+    const v1t_block_ptrs& GW = G->blk[i];
+    const BlockSaved& S = sv.blk[i];
+    // ================= MLP branch: x_out = x2 + drop(g W2^T + b2) =================
+    const float* dm = dx;
+    if (drop) {
+      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteMlp2), st));
+      dm = sc.dh;
+    }
+    V1T_TRY(gelu_forward(S.u, sc.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // recompute g
+    if (GW.w2) {  // dW2[e,m] = sum_r dm[r,e] g[r,m]
+      v1t_gemm_desc g = gd(d.E, d.M, R);
+      g.a_m = 1; g.a_k = d.Ep; g.b_k = d.Mp; g.b_n = 1; g.c_m = d.M;
+      V1T_TRY(gemm_fp32_splitk(g, dm, sc.g, GW.w2, sc.partials, kPartialBytes, st));
+    }
+    if (GW.b2) V1T_TRY(colsum(dm, GW.b2, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
+    {  // dg[r,m] = sum_e dm[r,e] W2[e,m]   -> sc.g (g no longer needed)
+      v1t_gemm_desc g = gd(R, d.M, d.E);
+      g.a_m = d.Ep; g.a_k = 1; g.b_k = d.M; g.b_n = 1; g.c_m = d.Mp;
+      // dW2 above reads sc.g: stream order keeps it safe (same stream)
+      V1T_TRY(gemm_fp32(g, dm, W.w2, sc.g, nullptr, nullptr, st));
+    }
+    V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
+    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
+    if (GW.w1) {  // dW1[m,e] = sum_r du[r,m] h2[r,e]
+      v1t_gemm_desc g = gd(d.M, d.E, R);
+      g.a_m = 1; g.a_k = d.Mp; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
+      V1T_TRY(gemm_fp32_splitk(g, sc.g, sc.h, GW.w1, sc.partials, kPartialBytes, st));
+    }
+    if (GW.b1) V1T_TRY(colsum(sc.g, GW.b1, 1, d.R, d.M, 0, d.Mp, 0, sc.partials, kPartialBytes, st));
+    {  // dh2[r,e] = sum_m du[r,m] W1[m,e]
+      v1t_gemm_desc g = gd(R, d.E, d.M);
+      g.a_m = d.Mp; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
+      V1T_TRY(gemm_fp32(g, sc.g, W.w1, sc.dh, nullptr, nullptr, st));
+    }
+    V1T_TRY(ln_backward(sc.dh, S.x2, S.st2, W.ln2_w, dx, GW.ln2_w, GW.ln2_b, sc.partials, kPartialBytes, d.R, d.E,
+                        d.Ep, st));
+    // ================= attention branch: x2 = x1 + drop(o Wproj^T + b) =================
+    const float* da = dx;
+    if (drop) {
+      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteProj), st));
+      da = sc.dh;
+    }
+    if (GW.wproj) {  // dWp[e,i] = sum_r da[r,e] o[r,i]
+      v1t_gemm_desc g = gd(d.E, d.I, R);
+      g.a_m = 1; g.a_k = d.Ep; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
+      V1T_TRY(gemm_fp32_splitk(g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st));
+    }
+    if (GW.bproj) V1T_TRY(colsum(da, GW.bproj, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
+    {  // dO[r,i] = sum_e da[r,e] Wp[e,i]
+      v1t_gemm_desc g = gd(R, d.I, d.E);
+      g.a_m = d.Ep; g.a_k = 1; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
+      V1T_TRY(gemm_fp32(g, da, W.wproj, sc.dO, nullptr, nullptr, st));
+    }
+    const int64_t ld = 3 * d.I;
+    for (int b0 = 0; b0 < d.B; b0 += sc.chunk) {
+      const int bc = std::min(sc.chunk, d.B - b0);
+      const float* q = S.qkv + (int64_t)b0 * d.T * ld;
+      const float* dO = sc.dO + (int64_t)b0 * d.T * d.I;
+      float* dq = sc.dqkv + (int64_t)b0 * d.T * ld;
+      const int64_t pb1 = (int64_t)d.heads * d.T * d.T, pb2 = (int64_t)d.T * d.T;
+      V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, no_drop(), st));  // P (no dropout)
+      {  // dPd = dO V^T
+        v1t_gemm_desc g = gd(d.T, d.T, d.E);
+        g.batch1 = bc; g.batch2 = d.heads;
+        g.a_m = d.I; g.a_k = 1; g.a_b1 = (int64_t)d.T * d.I; g.a_b2 = d.E;
+        g.b_k = 1; g.b_n = ld; g.b_b1 = d.T * ld; g.b_b2 = d.E;
+        g.c_m = d.T; g.c_b1 = pb1; g.c_b2 = pb2;
+        V1T_TRY(gemm_fp32(g, dO, q + 2 * d.I, sc.P2, nullptr, nullptr, st));
+      }
+      V1T_TRY(softmax_bwd_rows(sc.P1, sc.P2, (int64_t)bc * d.heads * d.T, d.T, d.T, site_drop(*shape, i, kSiteAttn),
+                               (int64_t)b0 * d.heads * d.T, st));  // P1 <- Pd, P2 <- dS
+      {  // dV[j,d] = sum_i Pd[i,j] dO[i,d]
+        v1t_gemm_desc g = gd(d.T, d.E, d.T);
+        g.batch1 = bc; g.batch2 = d.heads;
+        g.a_m = 1; g.a_k = d.T; g.a_b1 = pb1; g.a_b2 = pb2;
+        g.b_k = d.I; g.b_n = 1; g.b_b1 = (int64_t)d.T * d.I; g.b_b2 = d.E;
+        g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
+        V1T_TRY(gemm_fp32(g, sc.P1, dO, dq + 2 * d.I, nullptr, nullptr, st));
+      }
+      {  // dQ[i,d] = scale * sum_j dS[i,j] K[j,d]
+        v1t_gemm_desc g = gd(d.T, d.E, d.T);
+        g.batch1 = bc; g.batch2 = d.heads; g.alpha = scale;
+        g.a_m = d.T; g.a_k = 1; g.a_b1 = pb1; g.a_b2 = pb2;
+        g.b_k = ld; g.b_n = 1; g.b_b1 = d.T * ld; g.b_b2 = d.E;
+        g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
+        V1T_TRY(gemm_fp32(g, sc.P2, q + d.I, dq, nullptr, nullptr, st));
+      }
+      {  // dK[j,d] = scale * sum_i dS[i,j] Q[i,d]
+        v1t_gemm_desc g = gd(d.T, d.E, d.T);
+        g.batch1 = bc; g.batch2 = d.heads; g.alpha = scale;
+        g.a_m = 1; g.a_k = d.T; g.a_b1 = pb1; g.a_b2 = pb2;
+        g.b_k = ld; g.b_n = 1; g.b_b1 = d.T * ld; g.b_b2 = d.E;
+        g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
+        V1T_TRY(gemm_fp32(g, sc.P2, q, dq + d.I, nullptr, nullptr, st));
+      }
+    }
+    V1T_TRY(ln_forward(S.x1, nullptr, d.T, nullptr, W.ln1_w, W.ln1_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
+    if (GW.wqkv) {  // dWqkv[n,e] = sum_r dqkv[r,n] h1[r,e]
+      v1t_gemm_desc g = gd(3 * d.I, d.E, R);
+      g.a_m = 1; g.a_k = ld; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
+      V1T_TRY(gemm_fp32_splitk(g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st));
+    }
+    {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
+      v1t_gemm_desc g = gd(R, d.E, 3 * d.I);
+      g.a_m = ld; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
+      V1T_TRY(gemm_fp32(g, sc.dqkv, W.wqkv, sc.dh, nullptr, nullptr, st));
+    }
+    V1T_TRY(ln_backward(sc.dh, S.x1, S.st1, W.ln1_w, dx, GW.ln1_w, GW.ln1_b, sc.partials, kPartialBytes, d.R, d.E,
+                        d.Ep, st));
+    // ================= behaviour MLP: x1 = x_in + lat[b] =================
+    if (d.bdim > 0 && (GW.bw0 || GW.bb0 || GW.bw3 || GW.bb3)) {
+      V1T_TRY(colsum(dx, sc.dlat, d.B, d.T, d.E, (int64_t)d.T * d.Ep, d.Ep, d.E, sc.partials, kPartialBytes, st));
+      V1T_TRY(tanh_grad(sc.dlat, S.blat, sc.dz3, (int64_t)d.B * d.E, st));
+      if (GW.bw3) {  // dW3[e,j] = sum_b dz3[b,e] hid[b,j]
+        v1t_gemm_desc g = gd(d.E, d.hid, d.B);
+        g.a_m = 1; g.a_k = d.E; g.b_k = d.hid; g.b_n = 1; g.c_m = d.hid;
+        V1T_TRY(gemm_fp32(g, sc.dz3, S.bhid, GW.bw3, nullptr, nullptr, st));
+      }
+      if (GW.bb3) V1T_TRY(colsum(sc.dz3, GW.bb3, 1, d.B, d.E, 0, d.E, 0, sc.partials, kPartialBytes, st));
+      {  // dhid[b,j] = sum_e dz3[b,e] W3[e,j]
+        v1t_gemm_desc g = gd(d.B, d.hid, d.E);
+        g.a_m = d.E; g.a_k = 1; g.b_k = d.hid; g.b_n = 1; g.c_m = d.hid;
+        V1T_TRY(gemm_fp32(g, sc.dz3, W.bw3, sc.dhid, nullptr, nullptr, st));
+      }
+      V1T_TRY(tanh_grad(sc.dhid, S.bhid, sc.dhid, (int64_t)d.B * d.hid, st));  // dz0
+      if (GW.bw0) {  // dW0[j,i] = sum_b dz0[b,j] beh[b,i]
+        v1t_gemm_desc g = gd(d.hid, d.bdim, d.B);
+        g.a_m = 1; g.a_k = d.hid; g.b_k = d.bdim; g.b_n = 1; g.c_m = d.bdim;
+        V1T_TRY(gemm_fp32(g, sc.dhid, behaviors, GW.bw0, nullptr, nullptr, st));
+      }
+      if (GW.bb0) V1T_TRY(colsum(sc.dhid, GW.bb0, 1, d.B, d.hid, 0, d.hid, 0, sc.partials, kPartialBytes, st));
+    }
+  }
+
+  // ================= patch embedding =================
+  if (shape->p_drop_tokens > 0.f) V1T_TRY(dropout_rows(dx, dx, d.R, d.E, d.Ep, site_drop(*shape, 0, kSiteTokens), st));
+  V1T_TRY(batchsum(dx, sc.dpos, d.B, d.T, d.E, (int64_t)d.T * d.Ep, d.Ep, d.E, st));
+  if (G->pos) V1T_CUDA(cudaMemcpyAsync(G->pos, sc.dpos, sizeof(float) * d.T * d.E, cudaMemcpyDeviceToDevice, st));
+  if (G->cls) V1T_CUDA(cudaMemcpyAsync(G->cls, sc.dpos, sizeof(float) * d.E, cudaMemcpyDeviceToDevice, st));
+  if (G->bpe) V1T_TRY(colsum(sc.dpos + d.E, G->bpe, 1, d.L, d.E, 0, d.E, 0, sc.partials, kPartialBytes, st));
+  if (G->wpe) {  // dWpe[e,k] = sum_{b,l} dx[b,1+l,e] patches[b,l,k]: per-sample partials, then a fixed-order sum
+    V1T_TRY(im2col(images, sc.patches, d.B, d.C, d.H, d.W, d.p, d.s, d.gh, d.gw, st));
+    const int64_t per = (int64_t)d.E * d.pd;
+    int bstep = (int)std::max<int64_t>(1, std::min<int64_t>(d.B, (int64_t)(kPartialBytes / sizeof(float)) / per));
+    for (int b0 = 0; b0 < d.B; b0 += bstep) {
+      const int bc = std::min(bstep, d.B - b0);
+      v1t_gemm_desc g = gd(d.E, d.pd, d.L);
+      g.batch1 = bc;
+      g.a_m = 1; g.a_k = d.Ep; g.a_b1 = (int64_t)d.T * d.Ep;
+      g.b_k = d.pd; g.b_n = 1; g.b_b1 = (int64_t)d.L * d.pd;
+      g.c_m = d.pd; g.c_b1 = per;
+      V1T_TRY(gemm_fp32(g, dx + (int64_t)b0 * d.T * d.Ep + d.Ep, sc.patches + (int64_t)b0 * d.L * d.pd, sc.partials,
+                        nullptr, nullptr, st));
+      V1T_TRY(reduce_partials(sc.partials, G->wpe, bc, d.E, d.pd, d.pd, b0 > 0, st));
+    }
+  }
+  if (d_images) {  // d_patches = dtok Wpe -> fold
+    v1t_gemm_desc g = gd(d.L, d.pd, d.E);
+    g.batch1 = d.B;
+    g.a_m = d.Ep; g.a_k = 1; g.a_b1 = (int64_t)d.T * d.Ep;
+    g.b_k = d.pd; g.b_n = 1;
+    g.c_m = d.pd; g.c_b1 = (int64_t)d.L * d.pd;
+    V1T_TRY(gemm_fp32(g, dx + d.Ep, P->wpe, sc.patches, nullptr, nullptr, st));
+    V1T_TRY(col2im(sc.patches, d_images, d.B, d.C, d.H, d.W, d.p, d.s, d.gh, d.gw, st));
+  }
+  return V1T_OK;
+}
+
+extern "C" int v1t_attention_probs(const v1t_core_shape* shape, const void* saved_mem, int block, float* probs,
+                                   void* stream) {
+  Dims d;
+  V1T_TRY(make_dims(shape, d));
+  V1T_CHECK_ARG(saved_mem && probs && block >= 0 && block < d.blocks, "attention_probs: bad argument");
+  Saved sv = carve_saved(d, const_cast<void*>(saved_mem));
+  const int chunk = attn_chunk(d);
+  for (int b0 = 0; b0 < d.B; b0 += chunk) {
+    const int bc = std::min(chunk, d.B - b0);
+    V1T_TRY(attention_probs(d, sv.blk[block].qkv, b0, bc, probs + (int64_t)b0 * d.heads * d.T * d.T, no_drop(),
+                            (cudaStream_t)stream));
+  }
+  return V1T_OK;
+}

@@ -1,0 +1,514 @@
+// Row-wise / elementwise kernels of the ViT core: im2col for nn.Unfold (vit.py:68-71), CLS/pos rows
+// (vit.py:124-127), BehaviorMLP (vit.py:181-202), LayerNorm fwd/bwd (eps 1e-5, biased variance),
+// softmax fwd/bwd over the key dim (vit.py:262), exact-erf GELU fwd/bwd (vit.py:147), inverted dropout
+// with a replayable counter-based RNG, and the deterministic column/batch reductions used for the
+// bias / LayerNorm-affine / pos-embedding gradients.
+#include "common.cuh"
+#include "kernels.cuh"
+#include <algorithm>
+
+namespace v1t {
+namespace {
+
+constexpr float kLnEps = 1e-5f;
+
+// ---------------------------------------------------------------- patches ------------------------------
+__global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ patches, int B, int C, int H,
+                              int W, int p, int s, int gh, int gw) {
+  const int pd = C * p * p;
+  const int64_t total = (int64_t)B * gh * gw * pd;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % pd);
+    const int64_t row = i / pd;
+    const int l = (int)(row % (gh * gw));
+    const int b = (int)(row / (gh * gw));
+    const int kw = e % p, kh = (e / p) % p, ch = e / (p * p);
+    const int r = l / gw, c = l % gw;
+    patches[i] = __ldg(img + (((int64_t)b * C + ch) * H + r * s + kh) * W + c * s + kw);
+  }
+}
+
+// d_images[b,ch,y,x] = sum over patches covering (y,x) of d_patches  (gather form: atomic-free)
+__global__ void col2im_kernel(const float* __restrict__ dpatches, float* __restrict__ dimg, int B, int C, int H,
+                              int W, int p, int s, int gh, int gw) {
+  const int pd = C * p * p;
+  const int64_t total = (int64_t)B * C * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), ch = (int)((i / ((int64_t)W * H)) % C);
+    const int b = (int)(i / ((int64_t)W * H * C));
+    float acc = 0.f;
+    for (int kh = 0; kh < p; ++kh) {
+      const int ry = y - kh;
+      if (ry < 0 || ry % s != 0 || ry / s >= gh) continue;
+      for (int kw = 0; kw < p; ++kw) {
+        const int cx = x - kw;
+        if (cx < 0 || cx % s != 0 || cx / s >= gw) continue;
+        const int l = (ry / s) * gw + cx / s;
+        acc += __ldg(dpatches + ((int64_t)b * gh * gw + l) * pd + (ch * p + kh) * p + kw);
+      }
+    }
+    dimg[i] = acc;
+  }
+}
+
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
+                                int B, int T, int E, int ld) {
+  const int b = blockIdx.x;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) x[(int64_t)b * T * ld + e] = cls[e] + pos[e];
+}
+
+__global__ void dropout_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int cols,
+                                    int64_t ld, DropSpec dr) {
+  const float inv_keep = 1.f / (1.f - dr.p);
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i % cols);
+    dst[r * ld + c] = src[r * ld + c] * dropout_mult(dr.seed, dr.site, i, dr.p, inv_keep);
+  }
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ out, int64_t n, DropSpec dr) {
+  const float inv_keep = 1.f / (1.f - dr.p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = dropout_mult(dr.seed, dr.site, i, dr.p, inv_keep);
+}
+
+// ---------------------------------------------------------------- behaviour MLP ------------------------
+// grid = B; lat[b,:] = tanh(W3 tanh(W0 beh[b] + b0) + b3)
+__global__ void bmlp_forward_kernel(const float* __restrict__ beh, const float* __restrict__ w0,
+                                    const float* __restrict__ b0, const float* __restrict__ w3,
+                                    const float* __restrict__ b3, float* __restrict__ hid, float* __restrict__ lat,
+                                    int bdim, int H, int E) {
+  extern __shared__ float sh[];  // [H]
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float a = b0 ? b0[j] : 0.f;
+    for (int i = 0; i < bdim; ++i) a = fmaf(w0[j * bdim + i], beh[b * bdim + i], a);
+    a = tanhf(a);
+    sh[j] = a;
+    hid[(int64_t)b * H + j] = a;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float a = b3 ? b3[e] : 0.f;
+    for (int j = 0; j < H; ++j) a = fmaf(w3[e * H + j], sh[j], a);
+    lat[(int64_t)b * E + e] = tanhf(a);
+  }
+}
+
+__global__ void tanh_grad_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                                 int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    dz[i] = dy[i] * (1.f - v * v);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm ----------------------------
+// one warp per row; lane owns columns lane + 32*i.  NV = ceil(E/32) rounded to a compiled size.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict__ x_in, const float* __restrict__ add,
+                                                         int rows_per_batch, float* __restrict__ x_out,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ h,
+                                                         float* __restrict__ stats, int64_t rows, int E, int ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float g[NV], bt[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    g[i] = c < E ? gamma[c] : 0.f;
+    bt[i] = c < E ? beta[c] : 0.f;
+  }
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float v[NV];
+    const float* xr = x_in + r * ld;
+    const float* ar = add ? add + (r / rows_per_batch) * E : nullptr;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      float t = c < E ? xr[c] : 0.f;
+      if (ar && c < E) t += ar[c];
+      v[i] = t;
+      s += t;
+    }
+    const float mean = warp_sum(s) / (float)E;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      const float d = c < E ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)E + kLnEps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < ld) {
+        const bool in = c < E;
+        if (x_out) x_out[r * ld + c] = in ? v[i] : 0.f;
+        if (h) h[r * ld + c] = in ? (v[i] - mean) * rstd * g[i] + bt[i] : 0.f;
+      }
+    }
+    if (lane == 0 && stats) {
+      stats[2 * r] = mean;
+      stats[2 * r + 1] = rstd;
+    }
+  }
+}
+
+// dx_accum[r,:] += rstd*(dxh - mean(dxh) - xhat*mean(dxh*xhat)), dxh = dh*gamma; per-CTA partial dgamma/dbeta
+template <int NV>
+__global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restrict__ dh, const float* __restrict__ x,
+                                                          const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma,
+                                                          float* __restrict__ dx_accum, float* __restrict__ partials,
+                                                          int64_t rows, int E, int ld) {
+  __shared__ float red[2][8][32 * NV];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  float g[NV], dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    g[i] = c < E ? gamma[c] : 0.f;
+    dg[i] = 0.f;
+    db[i] = 0.f;
+  }
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    float xh[NV], dxh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      const bool in = c < E;
+      const float d = in ? dh[r * ld + c] : 0.f;
+      xh[i] = in ? (x[r * ld + c] - mean) * rstd : 0.f;
+      dxh[i] = d * g[i];
+      dg[i] += d * xh[i];
+      db[i] += d;
+      s1 += dxh[i];
+      s2 += dxh[i] * xh[i];
+    }
+    s1 = warp_sum(s1) / (float)E;
+    s2 = warp_sum(s2) / (float)E;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < E) dx_accum[r * ld + c] += rstd * (dxh[i] - s1 - xh[i] * s2);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    red[0][wid][lane + 32 * i] = dg[i];
+    red[1][wid][lane + 32 * i] = db[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += red[0][w][c];
+      b += red[1][w][c];
+    }
+    partials[((int64_t)blockIdx.x * 2) * E + c] = a;
+    partials[((int64_t)blockIdx.x * 2 + 1) * E + c] = b;
+  }
+}
+
+// dgamma[c] = sum_p partials[p][0][c], dbeta[c] = sum_p partials[p][1][c]   (fixed order: deterministic)
+__global__ void ln_finish_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
+                                 float* __restrict__ dbeta, int parts, int E) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= E) return;
+  float a = 0.f, b = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    a += partials[((int64_t)p * 2) * E + c];
+    b += partials[((int64_t)p * 2 + 1) * E + c];
+  }
+  if (dgamma) dgamma[c] = a;
+  if (dbeta) dbeta[c] = b;
+}
+
+// ---------------------------------------------------------------- softmax ------------------------------
+// one warp per row, in place; optional dropout applied to the stored probabilities (vit.py:262-263)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S, int64_t rows, int cols, int64_t ld,
+                                                           DropSpec dr, int64_t row_offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const float inv_keep = dr.p > 0.f ? 1.f / (1.f - dr.p) : 1.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float* row = S + r * ld;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, row[c]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float e = expf(row[c] - mx);
+      row[c] = e;
+      sum += e;
+    }
+    const float inv = 1.f / warp_sum(sum);
+    for (int c = lane; c < cols; c += 32) {
+      float p = row[c] * inv;
+      if (dr.p > 0.f) p *= dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * cols + c, dr.p, inv_keep);
+      row[c] = p;
+    }
+  }
+}
+
+// in: P = softmax probs (no dropout), dP = dL/d(dropped probs).  out: dP <- dS, P <- dropped probs.
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(float* __restrict__ P, float* __restrict__ dP,
+                                                               int64_t rows, int cols, int64_t ld, DropSpec dr,
+                                                               int64_t row_offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const float inv_keep = dr.p > 0.f ? 1.f / (1.f - dr.p) : 1.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float* p = P + r * ld;
+    float* d = dP + r * ld;
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      float dv = d[c];
+      if (dr.p > 0.f) {
+        const float m = dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * cols + c, dr.p, inv_keep);
+        dv *= m;
+        d[c] = dv;
+      }
+      dot += dv * p[c];
+    }
+    dot = warp_sum(dot);
+    for (int c = lane; c < cols; c += 32) {
+      const float pv = p[c];
+      d[c] = pv * (d[c] - dot);
+      if (dr.p > 0.f)
+        p[c] = pv * dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * cols + c, dr.p, inv_keep);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- GELU ---------------------------------
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_df(float u) {
+  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * expf(-0.5f * u * u);
+}
+
+__global__ void gelu_forward_kernel(const float* __restrict__ u, float* __restrict__ g, int64_t rows, int cols,
+                                    int64_t ld, DropSpec dr) {
+  const float inv_keep = dr.p > 0.f ? 1.f / (1.f - dr.p) : 1.f;
+  const int64_t total = rows * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld;
+    const int c = (int)(i % ld);
+    float v = 0.f;
+    if (c < cols) {
+      v = gelu_f(u[i]);
+      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * cols + c, dr.p, inv_keep);
+    }
+    g[i] = v;
+  }
+}
+
+__global__ void gelu_backward_kernel(float* __restrict__ dg, const float* __restrict__ u, int64_t rows, int cols,
+                                     int64_t ld, DropSpec dr) {
+  const float inv_keep = dr.p > 0.f ? 1.f / (1.f - dr.p) : 1.f;
+  const int64_t total = rows * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld;
+    const int c = (int)(i % ld);
+    float v = 0.f;
+    if (c < cols) {
+      v = dg[i] * gelu_df(u[i]);
+      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * cols + c, dr.p, inv_keep);
+    }
+    dg[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- reductions ---------------------------
+// partials[(b*strips + strip)*cols + c] = sum of X[b, rows in strip, c];  block (32, 8)
+__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ partials, int64_t rows, int cols,
+                              int64_t xb, int64_t ld, int strips) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int strip = blockIdx.y, b = blockIdx.z;
+  const int64_t per = (rows + strips - 1) / strips;
+  const int64_t r0 = strip * per, r1 = min(rows, r0 + per);
+  float s = 0.f;
+  if (c < cols)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += X[b * xb + r * ld + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    partials[((int64_t)b * strips + strip) * cols + c] = t;
+  }
+}
+
+// out[b*out_ld + c] = sum_strip partials[(b*strips+strip)*cols + c]
+__global__ void colsum_finish_kernel(const float* __restrict__ partials, float* __restrict__ out, int batch, int cols,
+                                     int strips, int64_t out_ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)batch * cols) return;
+  const int b = (int)(i / cols), c = (int)(i % cols);
+  float s = 0.f;
+  for (int k = 0; k < strips; ++k) s += partials[((int64_t)b * strips + k) * cols + c];
+  out[b * out_ld + c] = s;
+}
+
+__global__ void batchsum_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int64_t rows, int cols,
+                                int64_t xb, int64_t ld, int64_t out_ld) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i % cols);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += X[b * xb + r * ld + c];
+    out[r * out_ld + c] = s;
+  }
+}
+
+inline int ew_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int im2col(const float* img, float* patches, int B, int C, int H, int W, int p, int s, int gh, int gw,
+           cudaStream_t st) {
+  im2col_kernel<<<ew_grid((int64_t)B * gh * gw * C * p * p), 256, 0, st>>>(img, patches, B, C, H, W, p, s, gh, gw);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int col2im(const float* dpatches, float* dimg, int B, int C, int H, int W, int p, int s, int gh, int gw,
+           cudaStream_t st) {
+  col2im_kernel<<<ew_grid((int64_t)B * C * H * W), 256, 0, st>>>(dpatches, dimg, B, C, H, W, p, s, gh, gw);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int cls_rows(const float* cls, const float* pos, float* x, int B, int T, int E, int ld, cudaStream_t st) {
+  cls_rows_kernel<<<B, 128, 0, st>>>(cls, pos, x, B, T, E, ld);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st) {
+  dropout_rows_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(src, dst, rows, cols, ld, dr);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int dropout_mask(float* out, int64_t n, DropSpec dr, cudaStream_t st) {
+  dropout_mask_kernel<<<ew_grid(n), 256, 0, st>>>(out, n, dr);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int bmlp_forward(const float* beh, const float* w0, const float* b0, const float* w3, const float* b3, float* hid,
+                 float* lat, int B, int bdim, int H, int E, cudaStream_t st) {
+  bmlp_forward_kernel<<<B, 128, H * sizeof(float), st>>>(beh, w0, b0, w3, b3, hid, lat, bdim, H, E);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int tanh_grad(const float* dy, const float* y, float* dz, int64_t n, cudaStream_t st) {
+  tanh_grad_kernel<<<ew_grid(n), 256, 0, st>>>(dy, y, dz, n);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+#define V1T_LN_DISPATCH(NVV, KERNEL, ...)                       \
+  if (nv <= NVV) {                                              \
+    KERNEL<NVV><<<grid, 256, 0, st>>>(__VA_ARGS__);             \
+  } else
+
+int ln_forward(const float* x_in, const float* add, int rows_per_batch, float* x_out, const float* gamma,
+               const float* beta, float* h, float* stats, int64_t rows, int E, int ld, cudaStream_t st) {
+  const int nv = cdiv(ld, 32);
+  V1T_CHECK_ARG(nv <= 32 && ld >= E, "layer norm: emb dim %d (ld %d) unsupported (max 1024)", E, ld);
+  const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMs * 8);
+  V1T_LN_DISPATCH(1, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
+  V1T_LN_DISPATCH(2, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
+  V1T_LN_DISPATCH(5, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
+  V1T_LN_DISPATCH(8, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
+  V1T_LN_DISPATCH(16, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
+  { ln_forward_kernel<32><<<grid, 256, 0, st>>>(x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld); }
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+int ln_backward(const float* dh, const float* x, const float* stats, const float* gamma, float* dx_accum,
+                float* dgamma, float* dbeta, float* partials, size_t partial_bytes, int64_t rows, int E, int ld,
+                cudaStream_t st) {
+  const int nv = cdiv(ld, 32);
+  V1T_CHECK_ARG(nv <= 16 && ld >= E, "layer norm backward: emb dim %d unsupported (max 512)", E);
+  int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMs * 2);
+  const int64_t max_grid = (int64_t)(partial_bytes / (2 * (size_t)E * sizeof(float)));
+  V1T_CHECK_ARG(max_grid >= 1, "layer norm backward: partials workspace too small");
+  if (grid > max_grid) grid = (int)max_grid;
+  V1T_LN_DISPATCH(1, ln_backward_kernel, dh, x, stats, gamma, dx_accum, partials, rows, E, ld)
+  V1T_LN_DISPATCH(2, ln_backward_kernel, dh, x, stats, gamma, dx_accum, partials, rows, E, ld)
+  V1T_LN_DISPATCH(5, ln_backward_kernel, dh, x, stats, gamma, dx_accum, partials, rows, E, ld)
+  V1T_LN_DISPATCH(8, ln_backward_kernel, dh, x, stats, gamma, dx_accum, partials, rows, E, ld)
+  { ln_backward_kernel<16><<<grid, 256, 0, st>>>(dh, x, stats, gamma, dx_accum, partials, rows, E, ld); }
+  V1T_LAUNCH_CHECK();
+  ln_finish_kernel<<<cdiv(E, 128), 128, 0, st>>>(partials, dgamma, dbeta, grid, E);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+int softmax_rows(float* S, int64_t rows, int cols, int64_t ld, DropSpec dr, int64_t row_offset, cudaStream_t st) {
+  const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMs * 16);
+  softmax_rows_kernel<<<grid, 256, 0, st>>>(S, rows, cols, ld, dr, row_offset);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int softmax_bwd_rows(float* P, float* dP, int64_t rows, int cols, int64_t ld, DropSpec dr, int64_t row_offset,
+                     cudaStream_t st) {
+  const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMs * 16);
+  softmax_bwd_rows_kernel<<<grid, 256, 0, st>>>(P, dP, rows, cols, ld, dr, row_offset);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int gelu_forward(const float* u, float* g, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st) {
+  gelu_forward_kernel<<<ew_grid(rows * ld), 256, 0, st>>>(u, g, rows, cols, ld, dr);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int gelu_backward(float* dg_inout, const float* u, int64_t rows, int cols, int64_t ld, DropSpec dr,
+                  cudaStream_t st) {
+  gelu_backward_kernel<<<ew_grid(rows * ld), 256, 0, st>>>(dg_inout, u, rows, cols, ld, dr);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+int colsum(const float* X, float* out, int batch, int64_t rows, int cols, int64_t xb, int64_t ld, int64_t out_ld,
+           float* partials, size_t partial_bytes, cudaStream_t st) {
+  if (cols == 0 || batch == 0) return V1T_OK;
+  int strips = (int)std::min<int64_t>(64, std::max<int64_t>(1, rows / 64));
+  while (strips > 1 && (size_t)batch * strips * cols * sizeof(float) > partial_bytes) strips /= 2;
+  V1T_CHECK_ARG((size_t)batch * strips * cols * sizeof(float) <= partial_bytes, "colsum: partials workspace too small");
+  dim3 grid(cdiv(cols, 32), strips, batch), block(32, 8);
+  colsum_kernel<<<grid, block, 0, st>>>(X, partials, rows, cols, xb, ld, strips);
+  V1T_LAUNCH_CHECK();
+  colsum_finish_kernel<<<cdiv((int64_t)batch * cols, 256), 256, 0, st>>>(partials, out, batch, cols, strips, out_ld);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+int batchsum(const float* X, float* out, int B, int64_t rows, int cols, int64_t xb, int64_t ld, int64_t out_ld,
+             cudaStream_t st) {
+  batchsum_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(X, out, B, rows, cols, xb, ld, out_ld);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+}  // namespace v1t

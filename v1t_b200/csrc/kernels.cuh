@@ -1,0 +1,64 @@
+// Internal (non-ABI) declarations shared between the translation units of libv1t_b200.
+#pragma once
+#include "common.cuh"
+
+namespace v1t {
+
+struct DropSpec {  // inverted dropout; p == 0 -> disabled
+  uint64_t seed;
+  uint32_t site;
+  float p;
+};
+static inline DropSpec no_drop() { return DropSpec{0, 0, 0.f}; }
+
+struct GemmArgs {
+  v1t_gemm_desc d;
+  DropSpec drop;    // applied to alpha*acc + bias (element index m*n_cols + n), before the residual add
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;
+  const float* R;
+  int splits;       // split-K factor (blockIdx.z = (b1*batch2 + b2)*splits + split)
+  int k_chunk;      // K range per split
+  int64_t c_split;  // C element stride between splits (partials)
+};
+
+// gemm_fp32.cu
+int gemm_fp32(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
+              cudaStream_t st, DropSpec drop = no_drop());
+int gemm_fp32_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
+                     size_t partial_bytes, cudaStream_t st);
+int reduce_partials(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t ld_out,
+                    int accumulate, cudaStream_t st);
+
+// elementwise.cu
+int im2col(const float* img, float* patches, int B, int C, int H, int W, int p, int s, int gh, int gw,
+           cudaStream_t st);
+int col2im(const float* dpatches, float* dimg, int B, int C, int H, int W, int p, int s, int gh, int gw,
+           cudaStream_t st);
+int cls_rows(const float* cls, const float* pos, float* x, int B, int T, int E, int ld, cudaStream_t st);
+int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st);
+int bmlp_forward(const float* beh, const float* w0, const float* b0, const float* w3, const float* b3, float* hid,
+                 float* lat, int B, int bdim, int H, int E, cudaStream_t st);
+int tanh_grad(const float* dy, const float* y, float* dz, int64_t n, cudaStream_t st);  // dz = dy*(1-y^2)
+int ln_forward(const float* x_in, const float* add, int rows_per_batch, float* x_out, const float* gamma,
+               const float* beta, float* h, float* stats, int64_t rows, int E, int ld, cudaStream_t st);
+int ln_backward(const float* dh, const float* x, const float* stats, const float* gamma, float* dx_accum,
+                float* dgamma, float* dbeta, float* partials, size_t partial_bytes, int64_t rows, int E, int ld,
+                cudaStream_t st);
+int softmax_rows(float* S, int64_t rows, int cols, int64_t ld, DropSpec dr, int64_t row_offset, cudaStream_t st);
+int softmax_bwd_rows(float* P, float* dP, int64_t rows, int cols, int64_t ld, DropSpec dr, int64_t row_offset,
+                     cudaStream_t st);
+int gelu_forward(const float* u, float* g, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st);
+int gelu_backward(float* dg_inout, const float* u, int64_t rows, int cols, int64_t ld, DropSpec dr,
+                  cudaStream_t st);
+// out[b, c] = sum_r X[b, r, c]   (X element strides: batch xb, row ld, col 1)
+int colsum(const float* X, float* out, int batch, int64_t rows, int cols, int64_t xb, int64_t ld,
+           int64_t out_ld, float* partials, size_t partial_bytes, cudaStream_t st);
+// out[t, c] = sum_b X[b, t, c]
+int batchsum(const float* X, float* out, int B, int64_t rows, int cols, int64_t xb, int64_t ld, int64_t out_ld,
+             cudaStream_t st);
+int dropout_mask(float* out, int64_t n, DropSpec dr, cudaStream_t st);
+
+}  // namespace v1t

@@ -1,0 +1,347 @@
+"""torch.autograd.Function wrappers over the C-ABI (the only place pointers cross the boundary).
+
+Tensors stay owned by PyTorch (device memory, caching allocator, current stream); the native library
+launches the kernels.  No function here has a CPU path: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import BLOCK_FIELDS, CoreDims, CorePtrs, CoreShape, ReadoutShape
+
+EPS_F32 = float(torch.finfo(torch.float32).eps)
+
+# one reusable scratch arena per device (single-stream use; the library never allocates)
+_SCRATCH = {}
+
+
+def _scratch(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _SCRATCH.pop(key, None)
+        buf = None
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf
+
+
+def release_scratch():
+    _SCRATCH.clear()
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("v1t_b200 is CUDA-only (sm_100a kernels, no CPU path): got a tensor on "
+                               f"{t.device}; move the model and inputs to a B200 first")
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass(frozen=True)
+class CoreSpec:
+    """Static description of a ViT core (the shape-defining args of vit.py:374-405)."""
+
+    in_ch: int
+    in_h: int
+    in_w: int
+    patch: int
+    stride: int
+    emb: int
+    heads: int
+    mlp: int
+    blocks: int
+    bdim: int
+    impl: int = _lib.IMPL_FP32
+
+    def shape(self, batch: int, p_tokens: float = 0.0, p_block: float = 0.0, seed: int = 0) -> CoreShape:
+        return CoreShape(batch=batch, in_ch=self.in_ch, in_h=self.in_h, in_w=self.in_w, patch=self.patch,
+                         stride=self.stride, emb=self.emb, heads=self.heads, mlp=self.mlp, blocks=self.blocks,
+                         bdim=self.bdim, impl=self.impl, p_drop_tokens=p_tokens, p_drop_block=p_block,
+                         seed=seed & 0xFFFFFFFFFFFFFFFF)
+
+    def dims(self) -> CoreDims:
+        d = CoreDims()
+        _lib.check(_lib.load().v1t_core_dims_of(C.byref(self.shape(1)), C.byref(d)), "core_dims_of")
+        return d
+
+
+N_HEAD_PARAMS = 4
+N_BLOCK_PARAMS = len(BLOCK_FIELDS)
+
+
+def _fill_ptrs(tensors: Sequence[Optional[torch.Tensor]], blocks: int) -> CorePtrs:
+    p = CorePtrs()
+    p.cls, p.pos, p.wpe, p.bpe = (_ptr(t) for t in tensors[:N_HEAD_PARAMS])
+    for i in range(blocks):
+        chunk = tensors[N_HEAD_PARAMS + i * N_BLOCK_PARAMS: N_HEAD_PARAMS + (i + 1) * N_BLOCK_PARAMS]
+        for name, t in zip(BLOCK_FIELDS, chunk):
+            setattr(p.blk[i], name, _ptr(t))
+    return p
+
+
+class _CoreFunction(torch.autograd.Function):
+    """tokens[B,T,emb_ld] = ViTCore(images, behaviors; params)   (vit.py:423-436 without the final view)."""
+
+    @staticmethod
+    def forward(ctx, spec: CoreSpec, p_tokens: float, p_block: float, seed: int, keep_saved, images, behaviors,
+                *params):
+        lib = _lib.load()
+        _need_cuda(images, behaviors, *params)
+        images = _f32c(images)
+        behaviors = _f32c(behaviors)
+        params = [_f32c(p) for p in params]
+        B = images.shape[0]
+        shape = spec.shape(B, p_tokens, p_block, seed)
+        dims = spec.dims()
+        dev = images.device
+        need_grad = torch.is_grad_enabled() and (
+            images.requires_grad or any(p is not None and p.requires_grad for p in params))
+        keep = bool(need_grad or keep_saved)
+        saved = None
+        if keep:
+            saved = torch.empty(lib.v1t_core_saved_bytes(C.byref(shape)), dtype=torch.uint8, device=dev)
+        scratch = _scratch(dev, lib.v1t_core_scratch_bytes(C.byref(shape)))
+        tokens = torch.empty((B, dims.tokens, dims.emb_ld), dtype=torch.float32, device=dev)
+        ptrs = _fill_ptrs(params, spec.blocks)
+        with torch.cuda.device(dev):
+            rc = lib.v1t_core_forward(C.byref(shape), C.byref(ptrs), images.data_ptr(), _ptr(behaviors),
+                                      tokens.data_ptr(), _ptr(saved), scratch.data_ptr(), int(keep),
+                                      _stream_ptr(dev))
+        _lib.check(rc, "core_forward")
+        ctx.spec, ctx.shape_args = spec, (B, p_tokens, p_block, seed)
+        ctx.saved_buf = saved
+        ctx.has_beh = behaviors is not None
+        ctx.save_for_backward(images, *([behaviors] if behaviors is not None else []),
+                              *[p for p in params if p is not None])
+        ctx.param_present = [p is not None for p in params]
+        if isinstance(keep_saved, dict):
+            keep_saved["saved"], keep_saved["shape"] = saved, shape
+        return tokens
+
+    @staticmethod
+    def backward(ctx, d_tokens):
+        lib = _lib.load()
+        spec = ctx.spec
+        saved_t = list(ctx.saved_tensors)
+        images = saved_t.pop(0)
+        behaviors = saved_t.pop(0) if ctx.has_beh else None
+        params: List[Optional[torch.Tensor]] = [saved_t.pop(0) if present else None for present in ctx.param_present]
+        shape = spec.shape(*ctx.shape_args)
+        dev = images.device
+        d_tokens = d_tokens.contiguous().clone()  # clobbered by the library
+        needs = ctx.needs_input_grad[7:]
+        grads = [torch.empty_like(p) if (p is not None and need) else None for p, need in zip(params, needs)]
+        d_images = torch.empty_like(images) if ctx.needs_input_grad[5] else None
+        scratch = _scratch(dev, lib.v1t_core_scratch_bytes(C.byref(shape)))
+        pptr, gptr = _fill_ptrs(params, spec.blocks), _fill_ptrs(grads, spec.blocks)
+        with torch.cuda.device(dev):
+            rc = lib.v1t_core_backward(C.byref(shape), C.byref(pptr), images.data_ptr(), _ptr(behaviors),
+                                       d_tokens.data_ptr(), ctx.saved_buf.data_ptr(), scratch.data_ptr(),
+                                       C.byref(gptr), _ptr(d_images), _stream_ptr(dev))
+        _lib.check(rc, "core_backward")
+        return (None, None, None, None, None, d_images, None, *grads)
+
+
+def core_forward(spec: CoreSpec, images, behaviors, params, p_tokens=0.0, p_block=0.0, seed=0, keep_saved=None):
+    """Returns tokens [B, T, emb_ld] (fp32).  `params`: list in the order cls,pos,wpe,bpe + BLOCK_FIELDS per block."""
+    return _CoreFunction.apply(spec, float(p_tokens), float(p_block), int(seed), keep_saved, images, behaviors, *params)
+
+
+def attention_probs(spec: CoreSpec, keep: dict, block: int) -> torch.Tensor:
+    """softmax(QK^T/sqrt(E)) [B,H,T,T] of one block, from the saved activations of a core_forward call."""
+    lib = _lib.load()
+    shape, saved = keep["shape"], keep["saved"]
+    d = spec.dims()
+    out = torch.empty((shape.batch, spec.heads, d.tokens, d.tokens), dtype=torch.float32, device=saved.device)
+    with torch.cuda.device(saved.device):
+        rc = lib.v1t_attention_probs(C.byref(shape), saved.data_ptr(), block, out.data_ptr(),
+                                     _stream_ptr(saved.device))
+    _lib.check(rc, "attention_probs")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# readout
+# ------------------------------------------------------------------------------------------------------
+def _channel_last(fmap: torch.Tensor) -> torch.Tensor:
+    """[B,C,h,w] tensor whose channel stride is 1 (the core emits exactly that view)."""
+    if fmap.dtype != torch.float32:
+        fmap = fmap.float()
+    if fmap.stride(1) != 1 or fmap.stride(3) < fmap.shape[1] or fmap.stride(2) < fmap.stride(3) * 0:
+        fmap = fmap.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    return fmap
+
+
+def _readout_shape(fmap: torch.Tensor, n: int) -> ReadoutShape:
+    B, Cc, h, w = fmap.shape
+    return ReadoutShape(batch=B, neurons=n, channels=Cc, gh=h, gw=w, fs_b=fmap.stride(0), fs_y=fmap.stride(2),
+                        fs_x=fmap.stride(3))
+
+
+class _ReadoutFunction(torch.autograd.Function):
+    """z[B,N] = Gaussian2DReadout(fmap; mu, sigma, noise, shifts, features, bias)  (gaussian2d.py:237-278)."""
+
+    @staticmethod
+    def forward(ctx, fmap, mu, sigma, noise, shifts, features, bias):
+        lib = _lib.load()
+        _need_cuda(fmap, mu, sigma, noise, shifts, features, bias)
+        fmap = _channel_last(fmap)
+        mu, sigma, noise, shifts, features, bias = map(_f32c, (mu, sigma, noise, shifts, features, bias))
+        N = mu.shape[0]
+        rs = _readout_shape(fmap, N)
+        dev = fmap.device
+        z = torch.empty((fmap.shape[0], N), dtype=torch.float32, device=dev)
+        scratch = _scratch(dev, lib.v1t_readout_scratch_bytes(C.byref(rs)))
+        with torch.cuda.device(dev):
+            rc = lib.v1t_readout_forward(C.byref(rs), fmap.data_ptr(), mu.data_ptr(), _ptr(sigma), _ptr(noise),
+                                         _ptr(shifts), features.data_ptr(), _ptr(bias), None, 1.0, z.data_ptr(),
+                                         None, None, scratch.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "readout_forward")
+        ctx.flags = (sigma is not None, noise is not None, shifts is not None, bias is not None)
+        ctx.save_for_backward(*[t for t in (fmap, mu, sigma, noise, shifts, features) if t is not None])
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.load()
+        has_sigma, has_noise, has_shifts, has_bias = ctx.flags
+        sv = list(ctx.saved_tensors)
+        fmap, mu = sv.pop(0), sv.pop(0)
+        sigma = sv.pop(0) if has_sigma else None
+        noise = sv.pop(0) if has_noise else None
+        shifts = sv.pop(0) if has_shifts else None
+        features = sv.pop(0)
+        N = mu.shape[0]
+        rs = _readout_shape(fmap, N)
+        dev = fmap.device
+        dz = _f32c(dz)
+        need = ctx.needs_input_grad
+        d_fmap = None
+        if need[0]:
+            # same strides as fmap so the channel-last gather/scatter pattern is shared by fwd and bwd
+            d_fmap = torch.empty_strided(fmap.shape, fmap.stride(), dtype=torch.float32, device=dev)
+            d_fmap.zero_()
+        d_mu = torch.empty_like(mu) if need[1] else None
+        d_sigma = torch.empty_like(sigma) if (need[2] and sigma is not None) else None
+        d_shifts = torch.empty_like(shifts) if (need[4] and shifts is not None) else None
+        d_feat = torch.empty_like(features) if need[5] else None
+        d_bias = torch.empty((N,), dtype=torch.float32, device=dev) if (need[6] and has_bias) else None
+        scratch = _scratch(dev, lib.v1t_readout_scratch_bytes(C.byref(rs)))
+        with torch.cuda.device(dev):
+            rc = lib.v1t_readout_backward(C.byref(rs), fmap.data_ptr(), mu.data_ptr(), _ptr(sigma), _ptr(noise),
+                                          _ptr(shifts), features.data_ptr(), None, dz.data_ptr(), None, 1.0, 1.0,
+                                          _ptr(d_fmap), _ptr(d_mu), _ptr(d_sigma), _ptr(d_shifts), _ptr(d_feat),
+                                          _ptr(d_bias), scratch.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc, "readout_backward")
+        if d_sigma is not None and noise is None:
+            d_sigma.zero_()
+        return d_fmap, d_mu, d_sigma, None, d_shifts, d_feat, d_bias
+
+
+def readout_forward(fmap, mu, sigma, noise, shifts, features, bias):
+    """fmap [B,C,h,w] (channel stride 1), mu [N,2], sigma [N,2,2], noise [B,N,2]|None, shifts [B,2]|None,
+    features [C,N], bias [N]|None  ->  z [B,N]."""
+    return _ReadoutFunction.apply(fmap, mu, sigma, noise, shifts, features, bias)
+
+
+class _Elu1Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        lib = _lib.load()
+        _need_cuda(z)
+        z = _f32c(z)
+        y = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            _lib.check(lib.v1t_elu1_forward(z.data_ptr(), y.data_ptr(), z.numel(), _stream_ptr(z.device)), "elu1_forward")
+        ctx.save_for_backward(z)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (z,) = ctx.saved_tensors
+        dy = _f32c(dy)
+        dz = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            _lib.check(lib.v1t_elu1_backward(z.data_ptr(), dy.data_ptr(), dz.data_ptr(), z.numel(),
+                                             _stream_ptr(z.device)), "elu1_backward")
+        return dz
+
+
+def elu1(z):
+    return _Elu1Function.apply(z)
+
+
+class _PoissonFunction(torch.autograd.Function):
+    """loss = scale * sum((y+eps) - (t+eps) log(y+eps))   (losses.py:153-166 + :114-119)."""
+
+    @staticmethod
+    def forward(ctx, y_pred, y_true, eps, scale):
+        lib = _lib.load()
+        _need_cuda(y_pred, y_true)
+        y_pred, y_true = _f32c(y_pred), _f32c(y_true)
+        if y_pred.shape != y_true.shape:
+            raise RuntimeError(f"poisson loss: shape mismatch {tuple(y_pred.shape)} vs {tuple(y_true.shape)}")
+        dev = y_pred.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        n = y_pred.numel()
+        scratch = _scratch(dev, lib.v1t_poisson_scratch_bytes(n))
+        with torch.cuda.device(dev):
+            _lib.check(lib.v1t_poisson_forward(y_pred.data_ptr(), y_true.data_ptr(), n, eps, scale, loss.data_ptr(),
+                                               scratch.data_ptr(), _stream_ptr(dev)), "poisson_forward")
+        ctx.save_for_backward(y_pred, y_true)
+        ctx.consts = (eps, scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = _lib.load()
+        y_pred, y_true = ctx.saved_tensors
+        eps, scale = ctx.consts
+        dloss = _f32c(dloss)
+        dy = torch.empty_like(y_pred)
+        with torch.cuda.device(y_pred.device):
+            _lib.check(lib.v1t_poisson_backward(y_pred.data_ptr(), y_true.data_ptr(), y_pred.numel(), eps, scale,
+                                                dloss.data_ptr(), dy.data_ptr(), _stream_ptr(y_pred.device)),
+                       "poisson_backward")
+        return dy, None, None, None
+
+
+def poisson_loss(y_pred, y_true, eps: float = EPS_F32, scale: float = 1.0):
+    return _PoissonFunction.apply(y_pred, y_true, float(eps), float(scale))
+
+
+def dropout_mask(n: int, seed: int, site: int, p: float, device) -> torch.Tensor:
+    """The multipliers the kernels apply at a dropout site (test / replay helper)."""
+    lib = _lib.load()
+    out = torch.empty((n,), dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.v1t_dropout_mask(out.data_ptr(), n, seed & 0xFFFFFFFFFFFFFFFF, site, p,
+                                        _stream_ptr(out.device)), "dropout_mask")
+    return out
+
+
+def loss_scale(ds_size: float, batch_size: int, ds_scale: bool = True) -> float:
+    return math.sqrt(ds_size / batch_size) if ds_scale else 1.0
