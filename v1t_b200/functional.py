@@ -116,8 +116,7 @@ class _CoreFunction(torch.autograd.Function):
         shape = spec.shape(B, p_tokens, p_block, seed)
         dims = spec.dims()
         dev = images.device
-        need_grad = torch.is_grad_enabled() and (
-            images.requires_grad or any(p is not None and p.requires_grad for p in params))
+        need_grad = any(ctx.needs_input_grad)
         keep = bool(need_grad or keep_saved)
         saved = None
         if keep:
@@ -189,7 +188,7 @@ def _channel_last(fmap: torch.Tensor) -> torch.Tensor:
     """[B,C,h,w] tensor whose channel stride is 1 (the core emits exactly that view)."""
     if fmap.dtype != torch.float32:
         fmap = fmap.float()
-    if fmap.stride(1) != 1 or fmap.stride(3) < fmap.shape[1] or fmap.stride(2) < fmap.stride(3) * 0:
+    if fmap.stride(1) != 1:
         fmap = fmap.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
     return fmap
 
