@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the V1T hot path (ViT core + per-mouse Gaussian2d readout + Poisson loss, forward + backward).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU, NCCL
+    python bench.py --impl reference ...                      # the reference's CPU path (oracle port) on host cores
+
+Workload = BASELINE.json configs[1]: Sensorium+ 7-mouse shared V1T core (default vit args, 1x36x64 frames,
+1654 tokens), per-mouse gaussian2d readouts (~8k neurons each), behavior_mode 3, train mode (dropout + readout
+position sampling), batch 16 per mouse per GPU.  One STEP = one optimizer step's worth of forward/backward: every
+mouse batch once with gradient accumulation (train.py:84-111) + (N>1) the gradient all-reduce.  The optimizer
+update, the L1 regulariser and the image cropper are outside the metric.  Synthetic data, seeded.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train samples/sec (core+readout fwd/bwd)"
+SEED = 1234
+
+
+def neuron_counts(n_mice: int, base: int):
+    rng = np.random.default_rng(SEED)
+    return {chr(ord("A") + i): int(base * (1 + 0.1 * (2 * rng.random() - 1))) // 8 * 8 for i in range(n_mice)}
+
+
+def make_args(neurons, device, impl="fp32", **over):
+    a = dict(input_shape=(1, 36, 64), output_shapes={k: (n,) for k, n in neurons.items()}, device=device, core="vit",
+             readout="gaussian2d", behavior_mode=3, shift_mode=2, center_crop=1.0, resize_image=0,
+             ds_name="sensorium", patch_mode=0, patch_size=8, patch_stride=1, emb_dim=155, num_blocks=4, num_heads=4,
+             mlp_dim=488, p_dropout=0.0229, t_dropout=0.2544, drop_path=0.0, use_lsa=False, disable_bias=False,
+             grad_checkpointing=0, core_reg_scale=0.5379, readout_reg_scale=0.0076, disable_grid_predictor=False,
+             grid_predictor_dim=2, bias_mode=0, shifter_reg_scale=0.0, cropper_reg_scale=0.0, criterion="poisson",
+             ds_scale=1, verbose=0, b200_impl=impl)
+    a.update(over)
+    return SimpleNamespace(**a)
+
+
+class _DS:
+    def __init__(self, n, rng):
+        self.coordinates = rng.standard_normal((n, 3)).astype(np.float32)
+        self.response_stats = {"mean": np.ones(n, np.float32), "std": np.ones(n, np.float32)}
+
+    def __len__(self):
+        return 4500
+
+
+def make_ds(neurons):
+    rng = np.random.default_rng(SEED + 1)
+    return {k: SimpleNamespace(dataset=_DS(n, rng)) for k, n in neurons.items()}
+
+
+def host_batches(neurons, batch, rank, pin):
+    """Synthetic Sensorium-shaped inputs: images~N(0,1), behaviours/pupil~U(0,1), responses~U(0,2)."""
+    g = torch.Generator().manual_seed(SEED + 17 * (rank + 1))
+    out = {}
+    for m, n in neurons.items():
+        b = {"image": torch.randn((batch, 1, 36, 64), generator=g), "behavior": torch.rand((batch, 3), generator=g),
+             "pupil_center": torch.rand((batch, 2), generator=g), "response": torch.rand((batch, n), generator=g) * 2}
+        out[m] = {k: (v.pin_memory() if pin else v) for k, v in b.items()}
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# per-sample algorithmic forward FLOPs of the attention contractions (QK^T + PV), BASELINE.md §3
+def attn_flops_fwd(T=1654, E=155, H=4, blocks=4):
+    return blocks * 2 * (2 * H * T * T * E)
+
+
+def core_flops_fwd(T=1654, E=155, H=4, M=488, blocks=4, C=1):
+    L = T - 1
+    return 2 * L * 64 * C * E + blocks * (2 * T * E * 3 * H * E + 4 * H * T * T * E + 2 * T * H * E * E + 4 * T * E * M)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port: same ATen ops), all host threads, a bounded
+    sample of the workload per step: ONE mouse batch of `ref_batch` samples, train mode."""
+    from oracle import torch_port as TP
+    from oracle.v1t_oracle import CoreConfig
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    res = cpu_baseline_sample(args.ref_batch, max(args.steps, 1), max(args.warmup, 0), TP, CoreConfig, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1), "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(batch, steps, warmup, TP, CoreConfig, cores, train_mode=True):
+    import v1t_b200
+
+    neurons = {"A": neuron_counts(1, 8000)["A"]}
+    margs = make_args(neurons, torch.device("cpu"))
+    torch.manual_seed(SEED)
+    model = v1t_b200.Model(margs, ds=make_ds(neurons))  # parameter container only: never run on CPU
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and v.dim() > 0 and not k.endswith(("source_grid", "grid")):
+            v.requires_grad_(True)
+    cfg = CoreConfig()
+    b = host_batches(neurons, batch, 0, pin=False)["A"]
+    times = []
+    for i in range(warmup + steps):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        TP.step(sd, cfg, "A", b["image"], b["behavior"], b["pupil_center"], b["response"], ds_size=4500,
+                p_drop=margs.p_dropout, t_drop=margs.t_dropout, training=train_mode)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return {"value": batch / (ms / 1e3), "unit": "samples/s", "cores": cores, "kind": "port",
+            "ms_per_step": ms,
+            "sample": f"1 mouse batch of {batch} samples (N={neurons['A']} neurons), default V1T core, "
+                      f"{'train' if train_mode else 'eval'} mode fwd+bwd, fp32 torch CPU ops, {steps} timed steps"}
+
+
+def workload_config(args, world):
+    return {"workload": "Sensorium+ 7-mouse shared V1T core (default vit args, 1x36x64, 1654 tokens) + per-mouse "
+                        "gaussian2d readouts (~8k neurons), behavior_mode 3, train mode (dropout + position sampling)",
+            "mice": args.mice, "batch_per_mouse_per_gpu": args.batch, "global_batch": args.mice * args.batch * world,
+            "neurons_per_mouse": args.neurons, "parallelism": f"dp{world} ({args.dp_mode})", "impl": args.b200_impl,
+            "l2": "per-step working set (saved activations ~1.4 GB per mouse batch) >> 126 MB L2; no explicit flush"}
+
+
+def run_b200(args):
+    import v1t_b200
+    from v1t_b200 import _lib, parallel
+
+    rank, local, world = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU path); use --impl reference for the CPU baseline"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    neurons = neuron_counts(args.mice, args.neurons)
+    margs = make_args(neurons, dev, impl=args.b200_impl)
+    torch.manual_seed(SEED)
+    model = v1t_b200.Model(margs, ds=make_ds(neurons)).to(dev)
+    crit = v1t_b200.get_criterion(margs, ds=make_ds(neurons))
+    with torch.no_grad():  # "trained-like" readout weights so responses are not all ~1
+        g = torch.Generator(device=dev).manual_seed(SEED + 2)
+        for r in model.readouts.values():
+            r.features.add_(torch.randn(r.features.shape, device=dev, generator=g) * 0.05)
+            r.bias.add_(torch.randn(r.bias.shape, device=dev, generator=g) * 0.3)
+    model.train(True)
+    my_mice = parallel.mice_of_rank(list(neurons), rank, world, args.dp_mode)
+    sync = parallel.GradSync(model.parameters()) if world > 1 else None
+    host = host_batches({m: neurons[m] for m in my_mice}, args.batch, rank, pin=True)
+    resident = {m: {k: v.to(dev) for k, v in b.items()} for m, b in host.items()}
+    gb = {m: args.batch * (world if args.dp_mode == "batch" else 1) for m in neurons}
+    samples_per_step_rank = args.batch * len(my_mice)
+    h2d = sum(v.numel() * 4 for b in host.values() for v in b.values())
+
+    def step_resident():
+        model.zero_grad(set_to_none=True)
+        return parallel.sweep(model, crit, resident, gb, sync)
+
+    def step_e2e():
+        model.zero_grad(set_to_none=True)
+        dev_b = {m: {k: v.to(dev, non_blocking=True) for k, v in b.items()} for m, b in host.items()}
+        loss = parallel.sweep(model, crit, dev_b, gb, sync)
+        return float(loss.item()) if loss is not None else 0.0  # device->host read of the step's loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = lib.v1t_launch_count()
+    with ClockSampler(local) as clocks:
+        ms_total = timed(step_resident, args.steps)
+    launches = int(lib.v1t_launch_count() - launches0)
+    total_samples = torch.tensor([samples_per_step_rank], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(total_samples)
+    samples_per_step = float(total_samples.item())
+    ms_per_step = ms_total / args.steps
+    value = samples_per_step / (ms_per_step / 1e3)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e = {"value": samples_per_step / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
+
+    # per-phase device time (CUDA events on the launching stream) of one more timed window
+    lib.v1t_prof_enable(1)
+    lib.v1t_prof_reset()
+    psteps = min(args.steps, 3)
+    for _ in range(psteps):
+        step_resident()
+    torch.cuda.synchronize(dev)
+    phases = {}
+    for i, name in enumerate(_lib.PHASES):
+        tot, cnt = ctypes.c_float(0), ctypes.c_int(0)
+        lib.v1t_prof_read(i, ctypes.byref(tot), ctypes.byref(cnt))
+        phases[name] = {"ms_per_step": tot.value / psteps, "scopes_per_step": cnt.value / psteps}
+    lib.v1t_prof_enable(0)
+    lib.v1t_prof_reset()
+
+    peaks = load_peaks()
+    # dominant phase: attention forward+backward (79 % of the algorithmic FLOPs); bound = tensor pipe.
+    n_local = samples_per_step_rank
+    attn_ms = phases["attn_fwd"]["ms_per_step"] + phases["attn_bwd"]["ms_per_step"]
+    attn_flops = 3 * attn_flops_fwd() * n_local  # fwd + bwd counted 3x, no recompute credit
+    achieved = attn_flops / (attn_ms / 1e3) / 1e12 if attn_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "attention fwd+bwd phases", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                "share_of_step": attn_ms / max(sum(p["ms_per_step"] for p in phases.values()), 1e-9)}
+    ro_ms = phases["readout_fwd"]["ms_per_step"] + phases["readout_bwd"]["ms_per_step"]
+    L, E = 1653, 155
+    ro_bytes = 0
+    for m in my_mice:
+        n, B = neurons[m], args.batch
+        fwd = B * L * E * 4 + E * n * 4 + 7 * n * 4 + 2 * B * n * 4 + 2 * B * n * 4
+        ro_bytes += fwd + (fwd + B * L * E * 4 + E * n * 4)  # forward + backward
+    readout = {"bound": "hbm", "achieved": ro_bytes / (ro_ms / 1e3) / 1e9 if ro_ms > 0 else 0.0,
+               "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+    readout["frac"] = readout["achieved"] / readout["peak"]
+    total_flops = 3 * core_flops_fwd() * n_local
+
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32 accumulate)", "bf16": "bf16"}.get(args.b200_impl, args.b200_impl),
+            "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks.summary(), "roofline": roofline, "roofline_readout": readout, "phases": phases,
+            "model_tflops": total_flops / (ms_per_step / 1e3) / 1e12}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import torch_port as TP
+            from oracle.v1t_oracle import CoreConfig
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cb = cpu_baseline_sample(args.ref_batch, 2, 1, TP, CoreConfig, cores)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--b200-impl", dest="b200_impl", default=os.environ.get("V1T_IMPL", "fp32"))
+    ap.add_argument("--mice", type=int, default=7)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--neurons", type=int, default=8000)
+    ap.add_argument("--dp-mode", dest="dp_mode", default="batch", choices=["batch", "mouse"])
+    ap.add_argument("--ref-batch", dest="ref_batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -8,8 +8,9 @@
  *         scaled_dot_product_attention :253-265, MLP :153-154, Transformer.forward :348-362)
  *   v1t_readout_forward / v1t_readout_backward  Gaussian2DReadout.forward + autograd
  *                                                              src/v1t/models/readout/gaussian2d.py:195-278
- *   v1t_elu1_poisson_forward / _backward      ELU1 (src/v1t/models/utils.py:109-118) + PoissonLoss.forward
- *                                                              (src/v1t/losses.py:114-119,153-166)
+ *   v1t_elu1_forward/_backward, v1t_poisson_forward/_backward
+ *                                             ELU1 (src/v1t/models/utils.py:109-118), PoissonLoss.forward
+ *                                             (src/v1t/losses.py:114-119,153-166); also fused into the readout
  *   v1t_attention_probs                       what attention_rollout.Recorder's hook on Attention.attend
  *                                             observes (src/v1t/utils/attention_rollout.py:31-36)
  *
@@ -87,6 +88,23 @@ typedef struct v1t_core_ptrs { /* used both for parameters (read) and for their 
 
 const char* v1t_last_error(void);
 int v1t_version(void);
+
+/* instrumentation for bench.py: kernels launched by this library since load, and optional per-phase device
+ * timing with CUDA events recorded on the launching stream around each phase of the path */
+#define V1T_PHASE_PATCH 0       /* patch embedding + CLS/pos (K1) */
+#define V1T_PHASE_LN_QKV 1      /* behaviour add + LayerNorm + QKV GEMM (K2,K3) */
+#define V1T_PHASE_ATTN_FWD 2    /* softmax(QK^T)V (K4) */
+#define V1T_PHASE_PROJ 3        /* out projection + residual (K5) */
+#define V1T_PHASE_MLP 4         /* LN + MLP (K6,K7) */
+#define V1T_PHASE_ATTN_BWD 5    /* attention backward (K4b) */
+#define V1T_PHASE_LINEAR_BWD 6  /* dgrad/wgrad GEMMs, LN/GELU backward, reductions (K10) */
+#define V1T_PHASE_READOUT_FWD 7 /* readout + ELU1 + Poisson forward (K8) */
+#define V1T_PHASE_READOUT_BWD 8 /* readout backward (K9) */
+#define V1T_NUM_PHASES 9
+uint64_t v1t_launch_count(void);
+int v1t_prof_enable(int on);
+int v1t_prof_reset(void);
+int v1t_prof_read(int phase, float* total_ms, int* count);
 
 int v1t_core_dims_of(const v1t_core_shape* shape, v1t_core_dims* out);
 

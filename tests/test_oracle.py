@@ -79,3 +79,26 @@ def test_oracle_finite_difference_loss_grad():
         fd = (run(sp, False)["loss"] - run(sm, False)["loss"]) / (2 * h)
         an = base["grads"][key][idx]
         assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)) + 1e-6 * abs(base["loss"]) * 0 + 1e-4 * abs(an), (key, fd, an)
+
+
+@pytest.mark.parametrize("case", ["tiny_train", "color_mode4", "nobias_mu_param", "default_dims"])
+def test_torch_port_matches_reference_golden(case):
+    """The CPU-baseline port (same ATen ops as the reference) reproduces the reference's fp32 outputs."""
+    import torch
+    from oracle import torch_port as TP
+
+    g = Golden(case)
+    cfg = g.core_config()
+    for mouse_id, d in g.mice.items():
+        sd = {k: torch.from_numpy(np.asarray(v)).clone() for k, v in g.sd.items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and not k.endswith(("reg_scale", "scale", "keep_prop", "source_grid", "grid", "one")):
+                v.requires_grad_(True)
+        tt = lambda a: torch.from_numpy(np.asarray(a))
+        loss, y = TP.step(sd, cfg, mouse_id, tt(d["images"]), tt(d["behaviors"]), tt(d["pupil_centers"]),
+                          tt(d["y_true"]), ds_size=4500, noise=tt(d["noise"]) if "noise" in d else None)
+        assert rel_err(y.numpy(), d["y"]) < 1e-5
+        assert abs(loss.item() - float(d["loss"])) / abs(float(d["loss"])) < 1e-5
+        for k, ref in d["grads"].items():
+            if np.abs(ref).max() > 0:
+                assert rel_err(sd[k].grad.numpy(), ref) < 1e-4, k

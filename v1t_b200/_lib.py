@@ -11,6 +11,7 @@ import os
 
 V1T_MAX_BLOCKS = 16
 IMPL_FP32, IMPL_BF16X3, IMPL_BF16 = 0, 1, 2
+PHASES = ["patch", "ln_qkv", "attn_fwd", "proj", "mlp", "attn_bwd", "linear_bwd", "readout_fwd", "readout_bwd"]
 IMPL_NAMES = {"fp32": IMPL_FP32, "bf16x3": IMPL_BF16X3, "exact": IMPL_BF16X3, "bf16": IMPL_BF16, "fast": IMPL_BF16}
 
 _f32p = C.POINTER(C.c_float)
@@ -63,6 +64,10 @@ _vp, _i64, _f = C.c_void_p, C.c_int64, C.c_float
 SYMBOLS = {
     "v1t_last_error": (C.c_char_p, []),
     "v1t_version": (C.c_int, []),
+    "v1t_launch_count": (C.c_uint64, []),
+    "v1t_prof_enable": (C.c_int, [C.c_int]),
+    "v1t_prof_reset": (C.c_int, []),
+    "v1t_prof_read": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "v1t_core_dims_of": (C.c_int, [C.POINTER(CoreShape), C.POINTER(CoreDims)]),
     "v1t_core_saved_bytes": (C.c_size_t, [C.POINTER(CoreShape)]),
     "v1t_core_scratch_bytes": (C.c_size_t, [C.POINTER(CoreShape)]),

@@ -9,6 +9,16 @@
 namespace v1t {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+
+// Optional device-side phase timing (CUDA events on the launching stream), used by bench.py for the roofline
+// figures: v1t_prof_enable(1) ... run ... v1t_prof_read(phase).  Disabled -> zero overhead besides a branch.
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(int phase, cudaStream_t stream);
+  ~ProfScope();
+};
 
 #define V1T_CHECK_ARG(cond, ...)                \
   do {                                          \
@@ -29,6 +39,7 @@ void set_error(const char* fmt, ...);
 
 #define V1T_LAUNCH_CHECK()                                                                     \
   do {                                                                                         \
+    v1t::count_launch();                                                                       \
     cudaError_t _e = cudaGetLastError();                                                       \
     if (_e != cudaSuccess) {                                                                   \
       v1t::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

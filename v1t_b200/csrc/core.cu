@@ -4,6 +4,7 @@
 // the autograd of that graph.  This file implements V1T_IMPL_FP32 (CUDA-core GEMMs, materialised attention
 // probabilities per batch chunk); the tcgen05 paths plug into the same save/scratch layout.
 #include <algorithm>
+#include <memory>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -186,6 +187,8 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
   Scratch sc = carve_scratch(d, scratch_mem);
 
   // ---- Image2Patches (vit.py:122-129): unfold -> Linear -> [CLS; tokens] + pos -> dropout
+  {
+  ProfScope prof(V1T_PHASE_PATCH, st);
   V1T_CUDA(cudaMemsetAsync(x, 0, sizeof(float) * d.R * d.Ep, st));
   V1T_TRY(im2col(images, sc.patches, d.B, d.C, d.H, d.W, d.p, d.s, d.gh, d.gw, st));
   {
@@ -199,6 +202,7 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
   }
   V1T_TRY(cls_rows(P->cls, P->pos, x, d.B, d.T, d.E, d.Ep, st));
   if (shape->p_drop_tokens > 0.f) V1T_TRY(dropout_rows(x, x, d.R, d.E, d.Ep, site_drop(*shape, 0, kSiteTokens), st));
+  }
 
   for (int i = 0; i < d.blocks; ++i) {
     const v1t_block_ptrs& W = P->blk[i];
@@ -207,6 +211,8 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
                   "core_forward: block %d parameter missing", i);
     // ---- behaviour latent added to every token, persists in the residual stream (vit.py:355-359)
     const float* lat = nullptr;
+    {
+    ProfScope prof(V1T_PHASE_LN_QKV, st);
     if (d.bdim > 0) {
       V1T_CHECK_ARG(W.bw0 && W.bw3, "core_forward: block %d b-mlp weights missing", i);
       V1T_TRY(bmlp_forward(behaviors, W.bw0, W.bb0, W.bw3, W.bb3, S.bhid, S.blat, d.B, d.bdim, d.hid, d.E, st));
@@ -220,7 +226,9 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = 3 * d.I;
       V1T_TRY(gemm_fp32(g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st));
     }
+    }
     for (int b0 = 0; b0 < d.B; b0 += sc.chunk) {
+      ProfScope prof(V1T_PHASE_ATTN_FWD, st);
       const int bc = std::min(sc.chunk, d.B - b0);
       V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, site_drop(*shape, i, kSiteAttn), st));
       v1t_gemm_desc g = gd(d.T, d.E, d.T);  // O = P V
@@ -232,11 +240,13 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
                         nullptr, nullptr, st));
     }
     {  // x2 = x1 + dropout(o Wproj^T + b)
+      ProfScope prof(V1T_PHASE_PROJ, st);
       v1t_gemm_desc g = gd((int)d.R, d.E, d.I);
       g.a_m = d.I; g.a_k = 1; g.b_k = 1; g.b_n = d.I; g.c_m = d.Ep; g.r_m = d.Ep;
       V1T_TRY(gemm_fp32(g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj)));
     }
     // ---- MLP (vit.py:143-150)
+    ProfScope prof_mlp(V1T_PHASE_MLP, st);
     V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, S.st2, d.R, d.E, d.Ep, st));
     {
       v1t_gemm_desc g = gd((int)d.R, d.M, d.E);
@@ -271,6 +281,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     const v1t_block_ptrs& GW = G->blk[i];
     const BlockSaved& S = sv.blk[i];
     // ================= MLP branch: x_out = x2 + drop(g W2^T + b2) =================
+    std::unique_ptr<ProfScope> lin1(new ProfScope(V1T_PHASE_LINEAR_BWD, st));
     const float* dm = dx;
     if (drop) {
       V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteMlp2), st));
@@ -322,7 +333,9 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       V1T_TRY(gemm_fp32(g, da, W.wproj, sc.dO, nullptr, nullptr, st));
     }
     const int64_t ld = 3 * d.I;
+    lin1.reset();
     for (int b0 = 0; b0 < d.B; b0 += sc.chunk) {
+      ProfScope prof(V1T_PHASE_ATTN_BWD, st);
       const int bc = std::min(sc.chunk, d.B - b0);
       const float* q = S.qkv + (int64_t)b0 * d.T * ld;
       const float* dO = sc.dO + (int64_t)b0 * d.T * d.I;
@@ -364,6 +377,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
         V1T_TRY(gemm_fp32(g, sc.P2, q, dq + d.I, nullptr, nullptr, st));
       }
     }
+    ProfScope lin2(V1T_PHASE_LINEAR_BWD, st);
     V1T_TRY(ln_forward(S.x1, nullptr, d.T, nullptr, W.ln1_w, W.ln1_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
     if (GW.wqkv) {  // dWqkv[n,e] = sum_r dqkv[r,n] h1[r,e]
       v1t_gemm_desc g = gd(3 * d.I, d.E, R);
@@ -403,6 +417,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
   }
 
   // ================= patch embedding =================
+  ProfScope prof_pe(V1T_PHASE_LINEAR_BWD, st);
   if (shape->p_drop_tokens > 0.f) V1T_TRY(dropout_rows(dx, dx, d.R, d.E, d.Ep, site_drop(*shape, 0, kSiteTokens), st));
   V1T_TRY(batchsum(dx, sc.dpos, d.B, d.T, d.E, (int64_t)d.T * d.Ep, d.Ep, d.E, st));
   if (G->pos) V1T_CUDA(cudaMemcpyAsync(G->pos, sc.dpos, sizeof(float) * d.T * d.E, cudaMemcpyDeviceToDevice, st));

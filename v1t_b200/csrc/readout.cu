@@ -445,6 +445,7 @@ extern "C" int v1t_readout_forward(const v1t_readout_shape* s, const float* fmap
   V1T_CHECK_ARG(!noise || sigma, "readout_forward: noise given without sigma");
   V1T_CHECK_ARG(!loss_out || (y_true && scratch), "readout_forward: loss needs y_true and scratch");
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(V1T_PHASE_READOUT_FWD, st);
   ReadoutScratch ws = carve(*s, scratch);
   dim3 grid(cdiv(s->neurons, kNeuronsPerCta), cdiv(s->batch, kBatchTile));
   const size_t smem = fwd_smem(*s);
@@ -479,6 +480,7 @@ extern "C" int v1t_readout_backward(const v1t_readout_shape* s, const float* fma
   V1T_CHECK_ARG(dz || (z && y_true), "readout_backward: need dz, or z and y_true for the fused Poisson gradient");
   V1T_CHECK_ARG(!noise || sigma, "readout_backward: noise given without sigma");
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(V1T_PHASE_READOUT_BWD, st);
   ReadoutScratch ws = carve(*s, scratch);
   dim3 grid(cdiv(s->neurons, kNeuronsPerCta), cdiv(s->batch, kBatchTile));
   const int tiles = grid.y;
