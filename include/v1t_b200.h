@@ -181,6 +181,9 @@ typedef struct v1t_gemm_desc {
 } v1t_gemm_desc;
 int v1t_gemm_fp32(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
                   const float* R, void* stream);
+/* same contract on the tcgen05 tensor cores; impl = V1T_IMPL_BF16X3 or V1T_IMPL_BF16 */
+int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
+                const float* R, int impl, void* stream);
 
 /* the inverted-dropout multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` =
  * block*8 + {0 tokens, 1 attention probs, 2 proj out, 3 MLP hidden, 4 MLP out}; element index = row-major

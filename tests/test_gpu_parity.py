@@ -284,3 +284,81 @@ def test_full_size_properties_baseline_config():
     for k in g_a:
         s = (g_1[k] + g_2[k]).cpu().numpy()
         assert rel_err(s, g_a[k].cpu().numpy()) < 1e-3, k
+
+
+def _gemm_case(lib, fn_name, m, n, k, b1, b2, ta, tb, impl=None, pad=0, alpha=0.5):
+    """Run one strided/batched GEMM through the C-ABI; returns (got, fp64 reference)."""
+    import ctypes as C
+    from v1t_b200 import _lib
+    rng = torch.Generator(device=DEV).manual_seed(m * 7 + n * 3 + k)
+    kp, mp, npad = k + pad, m + pad, n + pad
+    A = torch.randn((b1, b2, k, mp) if ta else (b1, b2, m, kp), device=DEV, generator=rng)
+    Bm = torch.randn((b1, b2, n, kp) if tb else (b1, b2, k, npad), device=DEV, generator=rng)
+    bias = torch.randn(n, device=DEV, generator=rng)
+    R = torch.randn(b1, b2, m, npad, device=DEV, generator=rng)
+    Cm = torch.full((b1, b2, m, npad), float("nan"), device=DEV)
+    d = _lib.GemmDesc(m=m, n=n, k=k, batch1=b1, batch2=b2, alpha=alpha, accumulate=0)
+    d.a_m, d.a_k = (1, mp) if ta else (kp, 1)
+    d.a_b1, d.a_b2 = A.stride(0), A.stride(1)
+    d.b_k, d.b_n = (1, kp) if tb else (npad, 1)
+    d.b_b1, d.b_b2 = Bm.stride(0), Bm.stride(1)
+    d.c_m, d.c_b1, d.c_b2 = npad, Cm.stride(0), Cm.stride(1)
+    d.r_m, d.r_b1, d.r_b2 = npad, R.stride(0), R.stride(1)
+    st = torch.cuda.current_stream().cuda_stream
+    args = [C.byref(d), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), bias.data_ptr(), R.data_ptr()]
+    rc = getattr(lib, fn_name)(*args, *( [impl] if impl is not None else []), st)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    Am = (A.transpose(-1, -2)[..., :m, :] if ta else A[..., :k])
+    Bn = (Bm.transpose(-1, -2)[..., :, :n] if tb else Bm[..., :n])
+    Bn = Bn[..., :k, :]
+    ref = alpha * (Am.double() @ Bn.double()) + bias.double() + R[..., :n].double()
+    return Cm[..., :n].cpu().numpy(), ref.cpu().numpy()
+
+
+TC_SHAPES = [
+    (128, 160, 160, 1, 1, False, True, 0),     # one tile, NT (both K-major), aligned
+    (130, 70, 33, 1, 1, False, False, 0),      # ragged M/N/K, B is N-contiguous
+    (300, 155, 155, 2, 3, False, True, 5),     # batched, K=155 (unaligned rows -> scalar loads), N=155
+    (155, 488, 1000, 1, 1, True, False, 1),    # A is M-contiguous (transposing producer), long K
+    (257, 620, 77, 3, 1, True, True, 3),       # both transposed, N > 256 -> 3 N-tiles of 208
+    (1654, 1654, 155, 1, 2, False, True, 5),   # attention scores shape: 13x13 tiles per head
+    (4000, 1860, 160, 1, 1, False, True, 0),   # QKV shape: persistent loop over many tiles, TMEM double buffer
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_gemm_tc_bf16x3_matches_fp64(shape):
+    """tcgen05 GEMM, bf16 hi/lo split (3 MMAs): fp32-class accuracy against an fp64 reference."""
+    from v1t_b200 import _lib
+    m, n, k, b1, b2, ta, tb, pad = shape
+    got, ref = _gemm_case(_lib.load(), "v1t_gemm_tc", m, n, k, b1, b2, ta, tb, impl=_lib.IMPL_BF16X3, pad=pad)
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) < 2e-5, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES[:4])
+def test_gemm_tc_bf16_matches_bf16_rounded_reference(shape):
+    """Plain bf16 operands: agrees with an fp64 product of bf16-ROUNDED inputs (exact operand semantics)."""
+    from v1t_b200 import _lib
+    m, n, k, b1, b2, ta, tb, pad = shape
+    got, ref = _gemm_case(_lib.load(), "v1t_gemm_tc", m, n, k, b1, b2, ta, tb, impl=_lib.IMPL_BF16, pad=pad)
+    assert rel_err(got, ref) < 2e-2  # declared tolerance of the fast mode
+
+
+@pytest.mark.parametrize("impl,tol_fwd,tol_grad", [("bf16x3", 2e-4, 1e-3), ("bf16", 6e-2, 2e-1)])
+@pytest.mark.parametrize("case", ["tiny_train", "default_dims"])
+def test_model_tensor_core_impl_matches_golden(case, impl, tol_fwd, tol_grad):
+    g = Golden(case)
+    model, crit = build(g, b200_impl=impl)
+    model.train(True)
+    d = g.mice["A"]
+    y, _, _ = model(cu(d["images"]), mouse_id="A", behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]),
+                    noise=cu(d["noise"]))
+    loss = crit(y_true=cu(d["y_true"]), y_pred=y, mouse_id="A", batch_size=y.shape[0])
+    loss.backward()
+    assert rel_err(y.detach().cpu().numpy(), d["y"]) < tol_fwd
+    assert abs(loss.item() - float(d["loss"])) / abs(float(d["loss"])) < tol_fwd
+    worst = max((rel_err(p.grad.cpu().numpy(), d["grads"][k]), k) for k, p in model.named_parameters()
+                if np.abs(d["grads"][k]).max() > 0)
+    assert worst[0] < tol_grad, worst

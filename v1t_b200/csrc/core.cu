@@ -19,7 +19,7 @@ inline DropSpec site_drop(const v1t_core_shape& s, int block, Site site) {
 }
 
 struct Dims {
-  int B, C, H, W, p, s, gh, gw, L, T, E, Ep, heads, I, M, Mp, pd, hid, bdim, blocks;
+  int B, C, H, W, p, s, gh, gw, L, T, Tp, E, Ep, heads, I, M, Mp, pd, hid, bdim, blocks, impl;
   int64_t R;  // B*T rows
 };
 
@@ -33,12 +33,15 @@ int make_dims(const v1t_core_shape* sh, Dims& d) {
   V1T_CHECK_ARG(sh->bdim == 0 || sh->bdim == 3 || sh->bdim == 5, "core: bdim must be 0, 3 or 5");
   V1T_CHECK_ARG(sh->p_drop_tokens >= 0.f && sh->p_drop_tokens < 1.f && sh->p_drop_block >= 0.f &&
                     sh->p_drop_block < 1.f, "core: dropout p must be in [0,1)");
-  V1T_CHECK_ARG(sh->impl == V1T_IMPL_FP32, "core: impl %d not available in this build", sh->impl);
+  V1T_CHECK_ARG(sh->impl == V1T_IMPL_FP32 || sh->impl == V1T_IMPL_BF16X3 || sh->impl == V1T_IMPL_BF16,
+                "core: unknown impl %d", sh->impl);
   d.B = sh->batch; d.C = sh->in_ch; d.H = sh->in_h; d.W = sh->in_w; d.p = sh->patch; d.s = sh->stride;
   d.gh = (d.H - d.p) / d.s + 1;
   d.gw = (d.W - d.p) / d.s + 1;
   d.L = d.gh * d.gw;
   d.T = d.L + 1;
+  d.Tp = (int)round_up(d.T, 4);  // row stride of the materialised attention matrices
+  d.impl = sh->impl;
   d.E = sh->emb;
   d.Ep = (int)round_up(d.E, 32);
   d.heads = sh->heads;
@@ -99,7 +102,7 @@ struct Scratch {
   size_t total;
 };
 int attn_chunk(const Dims& d) {
-  const int64_t per = (int64_t)d.heads * d.T * d.T * (int64_t)sizeof(float);
+  const int64_t per = (int64_t)d.heads * d.T * d.Tp * (int64_t)sizeof(float);
   int64_t c = (1ll << 30) / std::max<int64_t>(per, 1);
   c = std::max<int64_t>(1, std::min<int64_t>(c, d.B));
   // keep grid.z = chunk*heads within limits
@@ -117,8 +120,8 @@ Scratch carve_scratch(const Dims& d, void* base) {
   s.dqkv = c.take(d.R * 3 * d.I);
   s.dO = c.take(d.R * d.I);
   s.patches = c.take((int64_t)d.B * d.L * d.pd);
-  s.P1 = c.take((int64_t)s.chunk * d.heads * d.T * d.T);
-  s.P2 = c.take((int64_t)s.chunk * d.heads * d.T * d.T);
+  s.P1 = c.take((int64_t)s.chunk * d.heads * d.T * d.Tp);
+  s.P2 = c.take((int64_t)s.chunk * d.heads * d.T * d.Tp);
   s.partials = c.take(kPartialBytes / sizeof(float));
   s.dlat = c.take((int64_t)d.B * d.E);
   s.dz3 = c.take((int64_t)d.B * d.E);
@@ -135,17 +138,18 @@ v1t_gemm_desc gd(int m, int n, int k) {
 }
 
 // P[b,h] = softmax(scale * Q K^T) (optionally with dropout) for samples [b0, b0+bc) into P1
-int attention_probs(const Dims& d, const float* qkv, int b0, int bc, float* P, DropSpec dr, cudaStream_t st) {
+int attention_probs(const Dims& d, const float* qkv, int b0, int bc, float* P, int64_t pld, DropSpec dr,
+                    cudaStream_t st) {
   const int64_t ld = 3 * d.I;
   v1t_gemm_desc g = gd(d.T, d.T, d.E);
   g.batch1 = bc; g.batch2 = d.heads;
   g.a_m = ld; g.a_k = 1; g.a_b1 = d.T * ld; g.a_b2 = d.E;
   g.b_k = 1; g.b_n = ld; g.b_b1 = d.T * ld; g.b_b2 = d.E;
-  g.c_m = d.T; g.c_b1 = (int64_t)d.heads * d.T * d.T; g.c_b2 = (int64_t)d.T * d.T;
+  g.c_m = pld; g.c_b1 = (int64_t)d.heads * d.T * pld; g.c_b2 = (int64_t)d.T * pld;
   g.alpha = 1.0f / sqrtf((float)d.E);  // emb_dim ** -0.5 (vit.py:234)
   const float* q = qkv + (int64_t)b0 * d.T * ld;
-  V1T_TRY(gemm_fp32(g, q, q + d.I, P, nullptr, nullptr, st));
-  return softmax_rows(P, (int64_t)bc * d.heads * d.T, d.T, d.T, dr, (int64_t)b0 * d.heads * d.T, st);
+  V1T_TRY(gemm_any(d.impl, g, q, q + d.I, P, nullptr, nullptr, st));
+  return softmax_rows(P, (int64_t)bc * d.heads * d.T, d.T, pld, dr, (int64_t)b0 * d.heads * d.T, st);
 }
 
 }  // namespace
@@ -198,7 +202,7 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     g.b_k = 1; g.b_n = d.pd;                       // Wpe [E, pd]
     g.c_m = d.Ep; g.c_b1 = (int64_t)d.T * d.Ep;
     g.r_m = d.E; g.r_b1 = 0;                       // + pos[1 + l]
-    V1T_TRY(gemm_fp32(g, sc.patches, P->wpe, x + d.Ep, P->bpe, P->pos + d.E, st));
+    V1T_TRY(gemm_any(d.impl, g, sc.patches, P->wpe, x + d.Ep, P->bpe, P->pos + d.E, st));
   }
   V1T_TRY(cls_rows(P->cls, P->pos, x, d.B, d.T, d.E, d.Ep, st));
   if (shape->p_drop_tokens > 0.f) V1T_TRY(dropout_rows(x, x, d.R, d.E, d.Ep, site_drop(*shape, 0, kSiteTokens), st));
@@ -224,26 +228,26 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       v1t_gemm_desc g = gd((int)d.R, 3 * d.I, d.E);
       V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = 3 * d.I;
-      V1T_TRY(gemm_fp32(g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st));
     }
     }
     for (int b0 = 0; b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);
       const int bc = std::min(sc.chunk, d.B - b0);
-      V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, site_drop(*shape, i, kSiteAttn), st));
+      V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, d.Tp, site_drop(*shape, i, kSiteAttn), st));
       v1t_gemm_desc g = gd(d.T, d.E, d.T);  // O = P V
       g.batch1 = bc; g.batch2 = d.heads;
-      g.a_m = d.T; g.a_k = 1; g.a_b1 = (int64_t)d.heads * d.T * d.T; g.a_b2 = (int64_t)d.T * d.T;
+      g.a_m = d.Tp; g.a_k = 1; g.a_b1 = (int64_t)d.heads * d.T * d.Tp; g.a_b2 = (int64_t)d.T * d.Tp;
       g.b_k = 3 * d.I; g.b_n = 1; g.b_b1 = (int64_t)d.T * 3 * d.I; g.b_b2 = d.E;
       g.c_m = d.I; g.c_b1 = (int64_t)d.T * d.I; g.c_b2 = d.E;
-      V1T_TRY(gemm_fp32(g, sc.P1, S.qkv + (int64_t)b0 * d.T * 3 * d.I + 2 * d.I, S.o + (int64_t)b0 * d.T * d.I,
+      V1T_TRY(gemm_any(d.impl, g, sc.P1, S.qkv + (int64_t)b0 * d.T * 3 * d.I + 2 * d.I, S.o + (int64_t)b0 * d.T * d.I,
                         nullptr, nullptr, st));
     }
     {  // x2 = x1 + dropout(o Wproj^T + b)
       ProfScope prof(V1T_PHASE_PROJ, st);
       v1t_gemm_desc g = gd((int)d.R, d.E, d.I);
       g.a_m = d.I; g.a_k = 1; g.b_k = 1; g.b_n = d.I; g.c_m = d.Ep; g.r_m = d.Ep;
-      V1T_TRY(gemm_fp32(g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj)));
+      V1T_TRY(gemm_any(d.impl, g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj)));
     }
     // ---- MLP (vit.py:143-150)
     ProfScope prof_mlp(V1T_PHASE_MLP, st);
@@ -251,13 +255,13 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     {
       v1t_gemm_desc g = gd((int)d.R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = d.Mp;
-      V1T_TRY(gemm_fp32(g, sc.h, W.w1, S.u, W.b1, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st));
     }
     V1T_TRY(gelu_forward(S.u, sc.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));
     {
       v1t_gemm_desc g = gd((int)d.R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = 1; g.b_n = d.M; g.c_m = d.Ep; g.r_m = d.Ep;
-      V1T_TRY(gemm_fp32(g, sc.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2)));
+      V1T_TRY(gemm_any(d.impl, g, sc.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2)));
     }
   }
   return V1T_OK;
@@ -291,27 +295,27 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     if (GW.w2) {  // dW2[e,m] = sum_r dm[r,e] g[r,m]
       v1t_gemm_desc g = gd(d.E, d.M, R);
       g.a_m = 1; g.a_k = d.Ep; g.b_k = d.Mp; g.b_n = 1; g.c_m = d.M;
-      V1T_TRY(gemm_fp32_splitk(g, dm, sc.g, GW.w2, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, dm, sc.g, GW.w2, sc.partials, kPartialBytes, st));
     }
     if (GW.b2) V1T_TRY(colsum(dm, GW.b2, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
     {  // dg[r,m] = sum_e dm[r,e] W2[e,m]   -> sc.g (g no longer needed)
       v1t_gemm_desc g = gd(R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.M; g.b_n = 1; g.c_m = d.Mp;
       // dW2 above reads sc.g: stream order keeps it safe (same stream)
-      V1T_TRY(gemm_fp32(g, dm, W.w2, sc.g, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st));
     }
     V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
     V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
     if (GW.w1) {  // dW1[m,e] = sum_r du[r,m] h2[r,e]
       v1t_gemm_desc g = gd(d.M, d.E, R);
       g.a_m = 1; g.a_k = d.Mp; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
-      V1T_TRY(gemm_fp32_splitk(g, sc.g, sc.h, GW.w1, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, sc.g, sc.h, GW.w1, sc.partials, kPartialBytes, st));
     }
     if (GW.b1) V1T_TRY(colsum(sc.g, GW.b1, 1, d.R, d.M, 0, d.Mp, 0, sc.partials, kPartialBytes, st));
     {  // dh2[r,e] = sum_m du[r,m] W1[m,e]
       v1t_gemm_desc g = gd(R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
-      V1T_TRY(gemm_fp32(g, sc.g, W.w1, sc.dh, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, sc.g, W.w1, sc.dh, nullptr, nullptr, st));
     }
     V1T_TRY(ln_backward(sc.dh, S.x2, S.st2, W.ln2_w, dx, GW.ln2_w, GW.ln2_b, sc.partials, kPartialBytes, d.R, d.E,
                         d.Ep, st));
@@ -324,13 +328,13 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     if (GW.wproj) {  // dWp[e,i] = sum_r da[r,e] o[r,i]
       v1t_gemm_desc g = gd(d.E, d.I, R);
       g.a_m = 1; g.a_k = d.Ep; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
-      V1T_TRY(gemm_fp32_splitk(g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st));
     }
     if (GW.bproj) V1T_TRY(colsum(da, GW.bproj, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
     {  // dO[r,i] = sum_e da[r,e] Wp[e,i]
       v1t_gemm_desc g = gd(R, d.I, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
-      V1T_TRY(gemm_fp32(g, da, W.wproj, sc.dO, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, da, W.wproj, sc.dO, nullptr, nullptr, st));
     }
     const int64_t ld = 3 * d.I;
     lin1.reset();
@@ -340,41 +344,41 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       const float* q = S.qkv + (int64_t)b0 * d.T * ld;
       const float* dO = sc.dO + (int64_t)b0 * d.T * d.I;
       float* dq = sc.dqkv + (int64_t)b0 * d.T * ld;
-      const int64_t pb1 = (int64_t)d.heads * d.T * d.T, pb2 = (int64_t)d.T * d.T;
-      V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, no_drop(), st));  // P (no dropout)
+      const int64_t pb1 = (int64_t)d.heads * d.T * d.Tp, pb2 = (int64_t)d.T * d.Tp;
+      V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, d.Tp, no_drop(), st));  // P (no dropout)
       {  // dPd = dO V^T
         v1t_gemm_desc g = gd(d.T, d.T, d.E);
         g.batch1 = bc; g.batch2 = d.heads;
         g.a_m = d.I; g.a_k = 1; g.a_b1 = (int64_t)d.T * d.I; g.a_b2 = d.E;
         g.b_k = 1; g.b_n = ld; g.b_b1 = d.T * ld; g.b_b2 = d.E;
-        g.c_m = d.T; g.c_b1 = pb1; g.c_b2 = pb2;
-        V1T_TRY(gemm_fp32(g, dO, q + 2 * d.I, sc.P2, nullptr, nullptr, st));
+        g.c_m = d.Tp; g.c_b1 = pb1; g.c_b2 = pb2;
+        V1T_TRY(gemm_any(d.impl, g, dO, q + 2 * d.I, sc.P2, nullptr, nullptr, st));
       }
-      V1T_TRY(softmax_bwd_rows(sc.P1, sc.P2, (int64_t)bc * d.heads * d.T, d.T, d.T, site_drop(*shape, i, kSiteAttn),
+      V1T_TRY(softmax_bwd_rows(sc.P1, sc.P2, (int64_t)bc * d.heads * d.T, d.T, d.Tp, site_drop(*shape, i, kSiteAttn),
                                (int64_t)b0 * d.heads * d.T, st));  // P1 <- Pd, P2 <- dS
       {  // dV[j,d] = sum_i Pd[i,j] dO[i,d]
         v1t_gemm_desc g = gd(d.T, d.E, d.T);
         g.batch1 = bc; g.batch2 = d.heads;
-        g.a_m = 1; g.a_k = d.T; g.a_b1 = pb1; g.a_b2 = pb2;
+        g.a_m = 1; g.a_k = d.Tp; g.a_b1 = pb1; g.a_b2 = pb2;
         g.b_k = d.I; g.b_n = 1; g.b_b1 = (int64_t)d.T * d.I; g.b_b2 = d.E;
         g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
-        V1T_TRY(gemm_fp32(g, sc.P1, dO, dq + 2 * d.I, nullptr, nullptr, st));
+        V1T_TRY(gemm_any(d.impl, g, sc.P1, dO, dq + 2 * d.I, nullptr, nullptr, st));
       }
       {  // dQ[i,d] = scale * sum_j dS[i,j] K[j,d]
         v1t_gemm_desc g = gd(d.T, d.E, d.T);
         g.batch1 = bc; g.batch2 = d.heads; g.alpha = scale;
-        g.a_m = d.T; g.a_k = 1; g.a_b1 = pb1; g.a_b2 = pb2;
+        g.a_m = d.Tp; g.a_k = 1; g.a_b1 = pb1; g.a_b2 = pb2;
         g.b_k = ld; g.b_n = 1; g.b_b1 = d.T * ld; g.b_b2 = d.E;
         g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
-        V1T_TRY(gemm_fp32(g, sc.P2, q + d.I, dq, nullptr, nullptr, st));
+        V1T_TRY(gemm_any(d.impl, g, sc.P2, q + d.I, dq, nullptr, nullptr, st));
       }
       {  // dK[j,d] = scale * sum_i dS[i,j] Q[i,d]
         v1t_gemm_desc g = gd(d.T, d.E, d.T);
         g.batch1 = bc; g.batch2 = d.heads; g.alpha = scale;
-        g.a_m = 1; g.a_k = d.T; g.a_b1 = pb1; g.a_b2 = pb2;
+        g.a_m = 1; g.a_k = d.Tp; g.a_b1 = pb1; g.a_b2 = pb2;
         g.b_k = ld; g.b_n = 1; g.b_b1 = d.T * ld; g.b_b2 = d.E;
         g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
-        V1T_TRY(gemm_fp32(g, sc.P2, q, dq + d.I, nullptr, nullptr, st));
+        V1T_TRY(gemm_any(d.impl, g, sc.P2, q, dq + d.I, nullptr, nullptr, st));
       }
     }
     ProfScope lin2(V1T_PHASE_LINEAR_BWD, st);
@@ -382,12 +386,12 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     if (GW.wqkv) {  // dWqkv[n,e] = sum_r dqkv[r,n] h1[r,e]
       v1t_gemm_desc g = gd(3 * d.I, d.E, R);
       g.a_m = 1; g.a_k = ld; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
-      V1T_TRY(gemm_fp32_splitk(g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st));
     }
     {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
       v1t_gemm_desc g = gd(R, d.E, 3 * d.I);
       g.a_m = ld; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
-      V1T_TRY(gemm_fp32(g, sc.dqkv, W.wqkv, sc.dh, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, sc.dqkv, W.wqkv, sc.dh, nullptr, nullptr, st));
     }
     V1T_TRY(ln_backward(sc.dh, S.x1, S.st1, W.ln1_w, dx, GW.ln1_w, GW.ln1_b, sc.partials, kPartialBytes, d.R, d.E,
                         d.Ep, st));
@@ -398,19 +402,19 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       if (GW.bw3) {  // dW3[e,j] = sum_b dz3[b,e] hid[b,j]
         v1t_gemm_desc g = gd(d.E, d.hid, d.B);
         g.a_m = 1; g.a_k = d.E; g.b_k = d.hid; g.b_n = 1; g.c_m = d.hid;
-        V1T_TRY(gemm_fp32(g, sc.dz3, S.bhid, GW.bw3, nullptr, nullptr, st));
+        V1T_TRY(gemm_any(d.impl, g, sc.dz3, S.bhid, GW.bw3, nullptr, nullptr, st));
       }
       if (GW.bb3) V1T_TRY(colsum(sc.dz3, GW.bb3, 1, d.B, d.E, 0, d.E, 0, sc.partials, kPartialBytes, st));
       {  // dhid[b,j] = sum_e dz3[b,e] W3[e,j]
         v1t_gemm_desc g = gd(d.B, d.hid, d.E);
         g.a_m = d.E; g.a_k = 1; g.b_k = d.hid; g.b_n = 1; g.c_m = d.hid;
-        V1T_TRY(gemm_fp32(g, sc.dz3, W.bw3, sc.dhid, nullptr, nullptr, st));
+        V1T_TRY(gemm_any(d.impl, g, sc.dz3, W.bw3, sc.dhid, nullptr, nullptr, st));
       }
       V1T_TRY(tanh_grad(sc.dhid, S.bhid, sc.dhid, (int64_t)d.B * d.hid, st));  // dz0
       if (GW.bw0) {  // dW0[j,i] = sum_b dz0[b,j] beh[b,i]
         v1t_gemm_desc g = gd(d.hid, d.bdim, d.B);
         g.a_m = 1; g.a_k = d.hid; g.b_k = d.bdim; g.b_n = 1; g.c_m = d.bdim;
-        V1T_TRY(gemm_fp32(g, sc.dhid, behaviors, GW.bw0, nullptr, nullptr, st));
+        V1T_TRY(gemm_any(d.impl, g, sc.dhid, behaviors, GW.bw0, nullptr, nullptr, st));
       }
       if (GW.bb0) V1T_TRY(colsum(sc.dhid, GW.bb0, 1, d.B, d.hid, 0, d.hid, 0, sc.partials, kPartialBytes, st));
     }
@@ -434,7 +438,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       g.a_m = 1; g.a_k = d.Ep; g.a_b1 = (int64_t)d.T * d.Ep;
       g.b_k = d.pd; g.b_n = 1; g.b_b1 = (int64_t)d.L * d.pd;
       g.c_m = d.pd; g.c_b1 = per;
-      V1T_TRY(gemm_fp32(g, dx + (int64_t)b0 * d.T * d.Ep + d.Ep, sc.patches + (int64_t)b0 * d.L * d.pd, sc.partials,
+      V1T_TRY(gemm_any(d.impl, g, dx + (int64_t)b0 * d.T * d.Ep + d.Ep, sc.patches + (int64_t)b0 * d.L * d.pd, sc.partials,
                         nullptr, nullptr, st));
       V1T_TRY(reduce_partials(sc.partials, G->wpe, bc, d.E, d.pd, d.pd, b0 > 0, st));
     }
@@ -445,7 +449,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     g.a_m = d.Ep; g.a_k = 1; g.a_b1 = (int64_t)d.T * d.Ep;
     g.b_k = d.pd; g.b_n = 1;
     g.c_m = d.pd; g.c_b1 = (int64_t)d.L * d.pd;
-    V1T_TRY(gemm_fp32(g, dx + d.Ep, P->wpe, sc.patches, nullptr, nullptr, st));
+    V1T_TRY(gemm_any(d.impl, g, dx + d.Ep, P->wpe, sc.patches, nullptr, nullptr, st));
     V1T_TRY(col2im(sc.patches, d_images, d.B, d.C, d.H, d.W, d.p, d.s, d.gh, d.gw, st));
   }
   return V1T_OK;
@@ -460,7 +464,7 @@ extern "C" int v1t_attention_probs(const v1t_core_shape* shape, const void* save
   const int chunk = attn_chunk(d);
   for (int b0 = 0; b0 < d.B; b0 += chunk) {
     const int bc = std::min(chunk, d.B - b0);
-    V1T_TRY(attention_probs(d, sv.blk[block].qkv, b0, bc, probs + (int64_t)b0 * d.heads * d.T * d.T, no_drop(),
+    V1T_TRY(attention_probs(d, sv.blk[block].qkv, b0, bc, probs + (int64_t)b0 * d.heads * d.T * d.T, d.T, no_drop(),
                             (cudaStream_t)stream));
   }
   return V1T_OK;

@@ -135,7 +135,28 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, float
   *o = accumulate ? *o + s : s;
 }
 
+__global__ void reduce_partials_ld_kernel(const float* __restrict__ partials, float* __restrict__ out, int parts,
+                                          int64_t rows, int64_t cols, int64_t in_ld, int64_t out_ld,
+                                          int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols, c = i % cols;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += partials[((int64_t)p * rows + r) * in_ld + c];
+  float* o = out + r * out_ld + c;
+  *o = accumulate ? *o + s : s;
+}
+
 }  // namespace
+
+int reduce_partials_ld(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t in_ld,
+                       int64_t out_ld, int accumulate, cudaStream_t st) {
+  if (rows * cols == 0) return V1T_OK;
+  reduce_partials_ld_kernel<<<cdiv(rows * cols, 256), 256, 0, st>>>(partials, out, parts, rows, cols, in_ld, out_ld,
+                                                                    accumulate);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
 
 int reduce_partials(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t ld_out,
                     int accumulate, cudaStream_t st) {

@@ -1,0 +1,340 @@
+// tcgen05 tensor-core GEMM with the same strided/batched/split-K contract as gemm_fp32.cu:
+//     C[b][m,n] = alpha * sum_k A[b][m,k] * B[b][k,n] (+ bias[n]) (dropout) (+ R[b][m,n])
+// Operands are fp32 in global memory with arbitrary leading dims and either orientation; PRODUCER warps load
+// them (128-bit where aligned), split each value into bf16 hi + bf16 lo (x ~= hi + lo), and store both planes
+// into shared memory in the K-major 64-byte-swizzled UMMA layout (a transposing store handles MN-contiguous
+// sources, so only K-major descriptors are needed).  ONE thread issues tcgen05.mma (M=128, N<=256, K=16):
+// hi*hi + lo*hi + hi*lo in "bf16x3" mode (fp32-class accuracy, fp32 accumulate in TMEM) or hi*hi only in "bf16"
+// mode.  Accumulators are double-buffered in TMEM (2 x 256 columns) so the EPILOGUE warps (tcgen05.ld -> bias /
+// dropout / residual -> global) overlap the next tile's main loop.  Persistent CTAs, one per SM.
+//
+// Warp roles (416 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMEM alloc + MMA issue,
+// warps 5-12 producers.  Pipelines: full/empty mbarriers per smem stage (4 stages x 48 KB), tmem_full/tmem_empty
+// per accumulator buffer.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace v1t {
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BK = 32, STAGES = 4, BN_MAX = 256;
+constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 416
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int A_PLANE = BM * 64;       // bytes of one bf16 plane of the A stage (128 rows x 32 k)
+constexpr int B_PLANE = BN_MAX * 64;
+constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // hi + lo planes of A and B
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcArgs {
+  GemmArgs g;
+  int bn;        // N tile (multiple of 16, <= 256)
+  int tiles_m, tiles_n;
+  int x3;        // 1: hi*hi + lo*hi + hi*lo, 0: hi*hi
+  int a_vec, b_vec, c_vec;  // 128-bit access allowed
+};
+
+struct Tile {
+  int m0, n0, k_begin, k_end;
+  int64_t a_off, b_off, c_off, r_off;
+};
+
+__device__ __forceinline__ Tile decode_tile(const TcArgs& a, int t) {
+  const GemmArgs& g = a.g;
+  Tile tl;
+  const int nt = t % a.tiles_n; t /= a.tiles_n;
+  const int mt = t % a.tiles_m; t /= a.tiles_m;
+  const int split = t % g.splits; t /= g.splits;
+  const int b2 = t % g.d.batch2, b1 = t / g.d.batch2;
+  tl.m0 = mt * BM;
+  tl.n0 = nt * a.bn;
+  tl.k_begin = split * g.k_chunk;
+  tl.k_end = min(g.d.k, tl.k_begin + g.k_chunk);
+  tl.a_off = b1 * g.d.a_b1 + b2 * g.d.a_b2;
+  tl.b_off = b1 * g.d.b_b1 + b2 * g.d.b_b2;
+  tl.c_off = b1 * g.d.c_b1 + b2 * g.d.c_b2 + (int64_t)split * g.c_split;
+  tl.r_off = b1 * g.d.r_b1 + b2 * g.d.r_b2;
+  return tl;
+}
+
+// 8 consecutive k of one row (zero-filled outside [0,rows) x [.,k_end))
+__device__ __forceinline__ void load8(const float* __restrict__ base, int64_t s_row, int64_t s_k, bool vec, int row,
+                                      int rows, int k, int k_end, float (&v)[8]) {
+  if (row >= rows || k >= k_end) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    return;
+  }
+  const float* p = base + (int64_t)row * s_row + (int64_t)k * s_k;
+  if (vec && k + 8 <= k_end) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 y = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k + j < k_end) ? __ldg(p + (int64_t)j * s_k) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GemmArgs& g = a.g;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], kProdThreads);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = g.d.batch1 * g.d.batch2 * g.splits * a.tiles_m * a.tiles_n;
+
+  if (warp > kEpiWarps) {
+    // ============================== PRODUCERS ==============================
+    const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;
+    const bool a_kc = (g.d.a_k == 1), b_kc = (g.d.b_k == 1);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile tl = decode_tile(a, t);
+      const float* A = g.A + tl.a_off;
+      const float* B = g.B + tl.b_off;
+      const int num_kb = (tl.k_end - tl.k_begin + BK - 1) / BK;
+      const int b_chunks = a.bn * 4;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int k0 = tl.k_begin + kb * BK;
+        const int stage = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        float va[2][8], vb[4][8];
+        // issue all global loads of this stage before waiting for the smem slot
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int q = ptid + i * kProdThreads;
+          const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
+          load8(A, g.d.a_m, g.d.a_k, a_kc && a.a_vec, tl.m0 + r, g.d.m, k0 + c * 8, tl.k_end, va[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = ptid + i * kProdThreads;
+          if (q < b_chunks) {
+            const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
+            load8(B, g.d.b_n, g.d.b_k, b_kc && a.b_vec, tl.n0 + r, g.d.n, k0 + c * 8, tl.k_end, vb[i]);
+          }
+        }
+        mbar_wait(&empty[stage], ph ^ 1);
+        uint8_t* sa_hi = smem + stage * STAGE_BYTES;
+        uint8_t* sa_lo = sa_hi + A_PLANE;
+        uint8_t* sb_hi = sa_hi + 2 * A_PLANE;
+        uint8_t* sb_lo = sb_hi + B_PLANE;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int q = ptid + i * kProdThreads;
+          const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
+          uint4 hi, lo;
+          split8(va[i], hi, lo);
+          const uint32_t off = sw64_offset(r, c);
+          *reinterpret_cast<uint4*>(sa_hi + off) = hi;
+          if (a.x3) *reinterpret_cast<uint4*>(sa_lo + off) = lo;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int q = ptid + i * kProdThreads;
+          if (q < b_chunks) {
+            const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
+            uint4 hi, lo;
+            split8(vb[i], hi, lo);
+            const uint32_t off = sw64_offset(r, c);
+            *reinterpret_cast<uint4*>(sb_hi + off) = hi;
+            if (a.x3) *reinterpret_cast<uint4*>(sb_lo + off) = lo;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full[stage]);
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // ============================== MMA ISSUER ==============================
+    const uint32_t idesc = idesc_bf16(BM, a.bn, 0, 0);
+    uint32_t it = 0, tl_i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
+      const Tile tl = decode_tile(a, t);
+      const int num_kb = (tl.k_end - tl.k_begin + BK - 1) / BK;
+      const uint32_t buf = tl_i & 1, tph = (tl_i >> 1) & 1;
+      mbar_wait(&tempty[buf], tph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN_MAX;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int stage = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + A_PLANE, sb_hi = sa_hi + 2 * A_PLANE, sb_lo = sb_hi + B_PLANE;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ah = desc_k_sw64(sa_hi + kk * 32), bh = desc_k_sw64(sb_hi + kk * 32);
+            umma_bf16(d_tmem, ah, bh, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            if (a.x3) {
+              const uint64_t al = desc_k_sw64(sa_lo + kk * 32), bl = desc_k_sw64(sb_lo + kk * 32);
+              umma_bf16(d_tmem, al, bh, idesc, 1u);
+              umma_bf16(d_tmem, ah, bl, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[stage]);                      // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull[buf]);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== EPILOGUE ==============================
+    uint32_t tl_i = 0;
+    const float inv_keep = g.drop.p > 0.f ? 1.f / (1.f - g.drop.p) : 1.f;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
+      const Tile tl = decode_tile(a, t);
+      const uint32_t buf = tl_i & 1, tph = (tl_i >> 1) & 1;
+      mbar_wait(&tfull[buf], tph);
+      tc_fence_after();
+      const int m = tl.m0 + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + buf * BN_MAX + ((uint32_t)(warp * 32) << 16);
+      float* crow = g.C + tl.c_off + (int64_t)m * g.d.c_m;
+      const float* rrow = g.R ? g.R + tl.r_off + (int64_t)m * g.d.r_m : nullptr;
+      for (int c0 = 0; c0 < a.bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (m < g.d.m) {
+          const int nb = tl.n0 + c0;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = nb + j;
+            float x = g.d.alpha * __uint_as_float(v[j]);
+            if (n < g.d.n) {
+              if (g.bias) x += __ldg(g.bias + n);
+              if (g.drop.p > 0.f)
+                x *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * g.d.n + n, g.drop.p, inv_keep);
+              if (rrow) x += __ldg(rrow + n);
+              if (g.d.accumulate) x += crow[n];
+            }
+            o[j] = x;
+          }
+          if (a.c_vec && nb + 16 <= g.d.n) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(crow + nb + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < g.d.n) crow[nb + j] = o[j];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) tmem_dealloc<512>(tmem_base);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
+              DropSpec drop, int x3, int splits, int k_chunk, int64_t c_split, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    V1T_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  TcArgs a;
+  a.g.d = d;
+  a.g.A = A; a.g.B = B; a.g.C = C; a.g.bias = bias; a.g.R = R;
+  a.g.drop = drop;
+  a.g.splits = splits; a.g.k_chunk = k_chunk; a.g.c_split = c_split;
+  const int nt = cdiv(d.n, BN_MAX);
+  a.bn = (int)round_up(cdiv(d.n, nt), 16);
+  a.tiles_n = cdiv(d.n, a.bn);
+  a.tiles_m = cdiv(d.m, BM);
+  a.x3 = x3;
+  a.a_vec = aligned16(A) && d.a_m % 4 == 0 && d.a_b1 % 4 == 0 && d.a_b2 % 4 == 0;
+  a.b_vec = aligned16(B) && d.b_n % 4 == 0 && d.b_b1 % 4 == 0 && d.b_b2 % 4 == 0;
+  a.c_vec = aligned16(C) && d.c_m % 4 == 0 && d.c_b1 % 4 == 0 && d.c_b2 % 4 == 0 && c_split % 4 == 0;
+  const int64_t total = (int64_t)d.batch1 * d.batch2 * splits * a.tiles_m * a.tiles_n;
+  V1T_CHECK_ARG(total < (1ll << 31), "tc gemm: too many tiles");
+  const int grid = (int)std::min<int64_t>(total, kNumSMs);
+  tc_gemm_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(a);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+bool tc_supported(const v1t_gemm_desc& d) {
+  return d.k > 0 && (d.a_k == 1 || d.a_m == 1) && (d.b_k == 1 || d.b_n == 1);
+}
+
+}  // namespace
+
+int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
+            cudaStream_t st, DropSpec drop, int x3) {
+  V1T_CHECK_ARG(d.m >= 0 && d.n >= 0 && d.k >= 0 && d.batch1 >= 1 && d.batch2 >= 1, "gemm: bad sizes");
+  if (d.m == 0 || d.n == 0) return V1T_OK;
+  if (!tc_supported(d)) return gemm_fp32(d, A, B, C, bias, R, st, drop);
+  return launch_tc(d, A, B, C, bias, R, drop, x3, 1, (int)round_up(d.k, BK), 0, st);
+}
+
+int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
+                   size_t partial_bytes, cudaStream_t st, int x3) {
+  V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1, "splitk gemm: no batch");
+  if (d.m == 0 || d.n == 0) return V1T_OK;
+  if (!tc_supported(d)) return gemm_fp32_splitk(d, A, B, C, partials, partial_bytes, st);
+  const int nt = cdiv(d.n, BN_MAX);
+  const int bn = (int)round_up(cdiv(d.n, nt), 16);
+  const int tiles = cdiv(d.n, bn) * cdiv(d.m, BM);
+  const int64_t n_ld = round_up(d.n, 4);
+  const int64_t per = (int64_t)d.m * n_ld * (int64_t)sizeof(float);
+  int splits = (2 * kNumSMs + tiles - 1) / tiles;
+  splits = std::min(splits, cdiv(d.k, 4 * BK));
+  splits = (int)std::min<int64_t>(splits, (int64_t)partial_bytes / per);
+  if (splits <= 1) return gemm_tc(d, A, B, C, nullptr, nullptr, st, no_drop(), x3);
+  const int k_chunk = (int)round_up(cdiv(d.k, splits), BK);
+  splits = cdiv(d.k, k_chunk);
+  v1t_gemm_desc p = d;
+  p.accumulate = 0;
+  p.c_m = n_ld;
+  V1T_TRY(launch_tc(p, A, B, partials, nullptr, nullptr, no_drop(), x3, splits, k_chunk, (int64_t)d.m * n_ld, st));
+  return reduce_partials_ld(partials, C, splits, d.m, d.n, n_ld, d.c_m, d.accumulate, st);
+}
+
+}  // namespace v1t
+
+extern "C" int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
+                           const float* R, int impl, void* stream) {
+  V1T_CHECK_ARG(d && A && B && C, "v1t_gemm_tc: null argument");
+  V1T_CHECK_ARG(impl == V1T_IMPL_BF16X3 || impl == V1T_IMPL_BF16, "v1t_gemm_tc: impl must be BF16X3 or BF16");
+  return v1t::gemm_tc(*d, A, B, C, bias, R, (cudaStream_t)stream, v1t::no_drop(), impl == V1T_IMPL_BF16X3);
+}

@@ -32,6 +32,29 @@ int gemm_fp32_splitk(const v1t_gemm_desc& d, const float* A, const float* B, flo
 int reduce_partials(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t ld_out,
                     int accumulate, cudaStream_t st);
 
+int reduce_partials_ld(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t in_ld,
+                       int64_t out_ld, int accumulate, cudaStream_t st);
+
+// gemm_tc.cu (tcgen05): same contract; x3 = 1 -> bf16 hi/lo split (3 MMAs), 0 -> plain bf16 operands
+int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
+            cudaStream_t st, DropSpec drop, int x3);
+int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
+                   size_t partial_bytes, cudaStream_t st, int x3);
+
+// impl dispatch used by the orchestrator
+inline int gemm_any(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias,
+                    const float* R, cudaStream_t st, DropSpec drop = no_drop()) {
+  const int64_t work = (int64_t)d.m * d.n * (d.k > 0 ? d.k : 1) * d.batch1 * d.batch2;
+  if (impl == V1T_IMPL_FP32 || work < (1ll << 22)) return gemm_fp32(d, A, B, C, bias, R, st, drop);
+  return gemm_tc(d, A, B, C, bias, R, st, drop, impl == V1T_IMPL_BF16X3);
+}
+inline int gemm_any_splitk(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C,
+                           float* partials, size_t partial_bytes, cudaStream_t st) {
+  const int64_t work = (int64_t)d.m * d.n * (d.k > 0 ? d.k : 1);
+  if (impl == V1T_IMPL_FP32 || work < (1ll << 22)) return gemm_fp32_splitk(d, A, B, C, partials, partial_bytes, st);
+  return gemm_tc_splitk(d, A, B, C, partials, partial_bytes, st, impl == V1T_IMPL_BF16X3);
+}
+
 // elementwise.cu
 int im2col(const float* img, float* patches, int B, int C, int H, int W, int p, int s, int gh, int gw,
            cudaStream_t st);
