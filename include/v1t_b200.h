@@ -129,6 +129,14 @@ int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptrs* params, 
  * Attention.attend emits); uses the fp32 kernels.  Needs the `saved` buffer of a keep_for_backward forward. */
 int v1t_attention_probs(const v1t_core_shape* shape, const void* saved, int block, float* probs, void* stream);
 
+/* Fused attention on the tcgen05 tensor cores (K4 of SURVEY.md): qkv [B,T,3*H*E] fp32 packed as to_qkv emits it
+ * (q | k | v, heads concatenated; vit.py:269-272) -> out [B,T,H*E] = softmax(q k^T E^-0.5) (dropout) v with heads
+ * concatenated ('b h n d -> b n (h d)').  lse_out [B*H, roundup(T,128)] receives the base-2 log-sum-exp per row
+ * (may be NULL).  impl = V1T_IMPL_BF16X3 | V1T_IMPL_BF16.  scratch: v1t_attn_scratch_bytes. */
+size_t v1t_attn_scratch_bytes(int B, int H, int T, int E);
+int v1t_attn_forward(const float* qkv, int B, int H, int T, int E, int impl, float p_drop, uint64_t seed,
+                     uint32_t site, float* out, float* lse_out, void* scratch, void* stream);
+
 /* ---- Gaussian2d readout ------------------------------------------------------------------------------ */
 typedef struct v1t_readout_shape {
   int32_t batch;        /* B */

@@ -362,3 +362,53 @@ def test_model_tensor_core_impl_matches_golden(case, impl, tol_fwd, tol_grad):
     worst = max((rel_err(p.grad.cpu().numpy(), d["grads"][k]), k) for k, p in model.named_parameters()
                 if np.abs(d["grads"][k]).max() > 0)
     assert worst[0] < tol_grad, worst
+
+
+def _attn_ref(qkv, H, E, mask=None):
+    B, T, _ = qkv.shape
+    q, k, v = [x.reshape(B, T, H, E).transpose(1, 2).double() for x in qkv.chunk(3, dim=-1)]
+    p = torch.softmax(q @ k.transpose(-1, -2) * E ** -0.5, dim=-1)
+    lse2 = torch.logsumexp(q @ k.transpose(-1, -2) * E ** -0.5, dim=-1) / np.log(2.0)
+    if mask is not None:
+        p = p * mask
+    return (p @ v).transpose(1, 2).reshape(B, T, H * E), lse2
+
+
+@pytest.mark.parametrize("B,H,T,E", [(1, 1, 64, 32), (2, 2, 200, 24), (1, 2, 1654, 155), (3, 4, 333, 155)])
+@pytest.mark.parametrize("impl,tol", [("bf16x3", 3e-5), ("bf16", 2e-2)])
+def test_fused_attention_forward(B, H, T, E, impl, tol):
+    """tcgen05 fused attention (two-pass softmax, S/O in TMEM) vs an fp64 softmax(QK^T)V, ragged T and head dims."""
+    import ctypes as C
+    from v1t_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + T)
+    qkv = torch.randn(B, T, 3 * H * E, device=DEV, generator=g) * 1.5
+    out = torch.full((B, T, H * E), float("nan"), device=DEV)
+    Tp = (T + 127) // 128 * 128
+    lse = torch.zeros(B * H, Tp, device=DEV)
+    scratch = torch.empty(lib.v1t_attn_scratch_bytes(B, H, T, E), dtype=torch.uint8, device=DEV)
+    rc = lib.v1t_attn_forward(qkv.data_ptr(), B, H, T, E, _lib.IMPL_NAMES[impl], 0.0, 0, 0, out.data_ptr(),
+                              lse.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    ref, lse2 = _attn_ref(qkv, H, E)
+    assert torch.isfinite(out).all()
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < tol
+    assert rel_err(lse.view(B, H, Tp)[:, :, :T].cpu().numpy(), lse2.cpu().numpy()) < max(tol, 1e-5)
+
+
+def test_fused_attention_forward_dropout_replay():
+    import ctypes as C
+    from v1t_b200 import _lib
+    lib = _lib.load()
+    B, H, T, E, p, seed, site = 2, 2, 150, 40, 0.25, 777, 9
+    g = torch.Generator(device=DEV).manual_seed(5)
+    qkv = torch.randn(B, T, 3 * H * E, device=DEV, generator=g)
+    out = torch.empty(B, T, H * E, device=DEV)
+    scratch = torch.empty(lib.v1t_attn_scratch_bytes(B, H, T, E), dtype=torch.uint8, device=DEV)
+    rc = lib.v1t_attn_forward(qkv.data_ptr(), B, H, T, E, _lib.IMPL_BF16X3, p, seed, site, out.data_ptr(), None,
+                              scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    mask = VF.dropout_mask(B * H * T * T, seed, site, p, DEV).view(B, H, T, T).double()
+    ref, _ = _attn_ref(qkv, H, E, mask)
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 3e-5

@@ -55,6 +55,31 @@ inline int gemm_any_splitk(int impl, const v1t_gemm_desc& d, const float* A, con
   return gemm_tc_splitk(d, A, B, C, partials, partial_bytes, st, impl == V1T_IMPL_BF16X3);
 }
 
+// planes.cu / attn_tc.cu (fused attention on tcgen05)
+size_t plane_bytes(int B, int H, int Tp, int Dp);
+int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tp, int E, int Dp, void* rm_hi,
+                void* rm_lo, void* tr_hi, void* tr_lo, cudaStream_t st);
+int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int T, int Tp, int E, int64_t ld,
+               cudaStream_t st);
+struct AttnFwdArgs {
+  const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo;  // pre-swizzled bf16 planes (planes.cu)
+  float* O;          // [B, T, o_ld]: O[(b*T+t)*o_ld + h*E + d]
+  int64_t o_ld;
+  float* lse;        // [B*H, Tp] log2-domain log-sum-exp (may be null)
+  int B, H, T, Tp, E, Dp;
+  float scale_log2;  // E^-0.5 * log2(e)
+  int x3;
+  DropSpec drop;
+};
+int attn_fwd_tc(const AttnFwdArgs& a, cudaStream_t st);
+struct AttnPlanes {  // [0] = hi, [1] = lo
+  uint8_t *q[2], *k[2], *vt[2];                       // forward
+  uint8_t *v[2], *qt[2], *kt[2], *dO[2], *dOt[2];     // backward
+  float *lse, *delta;                                 // [B*H, Tp]
+  size_t total;
+};
+AttnPlanes carve_attn_planes(void* base, int B, int H, int Tp, int Dp, bool with_backward);
+
 // elementwise.cu
 int im2col(const float* img, float* patches, int B, int C, int H, int W, int p, int s, int gh, int gw,
            cudaStream_t st);

@@ -1,0 +1,117 @@
+// "UMMA-ready" bf16 operand planes in HBM for the fused attention kernels.
+//
+// The attention operands (Q, K, V, dO per head) are re-read by many CTAs, so they are converted ONCE from the
+// fp32 GEMM outputs into bf16 hi (+ lo) planes laid out exactly like the shared-memory tiles tcgen05.mma reads:
+// 32-element (64-byte) K-atoms, rows 64 B apart, 16-byte chunks XOR-swizzled with ((row >> 1) & 3) — the
+// canonical K-major SWIZZLE_64B layout.  A tile of any 8-row-aligned row range of one atom is then a CONTIGUOUS
+// byte range, fetched with a single cp.async.bulk (no tensor map, no conversion work in the consumer).
+//
+//   RM plane  rows = tokens, K = head dim   [B*H][Dp/32 atoms][Tp rows][64 B]     (Q, K, V, dO as A/B operands
+//                                                                                  contracted over d)
+//   TR plane  rows = head dim, K = tokens   [B*H][Tp/32 atoms][Dp rows][64 B]     (V^T, Q^T, K^T, dO^T: operands
+//                                                                                  contracted over tokens)
+// Pad rows / columns (t >= T, d >= E) are written as zeros.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace v1t {
+namespace {
+
+using namespace tc;
+
+// grid (Tp/32, B*H); block 256.  Each block converts 32 tokens x Dp dims of one (b, h).
+__global__ void __launch_bounds__(256) make_planes_kernel(const float* __restrict__ X, int64_t ld, int col0, int B,
+                                                          int H, int T, int Tp, int E, int Dp,
+                                                          uint8_t* __restrict__ rm_hi, uint8_t* __restrict__ rm_lo,
+                                                          uint8_t* __restrict__ tr_hi, uint8_t* __restrict__ tr_lo) {
+  extern __shared__ float tile[];  // [32][Dp + 1]
+  const int tb = blockIdx.x, bh = blockIdx.y;
+  const int b = bh / H, h = bh % H;
+  const int t0 = tb * 32;
+  const int pitch = Dp + 1;
+  for (int i = threadIdx.x; i < 32 * Dp; i += blockDim.x) {
+    const int tl = i / Dp, d = i % Dp;
+    const int t = t0 + tl;
+    float v = 0.f;
+    if (t < T && d < E) v = __ldg(X + ((int64_t)b * T + t) * ld + col0 + h * E + d);
+    tile[tl * pitch + d] = v;
+  }
+  __syncthreads();
+  const int atoms_d = Dp / 32, atoms_t = Tp / 32;
+  // RM: one 16-byte chunk = 8 consecutive d of one token
+  if (rm_hi) {
+    for (int i = threadIdx.x; i < 32 * (Dp / 8); i += blockDim.x) {
+      const int tl = i % 32, ch = i / 32;  // lanes = consecutive tokens
+      const int a = ch / 4, c = ch % 4;
+      const int t = t0 + tl;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tile[tl * pitch + a * 32 + c * 8 + e];
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      const int64_t off = (((int64_t)bh * atoms_d + a) * Tp + t) * 64 + ((c ^ ((t >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(rm_hi + off) = hi;
+      if (rm_lo) *reinterpret_cast<uint4*>(rm_lo + off) = lo;
+    }
+  }
+  // TR: one 16-byte chunk = 8 consecutive tokens of one d
+  if (tr_hi) {
+    const int ka = tb;  // this block is exactly one 32-token atom
+    for (int i = threadIdx.x; i < Dp * 4; i += blockDim.x) {
+      const int d = i / 4, c = i % 4;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = tile[(c * 8 + e) * pitch + d];
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      const int64_t off = (((int64_t)bh * atoms_t + ka) * Dp + d) * 64 + ((c ^ ((d >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(tr_hi + off) = hi;
+      if (tr_lo) *reinterpret_cast<uint4*>(tr_lo + off) = lo;
+    }
+  }
+}
+
+// delta[b,h,t] = sum_d O[b,t,h*E+d] * dO[b,t,h*E+d]   (softmax backward row term); one warp per (b,t,h)
+__global__ void attn_delta_kernel(const float* __restrict__ O, const float* __restrict__ dO, float* __restrict__ delta,
+                                  int B, int H, int T, int Tp, int E, int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t total = (int64_t)B * T * H;
+  if (w >= total) return;
+  const int h = (int)(w % H);
+  const int64_t r = w / H;  // b*T + t
+  const int b = (int)(r / T), t = (int)(r % T);
+  const float* o = O + r * ld + h * E;
+  const float* g = dO + r * ld + h * E;
+  float s = 0.f;
+  for (int d = lane; d < E; d += 32) s = fmaf(o[d], g[d], s);
+  s = warp_sum(s);
+  if (lane == 0) delta[((int64_t)b * H + h) * Tp + t] = s;
+}
+
+}  // namespace
+
+size_t plane_bytes(int B, int H, int Tp, int Dp) { return (size_t)B * H * Tp * Dp * 2; }
+
+int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tp, int E, int Dp, void* rm_hi,
+                void* rm_lo, void* tr_hi, void* tr_lo, cudaStream_t st) {
+  V1T_CHECK_ARG(Tp % 128 == 0 && Dp % 32 == 0 && Tp >= T && Dp >= E, "make_planes: bad padded sizes");
+  dim3 grid(Tp / 32, B * H);
+  V1T_CHECK_ARG(grid.y <= 65535, "make_planes: too many (batch, head) pairs");
+  const size_t smem = sizeof(float) * 32 * (Dp + 1);
+  make_planes_kernel<<<grid, 256, smem, st>>>(X, ld, col0, B, H, T, Tp, E, Dp, (uint8_t*)rm_hi, (uint8_t*)rm_lo,
+                                              (uint8_t*)tr_hi, (uint8_t*)tr_lo);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int T, int Tp, int E, int64_t ld,
+               cudaStream_t st) {
+  const int64_t warps = (int64_t)B * T * H;
+  attn_delta_kernel<<<cdiv(warps, 8), 256, 0, st>>>(O, dO, delta, B, H, T, Tp, E, ld);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+}  // namespace v1t
