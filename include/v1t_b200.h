@@ -137,6 +137,12 @@ size_t v1t_attn_scratch_bytes(int B, int H, int T, int E);
 int v1t_attn_forward(const float* qkv, int B, int H, int T, int E, int impl, float p_drop, uint64_t seed,
                      uint32_t site, float* out, float* lse_out, void* scratch, void* stream);
 
+/* autograd of v1t_attn_forward: out / lse are the forward's results, d_out = dL/d(out); writes d_qkv [B,T,3*H*E]
+ * (dq | dk | dv).  Two atomic-free kernels (per key tile: dK, dV; per query tile: dQ), P recomputed from lse. */
+int v1t_attn_backward(const float* qkv, const float* out, const float* d_out, const float* lse, int B, int H, int T,
+                      int E, int impl, float p_drop, uint64_t seed, uint32_t site, float* d_qkv, void* scratch,
+                      void* stream);
+
 /* ---- Gaussian2d readout ------------------------------------------------------------------------------ */
 typedef struct v1t_readout_shape {
   int32_t batch;        /* B */
@@ -190,6 +196,8 @@ typedef struct v1t_gemm_desc {
 int v1t_gemm_fp32(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
                   const float* R, void* stream);
 /* same contract on the tcgen05 tensor cores; impl = V1T_IMPL_BF16X3 or V1T_IMPL_BF16 */
+/* test knob: stage M/N-contiguous operands un-transposed and use MN-major UMMA descriptors (default on) */
+int v1t_gemm_tc_set_mn_major(int on);
 int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
                 const float* R, int impl, void* stream);
 

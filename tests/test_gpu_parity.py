@@ -327,12 +327,19 @@ TC_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("mn_major", [1, 0])
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_gemm_tc_bf16x3_matches_fp64(shape):
-    """tcgen05 GEMM, bf16 hi/lo split (3 MMAs): fp32-class accuracy against an fp64 reference."""
+def test_gemm_tc_bf16x3_matches_fp64(shape, mn_major):
+    """tcgen05 GEMM, bf16 hi/lo split (3 MMAs): fp32-class accuracy against an fp64 reference.  M/N-contiguous
+    operands are staged either transposed (K-major descriptors) or as-is (MN-major descriptors)."""
     from v1t_b200 import _lib
+    lib = _lib.load()
     m, n, k, b1, b2, ta, tb, pad = shape
-    got, ref = _gemm_case(_lib.load(), "v1t_gemm_tc", m, n, k, b1, b2, ta, tb, impl=_lib.IMPL_BF16X3, pad=pad)
+    lib.v1t_gemm_tc_set_mn_major(mn_major)
+    try:
+        got, ref = _gemm_case(lib, "v1t_gemm_tc", m, n, k, b1, b2, ta, tb, impl=_lib.IMPL_BF16X3, pad=pad)
+    finally:
+        lib.v1t_gemm_tc_set_mn_major(1)
     assert np.isfinite(got).all()
     assert rel_err(got, ref) < 2e-5, rel_err(got, ref)
 
@@ -412,3 +419,38 @@ def test_fused_attention_forward_dropout_replay():
     mask = VF.dropout_mask(B * H * T * T, seed, site, p, DEV).view(B, H, T, T).double()
     ref, _ = _attn_ref(qkv, H, E, mask)
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 3e-5
+
+
+@pytest.mark.parametrize("B,H,T,E,p", [(1, 1, 64, 32, 0.0), (2, 2, 200, 24, 0.0), (1, 2, 1654, 155, 0.0),
+                                       (2, 3, 333, 155, 0.25)])
+@pytest.mark.parametrize("impl,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
+def test_fused_attention_backward(B, H, T, E, p, impl, tol):
+    """dQ, dK, dV of the fused tcgen05 attention vs fp64 autograd of softmax(QK^T)V (same dropout mask)."""
+    from v1t_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + T + 1)
+    qkv = torch.randn(B, T, 3 * H * E, device=DEV, generator=g)
+    d_out = torch.randn(B, T, H * E, device=DEV, generator=g)
+    out = torch.empty(B, T, H * E, device=DEV)
+    Tp = (T + 127) // 128 * 128
+    lse = torch.zeros(B * H, Tp, device=DEV)
+    d_qkv = torch.full((B, T, 3 * H * E), float("nan"), device=DEV)
+    scratch = torch.empty(lib.v1t_attn_scratch_bytes(B, H, T, E), dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    seed, site = 4242, 3
+    rc = lib.v1t_attn_forward(qkv.data_ptr(), B, H, T, E, _lib.IMPL_NAMES[impl], p, seed, site, out.data_ptr(),
+                              lse.data_ptr(), scratch.data_ptr(), st)
+    assert rc == 0, _lib.last_error()
+    rc = lib.v1t_attn_backward(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), B, H, T, E,
+                               _lib.IMPL_NAMES[impl], p, seed, site, d_qkv.data_ptr(), scratch.data_ptr(), st)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    mask = VF.dropout_mask(B * H * T * T, seed, site, p, DEV).view(B, H, T, T).double() if p > 0 else None
+    q64 = qkv.double().requires_grad_(True)
+    ref, _ = _attn_ref(q64, H, E, mask)
+    ref.backward(d_out.double())
+    assert torch.isfinite(d_qkv).all()
+    I = H * E
+    for name, sl in (("dq", slice(0, I)), ("dk", slice(I, 2 * I)), ("dv", slice(2 * I, 3 * I))):
+        err = rel_err(d_qkv[..., sl].cpu().numpy(), q64.grad[..., sl].cpu().numpy())
+        assert err < tol, (name, err)

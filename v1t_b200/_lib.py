@@ -86,10 +86,13 @@ SYMBOLS = {
     "v1t_poisson_forward": (C.c_int, [_vp, _vp, _i64, _f, _f, _vp, _vp, _vp]),
     "v1t_poisson_backward": (C.c_int, [_vp, _vp, _i64, _f, _f, _vp, _vp, _vp]),
     "v1t_gemm_fp32": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "v1t_gemm_tc_set_mn_major": (C.c_int, [C.c_int]),
     "v1t_gemm_tc": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "v1t_attn_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "v1t_attn_forward": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f, C.c_uint64, C.c_uint32,
                                    _vp, _vp, _vp, _vp]),
+    "v1t_attn_backward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f, C.c_uint64,
+                                    C.c_uint32, _vp, _vp, _vp]),
     "v1t_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint32, _f, _vp]),
 }
 

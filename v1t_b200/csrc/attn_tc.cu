@@ -337,6 +337,312 @@ int attn_fwd_tc(const AttnFwdArgs& a, cudaStream_t st) {
 
 }  // namespace v1t
 
+namespace v1t {
+namespace {
+using namespace tc;
+
+// =========================================================================================================
+// Backward.  Two launches of ONE kernel template, both atomic-free and deterministic:
+//   KV = true : CTA per (b, h, 128-key tile), streams query tiles      -> dV = Pd^T dO,  dK = scale * dS^T Q
+//   KV = false: CTA per (b, h, 128-query tile), streams key tiles      -> dQ = scale * dS K
+// with P = exp2(S*c - lse) recomputed from the saved log-sum-exp, Pd = P * dropout, dP = (dO V^T) * dropout,
+// dS = P * (dP - delta), delta = rowsum(dO * O).  Per streamed tile j (N tokens) the tensor core computes
+//   S' = X x_j^T,  dP' = Y y_j^T          (X, Y: resident 128-row operands; x_j, y_j: streamed, K-major over d)
+//   out1 += Pd' y_j (KV only),  out2 += dS' x_j      (x_j / y_j re-used un-transposed through MN-major descriptors)
+// S'/dP' are double-buffered in TMEM, the streamed tiles double-buffered in shared memory; Pd' and dS' go back to
+// shared memory as bf16 hi/lo A-operands (both share one 64-byte-row atom when N = 16).
+// bf16x3 uses N = 16 (hi+lo of everything: 2 x 80 KB resident), bf16 uses N = 32.
+// =========================================================================================================
+struct BwdSmem {
+  uint32_t x_hi, x_lo, y_hi, y_lo, st[2][4] /* xj_hi, xj_lo, yj_hi, yj_lo */, ps_hi, ps_lo, bars, total;
+};
+__host__ __device__ inline BwdSmem bwd_smem_layout(int Dp, int N, int x3) {
+  BwdSmem s;
+  const uint32_t ad = Dp / 32;
+  uint32_t o = 0;
+  s.x_hi = o; o += ad * 128 * 64;
+  s.x_lo = o; if (x3) o += ad * 128 * 64;
+  s.y_hi = o; o += ad * 128 * 64;
+  s.y_lo = o; if (x3) o += ad * 128 * 64;
+  for (int i = 0; i < 2; ++i)
+    for (int k = 0; k < 4; ++k) {
+      s.st[i][k] = o;
+      if (x3 || (k & 1) == 0) o += ad * N * 64;
+    }
+  const uint32_t ps_atoms = (2 * N + 31) / 32;
+  s.ps_hi = o; o += ps_atoms * 128 * 64;
+  s.ps_lo = o; if (x3) o += ps_atoms * 128 * 64;
+  s.bars = o; o += 256;
+  s.total = o + 1024;
+  return s;
+}
+
+template <bool KV, int N>
+__global__ void __launch_bounds__(kFwdThreads, 1) attn_bwd_kernel(const AttnBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const BwdSmem L = bwd_smem_layout(a.Dp, N, a.x3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* res_full = bars + 0;
+  uint64_t* ps_full = bars + 1;
+  uint64_t* ps_empty = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint64_t* st_full = bars + 4;   // [2]
+  uint64_t* st_empty = bars + 6;  // [2]
+  uint64_t* sp_full = bars + 8;   // [2]
+  uint64_t* sp_empty = bars + 10; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128, bh = blockIdx.y;   // first resident row (key for KV, query otherwise)
+  const int ad = a.Dp / 32;
+  const int nt = (a.T + N - 1) / N;
+  // resident / streamed planes
+  const uint8_t* X_hi = KV ? a.k_hi : a.q_hi;   const uint8_t* X_lo = KV ? a.k_lo : a.q_lo;
+  const uint8_t* Y_hi = KV ? a.v_hi : a.do_hi;  const uint8_t* Y_lo = KV ? a.v_lo : a.do_lo;
+  const uint8_t* xs_hi = KV ? a.q_hi : a.k_hi;  const uint8_t* xs_lo = KV ? a.q_lo : a.k_lo;
+  const uint8_t* ys_hi = KV ? a.do_hi : a.v_hi; const uint8_t* ys_lo = KV ? a.do_lo : a.v_lo;
+
+  if (threadIdx.x == 0) {
+    mbar_init(res_full, 1);
+    mbar_init(ps_full, kSoftmaxWarps * 32);
+    mbar_init(ps_empty, 1);
+    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1);
+      mbar_init(&sp_full[i], 1);
+      mbar_init(&sp_empty[i], kSoftmaxWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kSoftmaxWarps) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S'[2][N] | dP'[2][N] | out1[Dp] | out2[Dp]
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 2 * N, tm_o1 = tmem_base + 4 * N, tm_o2 = tm_o1 + a.Dp;
+
+  if (warp == kSoftmaxWarps + 1) {
+    // ============================== BULK-COPY PRODUCER ==============================
+    if (lane == 0) {
+      const uint32_t rb = ad * 128 * 64;
+      mbar_expect_tx(res_full, (a.x3 ? 4 : 2) * rb);
+      for (int at_i = 0; at_i < ad; ++at_i) {
+        const int64_t src = (((int64_t)bh * ad + at_i) * a.Tp + r0) * 64;
+        bulk_g2s(smem + L.x_hi + at_i * 8192, X_hi + src, 8192, res_full);
+        bulk_g2s(smem + L.y_hi + at_i * 8192, Y_hi + src, 8192, res_full);
+        if (a.x3) {
+          bulk_g2s(smem + L.x_lo + at_i * 8192, X_lo + src, 8192, res_full);
+          bulk_g2s(smem + L.y_lo + at_i * 8192, Y_lo + src, 8192, res_full);
+        }
+      }
+      const uint32_t tb = N * 64;  // bytes of one atom of a streamed tile
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        mbar_wait(&st_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&st_full[s], (a.x3 ? 4 : 2) * ad * tb);
+        for (int at_i = 0; at_i < ad; ++at_i) {
+          const int64_t src = (((int64_t)bh * ad + at_i) * a.Tp + (int64_t)j * N) * 64;
+          bulk_g2s(smem + L.st[s][0] + at_i * tb, xs_hi + src, tb, &st_full[s]);
+          bulk_g2s(smem + L.st[s][2] + at_i * tb, ys_hi + src, tb, &st_full[s]);
+          if (a.x3) {
+            bulk_g2s(smem + L.st[s][1] + at_i * tb, xs_lo + src, tb, &st_full[s]);
+            bulk_g2s(smem + L.st[s][3] + at_i * tb, ys_lo + src, tb, &st_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == kSoftmaxWarps) {
+    // ============================== MMA ISSUER ==============================
+    const uint32_t idesc_s = idesc_bf16(128, N, 0, 0);
+    const uint32_t idesc_o = idesc_bf16(128, a.Dp, 0, 1);  // B = streamed tile viewed MN-major (d contiguous)
+    const uint32_t sx_hi = smem_u32(smem + L.x_hi), sx_lo = smem_u32(smem + L.x_lo);
+    const uint32_t sy_hi = smem_u32(smem + L.y_hi), sy_lo = smem_u32(smem + L.y_lo);
+    const uint32_t sps_hi = smem_u32(smem + L.ps_hi), sps_lo = smem_u32(smem + L.ps_lo);
+    const uint32_t tb = N * 64;
+
+    auto issue_scores = [&](int j) {  // S'(j), dP'(j)
+      const int s = j & 1;
+      mbar_wait(&st_full[s], (j >> 1) & 1);
+      mbar_wait(&sp_empty[s], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t xj_hi = smem_u32(smem + L.st[s][0]), xj_lo = smem_u32(smem + L.st[s][1]);
+        const uint32_t yj_hi = smem_u32(smem + L.st[s][2]), yj_lo = smem_u32(smem + L.st[s][3]);
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t d = (which ? tm_dp : tm_s) + s * N;
+          const uint32_t Ah = which ? sy_hi : sx_hi, Al = which ? sy_lo : sx_lo;
+          const uint32_t Bh = which ? yj_hi : xj_hi, Bl = which ? yj_lo : xj_lo;
+          for (int ks = 0; ks < a.Dp / 16; ++ks) {
+            const uint32_t ao = (ks >> 1) * 8192 + (ks & 1) * 32, bo = (ks >> 1) * tb + (ks & 1) * 32;
+            const uint64_t ah = desc_k_sw64(Ah + ao), bhd = desc_k_sw64(Bh + bo);
+            umma_bf16(d, ah, bhd, idesc_s, ks > 0 ? 1u : 0u);
+            if (a.x3) {
+              umma_bf16(d, desc_k_sw64(Al + ao), bhd, idesc_s, 1u);
+              umma_bf16(d, ah, desc_k_sw64(Bl + bo), idesc_s, 1u);
+            }
+          }
+        }
+        umma_commit(&sp_full[s]);
+      }
+      __syncwarp();
+    };
+
+    mbar_wait(res_full, 0);
+    issue_scores(0);
+    for (int j = 0; j < nt; ++j) {
+      if (j + 1 < nt) issue_scores(j + 1);
+      const int s = j & 1;
+      mbar_wait(ps_full, j & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t xj_hi = smem_u32(smem + L.st[s][0]), xj_lo = smem_u32(smem + L.st[s][1]);
+        const uint32_t yj_hi = smem_u32(smem + L.st[s][2]), yj_lo = smem_u32(smem + L.st[s][3]);
+#pragma unroll 1
+        for (int which = KV ? 0 : 1; which < 2; ++which) {   // 0: out1 += Pd' y_j,  1: out2 += dS' x_j
+          const uint32_t d = which ? tm_o2 : tm_o1;
+          const uint32_t Bh = which ? xj_hi : yj_hi, Bl = which ? xj_lo : yj_lo;
+          for (int ks = 0; ks < N / 16; ++ks) {
+            const int kel = (which ? N : 0) + ks * 16;   // element offset along the packed [Pd' | dS'] K axis
+            const uint32_t ao = (kel >> 5) * 8192 + ((kel >> 4) & 1) * 32;
+            const uint64_t ah = desc_k_sw64(sps_hi + ao);
+            const uint64_t bhd = desc_mn_sw64(Bh + ks * 1024, tb);
+            umma_bf16(d, ah, bhd, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+            if (a.x3) {
+              umma_bf16(d, desc_k_sw64(sps_lo + ao), bhd, idesc_o, 1u);
+              umma_bf16(d, ah, desc_mn_sw64(Bl + ks * 1024, tb), idesc_o, 1u);
+            }
+          }
+        }
+        umma_commit(ps_empty);
+        umma_commit(&st_empty[s]);
+        if (j == nt - 1) umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================== SOFTMAX-BACKWARD / EPILOGUE ==============================
+    const int row = warp * 32 + lane;
+    const int ri = r0 + row;  // key index (KV) or query index
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int b = bh / a.H, h = bh % a.H;
+    const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
+    const float* lse = a.lse + (int64_t)bh * a.Tp;
+    const float* delta = a.delta + (int64_t)bh * a.Tp;
+    float lse_r = 0.f, delta_r = 0.f;
+    if (!KV && ri < a.T) { lse_r = lse[ri]; delta_r = delta[ri]; }
+    for (int j = 0; j < nt; ++j) {
+      const int s = j & 1;
+      mbar_wait(&sp_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      float sv[N], dv[N];
+      {
+        uint32_t v[N];
+        if constexpr (N == 16) tmem_ld16(tm_s + lane_off + s * N, reinterpret_cast<uint32_t(&)[16]>(v));
+        else tmem_ld32(tm_s + lane_off + s * N, reinterpret_cast<uint32_t(&)[32]>(v));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < N; ++c) sv[c] = __uint_as_float(v[c]);
+        if constexpr (N == 16) tmem_ld16(tm_dp + lane_off + s * N, reinterpret_cast<uint32_t(&)[16]>(v));
+        else tmem_ld32(tm_dp + lane_off + s * N, reinterpret_cast<uint32_t(&)[32]>(v));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < N; ++c) dv[c] = __uint_as_float(v[c]);
+      }
+      tc_fence_before();
+      mbar_arrive(&sp_empty[s]);
+      const int c0 = j * N;
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        const int ci = c0 + c;                       // query index (KV) or key index
+        const int qi = KV ? ci : ri, ki = KV ? ri : ci;
+        const bool valid = (qi < a.T) && (ki < a.T);
+        const float l2 = KV ? (ci < a.T ? __ldg(lse + ci) : 0.f) : lse_r;
+        const float dl = KV ? (ci < a.T ? __ldg(delta + ci) : 0.f) : delta_r;
+        const float p = valid ? exp2f(fmaf(sv[c], a.scale_log2, -l2)) : 0.f;
+        float mult = 1.f;
+        if (a.drop.p > 0.f && valid)
+          mult = dropout_mult(a.drop.seed, a.drop.site, ((uint64_t)bh * a.T + qi) * (uint64_t)a.T + ki, a.drop.p, inv_keep);
+        sv[c] = p * mult;                        // Pd'
+        dv[c] = p * (dv[c] * mult - dl);         // dS'
+      }
+      mbar_wait(ps_empty, (j & 1) ^ 1);
+#pragma unroll
+      for (int half = KV ? 0 : 1; half < 2; ++half) {
+#pragma unroll
+        for (int ch = 0; ch < N / 8; ++ch) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = half ? dv[ch * 8 + e] : sv[ch * 8 + e];
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const int kel = half * N + ch * 8;
+          const uint32_t off = (kel >> 5) * 8192 + sw64_offset(row, (kel >> 3) & 3);
+          *reinterpret_cast<uint4*>(smem + L.ps_hi + off) = hi;
+          if (a.x3) *reinterpret_cast<uint4*>(smem + L.ps_lo + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(ps_full);
+    }
+    // ---- epilogue: accumulators -> d_qkv (fp32, packed [B,T,3*H*E])
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int I = a.H * a.E;
+    float* grow = a.dqkv + ((int64_t)b * a.T + ri) * (3 * I) + h * a.E;
+    for (int which = KV ? 0 : 1; which < 2; ++which) {
+      // KV: out1 = dV (col block 2I), out2 = dK (col block I, scaled);  !KV: out2 = dQ (col block 0, scaled)
+      float* dst = grow + (KV ? (which ? I : 2 * I) : 0);
+      const float sc = which ? a.scale : 1.f;
+      const uint32_t tm = which ? tm_o2 : tm_o1;
+      for (int d0 = 0; d0 < a.Dp; d0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tm + lane_off + d0, v);
+        tmem_ld_wait();
+        if (ri < a.T) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == kSoftmaxWarps) tmem_dealloc<512>(tmem_base);
+}
+
+template <bool KV, int N>
+int launch_bwd(const AttnBwdArgs& a, cudaStream_t st) {
+  const BwdSmem L = bwd_smem_layout(a.Dp, N, a.x3);
+  V1T_CHECK_ARG(L.total <= 232448, "attn_bwd_tc: shared memory budget exceeded (%u bytes)", L.total);
+  V1T_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<KV, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  dim3 grid(cdiv(a.T, 128), a.B * a.H);
+  attn_bwd_kernel<KV, N><<<grid, kFwdThreads, L.total, st>>>(a);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+}  // namespace
+
+int attn_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
+  V1T_CHECK_ARG(a.Dp % 32 == 0 && a.Dp >= 32 && a.Dp <= 160 && a.Tp % 128 == 0 && a.Tp >= a.T && a.E <= a.Dp,
+                "attn_bwd_tc: unsupported dims (Dp %d, Tp %d)", a.Dp, a.Tp);
+  V1T_CHECK_ARG(a.B * a.H <= 65535, "attn_bwd_tc: too many (batch, head) pairs");
+  if (a.x3) {
+    V1T_TRY((launch_bwd<true, 16>(a, st)));
+    return launch_bwd<false, 16>(a, st);
+  }
+  V1T_TRY((launch_bwd<true, 32>(a, st)));
+  return launch_bwd<false, 32>(a, st);
+}
+
+}  // namespace v1t
+
 // ---------------------------------------------------------------------------------------------------------
 // C-ABI: fused attention on a packed fp32 qkv tensor [B, T, 3*H*E] (the layout to_qkv produces, vit.py:269)
 // ---------------------------------------------------------------------------------------------------------
@@ -391,4 +697,34 @@ extern "C" int v1t_attn_forward(const float* qkv, int B, int H, int T, int E, in
   a.x3 = x3;
   a.drop = DropSpec{seed, site, p_drop};
   return attn_fwd_tc(a, st);
+}
+
+extern "C" int v1t_attn_backward(const float* qkv, const float* out, const float* d_out, const float* lse, int B, int H,
+                                 int T, int E, int impl, float p_drop, uint64_t seed, uint32_t site, float* d_qkv,
+                                 void* scratch, void* stream) {
+  using namespace v1t;
+  V1T_CHECK_ARG(qkv && out && d_out && lse && d_qkv && scratch && B > 0 && H > 0 && T > 0 && E > 0,
+                "attn_backward: bad argument");
+  V1T_CHECK_ARG(impl == V1T_IMPL_BF16X3 || impl == V1T_IMPL_BF16, "attn_backward: impl must be BF16X3 or BF16");
+  V1T_CHECK_ARG(E <= 160, "attn_backward: fused kernel supports head dim <= 160 (got %d)", E);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Tp = (int)round_up(T, 128), Dp = (int)round_up(E, 32);
+  const int I = H * E;
+  const int x3 = impl == V1T_IMPL_BF16X3;
+  AttnPlanes p = carve_attn_planes(scratch, B, H, Tp, Dp, true);
+  V1T_TRY(make_planes(qkv, 3 * I, 0, B, H, T, Tp, E, Dp, p.q[0], x3 ? p.q[1] : nullptr, nullptr, nullptr, st));
+  V1T_TRY(make_planes(qkv, 3 * I, I, B, H, T, Tp, E, Dp, p.k[0], x3 ? p.k[1] : nullptr, nullptr, nullptr, st));
+  V1T_TRY(make_planes(qkv, 3 * I, 2 * I, B, H, T, Tp, E, Dp, p.v[0], x3 ? p.v[1] : nullptr, nullptr, nullptr, st));
+  V1T_TRY(make_planes(d_out, I, 0, B, H, T, Tp, E, Dp, p.dO[0], x3 ? p.dO[1] : nullptr, nullptr, nullptr, st));
+  V1T_TRY(attn_delta(out, d_out, p.delta, B, H, T, Tp, E, I, st));
+  AttnBwdArgs a{};
+  a.q_hi = p.q[0]; a.q_lo = p.q[1]; a.k_hi = p.k[0]; a.k_lo = p.k[1]; a.v_hi = p.v[0]; a.v_lo = p.v[1];
+  a.do_hi = p.dO[0]; a.do_lo = p.dO[1];
+  a.lse = lse; a.delta = p.delta; a.dqkv = d_qkv;
+  a.B = B; a.H = H; a.T = T; a.Tp = Tp; a.E = E; a.Dp = Dp;
+  a.scale = 1.0f / sqrtf((float)E);
+  a.scale_log2 = a.scale * 1.4426950408889634f;
+  a.x3 = x3;
+  a.drop = DropSpec{seed, site, p_drop};
+  return attn_bwd_tc(a, st);
 }

@@ -18,6 +18,7 @@
 #include "tc_common.cuh"
 
 namespace v1t {
+extern int g_use_mn_major;
 namespace {
 
 using namespace tc;
@@ -36,6 +37,7 @@ struct TcArgs {
   int bn;        // N tile (multiple of 16, <= 256)
   int tiles_m, tiles_n;
   int x3;        // 1: hi*hi + lo*hi + hi*lo, 0: hi*hi
+  int mn_a, mn_b;  // operand is M/N-contiguous in memory and staged un-transposed (MN-major UMMA descriptor)
   int a_vec, b_vec, c_vec;  // 128-bit access allowed
 };
 
@@ -132,15 +134,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int q = ptid + i * kProdThreads;
-          const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
-          load8(A, g.d.a_m, g.d.a_k, a_kc && a.a_vec, tl.m0 + r, g.d.m, k0 + c * 8, tl.k_end, va[i]);
+          if (a.mn_a) {  // 8 consecutive m of one k row: chunk (m/8) of row k
+            const int kr = q >> 4, mc = q & 15;
+            load8(A, g.d.a_k, g.d.a_m, a.a_vec, k0 + kr, tl.k_end, tl.m0 + mc * 8, g.d.m, va[i]);
+          } else {
+            const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
+            load8(A, g.d.a_m, g.d.a_k, a_kc && a.a_vec, tl.m0 + r, g.d.m, k0 + c * 8, tl.k_end, va[i]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int q = ptid + i * kProdThreads;
           if (q < b_chunks) {
-            const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
-            load8(B, g.d.b_n, g.d.b_k, b_kc && a.b_vec, tl.n0 + r, g.d.n, k0 + c * 8, tl.k_end, vb[i]);
+            if (a.mn_b) {
+              const int ncw = a.bn >> 3;  // 16-byte chunks per k row
+              const int kr = q / ncw, nc = q % ncw;
+              load8(B, g.d.b_k, g.d.b_n, a.b_vec, k0 + kr, tl.k_end, tl.n0 + nc * 8, g.d.n, vb[i]);
+            } else {
+              const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
+              load8(B, g.d.b_n, g.d.b_k, b_kc && a.b_vec, tl.n0 + r, g.d.n, k0 + c * 8, tl.k_end, vb[i]);
+            }
           }
         }
         mbar_wait(&empty[stage], ph ^ 1);
@@ -151,10 +164,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int q = ptid + i * kProdThreads;
-          const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
           uint4 hi, lo;
           split8(va[i], hi, lo);
-          const uint32_t off = sw64_offset(r, c);
+          uint32_t off;
+          if (a.mn_a) {  // [M atoms of 32][32 k rows][64 B]
+            const int kr = q >> 4, mc = q & 15;
+            off = (mc >> 2) * (BK * 64) + sw64_offset(kr, mc & 3);
+          } else {
+            const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
+            off = sw64_offset(r, c);
+          }
           *reinterpret_cast<uint4*>(sa_hi + off) = hi;
           if (a.x3) *reinterpret_cast<uint4*>(sa_lo + off) = lo;
         }
@@ -162,10 +181,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         for (int i = 0; i < 4; ++i) {
           const int q = ptid + i * kProdThreads;
           if (q < b_chunks) {
-            const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
             uint4 hi, lo;
             split8(vb[i], hi, lo);
-            const uint32_t off = sw64_offset(r, c);
+            uint32_t off;
+            if (a.mn_b) {
+              const int ncw = a.bn >> 3;
+              const int kr = q / ncw, nc = q % ncw;
+              off = (nc >> 2) * (BK * 64) + sw64_offset(kr, nc & 3);
+            } else {
+              const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
+              off = sw64_offset(r, c);
+            }
             *reinterpret_cast<uint4*>(sb_hi + off) = hi;
             if (a.x3) *reinterpret_cast<uint4*>(sb_lo + off) = lo;
           }
@@ -176,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     }
   } else if (warp == kEpiWarps) {
     // ============================== MMA ISSUER ==============================
-    const uint32_t idesc = idesc_bf16(BM, a.bn, 0, 0);
+    const uint32_t idesc = idesc_bf16(BM, a.bn, a.mn_a, a.mn_b);
     uint32_t it = 0, tl_i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
       const Tile tl = decode_tile(a, t);
@@ -195,10 +221,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           const uint32_t sa_lo = sa_hi + A_PLANE, sb_hi = sa_hi + 2 * A_PLANE, sb_lo = sb_hi + B_PLANE;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t ah = desc_k_sw64(sa_hi + kk * 32), bh = desc_k_sw64(sb_hi + kk * 32);
+            // K-major: advance 16 k = 32 B inside the 64 B atom row; MN-major: advance 16 k rows = 1024 B,
+            // atoms along M/N are BK*64 = 2048 B apart (LBO)
+            const uint64_t ah = a.mn_a ? desc_mn_sw64(sa_hi + kk * 1024, BK * 64) : desc_k_sw64(sa_hi + kk * 32);
+            const uint64_t bh = a.mn_b ? desc_mn_sw64(sb_hi + kk * 1024, BK * 64) : desc_k_sw64(sb_hi + kk * 32);
             umma_bf16(d_tmem, ah, bh, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
             if (a.x3) {
-              const uint64_t al = desc_k_sw64(sa_lo + kk * 32), bl = desc_k_sw64(sb_lo + kk * 32);
+              const uint64_t al = a.mn_a ? desc_mn_sw64(sa_lo + kk * 1024, BK * 64) : desc_k_sw64(sa_lo + kk * 32);
+              const uint64_t bl = a.mn_b ? desc_mn_sw64(sb_lo + kk * 1024, BK * 64) : desc_k_sw64(sb_lo + kk * 32);
               umma_bf16(d_tmem, al, bh, idesc, 1u);
               umma_bf16(d_tmem, ah, bl, idesc, 1u);
             }
@@ -265,6 +295,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+}  // namespace
+int g_use_mn_major = 1;  // stage M/N-contiguous operands un-transposed (vector loads) with MN-major descriptors
+namespace {
+
 int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
               DropSpec drop, int x3, int splits, int k_chunk, int64_t c_split, cudaStream_t st) {
   static bool attr_set = false;
@@ -282,8 +316,11 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.tiles_n = cdiv(d.n, a.bn);
   a.tiles_m = cdiv(d.m, BM);
   a.x3 = x3;
-  a.a_vec = aligned16(A) && d.a_m % 4 == 0 && d.a_b1 % 4 == 0 && d.a_b2 % 4 == 0;
-  a.b_vec = aligned16(B) && d.b_n % 4 == 0 && d.b_b1 % 4 == 0 && d.b_b2 % 4 == 0;
+  a.mn_a = g_use_mn_major && d.a_k != 1 && d.a_m == 1;
+  a.mn_b = g_use_mn_major && d.b_k != 1 && d.b_n == 1 && a.bn % 32 == 0;
+  // row stride of the staged rows: a_m / b_n for K-contiguous sources, a_k / b_k for MN-major staging
+  a.a_vec = aligned16(A) && (a.mn_a ? d.a_k : d.a_m) % 4 == 0 && d.a_b1 % 4 == 0 && d.a_b2 % 4 == 0;
+  a.b_vec = aligned16(B) && (a.mn_b ? d.b_k : d.b_n) % 4 == 0 && d.b_b1 % 4 == 0 && d.b_b2 % 4 == 0;
   a.c_vec = aligned16(C) && d.c_m % 4 == 0 && d.c_b1 % 4 == 0 && d.c_b2 % 4 == 0 && c_split % 4 == 0;
   const int64_t total = (int64_t)d.batch1 * d.batch2 * splits * a.tiles_m * a.tiles_n;
   V1T_CHECK_ARG(total < (1ll << 31), "tc gemm: too many tiles");
@@ -331,6 +368,11 @@ int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float
 }
 
 }  // namespace v1t
+
+extern "C" int v1t_gemm_tc_set_mn_major(int on) {
+  v1t::g_use_mn_major = on != 0;
+  return V1T_OK;
+}
 
 extern "C" int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
                            const float* R, int impl, void* stream) {

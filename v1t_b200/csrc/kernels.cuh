@@ -72,6 +72,17 @@ struct AttnFwdArgs {
   DropSpec drop;
 };
 int attn_fwd_tc(const AttnFwdArgs& a, cudaStream_t st);
+struct AttnBwdArgs {
+  const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo, *do_hi, *do_lo;  // RM planes (rows = tokens, K = head dim)
+  const float* lse;    // [B*H, Tp] base-2 log-sum-exp saved by the forward
+  const float* delta;  // [B*H, Tp] rowsum(dO * O)
+  float* dqkv;         // [B, T, 3*H*E] packed like to_qkv's output: dQ | dK | dV
+  int B, H, T, Tp, E, Dp;
+  float scale_log2, scale;
+  int x3;
+  DropSpec drop;
+};
+int attn_bwd_tc(const AttnBwdArgs& a, cudaStream_t st);
 struct AttnPlanes {  // [0] = hi, [1] = lo
   uint8_t *q[2], *k[2], *vt[2];                       // forward
   uint8_t *v[2], *qt[2], *kt[2], *dO[2], *dOt[2];     // backward
