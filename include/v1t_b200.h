@@ -203,7 +203,8 @@ int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C
 
 /* the inverted-dropout multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` =
  * block*8 + {0 tokens, 1 attention probs, 2 proj out, 3 MLP hidden, 4 MLP out}; element index = row-major
- * index in the logical tensor ([B,T,E], [B,H,T,T], [B,T,M]).  Lets tests replay the exact masks. */
+ * index in the logical tensor ([B,T,E], [B,T,M]); attention probabilities use [B,H,T,Tc] with Tc = T rounded up
+ * to 4 (so one Philox call covers 4 adjacent keys).  Lets tests replay the exact masks. */
 int v1t_dropout_mask(float* out, int64_t n, uint64_t seed, uint32_t site, float p, void* stream);
 
 #ifdef __cplusplus

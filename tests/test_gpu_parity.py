@@ -149,7 +149,8 @@ def test_dropout_masks_replay_exactly_against_oracle():
     mk = lambda site, shape, p: VF.dropout_mask(int(np.prod(shape)), seed, site, p, DEV).cpu().numpy().reshape(shape).astype(np.float64)
     masks = {"tokens": mk(0, (B, T, E), p_tok)}
     for i in range(cfg.num_blocks):
-        masks[(i, "attn")] = mk(i * 8 + 1, (B, H, T, T), p_blk)
+        Tc = (T + 3) // 4 * 4  # attention-mask rows are indexed with a 4-aligned stride
+        masks[(i, "attn")] = mk(i * 8 + 1, (B, H, T, Tc), p_blk)[..., :T]
         masks[(i, "proj")] = mk(i * 8 + 2, (B, T, E), p_blk)
         masks[(i, "mlp1")] = mk(i * 8 + 3, (B, T, M), p_blk)
         masks[(i, "mlp2")] = mk(i * 8 + 4, (B, T, E), p_blk)
@@ -416,7 +417,8 @@ def test_fused_attention_forward_dropout_replay():
     rc = lib.v1t_attn_forward(qkv.data_ptr(), B, H, T, E, _lib.IMPL_BF16X3, p, seed, site, out.data_ptr(), None,
                               scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0, _lib.last_error()
-    mask = VF.dropout_mask(B * H * T * T, seed, site, p, DEV).view(B, H, T, T).double()
+    Tc = (T + 3) // 4 * 4
+    mask = VF.dropout_mask(B * H * T * Tc, seed, site, p, DEV).view(B, H, T, Tc)[..., :T].double()
     ref, _ = _attn_ref(qkv, H, E, mask)
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 3e-5
 
@@ -445,7 +447,8 @@ def test_fused_attention_backward(B, H, T, E, p, impl, tol):
                                _lib.IMPL_NAMES[impl], p, seed, site, d_qkv.data_ptr(), scratch.data_ptr(), st)
     assert rc == 0, _lib.last_error()
     torch.cuda.synchronize()
-    mask = VF.dropout_mask(B * H * T * T, seed, site, p, DEV).view(B, H, T, T).double() if p > 0 else None
+    Tc = (T + 3) // 4 * 4
+    mask = VF.dropout_mask(B * H * T * Tc, seed, site, p, DEV).view(B, H, T, Tc)[..., :T].double() if p > 0 else None
     q64 = qkv.double().requires_grad_(True)
     ref, _ = _attn_ref(q64, H, E, mask)
     ref.backward(d_out.double())

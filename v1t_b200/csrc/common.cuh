@@ -97,4 +97,15 @@ __device__ __forceinline__ float dropout_mult(uint64_t seed, uint32_t site, uint
   return u >= p ? inv_keep : 0.0f;
 }
 
+
+// 4 multipliers of the aligned group `group` (elements 4*group .. 4*group+3) with ONE Philox call
+__device__ __forceinline__ void dropout_mult4(uint64_t seed, uint32_t site, uint64_t group, float p, float inv_keep,
+                                              float (&m)[4]) {
+  const uint4 r = philox4x32(seed, group, site, 0x5eedu);
+  m[0] = (float)(r.x >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
+  m[1] = (float)(r.y >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
+  m[2] = (float)(r.z >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
+  m[3] = (float)(r.w >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
+}
+
 }  // namespace v1t

@@ -19,7 +19,8 @@ inline DropSpec site_drop(const v1t_core_shape& s, int block, Site site) {
 }
 
 struct Dims {
-  int B, C, H, W, p, s, gh, gw, L, T, Tp, E, Ep, heads, I, M, Mp, pd, hid, bdim, blocks, impl;
+  int B, C, H, W, p, s, gh, gw, L, T, Tp, Tq, E, Ep, heads, I, M, Mp, pd, hid, bdim, blocks, impl;
+  bool fused;  // fused tcgen05 attention (tensor-core impls, head dim <= 160)
   int64_t R;  // B*T rows
 };
 
@@ -53,6 +54,8 @@ int make_dims(const v1t_core_shape* sh, Dims& d) {
   d.bdim = sh->bdim;
   d.blocks = sh->blocks;
   d.R = (int64_t)d.B * d.T;
+  d.Tq = (int)round_up(d.T, 128);  // token padding of the attention operand planes
+  d.fused = d.impl != V1T_IMPL_FP32 && d.Ep <= 160 && (int64_t)d.B * d.heads <= 65535;
   return V1T_OK;
 }
 
@@ -68,7 +71,7 @@ struct Carver {
 };
 
 struct BlockSaved {
-  float *x1, *st1, *qkv, *o, *x2, *st2, *u, *bhid, *blat;
+  float *x1, *st1, *qkv, *o, *x2, *st2, *u, *bhid, *blat, *lse;
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -84,6 +87,7 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
   b.u = c.take(d.R * d.Mp);
   b.bhid = c.take((int64_t)d.B * d.hid + 1);
   b.blat = c.take((int64_t)d.B * d.E);
+  b.lse = c.take(d.fused ? (int64_t)d.B * d.heads * d.Tq : 1);
 }
 Saved carve_saved(const Dims& d, void* base) {
   Carver c(base);
@@ -98,6 +102,7 @@ constexpr size_t kPartialBytes = 64u << 20;
 struct Scratch {
   BlockSaved tmp;    // one block of "saved" space for inference (keep_for_backward == 0)
   float *h, *dh, *g, *dqkv, *dO, *patches, *P1, *P2, *partials, *dlat, *dz3, *dhid, *dpos;
+  AttnPlanes planes;
   int chunk;         // attention batch chunk
   size_t total;
 };
@@ -120,8 +125,16 @@ Scratch carve_scratch(const Dims& d, void* base) {
   s.dqkv = c.take(d.R * 3 * d.I);
   s.dO = c.take(d.R * d.I);
   s.patches = c.take((int64_t)d.B * d.L * d.pd);
-  s.P1 = c.take((int64_t)s.chunk * d.heads * d.T * d.Tp);
-  s.P2 = c.take((int64_t)s.chunk * d.heads * d.T * d.Tp);
+  // materialised attention matrices only for the fp32 path; the fused path keeps bf16 operand planes instead
+  s.P1 = c.take(d.fused ? 1 : (int64_t)s.chunk * d.heads * d.T * d.Tp);
+  s.P2 = c.take(d.fused ? 1 : (int64_t)s.chunk * d.heads * d.T * d.Tp);
+  if (d.fused) {
+    const size_t pb = carve_attn_planes(nullptr, d.B, d.heads, d.Tq, d.Ep, true).total;
+    float* pbase = c.take((int64_t)(pb / sizeof(float)) + 256);
+    s.planes = carve_attn_planes(pbase, d.B, d.heads, d.Tq, d.Ep, true);
+  } else {
+    s.planes = AttnPlanes{};
+  }
   s.partials = c.take(kPartialBytes / sizeof(float));
   s.dlat = c.take((int64_t)d.B * d.E);
   s.dz3 = c.take((int64_t)d.B * d.E);
@@ -231,7 +244,26 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st));
     }
     }
-    for (int b0 = 0; b0 < d.B; b0 += sc.chunk) {
+    if (d.fused) {  // tcgen05 fused attention: qkv -> bf16 operand planes -> O, lse (nothing T x T in HBM)
+      ProfScope prof(V1T_PHASE_ATTN_FWD, st);
+      const int x3 = d.impl == V1T_IMPL_BF16X3;
+      const AttnPlanes& pl = sc.planes;
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.q[0], x3 ? pl.q[1] : nullptr,
+                          nullptr, nullptr, st));
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.k[0], x3 ? pl.k[1] : nullptr,
+                          nullptr, nullptr, st));
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, nullptr, nullptr, pl.vt[0],
+                          x3 ? pl.vt[1] : nullptr, st));
+      AttnFwdArgs fa{};
+      fa.q_hi = pl.q[0]; fa.q_lo = pl.q[1]; fa.k_hi = pl.k[0]; fa.k_lo = pl.k[1]; fa.vt_hi = pl.vt[0]; fa.vt_lo = pl.vt[1];
+      fa.O = S.o; fa.o_ld = d.I; fa.lse = S.lse;
+      fa.B = d.B; fa.H = d.heads; fa.T = d.T; fa.Tp = d.Tq; fa.E = d.E; fa.Dp = d.Ep;
+      fa.scale_log2 = (1.0f / sqrtf((float)d.E)) * 1.4426950408889634f;
+      fa.x3 = x3;
+      fa.drop = site_drop(*shape, i, kSiteAttn);
+      V1T_TRY(attn_fwd_tc(fa, st));
+    }
+    for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);
       const int bc = std::min(sc.chunk, d.B - b0);
       V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, d.Tp, site_drop(*shape, i, kSiteAttn), st));
@@ -338,7 +370,30 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     }
     const int64_t ld = 3 * d.I;
     lin1.reset();
-    for (int b0 = 0; b0 < d.B; b0 += sc.chunk) {
+    if (d.fused) {
+      ProfScope prof(V1T_PHASE_ATTN_BWD, st);
+      const int x3 = d.impl == V1T_IMPL_BF16X3;
+      const AttnPlanes& pl = sc.planes;
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.q[0], x3 ? pl.q[1] : nullptr,
+                          nullptr, nullptr, st));
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.k[0], x3 ? pl.k[1] : nullptr,
+                          nullptr, nullptr, st));
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.v[0], x3 ? pl.v[1] : nullptr,
+                          nullptr, nullptr, st));
+      V1T_TRY(make_planes(sc.dO, d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.dO[0], x3 ? pl.dO[1] : nullptr,
+                          nullptr, nullptr, st));
+      V1T_TRY(attn_delta(S.o, sc.dO, pl.delta, d.B, d.heads, d.T, d.Tq, d.E, d.I, st));
+      AttnBwdArgs ba{};
+      ba.q_hi = pl.q[0]; ba.q_lo = pl.q[1]; ba.k_hi = pl.k[0]; ba.k_lo = pl.k[1]; ba.v_hi = pl.v[0]; ba.v_lo = pl.v[1];
+      ba.do_hi = pl.dO[0]; ba.do_lo = pl.dO[1];
+      ba.lse = S.lse; ba.delta = pl.delta; ba.dqkv = sc.dqkv;
+      ba.B = d.B; ba.H = d.heads; ba.T = d.T; ba.Tp = d.Tq; ba.E = d.E; ba.Dp = d.Ep;
+      ba.scale = scale; ba.scale_log2 = scale * 1.4426950408889634f;
+      ba.x3 = x3;
+      ba.drop = site_drop(*shape, i, kSiteAttn);
+      V1T_TRY(attn_bwd_tc(ba, st));
+    }
+    for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_BWD, st);
       const int bc = std::min(sc.chunk, d.B - b0);
       const float* q = S.qkv + (int64_t)b0 * d.T * ld;

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S
     const float inv = 1.f / warp_sum(sum);
     for (int c = lane; c < cols; c += 32) {
       float p = row[c] * inv;
-      if (dr.p > 0.f) p *= dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * cols + c, dr.p, inv_keep);
+      if (dr.p > 0.f) p *= dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * ((cols + 3) & ~3) + c, dr.p, inv_keep);
       row[c] = p;
     }
   }
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(float* __restrict
     for (int c = lane; c < cols; c += 32) {
       float dv = d[c];
       if (dr.p > 0.f) {
-        const float m = dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * cols + c, dr.p, inv_keep);
+        const float m = dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * ((cols + 3) & ~3) + c, dr.p, inv_keep);
         dv *= m;
         d[c] = dv;
       }
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(float* __restrict
       const float pv = p[c];
       d[c] = pv * (d[c] - dot);
       if (dr.p > 0.f)
-        p[c] = pv * dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * cols + c, dr.p, inv_keep);
+        p[c] = pv * dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * ((cols + 3) & ~3) + c, dr.p, inv_keep);
     }
   }
 }

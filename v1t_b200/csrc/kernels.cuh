@@ -84,8 +84,8 @@ struct AttnBwdArgs {
 };
 int attn_bwd_tc(const AttnBwdArgs& a, cudaStream_t st);
 struct AttnPlanes {  // [0] = hi, [1] = lo
-  uint8_t *q[2], *k[2], *vt[2];                       // forward
-  uint8_t *v[2], *qt[2], *kt[2], *dO[2], *dOt[2];     // backward
+  uint8_t *q[2], *k[2], *vt[2];   // forward (vt: V transposed, rows = head dim)
+  uint8_t *v[2], *dO[2];          // backward (v aliases vt's storage)
   float *lse, *delta;                                 // [B*H, Tp]
   size_t total;
 };

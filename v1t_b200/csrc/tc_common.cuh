@@ -97,6 +97,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -135,6 +141,21 @@ __device__ __forceinline__ uint64_t desc_mn_sw64(uint32_t smem_addr, uint32_t lb
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)4 << 61;
   return d;
+}
+// constant (address-independent) parts: descriptor(addr) = base | (addr >> 4); advancing the start address by
+// `bytes` is a plain add of (bytes >> 4) to the low word.
+constexpr uint64_t kDescK64 = ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+__device__ __forceinline__ uint64_t desc_mn_sw64_base(uint32_t lbo_bytes) {
+  return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ uint32_t sw64_offset(int row, int chunk) {
   return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
