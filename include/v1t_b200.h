@@ -201,6 +201,10 @@ int v1t_gemm_tc_set_mn_major(int on);
 int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
                 const float* R, int impl, void* stream);
 
+/* measurement helper: cycles for iters*8 tcgen05.mma (M=128, K=16, bf16) of width N on all SMs; ts=1: A operand
+ * from tensor memory, mn_b=1: MN-major B.  out_dev: 148 int64 cycle counts (device memory). */
+int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long* out_dev, void* stream);
+
 /* the inverted-dropout multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` =
  * block*8 + {0 tokens, 1 attention probs, 2 proj out, 3 MLP hidden, 4 MLP out}; element index = row-major
  * index in the logical tensor ([B,T,E], [B,T,M]); attention probabilities use [B,H,T,Tc] with Tc = T rounded up

@@ -1,0 +1,69 @@
+// Measurement helper (not on the product path): cycles per tcgen05.mma (M=128, K=16, bf16) as a function of N and
+// of the operand source (A from shared memory "SS" vs A from tensor memory "TS").  Used to size the attention /
+// GEMM tiles ("MMA cost model").
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace v1t {
+namespace {
+using namespace tc;
+
+__global__ void __launch_bounds__(128, 1) mma_microbench_kernel(int N, int ts, int iters, int mn_b, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16(128, N, 0, mn_b);
+    const uint64_t da = kDescK64 | (smem_u32(smem) >> 4);
+    const uint64_t db = (mn_b ? desc_mn_sw64_base(2048) : kDescK64) | (smem_u32(smem + 32768) >> 4);
+    long long t0 = 0, t1 = 0;
+    for (int rep = 0; rep < 2; ++rep) {  // rep 0 = warm-up
+      t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        if (leader) {
+          // 8 distinct k-steps like a real main loop (A: 4 atoms x 2 halves)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t ao = (ks >> 1) * 512 + (ks & 1) * 2, bo = mn_b ? ks * 64 : (ks >> 1) * 1024 + (ks & 1) * 2;
+            if (ts) umma_bf16_ts(tmem + 256, tmem + ks * 8, db + bo, idesc, 1u);
+            else umma_bf16(tmem + 256, da + ao, db + bo, idesc, 1u);
+          }
+        }
+      }
+      if (leader) umma_commit(&bar);
+      __syncwarp();
+      mbar_wait(&bar, rep & 1);
+      t1 = clock64();
+    }
+    if (leader) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+}  // namespace
+}  // namespace v1t
+
+// cycles for `iters * 8` MMAs of shape 128 x N x 16 on every SM concurrently (grid = 148); returns the max over SMs
+extern "C" int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long* out_dev, void* stream) {
+  using namespace v1t;
+  V1T_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && out_dev, "mma_microbench: bad argument");
+  V1T_CUDA(cudaFuncSetAttribute(mma_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  mma_microbench_kernel<<<kNumSMs, 128, 100 * 1024, (cudaStream_t)stream>>>(N, ts, iters, mn_b, out_dev);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
