@@ -8,8 +8,8 @@
 // mode.  Accumulators are double-buffered in TMEM (2 x 256 columns) so the EPILOGUE warps (tcgen05.ld -> bias /
 // dropout / residual -> global) overlap the next tile's main loop.  Persistent CTAs, one per SM.
 //
-// Warp roles (416 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMEM alloc + MMA issue,
-// warps 5-12 producers.  Pipelines: full/empty mbarriers per smem stage (4 stages x 48 KB), tmem_full/tmem_empty
+// Warp roles (544 threads): warps 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), warp 8
+// TMEM alloc + MMA issue, warps 9-16 producers.  Pipelines: full/empty mbarriers per smem stage (4 stages x 48 KB), tmem_full/tmem_empty
 // per accumulator buffer.
 #include <algorithm>
 
@@ -24,8 +24,8 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = 32, STAGES = 4, BN_MAX = 256;
-constexpr int kEpiWarps = 4, kProdWarps = 8;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 416
+constexpr int kEpiWarps = 8, kProdWarps = 8;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int A_PLANE = BM * 64;       // bytes of one bf16 plane of the A stage (128 rows x 32 k)
 constexpr int B_PLANE = BN_MAX * 64;
@@ -38,7 +38,7 @@ struct TcArgs {
   int tiles_m, tiles_n;
   int x3;        // 1: hi*hi + lo*hi + hi*lo, 0: hi*hi
   int mn_a, mn_b;  // operand is M/N-contiguous in memory and staged un-transposed (MN-major UMMA descriptor)
-  int a_vec, b_vec, c_vec;  // 128-bit access allowed
+  int a_vec, b_vec, c_vec, r_vec;  // 128-bit access allowed
 };
 
 struct Tile {
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
   } else if (warp == kEpiWarps) {
     // ============================== MMA ISSUER ==============================
     const uint32_t idesc = idesc_bf16(BM, a.bn, a.mn_a, a.mn_b);
+    const bool leader = elect_one();  // one lane issues every tcgen05.mma / commit; address math stays warp-uniform
     uint32_t it = 0, tl_i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
       const Tile tl = decode_tile(a, t);
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[stage], ph);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sa_lo = sa_hi + A_PLANE, sb_hi = sa_hi + 2 * A_PLANE, sb_lo = sb_hi + B_PLANE;
 #pragma unroll
@@ -225,61 +226,78 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             // atoms along M/N are BK*64 = 2048 B apart (LBO)
             const uint64_t ah = a.mn_a ? desc_mn_sw64(sa_hi + kk * 1024, BK * 64) : desc_k_sw64(sa_hi + kk * 32);
             const uint64_t bh = a.mn_b ? desc_mn_sw64(sb_hi + kk * 1024, BK * 64) : desc_k_sw64(sb_hi + kk * 32);
-            umma_bf16(d_tmem, ah, bh, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-            if (a.x3) {
-              const uint64_t al = a.mn_a ? desc_mn_sw64(sa_lo + kk * 1024, BK * 64) : desc_k_sw64(sa_lo + kk * 32);
-              const uint64_t bl = a.mn_b ? desc_mn_sw64(sb_lo + kk * 1024, BK * 64) : desc_k_sw64(sb_lo + kk * 32);
-              umma_bf16(d_tmem, al, bh, idesc, 1u);
-              umma_bf16(d_tmem, ah, bl, idesc, 1u);
+            const uint64_t al = a.mn_a ? desc_mn_sw64(sa_lo + kk * 1024, BK * 64) : desc_k_sw64(sa_lo + kk * 32);
+            const uint64_t bl = a.mn_b ? desc_mn_sw64(sb_lo + kk * 1024, BK * 64) : desc_k_sw64(sb_lo + kk * 32);
+            if (leader) {
+              umma_bf16(d_tmem, ah, bh, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+              if (a.x3) {
+                umma_bf16(d_tmem, al, bh, idesc, 1u);
+                umma_bf16(d_tmem, ah, bl, idesc, 1u);
+              }
             }
           }
-          umma_commit(&empty[stage]);                      // smem slot free once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull[buf]);  // accumulator complete
+          if (leader) {
+            umma_commit(&empty[stage]);                      // smem slot free once these MMAs retire
+            if (kb == num_kb - 1) umma_commit(&tfull[buf]);  // accumulator complete
+          }
         }
         __syncwarp();
       }
     }
   } else {
     // ============================== EPILOGUE ==============================
+    // 8 warps: TMEM lane quarter = warp & 3 (row block), column half = warp >> 2 (alternate 16-column chunks).
+    // Fast path (full, aligned chunk): 4 x 128-bit stores per 16 columns with bias / residual fetched as vectors;
+    // dropout, accumulate and ragged chunks take the element-wise path.
     uint32_t tl_i = 0;
+    const int quarter = warp & 3, half = warp >> 2;
     const float inv_keep = g.drop.p > 0.f ? 1.f / (1.f - g.drop.p) : 1.f;
+    const bool plain = !(g.drop.p > 0.f) && !g.d.accumulate;
+    const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
       const Tile tl = decode_tile(a, t);
       const uint32_t buf = tl_i & 1, tph = (tl_i >> 1) & 1;
       mbar_wait(&tfull[buf], tph);
       tc_fence_after();
-      const int m = tl.m0 + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + buf * BN_MAX + ((uint32_t)(warp * 32) << 16);
+      const int m = tl.m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + buf * BN_MAX + ((uint32_t)(quarter * 32) << 16);
       float* crow = g.C + tl.c_off + (int64_t)m * g.d.c_m;
       const float* rrow = g.R ? g.R + tl.r_off + (int64_t)m * g.d.r_m : nullptr;
-      for (int c0 = 0; c0 < a.bn; c0 += 16) {
+      const bool r_vec = rrow && a.r_vec;
+      for (int c0 = half * 16; c0 < a.bn; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
-        if (m < g.d.m) {
-          const int nb = tl.n0 + c0;
-          float o[16];
+        if (m >= g.d.m) continue;
+        const int nb = tl.n0 + c0;
+        if (plain && a.c_vec && nb + 16 <= g.d.n && (!g.bias || bias_vec) && (!rrow || r_vec)) {
 #pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o = make_float4(g.d.alpha * __uint_as_float(v[4 * q]), g.d.alpha * __uint_as_float(v[4 * q + 1]),
+                                   g.d.alpha * __uint_as_float(v[4 * q + 2]), g.d.alpha * __uint_as_float(v[4 * q + 3]));
+            if (g.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + q);
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            }
+            if (rrow) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + nb) + q);
+              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+            }
+            *(reinterpret_cast<float4*>(crow + nb) + q) = o;
+          }
+        } else {
+#pragma unroll 4
           for (int j = 0; j < 16; ++j) {
             const int n = nb + j;
-            float x = g.d.alpha * __uint_as_float(v[j]);
             if (n < g.d.n) {
+              float x = g.d.alpha * __uint_as_float(v[j]);
               if (g.bias) x += __ldg(g.bias + n);
               if (g.drop.p > 0.f)
                 x *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * g.d.n + n, g.drop.p, inv_keep);
               if (rrow) x += __ldg(rrow + n);
               if (g.d.accumulate) x += crow[n];
+              crow[n] = x;
             }
-            o[j] = x;
-          }
-          if (a.c_vec && nb + 16 <= g.d.n) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(crow + nb + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nb + j < g.d.n) crow[nb + j] = o[j];
           }
         }
       }
@@ -322,6 +340,7 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.a_vec = aligned16(A) && (a.mn_a ? d.a_k : d.a_m) % 4 == 0 && d.a_b1 % 4 == 0 && d.a_b2 % 4 == 0;
   a.b_vec = aligned16(B) && (a.mn_b ? d.b_k : d.b_n) % 4 == 0 && d.b_b1 % 4 == 0 && d.b_b2 % 4 == 0;
   a.c_vec = aligned16(C) && d.c_m % 4 == 0 && d.c_b1 % 4 == 0 && d.c_b2 % 4 == 0 && c_split % 4 == 0;
+  a.r_vec = R && aligned16(R) && d.r_m % 4 == 0 && d.r_b1 % 4 == 0 && d.r_b2 % 4 == 0;
   const int64_t total = (int64_t)d.batch1 * d.batch2 * splits * a.tiles_m * a.tiles_n;
   V1T_CHECK_ARG(total < (1ll << 31), "tc gemm: too many tiles");
   const int grid = (int)std::min<int64_t>(total, kNumSMs);
