@@ -205,6 +205,9 @@ int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C
  * from tensor memory, mn_b=1: MN-major B.  out_dev: 148 int64 cycle counts (device memory). */
 int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long* out_dev, void* stream);
 
+/* self-test of the tensor-memory A operand (tcgen05.st + TS-form tcgen05.mma): C[128,N] = bf16(A[128,K]) bf16(B[N,K])^T */
+int v1t_ts_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
+
 /* the inverted-dropout multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` =
  * block*8 + {0 tokens, 1 attention probs, 2 proj out, 3 MLP hidden, 4 MLP out}; element index = row-major
  * index in the logical tensor ([B,T,E], [B,T,M]); attention probabilities use [B,H,T,Tc] with Tc = T rounded up

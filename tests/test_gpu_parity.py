@@ -457,3 +457,19 @@ def test_fused_attention_backward(B, H, T, E, p, impl, tol):
     for name, sl in (("dq", slice(0, I)), ("dk", slice(I, 2 * I)), ("dv", slice(2 * I, 3 * I))):
         err = rel_err(d_qkv[..., sl].cpu().numpy(), q64.grad[..., sl].cpu().numpy())
         assert err < tol, (name, err)
+
+
+@pytest.mark.parametrize("N,K", [(16, 32), (64, 160), (160, 64), (256, 128)])
+def test_ts_mma_tensor_memory_operand(N, K):
+    """tcgen05.st + TS-form tcgen05.mma (A operand in tensor memory) against a bf16-rounded fp64 product."""
+    from v1t_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(N + K)
+    A = torch.randn(128, K, device=DEV, generator=g)
+    Bm = torch.randn(N, K, device=DEV, generator=g)
+    Cm = torch.full((128, N), float("nan"), device=DEV)
+    rc = lib.v1t_ts_selftest(A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), N, K, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    ref = A.bfloat16().double() @ Bm.bfloat16().double().T
+    assert rel_err(Cm.cpu().numpy(), ref.cpu().numpy()) < 1e-5

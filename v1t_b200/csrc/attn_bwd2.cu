@@ -1,0 +1,428 @@
+// Attention backward, second generation: the 128-row RESIDENT operands live in TENSOR MEMORY and feed tcgen05.mma
+// in its TS form (A from TMEM costs ~10 + N/2 cycles per MMA instead of 43 + N/2 from shared memory, measured by
+// scripts/mma_microbench.py), which also frees shared memory for larger, double-buffered streamed tiles.
+//
+//   MODE_V  (CTA per 128-key tile)            dV = Pd^T dO                  X = K in TMEM; streams (Q_j, dO_j), N = 64
+//   MODE_S, KV = true  (per 128-key tile)     dK = scale * dS^T Q           X = K, Y = V;  streams (Q_j, dO_j), N = 32
+//   MODE_S, KV = false (per 128-query tile)   dQ = scale * dS K             X = Q, Y = dO; streams (K_j, V_j),  N = 32
+//
+// Per streamed tile j:   S' = X x_j^T        (TS: X hi/lo in TMEM)
+//                        dP' = Y y_j^T       (TS for Y hi; the Y lo plane stays in shared memory, SS form)
+//                        P' = exp2(S' c - lse),  Pd' = P' * dropout,  dS' = P' (dP' * dropout - delta)
+//                        out += Pd' y_j (MODE_V)  |  out += dS' x_j (MODE_S)   — A operand (Pd'/dS' as bf16 hi/lo)
+//                        written by the softmax warps straight into TMEM (tcgen05.st), B = the streamed tile
+//                        re-used un-transposed through an MN-major descriptor.
+// Atomic-free, deterministic; P recomputed from the forward's base-2 log-sum-exp.
+//
+// TMEM columns (HC = Dp/2 columns per 128 x Dp bf16 plane):
+//   MODE_S: X_hi | X_lo | Y_hi | S'[N] | dP'[N] | dS'_hi[N/2] | dS'_lo[N/2] | out[Dp]     = 3 HC + 3 N + Dp  (496 @ N=32)
+//   MODE_V: X_hi | X_lo | S'[2][N] | Pd'_hi[N/2] | Pd'_lo[N/2] | out[Dp]                  = 2 HC + 3 N + Dp  (512 @ N=64)
+// Warp roles (320 threads): warps 0-7 softmax-backward/epilogue (lane quarter = warp & 3, column half = warp >> 2),
+// warp 8 MMA issue + TMEM alloc, warp 9 bulk-copy producer.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace v1t {
+namespace {
+
+using namespace tc;
+
+constexpr int kSmWarps = 8;
+constexpr int kSmThreads = kSmWarps * 32;
+constexpr int kThreadsAttn = (kSmWarps + 2) * 32;
+constexpr int kMmaWarp = kSmWarps, kLoadWarp = kSmWarps + 1;
+constexpr int MODE_V = 0, MODE_S = 1;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int MODE, int N, int AD>
+struct Smem2 {
+  static constexpr int kStages = MODE == MODE_V ? 2 : 3;
+  static constexpr uint32_t kTile = AD * N * 64;     // one bf16 plane of one streamed operand tile
+  static constexpr uint32_t kYlo = AD * 128 * 64;    // resident Y lo plane (MODE_S, bf16x3)
+  // layout: [Y_lo] [stage: x_hi, x_lo, y_hi, y_lo] x kStages [barriers]
+  static constexpr uint32_t y_lo = 0;
+  static constexpr uint32_t stage0 = MODE == MODE_S ? kYlo : 0;
+  static constexpr uint32_t kStageBytes = 4 * kTile;
+  static constexpr uint32_t bars = stage0 + kStages * kStageBytes;
+  static constexpr uint32_t mask = bars + 256;                          // dropout multipliers, [warp][N/2][32] floats
+  static constexpr uint32_t total = mask + kSmWarps * (N / 2) * 32 * 4 + 1024;
+};
+
+template <int MODE, bool KV, int N, int AD>
+__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a) {
+  constexpr int Dp = AD * 32, HC = AD * 16, NH = N / 2;
+  using L = Smem2<MODE, N, AD>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint64_t* res_full = bars + 0;   // resident operands ready (TMEM stores by 256 threads + Y_lo bulk copy)
+  uint64_t* ps_full = bars + 1;
+  uint64_t* ps_empty = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint64_t* st_full = bars + 4;    // [kStages]
+  uint64_t* st_empty = bars + 8;   // [kStages]
+  uint64_t* sp_full = bars + 12;   // [2]
+  uint64_t* sp_empty = bars + 14;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128, bh = blockIdx.y;
+  const int nt = (a.T + N - 1) / N;
+  constexpr bool kv_roles = MODE == MODE_V ? true : KV;  // rows = keys, streamed = queries
+  const uint8_t* X_hi = kv_roles ? a.k_hi : a.q_hi;   const uint8_t* X_lo = kv_roles ? a.k_lo : a.q_lo;
+  const uint8_t* Y_hi = kv_roles ? a.v_hi : a.do_hi;  const uint8_t* Y_lo = kv_roles ? a.v_lo : a.do_lo;
+  const uint8_t* xs_hi = kv_roles ? a.q_hi : a.k_hi;  const uint8_t* xs_lo = kv_roles ? a.q_lo : a.k_lo;
+  const uint8_t* ys_hi = kv_roles ? a.do_hi : a.v_hi; const uint8_t* ys_lo = kv_roles ? a.do_lo : a.v_lo;
+
+  if (threadIdx.x == 0) {
+    mbar_init(res_full, kSmThreads + 1);
+    mbar_init(ps_full, kSmThreads);
+    mbar_init(ps_empty, 1);
+    mbar_init(o_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sp_full[i], 1);
+      mbar_init(&sp_empty[i], kSmThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // column map
+  constexpr uint32_t cX_hi = 0, cX_lo = HC;
+  constexpr uint32_t cY_hi = 2 * HC;                                     // MODE_S only
+  constexpr uint32_t cS = MODE == MODE_S ? 3 * HC : 2 * HC;              // S' (MODE_V: two buffers of N)
+  constexpr uint32_t cDP = cS + N;                                       // MODE_S: dP'
+  constexpr uint32_t cPS_hi = cS + 2 * N, cPS_lo = cPS_hi + NH;          // A operand of the output MMA
+  constexpr uint32_t cOut = cPS_lo + NH;
+  static_assert(cOut + Dp <= 512, "TMEM budget exceeded");
+
+  if (warp == kLoadWarp) {
+    // ============================== BULK-COPY PRODUCER ==============================
+    if (lane == 0) {
+      if (MODE == MODE_S && a.x3) {
+        mbar_expect_tx(res_full, L::kYlo);
+#pragma unroll
+        for (int at_i = 0; at_i < AD; ++at_i) {
+          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + r0) * 64;
+          bulk_g2s(smem + L::y_lo + at_i * 8192, Y_lo + src, 8192, res_full);
+        }
+      } else {
+        mbar_arrive(res_full);
+      }
+      constexpr uint32_t tb = N * 64;
+      for (int j = 0; j < nt; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        mbar_wait(&st_empty[s], ph ^ 1);
+        uint8_t* base = smem + L::stage0 + s * L::kStageBytes;
+        mbar_expect_tx(&st_full[s], (a.x3 ? 4 : 2) * L::kTile);
+#pragma unroll
+        for (int at_i = 0; at_i < AD; ++at_i) {
+          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + (int64_t)j * N) * 64;
+          bulk_g2s(base + 0 * L::kTile + at_i * tb, xs_hi + src, tb, &st_full[s]);
+          bulk_g2s(base + 2 * L::kTile + at_i * tb, ys_hi + src, tb, &st_full[s]);
+          if (a.x3) {
+            bulk_g2s(base + 1 * L::kTile + at_i * tb, xs_lo + src, tb, &st_full[s]);
+            bulk_g2s(base + 3 * L::kTile + at_i * tb, ys_lo + src, tb, &st_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ============================== MMA ISSUER ==============================
+    const bool leader = elect_one();
+    const uint32_t idesc_s = idesc_bf16(128, N, 0, 0);
+    const uint32_t idesc_o = idesc_bf16(128, Dp, 0, 1);  // B = streamed tile viewed MN-major (head dim contiguous)
+    constexpr uint32_t tb = N * 64;
+    const uint32_t st0 = smem_u32(smem + L::stage0) >> 4;
+    const uint64_t dYlo = kDescK64 | (smem_u32(smem + L::y_lo) >> 4);
+    const uint64_t mn_base = desc_mn_sw64_base(tb);
+    const uint32_t tX_hi = tmem_base + cX_hi, tX_lo = tmem_base + cX_lo, tY_hi = tmem_base + cY_hi;
+    const uint32_t tPS_hi = tmem_base + cPS_hi, tPS_lo = tmem_base + cPS_lo, tOut = tmem_base + cOut;
+
+    auto issue_scores = [&](int j) {
+      const int s = j % kStages;
+      const uint32_t sb = st0 + s * (L::kStageBytes >> 4);
+      const int buf = MODE == MODE_V ? (j & 1) : 0;
+      mbar_wait(&st_full[s], (j / kStages) & 1);
+      if (MODE == MODE_V) mbar_wait(&sp_empty[buf], ((j >> 1) & 1) ^ 1);
+      else mbar_wait(&sp_empty[0], (j & 1) ^ 1);
+      tc_fence_after();
+      const uint64_t xh = kDescK64 | (uint64_t)(sb + 0 * (L::kTile >> 4)), xl = kDescK64 | (uint64_t)(sb + 1 * (L::kTile >> 4));
+      const uint64_t yh = kDescK64 | (uint64_t)(sb + 2 * (L::kTile >> 4)), yl = kDescK64 | (uint64_t)(sb + 3 * (L::kTile >> 4));
+      const uint32_t dS = tmem_base + cS + buf * N;
+#pragma unroll
+      for (int ks = 0; ks < 2 * AD; ++ks) {
+        const uint32_t bo = (ks >> 1) * (tb / 16) + (ks & 1) * 2;
+        if (leader) {
+          umma_bf16_ts(dS, tX_hi + ks * 8, xh + bo, idesc_s, ks > 0 ? 1u : 0u);
+          if (a.x3) {
+            umma_bf16_ts(dS, tX_lo + ks * 8, xh + bo, idesc_s, 1u);
+            umma_bf16_ts(dS, tX_hi + ks * 8, xl + bo, idesc_s, 1u);
+          }
+        }
+      }
+      if (MODE == MODE_S) {
+        const uint32_t dDP = tmem_base + cDP;
+#pragma unroll
+        for (int ks = 0; ks < 2 * AD; ++ks) {
+          const uint32_t bo = (ks >> 1) * (tb / 16) + (ks & 1) * 2, ao = (ks >> 1) * (8192 / 16) + (ks & 1) * 2;
+          if (leader) {
+            umma_bf16_ts(dDP, tY_hi + ks * 8, yh + bo, idesc_s, ks > 0 ? 1u : 0u);
+            if (a.x3) {
+              umma_bf16(dDP, dYlo + ao, yh + bo, idesc_s, 1u);
+              umma_bf16_ts(dDP, tY_hi + ks * 8, yl + bo, idesc_s, 1u);
+            }
+          }
+        }
+      }
+      if (leader) umma_commit(&sp_full[buf]);
+      __syncwarp();
+    };
+    auto issue_out = [&](int j, bool last) {
+      const int s = j % kStages;
+      const uint32_t sb = st0 + s * (L::kStageBytes >> 4);
+      mbar_wait(ps_full, j & 1);
+      tc_fence_after();
+      // MODE_V: B = y_j (dO_j); MODE_S: B = x_j
+      const uint32_t boff = MODE == MODE_V ? 2 * (L::kTile >> 4) : 0;
+      const uint64_t bh_ = mn_base | (uint64_t)(sb + boff), bl_ = mn_base | (uint64_t)(sb + boff + (L::kTile >> 4));
+#pragma unroll
+      for (int ks = 0; ks < N / 16; ++ks) {
+        if (leader) {
+          umma_bf16_ts(tOut, tPS_hi + ks * 8, bh_ + ks * 64, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          if (a.x3) {
+            umma_bf16_ts(tOut, tPS_lo + ks * 8, bh_ + ks * 64, idesc_o, 1u);
+            umma_bf16_ts(tOut, tPS_hi + ks * 8, bl_ + ks * 64, idesc_o, 1u);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(ps_empty);
+        umma_commit(&st_empty[s]);
+        if (last) umma_commit(o_full);
+      }
+      __syncwarp();
+    };
+
+    mbar_wait(res_full, 0);
+    tc_fence_after();
+    issue_scores(0);
+    for (int j = 0; j + 1 < nt; ++j) {
+      issue_scores(j + 1);
+      issue_out(j, false);
+    }
+    issue_out(nt - 1, true);
+  } else {
+    // ============================== SOFTMAX-BACKWARD / EPILOGUE ==============================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int ri = r0 + row;  // key index (kv_roles) or query index
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int b = bh / a.H, h = bh % a.H;
+
+    // ---- resident operands: plane rows -> TMEM (thread = row; half 0 = hi plane, half 1 = lo plane)
+    {
+      const int sw = (ri >> 1) & 3;
+      auto load_plane_row = [&](const uint8_t* plane, uint32_t tcol) {
+#pragma unroll
+        for (int at_i = 0; at_i < AD; ++at_i) {
+          const uint4* src = reinterpret_cast<const uint4*>(plane + (((int64_t)bh * AD + at_i) * a.Tp + ri) * 64);
+          uint4 ph[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // logical chunk c sits at physical position c ^ sw
+            const uint4 v = ph[c ^ sw];
+            tmem_st4(tmem_base + lane_off + tcol + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
+          }
+        }
+      };
+      if (half == 0) {
+        load_plane_row(X_hi, cX_hi);
+      } else {
+        if (a.x3) load_plane_row(X_lo, cX_lo);
+        if (MODE == MODE_S) load_plane_row(Y_hi, cY_hi);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(res_full);
+    }
+
+    const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
+    const int Tc = (a.T + 3) & ~3;
+    const float* lse = a.lse + (int64_t)bh * a.Tp;
+    const float* delta = a.delta + (int64_t)bh * a.Tp;
+    float lse_r = 0.f, delta_r = 0.f;
+    if (!kv_roles && ri < a.T) { lse_r = lse[ri]; delta_r = delta[ri]; }
+
+    for (int j = 0; j < nt; ++j) {
+      const int buf = MODE == MODE_V ? (j & 1) : 0;
+      mbar_wait(&sp_full[buf], MODE == MODE_V ? ((j >> 1) & 1) : (j & 1));
+      tc_fence_after();
+      float sv[NH], dv[NH];
+      {
+        uint32_t v1[NH];
+        if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cS + buf * N + half * NH, v1);
+        else tmem_ld32(tmem_base + lane_off + cS + buf * N + half * NH, v1);
+        if constexpr (MODE == MODE_S) {
+          uint32_t v2[NH];
+          if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cDP + half * NH, v2);
+          else tmem_ld32(tmem_base + lane_off + cDP + half * NH, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NH; ++c) dv[c] = __uint_as_float(v2[c]);
+        } else {
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int c = 0; c < NH; ++c) sv[c] = __uint_as_float(v1[c]);
+      }
+      tc_fence_before();
+      mbar_arrive(&sp_empty[buf]);
+
+      const int c0 = j * N + half * NH;
+      float mult[NH];
+#pragma unroll
+      for (int c = 0; c < NH; ++c) mult[c] = 1.f;
+      if (a.drop.p > 0.f) {
+        if constexpr (kv_roles) {
+          // thread = key row, columns = queries.  One Philox call covers 4 adjacent KEYS of one query, i.e. 4
+          // adjacent lanes: lane (kg = lane/4, cq = lane%4) generates the calls of key-group kg for the columns
+          // c = 4i + cq and the warp transposes them through a private smem tile [column][lane].
+          float* mt = reinterpret_cast<float*>(smem + L::mask) + warp * (NH * 32);
+          const int kg = lane >> 2, cq = lane & 3;
+          const int key0 = r0 + quarter * 32 + kg * 4;
+#pragma unroll
+          for (int i = 0; i < NH / 4; ++i) {
+            const int c = 4 * i + cq;
+            float mk[4];
+            const uint64_t idx = ((uint64_t)bh * a.T + (uint64_t)min(c0 + c, a.T - 1)) * (uint64_t)Tc + key0;
+            dropout_mult4(a.drop.seed, a.drop.site, idx >> 2, a.drop.p, inv_keep, mk);
+            *reinterpret_cast<float4*>(mt + c * 32 + kg * 4) = make_float4(mk[0], mk[1], mk[2], mk[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < NH; ++c) mult[c] = mt[c * 32 + lane];
+          __syncwarp();
+        } else {                   // thread = query row, columns = keys: 4 adjacent keys share one Philox call
+          const uint64_t rowb = ((uint64_t)bh * a.T + (uint64_t)min(ri, a.T - 1)) * (uint64_t)Tc;
+#pragma unroll
+          for (int g = 0; g < NH / 4; ++g) {
+            float mk[4];
+            dropout_mult4(a.drop.seed, a.drop.site, (rowb + (uint64_t)(c0 + 4 * g)) >> 2, a.drop.p, inv_keep, mk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) mult[4 * g + e] = mk[e];
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NH; ++c) {
+        const int ci = c0 + c;  // query index (kv_roles) or key index
+        const bool valid = (ci < a.T) && (ri < a.T);
+        const float l2 = kv_roles ? (ci < a.T ? __ldg(lse + ci) : 0.f) : lse_r;
+        const float p = valid ? fast_exp2(fmaf(sv[c], a.scale_log2, -l2)) : 0.f;
+        if constexpr (MODE == MODE_S) {
+          const float dl = kv_roles ? (ci < a.T ? __ldg(delta + ci) : 0.f) : delta_r;
+          sv[c] = p * (dv[c] * mult[c] - dl);  // dS'
+        } else {
+          sv[c] = p * mult[c];                 // Pd'
+        }
+      }
+      // A operand of the output MMA -> TMEM (two bf16 per column), hi and lo planes
+      mbar_wait(ps_empty, (j & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < NH / 8; ++ch) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = sv[ch * 8 + e];
+        uint32_t hw[4], lw[4];
+        split8_words(x, hw, lw);
+        const uint32_t col = (half * NH + ch * 8) / 2;
+        tmem_st4(tmem_base + lane_off + cPS_hi + col, hw[0], hw[1], hw[2], hw[3]);
+        if (a.x3) tmem_st4(tmem_base + lane_off + cPS_lo + col, lw[0], lw[1], lw[2], lw[3]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ps_full);
+    }
+    // ---- epilogue: accumulator -> d_qkv (fp32, packed [B,T,3*H*E]); each half writes AD*16 columns
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int I = a.H * a.E;
+    // MODE_V: dV (col block 2I);  MODE_S/KV: dK (col block I, scaled);  MODE_S/!KV: dQ (col block 0, scaled)
+    float* dst = a.dqkv + ((int64_t)b * a.T + ri) * (3 * I) + h * a.E + (MODE == MODE_V ? 2 * I : (KV ? I : 0));
+    const float sc = MODE == MODE_V ? 1.f : a.scale;
+#pragma unroll
+    for (int cc = 0; cc < AD; ++cc) {
+      const int d0 = half * (AD * 16) + cc * 16;
+      uint32_t v[16];
+      tmem_ld16(tmem_base + lane_off + cOut + d0, v);
+      tmem_ld_wait();
+      if (ri < a.T) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+template <int MODE, bool KV, int N, int AD>
+int launch_bwd2(const AttnBwdArgs& a, cudaStream_t st) {
+  using L = Smem2<MODE, N, AD>;
+  static_assert(L::total <= 232448, "shared memory budget exceeded");
+  V1T_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<MODE, KV, N, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+  dim3 grid(cdiv(a.T, 128), a.B * a.H);
+  attn_bwd2_kernel<MODE, KV, N, AD><<<grid, kThreadsAttn, L::total, st>>>(a);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+template <int AD>
+int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
+  V1T_TRY((launch_bwd2<MODE_V, true, 64, AD>(a, st)));   // dV
+  V1T_TRY((launch_bwd2<MODE_S, true, 32, AD>(a, st)));   // dK
+  return launch_bwd2<MODE_S, false, 32, AD>(a, st);      // dQ
+}
+
+}  // namespace
+
+int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st) {
+  V1T_CHECK_ARG(a.Dp % 32 == 0 && a.Dp >= 32 && a.Dp <= 160 && a.Tp % 128 == 0 && a.Tp >= a.T && a.E <= a.Dp,
+                "attn_bwd2_tc: unsupported dims (Dp %d, Tp %d)", a.Dp, a.Tp);
+  V1T_CHECK_ARG(a.B * a.H <= 65535, "attn_bwd2_tc: too many (batch, head) pairs");
+  switch (a.Dp / 32) {
+    case 1: return bwd2_all<1>(a, st);
+    case 2: return bwd2_all<2>(a, st);
+    case 3: return bwd2_all<3>(a, st);
+    case 4: return bwd2_all<4>(a, st);
+    default: return bwd2_all<5>(a, st);
+  }
+}
+
+}  // namespace v1t

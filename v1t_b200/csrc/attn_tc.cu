@@ -778,6 +778,14 @@ AttnPlanes carve_attn_planes(void* base, int B, int H, int Tp, int Dp, bool with
 }
 }  // namespace v1t
 
+namespace v1t {
+int attn_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t st) {
+  const char* gen = getenv("V1T_ATTN_BWD");  // "1" selects the first-generation (smem-resident) kernels
+  if (gen && atoi(gen) == 1) return attn_bwd_tc(a, st);
+  return attn_bwd2_tc(a, st);
+}
+}  // namespace v1t
+
 extern "C" size_t v1t_attn_scratch_bytes(int B, int H, int T, int E) {
   const int Tp = (int)v1t::round_up(T, 128), Dp = (int)v1t::round_up(E, 32);
   return v1t::carve_attn_planes(nullptr, B, H, Tp, Dp, true).total;
@@ -834,5 +842,5 @@ extern "C" int v1t_attn_backward(const float* qkv, const float* out, const float
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.x3 = x3;
   a.drop = DropSpec{seed, site, p_drop};
-  return attn_bwd_tc(a, st);
+  return attn_bwd_dispatch(a, st);
 }

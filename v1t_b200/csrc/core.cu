@@ -391,7 +391,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       ba.scale = scale; ba.scale_log2 = scale * 1.4426950408889634f;
       ba.x3 = x3;
       ba.drop = site_drop(*shape, i, kSiteAttn);
-      V1T_TRY(attn_bwd_tc(ba, st));
+      V1T_TRY(attn_bwd_dispatch(ba, st));
     }
     for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_BWD, st);

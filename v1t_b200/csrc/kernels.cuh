@@ -82,7 +82,9 @@ struct AttnBwdArgs {
   int x3;
   DropSpec drop;
 };
-int attn_bwd_tc(const AttnBwdArgs& a, cudaStream_t st);
+int attn_bwd_tc(const AttnBwdArgs& a, cudaStream_t st);   // generation 1: resident operands in shared memory
+int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st);  // generation 2: resident operands in tensor memory
+int attn_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t st);
 struct AttnPlanes {  // [0] = hi, [1] = lo
   uint8_t *q[2], *k[2], *vt[2];   // forward (vt: V transposed, rows = head dim)
   uint8_t *v[2], *dO[2];          // backward (v aliases vt's storage)

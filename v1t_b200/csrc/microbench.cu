@@ -55,8 +55,90 @@ __global__ void __launch_bounds__(128, 1) mma_microbench_kernel(int N, int ts, i
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
+// Self-test of the TS form (A operand in tensor memory): C[128 x N] = A[128 x K] B[N x K]^T with A written to TMEM
+// by tcgen05.st (thread = row, two bf16 per 32-bit column), B staged K-major SWIZZLE_64B in shared memory.
+__global__ void __launch_bounds__(128, 1) ts_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                             float* __restrict__ C, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  // A row -> TMEM columns [256, 256 + K/2): 8 columns (16 bf16) per tcgen05.st
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat162 v = __floats2bfloat162_rn(A[row * K + k0 + 2 * i], A[row * K + k0 + 2 * i + 1]);
+      r[i] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(tmem + lane_off + 256 + k0 / 2),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  }
+  tmem_st_wait();
+  // B -> smem, K-major SW64: atoms of 32 k, each [N rows][64 B]
+  for (int i = threadIdx.x; i < N * (K / 8); i += blockDim.x) {
+    const int n = i % N, ch = i / N;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = B[n * K + ch * 8 + e];
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    *reinterpret_cast<uint4*>(smem + (ch >> 2) * (N * 64) + sw64_offset(n, ch & 3)) = hi;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16(128, N, 0, 0);
+    const uint64_t db = kDescK64 | (smem_u32(smem) >> 4);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t bo = (ks >> 1) * (N * 64 / 16) + (ks & 1) * 2;
+      if (leader) umma_bf16_ts(tmem, tmem + 256 + ks * 8, db + bo, idesc, ks > 0 ? 1u : 0u);
+    }
+    if (leader) umma_commit(&bar);
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + lane_off + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) C[row * N + c0 + c] = __uint_as_float(v[c]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
 }  // namespace
 }  // namespace v1t
+
+extern "C" int v1t_ts_selftest(const float* A, const float* B, float* C, int N, int K, void* stream) {
+  using namespace v1t;
+  V1T_CHECK_ARG(A && B && C && N % 16 == 0 && N >= 16 && N <= 256 && K % 32 == 0 && K >= 32 && K <= 256,
+                "ts_selftest: bad argument");
+  V1T_CUDA(cudaFuncSetAttribute(ts_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  ts_selftest_kernel<<<1, 128, 160 * 1024, (cudaStream_t)stream>>>(A, B, C, N, K);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
 
 // cycles for `iters * 8` MMAs of shape 128 x N x 16 on every SM concurrently (grid = 148); returns the max over SMs
 extern "C" int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long* out_dev, void* stream) {
