@@ -23,14 +23,14 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BK = 32, STAGES = 4, BN_MAX = 256;
+constexpr int BM = 128, BK = 32, STAGES = 2, RAW = 2, BN_MAX = 256;  // UMMA stages, raw fp32 staging slots
 constexpr int kEpiWarps = 8, kProdWarps = 8;
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int A_PLANE = BM * 64;       // bytes of one bf16 plane of the A stage (128 rows x 32 k)
 constexpr int B_PLANE = BN_MAX * 64;
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // hi + lo planes of A and B
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = (STAGES + RAW) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct TcArgs {
   GemmArgs g;
@@ -86,7 +86,7 @@ __device__ __forceinline__ void load8(const float* __restrict__ base, int64_t s_
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (STAGES + RAW) * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -116,90 +116,159 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 
   if (warp > kEpiWarps) {
     // ============================== PRODUCERS ==============================
+    // Two-level pipeline.  (1) cp.async copies the raw fp32 operand chunks of k-block i+RAW into a per-thread
+    // staging slot (each thread later reads only what it copied itself, so no cross-thread synchronisation is
+    // needed and the global-memory latency of RAW k-blocks is in flight without holding registers);
+    // (2) the same thread reads its chunks back, splits them into bf16 hi/lo and stores them into the swizzled
+    // UMMA stage.  Thread -> chunk assignment is fixed per launch.
     const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;
     const bool a_kc = (g.d.a_k == 1), b_kc = (g.d.b_k == 1);
-    uint32_t it = 0;
+    const int b_chunks = a.bn * 4;
+    uint8_t* raw = smem + STAGES * STAGE_BYTES;
+
+    // ---- per-thread chunk geometry (constant for the whole launch: no divisions in the k loop) ----
+    // A chunk = 8 consecutive elements along the memory-contiguous direction ("c" coordinate) of one line ("l"
+    // coordinate).  K-contiguous operand: l = row (m or n), c = k.  MN-major staging: l = k, c = row.
+    struct Chunk { int lc; uint32_t soff; int goff; };  // lc = (l << 12) | c
+    Chunk ca[2], cb[4];
+    const int64_t a_sl = a.mn_a ? g.d.a_k : g.d.a_m, a_sc = a.mn_a ? g.d.a_m : g.d.a_k;
+    const int64_t b_sl = a.mn_b ? g.d.b_k : g.d.b_n, b_sc = a.mn_b ? g.d.b_n : g.d.b_k;
+    const bool a_vec = (a_sc == 1) && a.a_vec, b_vec = (b_sc == 1) && a.b_vec;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int q = ptid + i * kProdThreads;
+      int l, c;
+      if (a.mn_a) { l = q >> 4; c = (q & 15) * 8; ca[i].soff = ((q & 15) >> 2) * (BK * 64) + sw64_offset(q >> 4, q & 3); }
+      else {
+        const int r = a_kc ? (q >> 2) : (q % BM), cc = a_kc ? (q & 3) : (q / BM);
+        l = r; c = cc * 8; ca[i].soff = sw64_offset(r, cc);
+      }
+      ca[i].lc = (l << 12) | c;
+      ca[i].goff = (int)(l * a_sl + c * a_sc);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = ptid + i * kProdThreads;
+      int l, c;
+      if (a.mn_b) {
+        const int ncw = a.bn >> 3;
+        const int kr = q / ncw, nc = q % ncw;
+        l = kr; c = nc * 8; cb[i].soff = (nc >> 2) * (BK * 64) + sw64_offset(kr, nc & 3);
+      } else {
+        const int r = b_kc ? (q >> 2) : (q % a.bn), cc = b_kc ? (q & 3) : (q / a.bn);
+        l = r; c = cc * 8; cb[i].soff = sw64_offset(r, cc);
+      }
+      cb[i].lc = (l << 12) | c;
+      cb[i].goff = (int)(l * b_sl + c * b_sc);
+    }
+
+    // prefetch cursor over (tile, k-block); the consumer side only needs the iteration count
+    int pf_t = blockIdx.x, pf_kb = 0, pf_nkb = 0;
+    Tile pf_tl{};
+    int total_iters = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const Tile tl = decode_tile(a, t);
-      const float* A = g.A + tl.a_off;
-      const float* B = g.B + tl.b_off;
-      const int num_kb = (tl.k_end - tl.k_begin + BK - 1) / BK;
-      const int b_chunks = a.bn * 4;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int k0 = tl.k_begin + kb * BK;
-        const int stage = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        float va[2][8], vb[4][8];
-        // issue all global loads of this stage before waiting for the smem slot
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int q = ptid + i * kProdThreads;
-          if (a.mn_a) {  // 8 consecutive m of one k row: chunk (m/8) of row k
-            const int kr = q >> 4, mc = q & 15;
-            load8(A, g.d.a_k, g.d.a_m, a.a_vec, k0 + kr, tl.k_end, tl.m0 + mc * 8, g.d.m, va[i]);
-          } else {
-            const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
-            load8(A, g.d.a_m, g.d.a_k, a_kc && a.a_vec, tl.m0 + r, g.d.m, k0 + c * 8, tl.k_end, va[i]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = ptid + i * kProdThreads;
-          if (q < b_chunks) {
-            if (a.mn_b) {
-              const int ncw = a.bn >> 3;  // 16-byte chunks per k row
-              const int kr = q / ncw, nc = q % ncw;
-              load8(B, g.d.b_k, g.d.b_n, a.b_vec, k0 + kr, tl.k_end, tl.n0 + nc * 8, g.d.n, vb[i]);
-            } else {
-              const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
-              load8(B, g.d.b_n, g.d.b_k, b_kc && a.b_vec, tl.n0 + r, g.d.n, k0 + c * 8, tl.k_end, vb[i]);
-            }
-          }
-        }
-        mbar_wait(&empty[stage], ph ^ 1);
-        uint8_t* sa_hi = smem + stage * STAGE_BYTES;
-        uint8_t* sa_lo = sa_hi + A_PLANE;
-        uint8_t* sb_hi = sa_hi + 2 * A_PLANE;
-        uint8_t* sb_lo = sb_hi + B_PLANE;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int q = ptid + i * kProdThreads;
-          uint4 hi, lo;
-          split8(va[i], hi, lo);
-          uint32_t off;
-          if (a.mn_a) {  // [M atoms of 32][32 k rows][64 B]
-            const int kr = q >> 4, mc = q & 15;
-            off = (mc >> 2) * (BK * 64) + sw64_offset(kr, mc & 3);
-          } else {
-            const int r = a_kc ? (q >> 2) : (q % BM), c = a_kc ? (q & 3) : (q / BM);
-            off = sw64_offset(r, c);
-          }
-          *reinterpret_cast<uint4*>(sa_hi + off) = hi;
-          if (a.x3) *reinterpret_cast<uint4*>(sa_lo + off) = lo;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = ptid + i * kProdThreads;
-          if (q < b_chunks) {
-            uint4 hi, lo;
-            split8(vb[i], hi, lo);
-            uint32_t off;
-            if (a.mn_b) {
-              const int ncw = a.bn >> 3;
-              const int kr = q / ncw, nc = q % ncw;
-              off = (nc >> 2) * (BK * 64) + sw64_offset(kr, nc & 3);
-            } else {
-              const int r = b_kc ? (q >> 2) : (q % a.bn), c = b_kc ? (q & 3) : (q / a.bn);
-              off = sw64_offset(r, c);
-            }
-            *reinterpret_cast<uint4*>(sb_hi + off) = hi;
-            if (a.x3) *reinterpret_cast<uint4*>(sb_lo + off) = lo;
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(&full[stage]);
-      }
+      total_iters += (tl.k_end - tl.k_begin + BK - 1) / BK;
     }
+    auto pf_load = [&]() {
+      if (pf_t < total_tiles) {
+        pf_tl = decode_tile(a, pf_t);
+        pf_nkb = (pf_tl.k_end - pf_tl.k_begin + BK - 1) / BK;
+      }
+    };
+    auto pf_next = [&]() {
+      if (++pf_kb >= pf_nkb) {
+        pf_kb = 0;
+        pf_t += gridDim.x;
+        pf_load();
+      }
+    };
+    // copy 8 elements starting at p (element stride sc) into the 32-byte staging slot; zero-fill beyond limits
+    auto copy_chunk = [&](uint8_t* dst, const float* p, bool in_line, int nv, int64_t sc, bool vec) {
+      const uint32_t d = smem_u32(dst);
+      if (!in_line || nv <= 0) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst + 16) = make_uint4(0, 0, 0, 0);
+      } else if (vec && nv >= 8) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(p) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(p + 4) : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nv) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4 * j), "l"(p + (int64_t)j * sc) : "memory");
+          else *reinterpret_cast<float*>(dst + 4 * j) = 0.f;
+        }
+      }
+    };
+    auto issue_stage = [&](int rs) {
+      const int k0 = pf_tl.k_begin + pf_kb * BK;
+      uint8_t* rbase = raw + rs * STAGE_BYTES + ptid * 32;
+      {
+        const int l0 = a.mn_a ? k0 : pf_tl.m0, c0 = a.mn_a ? pf_tl.m0 : k0;
+        const int l_lim = a.mn_a ? pf_tl.k_end : g.d.m, c_lim = a.mn_a ? g.d.m : pf_tl.k_end;
+        const float* base = g.A + pf_tl.a_off + (int64_t)l0 * a_sl + (int64_t)c0 * a_sc;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          copy_chunk(rbase + i * (kProdThreads * 32), base + ca[i].goff, l0 + (ca[i].lc >> 12) < l_lim,
+                     c_lim - (c0 + (ca[i].lc & 4095)), a_sc, a_vec);
+      }
+      {
+        const int l0 = a.mn_b ? k0 : pf_tl.n0, c0 = a.mn_b ? pf_tl.n0 : k0;
+        const int l_lim = a.mn_b ? pf_tl.k_end : g.d.n, c_lim = a.mn_b ? g.d.n : pf_tl.k_end;
+        const float* base = g.B + pf_tl.b_off + (int64_t)l0 * b_sl + (int64_t)c0 * b_sc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ptid + i * kProdThreads < b_chunks)
+            copy_chunk(rbase + (2 + i) * (kProdThreads * 32), base + cb[i].goff, l0 + (cb[i].lc >> 12) < l_lim,
+                       c_lim - (c0 + (cb[i].lc & 4095)), b_sc, b_vec);
+      }
+    };
+
+    pf_load();
+#pragma unroll
+    for (int s = 0; s < RAW; ++s) {
+      if (pf_t < total_tiles) {
+        issue_stage(s);
+        pf_next();
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int it = 0; it < total_iters; ++it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(RAW - 1) : "memory");
+      const int rs = it % RAW, stage = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      const uint8_t* rbase = raw + rs * STAGE_BYTES + ptid * 32;
+      mbar_wait(&empty[stage], ph ^ 1);
+      uint8_t* sa_hi = smem + stage * STAGE_BYTES;
+      uint8_t* sa_lo = sa_hi + A_PLANE;
+      uint8_t* sb_hi = sa_hi + 2 * A_PLANE;
+      uint8_t* sb_lo = sb_hi + B_PLANE;
+      // chunk by chunk: staging slot -> registers -> bf16 hi/lo -> swizzled UMMA stage
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (i < 2 || ptid + (i - 2) * kProdThreads < b_chunks) {
+          const float4 x = *reinterpret_cast<const float4*>(rbase + i * (kProdThreads * 32));
+          const float4 y = *reinterpret_cast<const float4*>(rbase + i * (kProdThreads * 32) + 16);
+          const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          const uint32_t soff = i < 2 ? ca[i].soff : cb[i - 2].soff;
+          uint8_t* dh = (i < 2 ? sa_hi : sb_hi) + soff;
+          uint8_t* dl = (i < 2 ? sa_lo : sb_lo) + soff;
+          *reinterpret_cast<uint4*>(dh) = hi;
+          if (a.x3) *reinterpret_cast<uint4*>(dl) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[stage]);
+      // refill this raw slot with k-block it + RAW (after its contents were consumed above)
+      if (pf_t < total_tiles) {
+        issue_stage(rs);
+        pf_next();
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == kEpiWarps) {
     // ============================== MMA ISSUER ==============================
     const uint32_t idesc = idesc_bf16(BM, a.bn, a.mn_a, a.mn_b);
