@@ -34,8 +34,8 @@ using namespace tc;
 
 constexpr int kSmWarps = 8;
 constexpr int kSmThreads = kSmWarps * 32;
-constexpr int kThreadsAttn = (kSmWarps + 2) * 32;
-constexpr int kMmaWarp = kSmWarps, kLoadWarp = kSmWarps + 1;
+constexpr int kThreadsAttn = (kSmWarps + 3) * 32;
+constexpr int kMmaWarp = kSmWarps, kLoadWarpX = kSmWarps + 1, kLoadWarpY = kSmWarps + 2;
 constexpr int MODE_V = 0, MODE_S = 1;
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -47,15 +47,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 template <int MODE, int N, int AD>
 struct Smem2 {
-  static constexpr int kStages = MODE == MODE_V ? 2 : 3;
-  static constexpr uint32_t kTile = AD * N * 64;     // one bf16 plane of one streamed operand tile
-  static constexpr uint32_t kYlo = AD * 128 * 64;    // resident Y lo plane (MODE_S, bf16x3)
-  // layout: [Y_lo] [stage: x_hi, x_lo, y_hi, y_lo] x kStages [barriers]
+  // The two streamed operands have different lifetimes, so each gets its own ring:
+  //   MODE_V: x_j (queries, for S') is free after the score MMAs, y_j (dO, for out) after the output MMAs
+  //   MODE_S: y_j (for dP') is free after the score MMAs, x_j (for S' and out) after the output MMAs
+  static constexpr int kXS = MODE == MODE_V ? 2 : 4;  // ring slots
+  static constexpr int kYS = 2;
+  static constexpr uint32_t kTile = AD * N * 64;      // one bf16 plane of one streamed operand tile
+  static constexpr uint32_t kSlot = 2 * kTile;        // hi + lo planes
+  static constexpr uint32_t kYlo = AD * 128 * 64;     // resident Y lo plane (MODE_S, bf16x3)
   static constexpr uint32_t y_lo = 0;
-  static constexpr uint32_t stage0 = MODE == MODE_S ? kYlo : 0;
-  static constexpr uint32_t kStageBytes = 4 * kTile;
-  static constexpr uint32_t bars = stage0 + kStages * kStageBytes;
-  static constexpr uint32_t mask = bars + 256;                          // dropout multipliers, [warp][N/2][32] floats
+  static constexpr uint32_t x_ring = MODE == MODE_S ? kYlo : 0;
+  static constexpr uint32_t y_ring = x_ring + kXS * kSlot;
+  static constexpr uint32_t bars = y_ring + kYS * kSlot;
+  static constexpr uint32_t mask = bars + 256;        // dropout multipliers, [warp][N/2][32] floats
   static constexpr uint32_t total = mask + kSmWarps * (N / 2) * 32 * 4 + 1024;
 };
 
@@ -63,7 +67,7 @@ template <int MODE, bool KV, int N, int AD>
 __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a) {
   constexpr int Dp = AD * 32, HC = AD * 16, NH = N / 2;
   using L = Smem2<MODE, N, AD>;
-  constexpr int kStages = L::kStages;
+  constexpr int kXS = L::kXS, kYS = L::kYS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
@@ -71,11 +75,13 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
   uint64_t* ps_full = bars + 1;
   uint64_t* ps_empty = bars + 2;
   uint64_t* o_full = bars + 3;
-  uint64_t* st_full = bars + 4;    // [kStages]
-  uint64_t* st_empty = bars + 8;   // [kStages]
-  uint64_t* sp_full = bars + 12;   // [2]
-  uint64_t* sp_empty = bars + 14;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* x_full = bars + 4;     // [kXS]
+  uint64_t* x_empty = bars + 8;    // [kXS]
+  uint64_t* y_full = bars + 12;    // [kYS]
+  uint64_t* y_empty = bars + 14;   // [kYS]
+  uint64_t* sp_full = bars + 16;   // [2]
+  uint64_t* sp_empty = bars + 18;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 128, bh = blockIdx.y;
@@ -91,9 +97,13 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
     mbar_init(ps_full, kSmThreads);
     mbar_init(ps_empty, 1);
     mbar_init(o_full, 1);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&st_full[i], 1);
-      mbar_init(&st_empty[i], 1);
+    for (int i = 0; i < kXS; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+    }
+    for (int i = 0; i < kYS; ++i) {
+      mbar_init(&y_full[i], 1);
+      mbar_init(&y_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sp_full[i], 1);
@@ -115,35 +125,39 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
   constexpr uint32_t cOut = cPS_lo + NH;
   static_assert(cOut + Dp <= 512, "TMEM budget exceeded");
 
-  if (warp == kLoadWarp) {
-    // ============================== BULK-COPY PRODUCER ==============================
+  if (warp == kLoadWarpX || warp == kLoadWarpY) {
+    // ============================== BULK-COPY PRODUCERS (one warp per ring) ==============================
     if (lane == 0) {
-      if (MODE == MODE_S && a.x3) {
-        mbar_expect_tx(res_full, L::kYlo);
+      const bool is_x = warp == kLoadWarpX;
+      if (is_x) {  // also fetches the resident Y lo plane
+        if (MODE == MODE_S && a.x3) {
+          mbar_expect_tx(res_full, L::kYlo);
 #pragma unroll
-        for (int at_i = 0; at_i < AD; ++at_i) {
-          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + r0) * 64;
-          bulk_g2s(smem + L::y_lo + at_i * 8192, Y_lo + src, 8192, res_full);
+          for (int at_i = 0; at_i < AD; ++at_i) {
+            const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + r0) * 64;
+            bulk_g2s(smem + L::y_lo + at_i * 8192, Y_lo + src, 8192, res_full);
+          }
+        } else {
+          mbar_arrive(res_full);
         }
-      } else {
-        mbar_arrive(res_full);
       }
       constexpr uint32_t tb = N * 64;
+      const int slots = is_x ? kXS : kYS;
+      uint64_t* fullb = is_x ? x_full : y_full;
+      uint64_t* emptyb = is_x ? x_empty : y_empty;
+      const uint8_t* src_hi = is_x ? xs_hi : ys_hi;
+      const uint8_t* src_lo = is_x ? xs_lo : ys_lo;
+      uint8_t* ring = smem + (is_x ? L::x_ring : L::y_ring);
       for (int j = 0; j < nt; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        mbar_wait(&st_empty[s], ph ^ 1);
-        uint8_t* base = smem + L::stage0 + s * L::kStageBytes;
-        mbar_expect_tx(&st_full[s], (a.x3 ? 4 : 2) * L::kTile);
+        const int s = j % slots;
+        mbar_wait(&emptyb[s], ((j / slots) & 1) ^ 1);
+        uint8_t* base = ring + s * L::kSlot;
+        mbar_expect_tx(&fullb[s], (a.x3 ? 2 : 1) * L::kTile);
 #pragma unroll
         for (int at_i = 0; at_i < AD; ++at_i) {
           const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + (int64_t)j * N) * 64;
-          bulk_g2s(base + 0 * L::kTile + at_i * tb, xs_hi + src, tb, &st_full[s]);
-          bulk_g2s(base + 2 * L::kTile + at_i * tb, ys_hi + src, tb, &st_full[s]);
-          if (a.x3) {
-            bulk_g2s(base + 1 * L::kTile + at_i * tb, xs_lo + src, tb, &st_full[s]);
-            bulk_g2s(base + 3 * L::kTile + at_i * tb, ys_lo + src, tb, &st_full[s]);
-          }
+          bulk_g2s(base + at_i * tb, src_hi + src, tb, &fullb[s]);
+          if (a.x3) bulk_g2s(base + L::kTile + at_i * tb, src_lo + src, tb, &fullb[s]);
         }
       }
     }
@@ -153,22 +167,23 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
     const uint32_t idesc_s = idesc_bf16(128, N, 0, 0);
     const uint32_t idesc_o = idesc_bf16(128, Dp, 0, 1);  // B = streamed tile viewed MN-major (head dim contiguous)
     constexpr uint32_t tb = N * 64;
-    const uint32_t st0 = smem_u32(smem + L::stage0) >> 4;
+    const uint32_t xr0 = smem_u32(smem + L::x_ring) >> 4, yr0 = smem_u32(smem + L::y_ring) >> 4;
     const uint64_t dYlo = kDescK64 | (smem_u32(smem + L::y_lo) >> 4);
     const uint64_t mn_base = desc_mn_sw64_base(tb);
     const uint32_t tX_hi = tmem_base + cX_hi, tX_lo = tmem_base + cX_lo, tY_hi = tmem_base + cY_hi;
     const uint32_t tPS_hi = tmem_base + cPS_hi, tPS_lo = tmem_base + cPS_lo, tOut = tmem_base + cOut;
 
     auto issue_scores = [&](int j) {
-      const int s = j % kStages;
-      const uint32_t sb = st0 + s * (L::kStageBytes >> 4);
+      const int xs = j % kXS, ys = j % kYS;
+      const uint32_t xb = xr0 + xs * (L::kSlot >> 4), yb = yr0 + ys * (L::kSlot >> 4);
       const int buf = MODE == MODE_V ? (j & 1) : 0;
-      mbar_wait(&st_full[s], (j / kStages) & 1);
+      mbar_wait(&x_full[xs], (j / kXS) & 1);
+      if (MODE == MODE_S) mbar_wait(&y_full[ys], (j / kYS) & 1);
       if (MODE == MODE_V) mbar_wait(&sp_empty[buf], ((j >> 1) & 1) ^ 1);
       else mbar_wait(&sp_empty[0], (j & 1) ^ 1);
       tc_fence_after();
-      const uint64_t xh = kDescK64 | (uint64_t)(sb + 0 * (L::kTile >> 4)), xl = kDescK64 | (uint64_t)(sb + 1 * (L::kTile >> 4));
-      const uint64_t yh = kDescK64 | (uint64_t)(sb + 2 * (L::kTile >> 4)), yl = kDescK64 | (uint64_t)(sb + 3 * (L::kTile >> 4));
+      const uint64_t xh = kDescK64 | (uint64_t)xb, xl = kDescK64 | (uint64_t)(xb + (L::kTile >> 4));
+      const uint64_t yh = kDescK64 | (uint64_t)yb, yl = kDescK64 | (uint64_t)(yb + (L::kTile >> 4));
       const uint32_t dS = tmem_base + cS + buf * N;
 #pragma unroll
       for (int ks = 0; ks < 2 * AD; ++ks) {
@@ -195,17 +210,21 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
           }
         }
       }
-      if (leader) umma_commit(&sp_full[buf]);
+      if (leader) {
+        if (MODE == MODE_V) umma_commit(&x_empty[xs]);   // queries no longer needed
+        else umma_commit(&y_empty[ys]);                  // dP' operand no longer needed
+        umma_commit(&sp_full[buf]);
+      }
       __syncwarp();
     };
     auto issue_out = [&](int j, bool last) {
-      const int s = j % kStages;
-      const uint32_t sb = st0 + s * (L::kStageBytes >> 4);
+      const int xs = j % kXS, ys = j % kYS;
+      if (MODE == MODE_V) mbar_wait(&y_full[ys], (j / kYS) & 1);
       mbar_wait(ps_full, j & 1);
       tc_fence_after();
       // MODE_V: B = y_j (dO_j); MODE_S: B = x_j
-      const uint32_t boff = MODE == MODE_V ? 2 * (L::kTile >> 4) : 0;
-      const uint64_t bh_ = mn_base | (uint64_t)(sb + boff), bl_ = mn_base | (uint64_t)(sb + boff + (L::kTile >> 4));
+      const uint32_t sb = MODE == MODE_V ? yr0 + ys * (L::kSlot >> 4) : xr0 + xs * (L::kSlot >> 4);
+      const uint64_t bh_ = mn_base | (uint64_t)sb, bl_ = mn_base | (uint64_t)(sb + (L::kTile >> 4));
 #pragma unroll
       for (int ks = 0; ks < N / 16; ++ks) {
         if (leader) {
@@ -218,7 +237,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
       }
       if (leader) {
         umma_commit(ps_empty);
-        umma_commit(&st_empty[s]);
+        if (MODE == MODE_V) umma_commit(&y_empty[ys]);
+        else umma_commit(&x_empty[xs]);
         if (last) umma_commit(o_full);
       }
       __syncwarp();
@@ -273,10 +293,25 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
     const float* lse = a.lse + (int64_t)bh * a.Tp;
     const float* delta = a.delta + (int64_t)bh * a.Tp;
     float lse_r = 0.f, delta_r = 0.f;
-    if (!kv_roles && ri < a.T) { lse_r = lse[ri]; delta_r = delta[ri]; }
+    if (!kv_roles) { lse_r = lse[ri]; delta_r = delta[ri]; }  // padded rows: lse = +inf, delta = 0
 
     for (int j = 0; j < nt; ++j) {
       const int buf = MODE == MODE_V ? (j & 1) : 0;
+      // per-column softmax statistics of this tile, fetched before the scores arrive
+      float lsv[kv_roles ? NH : 1], dlv[(kv_roles && MODE == MODE_S) ? NH : 1];
+      if constexpr (kv_roles) {
+        const float4* l4 = reinterpret_cast<const float4*>(lse + j * N + half * NH);
+        const float4* d4 = reinterpret_cast<const float4*>(delta + j * N + half * NH);
+#pragma unroll
+        for (int g = 0; g < NH / 4; ++g) {
+          const float4 lv = __ldg(l4 + g);
+          lsv[4 * g] = lv.x; lsv[4 * g + 1] = lv.y; lsv[4 * g + 2] = lv.z; lsv[4 * g + 3] = lv.w;
+          if constexpr (MODE == MODE_S) {
+            const float4 dd = __ldg(d4 + g);
+            dlv[4 * g] = dd.x; dlv[4 * g + 1] = dd.y; dlv[4 * g + 2] = dd.z; dlv[4 * g + 3] = dd.w;
+          }
+        }
+      }
       mbar_wait(&sp_full[buf], MODE == MODE_V ? ((j >> 1) & 1) : (j & 1));
       tc_fence_after();
       float sv[NH], dv[NH];
@@ -335,17 +370,20 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
           }
         }
       }
+      // No bounds checks: the forward stores lse = +inf for padded queries (so P' = exp2(-inf) = 0 there), delta
+      // is zero-padded, and padded KEY rows only pollute accumulator rows that are never stored.
+      if constexpr (kv_roles) {
 #pragma unroll
-      for (int c = 0; c < NH; ++c) {
-        const int ci = c0 + c;  // query index (kv_roles) or key index
-        const bool valid = (ci < a.T) && (ri < a.T);
-        const float l2 = kv_roles ? (ci < a.T ? __ldg(lse + ci) : 0.f) : lse_r;
-        const float p = valid ? fast_exp2(fmaf(sv[c], a.scale_log2, -l2)) : 0.f;
-        if constexpr (MODE == MODE_S) {
-          const float dl = kv_roles ? (ci < a.T ? __ldg(delta + ci) : 0.f) : delta_r;
-          sv[c] = p * (dv[c] * mult[c] - dl);  // dS'
-        } else {
-          sv[c] = p * mult[c];                 // Pd'
+        for (int c = 0; c < NH; ++c) {
+          const float p = fast_exp2(fmaf(sv[c], a.scale_log2, -lsv[c]));
+          if constexpr (MODE == MODE_S) sv[c] = p * (dv[c] * mult[c] - dlv[c]);  // dS'
+          else sv[c] = p * mult[c];                                               // Pd'
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NH; ++c) {
+          const float p = (c0 + c < a.T) ? fast_exp2(fmaf(sv[c], a.scale_log2, -lse_r)) : 0.f;
+          sv[c] = p * (dv[c] * mult[c] - delta_r);  // dS'
         }
       }
       // A operand of the output MMA -> TMEM (two bf16 per column), hi and lo planes

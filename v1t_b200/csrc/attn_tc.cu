@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd_kernel(const AttnFwd
           if (c0 + c < a.E) orow[c0 + c] = __uint_as_float(v[c]) * inv_l;
       }
     }
-    if (half == 0 && qi < a.T && a.lse) a.lse[(int64_t)bh * a.Tp + qi] = m2 + log2f(l);
+    // padded query rows get +inf so that the backward's exp2(S*c - lse) vanishes there without bounds checks
+    if (half == 0 && a.lse) a.lse[(int64_t)bh * a.Tp + qi] = qi < a.T ? m2 + log2f(l) : INFINITY;
     tc_fence_before();
   }
 

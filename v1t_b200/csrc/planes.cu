@@ -109,6 +109,7 @@ int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int T
 int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int T, int Tp, int E, int64_t ld,
                cudaStream_t st) {
   const int64_t warps = (int64_t)B * T * H;
+  V1T_CUDA(cudaMemsetAsync(delta, 0, sizeof(float) * (size_t)B * H * Tp, st));  // zero the padded rows
   attn_delta_kernel<<<cdiv(warps, 8), 256, 0, st>>>(O, dO, delta, B, H, T, Tp, E, ld);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
