@@ -319,7 +319,8 @@ def run_b200(args):
     total_flops = 3 * core_flops_fwd() * n_local
 
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if args.dp_mode == "batch" else "strong",
             "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32 accumulate)", "bf16": "bf16"}.get(args.b200_impl, args.b200_impl),
             "data": "synthetic", "config": workload_config(args, world), "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks.summary(), "roofline": roofline, "roofline_readout": readout, "phases": phases,

@@ -30,7 +30,8 @@ constexpr int kProdThreads = kProdWarps * 32;
 constexpr int A_PLANE = BM * 64;       // bytes of one bf16 plane of the A stage (128 rows x 32 k)
 constexpr int B_PLANE = BN_MAX * 64;
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // hi + lo planes of A and B
-constexpr int SMEM_BYTES = (STAGES + RAW) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kEpiStage = 8 * 4096;  // per-warp 32 x 32 fp32 transpose tiles of the epilogue
+constexpr int SMEM_BYTES = (STAGES + RAW) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + kEpiStage;
 
 struct TcArgs {
   GemmArgs g;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* stage_base = smem + (STAGES + RAW) * STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GemmArgs& g = a.g;
@@ -332,33 +334,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       const uint32_t taddr = tmem_base + buf * BN_MAX + ((uint32_t)(quarter * 32) << 16);
       float* crow = g.C + tl.c_off + (int64_t)m * g.d.c_m;
       const float* rrow = g.R ? g.R + tl.r_off + (int64_t)m * g.d.r_m : nullptr;
-      const bool r_vec = rrow && a.r_vec;
-      for (int c0 = half * 16; c0 < a.bn; c0 += 32) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (m >= g.d.m) continue;
+      // 32-column groups alternate between the two column halves
+      for (int c0 = half * 32; c0 < a.bn; c0 += 64) {
         const int nb = tl.n0 + c0;
-        if (plain && a.c_vec && nb + 16 <= g.d.n && (!g.bias || bias_vec) && (!rrow || r_vec)) {
+        const int width = min(32, a.bn - c0);  // 16 or 32 (bn is a multiple of 16)
+        uint32_t v[32];
+        tmem_ld16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(v[0]));
+        if (width > 16) tmem_ld16(taddr + c0 + 16, reinterpret_cast<uint32_t(&)[16]>(v[16]));
+        tmem_ld_wait();
+        if (plain && a.c_vec && width == 32 && nb + 32 <= g.d.n && (!g.bias || bias_vec) && (!g.R || a.r_vec)) {
+          // ---- coalesced path: transpose the 32 x 32 block through a private smem tile so that every
+          // 128-bit store instruction writes four full 128-byte row segments (instead of 32 scattered 16 B pieces)
+          float* stg = reinterpret_cast<float*>(stage_base + warp * 4096);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 o = make_float4(g.d.alpha * __uint_as_float(v[4 * q]), g.d.alpha * __uint_as_float(v[4 * q + 1]),
-                                   g.d.alpha * __uint_as_float(v[4 * q + 2]), g.d.alpha * __uint_as_float(v[4 * q + 3]));
-            if (g.bias) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + q);
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+                make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          __syncwarp();
+          const int cq = lane & 7;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias) bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + cq);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const int mm = tl.m0 + quarter * 32 + r;
+            const float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
+            if (mm < g.d.m) {
+              float4 o = make_float4(fmaf(g.d.alpha, x.x, bv.x), fmaf(g.d.alpha, x.y, bv.y), fmaf(g.d.alpha, x.z, bv.z),
+                                     fmaf(g.d.alpha, x.w, bv.w));
+              if (g.R) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(g.R + tl.r_off + (int64_t)mm * g.d.r_m + nb) + cq);
+                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+              }
+              *(reinterpret_cast<float4*>(g.C + tl.c_off + (int64_t)mm * g.d.c_m + nb) + cq) = o;
             }
-            if (rrow) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + nb) + q);
-              o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-            }
-            *(reinterpret_cast<float4*>(crow + nb) + q) = o;
           }
-        } else {
+          __syncwarp();
+        } else if (m < g.d.m) {
 #pragma unroll 4
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 32; ++j) {
             const int n = nb + j;
-            if (n < g.d.n) {
+            if (j < width && n < g.d.n) {
               float x = g.d.alpha * __uint_as_float(v[j]);
               if (g.bias) x += __ldg(g.bias + n);
               if (g.drop.p > 0.f)
