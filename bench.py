@@ -39,7 +39,7 @@ def neuron_counts(n_mice: int, base: int):
     return {chr(ord("A") + i): int(base * (1 + 0.1 * (2 * rng.random() - 1))) // 8 * 8 for i in range(n_mice)}
 
 
-def make_args(neurons, device, impl="fp32", **over):
+def make_args(neurons, device, impl="bf16x3", **over):
     a = dict(input_shape=(1, 36, 64), output_shapes={k: (n,) for k, n in neurons.items()}, device=device, core="vit",
              readout="gaussian2d", behavior_mode=3, shift_mode=2, center_crop=1.0, resize_image=0,
              ds_name="sensorium", patch_mode=0, patch_size=8, patch_stride=1, emb_dim=155, num_blocks=4, num_heads=4,
@@ -345,7 +345,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--b200-impl", dest="b200_impl", default=os.environ.get("V1T_IMPL", "fp32"))
+    ap.add_argument("--b200-impl", dest="b200_impl", default=os.environ.get("V1T_IMPL", "bf16x3"),
+                    help="fp32 | bf16x3 (exact, default) | bf16 (fast)")
     ap.add_argument("--mice", type=int, default=7)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--neurons", type=int, default=8000)

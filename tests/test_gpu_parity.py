@@ -30,10 +30,12 @@ def build(g: Golden, **over):
     return model.to(DEV), crit
 
 
+@pytest.mark.parametrize("impl", ["bf16x3", "fp32"])
 @pytest.mark.parametrize("case", CASES)
-def test_model_matches_reference_golden(case):
+def test_model_matches_reference_golden(case, impl):
+    """Every golden fixture (reference outputs) in the default tensor-core mode (bf16x3) and the fp32 CUDA-core mode."""
     g = Golden(case)
-    model, crit = build(g)
+    model, crit = build(g, b200_impl=impl)
     model.train(g.meta["mode"] == "train")
     for mouse_id, d in g.mice.items():
         model.zero_grad(set_to_none=True)

@@ -1,0 +1,395 @@
+// Attention forward, second generation: Q (the 128-row resident operand) and P (the A operand of P V) live in
+// TENSOR MEMORY, so every tcgen05.mma runs in its TS form (~10 + N/2 cycles instead of 43 + N/2, measured by
+// scripts/mma_microbench.py) and shared memory only holds the streamed K and V^T tiles, each in its own
+// double-buffered ring (K(j) is free after S(j), V(j) after P V(j)), which hides the bulk-copy latency.
+// Same two-pass softmax as generation 1 (attn_tc.cu): pass 1 = row maxima from the hi planes, pass 2 = exact.
+//
+// TMEM columns (Dp = 160): Q_hi[80] | Q_lo[80] | S[2][64] | P_hi[32] | P_lo[32] | O[160]  = 512.
+// Warp roles (352 threads): warps 0-7 softmax/epilogue (lane quarter = warp & 3, column half = warp >> 2),
+// warp 8 MMA issue + TMEM alloc, warp 9 K-ring producer, warp 10 V-ring producer.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace v1t {
+namespace {
+
+using namespace tc;
+
+constexpr int BQ = 128, BKEY = 64;
+constexpr int kSmWarps = 8;
+constexpr int kSmThreads = kSmWarps * 32;
+constexpr int kThreadsAttn = (kSmWarps + 3) * 32;
+constexpr int kMmaWarp = kSmWarps, kLoadWarpK = kSmWarps + 1, kLoadWarpV = kSmWarps + 2;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int AD>
+struct FSmem {
+  static constexpr uint32_t kKTile = AD * BKEY * 64;       // one plane of a K tile (64 keys x Dp)
+  static constexpr uint32_t kVTile = 2 * AD * 32 * 64;     // one plane of a V^T tile (Dp rows x 64 keys)
+  static constexpr uint32_t k_ring = 0;                    // 2 slots x (hi, lo); pass 1: 4 hi-only slots
+  static constexpr uint32_t v_ring = 4 * kKTile;           // 2 slots x (hi, lo)
+  static constexpr uint32_t bars = v_ring + 4 * kVTile;
+  static constexpr uint32_t xch = bars + 256;              // cross-half exchange of row max / row sum
+  static constexpr uint32_t total = xch + 2 * BQ * 4 + 1024;
+};
+
+template <int AD>
+__global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFwdArgs a) {
+  constexpr int Dp = AD * 32, HC = AD * 16;
+  using L = FSmem<AD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint64_t* q_ready = bars + 0;   // Q rows stored to TMEM by the 256 softmax threads
+  uint64_t* p_full = bars + 1;
+  uint64_t* p_empty = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint64_t* k_full = bars + 4;    // [2]
+  uint64_t* k_empty = bars + 6;   // [2]
+  uint64_t* v_full = bars + 8;    // [2]
+  uint64_t* v_empty = bars + 10;  // [2]
+  uint64_t* s_full = bars + 12;   // [2]
+  uint64_t* s_empty = bars + 14;  // [2]
+  uint64_t* r_full = bars + 16;   // [4] pass-1 ring
+  uint64_t* r_empty = bars + 20;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* xch = reinterpret_cast<float*>(smem + L::xch);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, bh = blockIdx.y;
+  const int q0 = qt * BQ;
+  const int at = a.Tp / 32;
+  const int nk = (a.T + BKEY - 1) / BKEY;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_ready, kSmThreads);
+    mbar_init(p_full, kSmThreads);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], kSmThreads);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&r_full[i], 1);
+      mbar_init(&r_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t cQ_hi = 0, cQ_lo = HC, cS = 2 * HC, cP_hi = cS + 2 * BKEY, cP_lo = cP_hi + BKEY / 2,
+                     cO = cP_lo + BKEY / 2;
+  static_assert(cO + Dp <= 512, "TMEM budget exceeded");
+
+  if (warp == kLoadWarpK) {
+    // ============================== K PRODUCER ==============================
+    if (lane == 0) {
+      auto load_k = [&](uint32_t dst_hi, uint32_t dst_lo, int j, bool lo, uint64_t* bar) {
+        mbar_expect_tx(bar, lo ? 2 * L::kKTile : L::kKTile);
+#pragma unroll
+        for (int at_i = 0; at_i < AD; ++at_i) {
+          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + j * BKEY) * 64;
+          bulk_g2s(smem + dst_hi + at_i * BKEY * 64, a.k_hi + src, BKEY * 64, bar);
+          if (lo) bulk_g2s(smem + dst_lo + at_i * BKEY * 64, a.k_lo + src, BKEY * 64, bar);
+        }
+      };
+      // pass 1: hi planes only, 4-slot ring over the K region
+      for (int j = 0; j < nk; ++j) {
+        const int slot = j & 3;
+        mbar_wait(&r_empty[slot], ((j >> 2) & 1) ^ 1);
+        load_k(L::k_ring + slot * L::kKTile, 0, j, false, &r_full[slot]);
+      }
+      for (int slot = 0; slot < 4 && slot < nk; ++slot) {  // all pass-1 MMAs have released their slots
+        const int last = ((nk - 1 - slot) / 4) * 4 + slot;
+        mbar_wait(&r_empty[slot], (last >> 2) & 1);
+      }
+      // pass 2: 2 slots of (hi, lo)
+      for (int j = 0; j < nk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+        load_k(L::k_ring + s * 2 * L::kKTile, L::k_ring + s * 2 * L::kKTile + L::kKTile, j, a.x3 != 0, &k_full[s]);
+      }
+    }
+  } else if (warp == kLoadWarpV) {
+    // ============================== V^T PRODUCER ==============================
+    if (lane == 0) {
+      for (int j = 0; j < nk; ++j) {
+        const int s = j & 1;
+        mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[s], a.x3 ? 2 * L::kVTile : L::kVTile);
+        uint8_t* base = smem + L::v_ring + s * 2 * L::kVTile;
+#pragma unroll
+        for (int ka = 0; ka < 2; ++ka) {
+          const int64_t src = (((int64_t)bh * at + (j * 2 + ka)) * Dp) * 64;
+          bulk_g2s(base + ka * Dp * 64, a.vt_hi + src, Dp * 64, &v_full[s]);
+          if (a.x3) bulk_g2s(base + L::kVTile + ka * Dp * 64, a.vt_lo + src, Dp * 64, &v_full[s]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ============================== MMA ISSUER ==============================
+    const bool leader = elect_one();
+    const uint32_t idesc_s = idesc_bf16(BQ, BKEY, 0, 0);
+    const uint32_t idesc_o = idesc_bf16(BQ, Dp, 0, 0);
+    const uint32_t kr0 = smem_u32(smem + L::k_ring) >> 4, vr0 = smem_u32(smem + L::v_ring) >> 4;
+    const uint32_t tQ_hi = tmem_base + cQ_hi, tQ_lo = tmem_base + cQ_lo;
+    const uint32_t tP_hi = tmem_base + cP_hi, tP_lo = tmem_base + cP_lo, tO = tmem_base + cO;
+    uint32_t its = 0;
+
+    auto issue_s = [&](uint64_t kh, uint64_t kl, bool full_precision, uint64_t* k_ready, uint32_t k_parity,
+                       uint64_t* k_done) {
+      const uint32_t buf = its & 1;
+      mbar_wait(k_ready, k_parity);
+      mbar_wait(&s_empty[buf], ((its >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + cS + buf * BKEY;
+#pragma unroll
+      for (int ks = 0; ks < 2 * AD; ++ks) {
+        constexpr uint32_t kKA = BKEY * 64 / 16;
+        const uint32_t ko = (ks >> 1) * kKA + (ks & 1) * 2;
+        if (leader) {
+          umma_bf16_ts(d, tQ_hi + ks * 8, kh + ko, idesc_s, ks > 0 ? 1u : 0u);
+          if (full_precision) {
+            umma_bf16_ts(d, tQ_lo + ks * 8, kh + ko, idesc_s, 1u);
+            umma_bf16_ts(d, tQ_hi + ks * 8, kl + ko, idesc_s, 1u);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(k_done);
+        umma_commit(&s_full[buf]);
+      }
+      __syncwarp();
+      ++its;
+    };
+    auto issue_s2 = [&](int j) {
+      const int s = j & 1;
+      const uint64_t kh = kDescK64 | (uint64_t)(kr0 + s * 2 * (L::kKTile >> 4));
+      issue_s(kh, kh + (L::kKTile >> 4), a.x3 != 0, &k_full[s], (j >> 1) & 1, &k_empty[s]);
+    };
+    auto issue_pv = [&](int j, bool last) {
+      const int s = j & 1;
+      mbar_wait(&v_full[s], (j >> 1) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      const uint64_t vh = kDescK64 | (uint64_t)(vr0 + s * 2 * (L::kVTile >> 4)), vl = vh + (L::kVTile >> 4);
+#pragma unroll
+      for (int ks = 0; ks < BKEY / 16; ++ks) {
+        constexpr uint32_t kVA = Dp * 64 / 16;
+        const uint32_t vo = (ks >> 1) * kVA + (ks & 1) * 2;
+        if (leader) {
+          umma_bf16_ts(tO, tP_hi + ks * 8, vh + vo, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          if (a.x3) {
+            umma_bf16_ts(tO, tP_lo + ks * 8, vh + vo, idesc_o, 1u);
+            umma_bf16_ts(tO, tP_hi + ks * 8, vl + vo, idesc_o, 1u);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(p_empty);
+        umma_commit(&v_empty[s]);
+        if (last) umma_commit(o_full);
+      }
+      __syncwarp();
+    };
+
+    mbar_wait(q_ready, 0);
+    tc_fence_after();
+    for (int j = 0; j < nk; ++j) {  // pass 1: reference row max from the hi planes
+      const int slot = j & 3;
+      issue_s(kDescK64 | (uint64_t)(kr0 + slot * (L::kKTile >> 4)), 0, false, &r_full[slot], (j >> 2) & 1, &r_empty[slot]);
+    }
+    issue_s2(0);
+    for (int j = 0; j + 1 < nk; ++j) {
+      issue_s2(j + 1);  // S(j+1) overlaps softmax(j)
+      issue_pv(j, false);
+    }
+    issue_pv(nk - 1, true);
+  } else {
+    // ============================== SOFTMAX / EPILOGUE ==============================
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int qi = q0 + row;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int b = bh / a.H, h = bh % a.H;
+    // ---- Q rows -> TMEM (half 0: hi plane, half 1: lo plane)
+    {
+      const int sw = (qi >> 1) & 3;
+      const uint8_t* plane = half == 0 ? a.q_hi : a.q_lo;
+      if (half == 0 || a.x3) {
+#pragma unroll
+        for (int at_i = 0; at_i < AD; ++at_i) {
+          const uint4* src = reinterpret_cast<const uint4*>(plane + (((int64_t)bh * AD + at_i) * a.Tp + qi) * 64);
+          uint4 ph[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 v = ph[c ^ sw];
+            tmem_st4(tmem_base + lane_off + (half == 0 ? cQ_hi : cQ_lo) + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(q_ready);
+    }
+    uint32_t its = 0;
+    float m = -INFINITY;
+    // ---- pass 1: row max over this warp's 32 of the 64 key columns
+    for (int j = 0; j < nk; ++j, ++its) {
+      const uint32_t buf = its & 1;
+      mbar_wait(&s_full[buf], (its >> 1) & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + lane_off + cS + buf * BKEY + half * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[buf]);
+      const int jb = j * BKEY + half * 32;
+      if (jb + 32 <= a.T) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (jb + c < a.T) m = fmaxf(m, __uint_as_float(v[c]));
+      }
+    }
+    xch[half * BQ + row] = m;
+    named_bar_sync(1, kSmThreads);
+    m = fmaxf(xch[row], xch[BQ + row]);
+    named_bar_sync(1, kSmThreads);
+    const float m2 = m * a.scale_log2;
+    float l = 0.f;
+    const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
+    const int Tc = (a.T + 3) & ~3;
+    const uint64_t drop_row = ((uint64_t)bh * a.T + (uint64_t)min(qi, a.T - 1)) * (uint64_t)Tc;
+    // ---- pass 2
+    for (int j = 0; j < nk; ++j, ++its) {
+      const uint32_t buf = its & 1;
+      mbar_wait(&s_full[buf], (its >> 1) & 1);
+      tc_fence_after();
+      float p[32];
+      {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + cS + buf * BKEY + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) p[c] = __uint_as_float(v[c]);
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[buf]);
+      const int jb = j * BKEY + half * 32;
+      if (jb + 32 <= a.T) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          p[c] = fast_exp2(fmaf(p[c], a.scale_log2, -m2));
+          l += p[c];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          p[c] = (jb + c < a.T) ? fast_exp2(fmaf(p[c], a.scale_log2, -m2)) : 0.f;
+          l += p[c];
+        }
+      }
+      if (a.drop.p > 0.f) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float mk[4];
+          dropout_mult4(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 4 * g)) >> 2, a.drop.p, inv_keep, mk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) p[4 * g + e] *= mk[e];
+        }
+      }
+      mbar_wait(p_empty, (j & 1) ^ 1);  // P V of the previous tile has consumed the operand
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = p[ch * 8 + e];
+        uint32_t hw[4], lw[4];
+        split8_words(x, hw, lw);
+        const uint32_t col = (half * 32 + ch * 8) / 2;
+        tmem_st4(tmem_base + lane_off + cP_hi + col, hw[0], hw[1], hw[2], hw[3]);
+        if (a.x3) tmem_st4(tmem_base + lane_off + cP_lo + col, lw[0], lw[1], lw[2], lw[3]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    xch[half * BQ + row] = l;
+    named_bar_sync(1, kSmThreads);
+    l = xch[row] + xch[BQ + row];
+    // ---- epilogue
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    float* orow = a.O + ((int64_t)b * a.T + qi) * a.o_ld + h * a.E;
+#pragma unroll
+    for (int cc = 0; cc < AD; ++cc) {
+      const int c0 = half * (AD * 16) + cc * 16;
+      uint32_t v[16];
+      tmem_ld16(tmem_base + lane_off + cO + c0, v);
+      tmem_ld_wait();
+      if (qi < a.T) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c0 + c < a.E) orow[c0 + c] = __uint_as_float(v[c]) * inv_l;
+      }
+    }
+    // padded query rows get +inf so that the backward's exp2(S*c - lse) vanishes there without bounds checks
+    if (half == 0 && a.lse) a.lse[(int64_t)bh * a.Tp + qi] = qi < a.T ? m2 + log2f(l) : INFINITY;
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+template <int AD>
+int launch_fwd2(const AttnFwdArgs& a, cudaStream_t st) {
+  using L = FSmem<AD>;
+  static_assert(L::total <= 232448, "shared memory budget exceeded");
+  V1T_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+  dim3 grid(cdiv(a.T, BQ), a.B * a.H);
+  attn_fwd2_kernel<AD><<<grid, kThreadsAttn, L::total, st>>>(a);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+}  // namespace
+
+int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st) {
+  V1T_CHECK_ARG(a.Dp % 32 == 0 && a.Dp >= 32 && a.Dp <= 160 && a.Tp % 128 == 0 && a.Tp >= a.T && a.E <= a.Dp,
+                "attn_fwd2_tc: unsupported dims (Dp %d, Tp %d)", a.Dp, a.Tp);
+  V1T_CHECK_ARG(a.B * a.H <= 65535, "attn_fwd2_tc: too many (batch, head) pairs");
+  switch (a.Dp / 32) {
+    case 1: return launch_fwd2<1>(a, st);
+    case 2: return launch_fwd2<2>(a, st);
+    case 3: return launch_fwd2<3>(a, st);
+    case 4: return launch_fwd2<4>(a, st);
+    default: return launch_fwd2<5>(a, st);
+  }
+}
+
+}  // namespace v1t

@@ -780,6 +780,11 @@ AttnPlanes carve_attn_planes(void* base, int B, int H, int Tp, int Dp, bool with
 }  // namespace v1t
 
 namespace v1t {
+int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
+  const char* gen = getenv("V1T_ATTN_FWD");  // "1" selects the first-generation (smem-resident) kernel
+  if (gen && atoi(gen) == 1) return attn_fwd_tc(a, st);
+  return attn_fwd2_tc(a, st);
+}
 int attn_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t st) {
   const char* gen = getenv("V1T_ATTN_BWD");  // "1" selects the first-generation (smem-resident) kernels
   if (gen && atoi(gen) == 1) return attn_bwd_tc(a, st);
@@ -813,7 +818,7 @@ extern "C" int v1t_attn_forward(const float* qkv, int B, int H, int T, int E, in
   a.scale_log2 = (1.0f / sqrtf((float)E)) * 1.4426950408889634f;
   a.x3 = x3;
   a.drop = DropSpec{seed, site, p_drop};
-  return attn_fwd_tc(a, st);
+  return attn_fwd_dispatch(a, st);
 }
 
 extern "C" int v1t_attn_backward(const float* qkv, const float* out, const float* d_out, const float* lse, int B, int H,

@@ -261,7 +261,7 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       fa.scale_log2 = (1.0f / sqrtf((float)d.E)) * 1.4426950408889634f;
       fa.x3 = x3;
       fa.drop = site_drop(*shape, i, kSiteAttn);
-      V1T_TRY(attn_fwd_tc(fa, st));
+      V1T_TRY(attn_fwd_dispatch(fa, st));
     }
     for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);

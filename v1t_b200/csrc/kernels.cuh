@@ -71,7 +71,9 @@ struct AttnFwdArgs {
   int x3;
   DropSpec drop;
 };
-int attn_fwd_tc(const AttnFwdArgs& a, cudaStream_t st);
+int attn_fwd_tc(const AttnFwdArgs& a, cudaStream_t st);   // generation 1: Q and P in shared memory
+int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // generation 2: Q and P in tensor memory
+int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st);
 struct AttnBwdArgs {
   const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo, *do_hi, *do_lo;  // RM planes (rows = tokens, K = head dim)
   const float* lse;    // [B*H, Tp] base-2 log-sum-exp saved by the forward

@@ -18,6 +18,7 @@ The sub-modules (Attention, MLP, ...) are parameter containers with the referenc
 from __future__ import annotations
 
 import math
+import os
 import typing as t
 
 import numpy as np
@@ -216,7 +217,7 @@ class ViTCore(Core):
         self.p_dropout, self.t_dropout = float(args.p_dropout), float(args.t_dropout)
         if args.num_blocks > _lib.V1T_MAX_BLOCKS:
             raise NotImplementedError(f"v1t_b200: at most {_lib.V1T_MAX_BLOCKS} blocks")
-        impl = getattr(args, "b200_impl", "fp32")
+        impl = getattr(args, "b200_impl", None) or os.environ.get("V1T_IMPL", "bf16x3")
         c, ih, iw = input_shape
         bdim = {0: 0, 1: 0, 2: 3, 3: 5, 4: 5}[self.behavior_mode]
         self.spec = VF.CoreSpec(in_ch=c, in_h=ih, in_w=iw, patch=args.patch_size, stride=args.patch_stride,
