@@ -210,8 +210,8 @@ int v1t_ts_selftest(const float* A, const float* B, float* C, int N, int K, void
 
 /* the inverted-dropout multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` =
  * block*8 + {0 tokens, 1 attention probs, 2 proj out, 3 MLP hidden, 4 MLP out}; element index = row-major
- * index in the logical tensor ([B,T,E], [B,T,M]); attention probabilities use [B,H,T,Tc] with Tc = T rounded up
- * to 4 (so one Philox call covers 4 adjacent keys).  Lets tests replay the exact masks. */
+ * index in the logical tensor ([B,T,E], [B,T,M], [B,H,T,T]) with the LAST dimension's stride rounded up to 4
+ * (so one Philox call covers 4 adjacent columns).  Lets tests replay the exact masks. */
 int v1t_dropout_mask(float* out, int64_t n, uint64_t seed, uint32_t site, float p, void* stream);
 
 #ifdef __cplusplus

@@ -148,11 +148,13 @@ def test_dropout_masks_replay_exactly_against_oracle():
     d = g.mice["A"]
     cfg = g.core_config()
     B, T, E, H, M = d["images"].shape[0], cfg.num_tokens, cfg.emb_dim, cfg.num_heads, cfg.mlp_dim
-    mk = lambda site, shape, p: VF.dropout_mask(int(np.prod(shape)), seed, site, p, DEV).cpu().numpy().reshape(shape).astype(np.float64)
+    def mk(site, shape, p):  # rows of every mask are indexed with a 4-aligned stride (one Philox call = 4 columns)
+        padded = tuple(shape[:-1]) + ((shape[-1] + 3) // 4 * 4,)
+        full = VF.dropout_mask(int(np.prod(padded)), seed, site, p, DEV).cpu().numpy().reshape(padded)
+        return full[..., :shape[-1]].astype(np.float64)
     masks = {"tokens": mk(0, (B, T, E), p_tok)}
     for i in range(cfg.num_blocks):
-        Tc = (T + 3) // 4 * 4  # attention-mask rows are indexed with a 4-aligned stride
-        masks[(i, "attn")] = mk(i * 8 + 1, (B, H, T, Tc), p_blk)[..., :T]
+        masks[(i, "attn")] = mk(i * 8 + 1, (B, H, T, T), p_blk)
         masks[(i, "proj")] = mk(i * 8 + 2, (B, T, E), p_blk)
         masks[(i, "mlp1")] = mk(i * 8 + 3, (B, T, M), p_blk)
         masks[(i, "mlp2")] = mk(i * 8 + 4, (B, T, E), p_blk)

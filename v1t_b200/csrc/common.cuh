@@ -98,6 +98,11 @@ __device__ __forceinline__ float dropout_mult(uint64_t seed, uint32_t site, uint
 }
 
 
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_df(float u) {
+  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * expf(-0.5f * u * u);
+}
+
 // 4 multipliers of the aligned group `group` (elements 4*group .. 4*group+3) with ONE Philox call
 __device__ __forceinline__ void dropout_mult4(uint64_t seed, uint32_t site, uint64_t group, float p, float inv_keep,
                                               float (&m)[4]) {

@@ -71,7 +71,7 @@ struct Carver {
 };
 
 struct BlockSaved {
-  float *x1, *st1, *qkv, *o, *x2, *st2, *u, *bhid, *blat, *lse;
+  float *x1, *st1, *qkv, *o, *x2, *st2, *u, *g, *bhid, *blat, *lse;
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -85,6 +85,7 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
   b.x2 = c.take(d.R * d.Ep);
   b.st2 = c.take(d.R * 2);
   b.u = c.take(d.R * d.Mp);
+  b.g = c.take(d.R * d.Mp);  // gelu(u) * dropout, kept for the MLP weight gradient
   b.bhid = c.take((int64_t)d.B * d.hid + 1);
   b.blat = c.take((int64_t)d.B * d.E);
   b.lse = c.take(d.fused ? (int64_t)d.B * d.heads * d.Tq : 1);
@@ -287,13 +288,18 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     {
       v1t_gemm_desc g = gd((int)d.R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = d.Mp;
-      V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st));
+      if (gemm_uses_tc(d.impl, g)) {  // u and gelu(u)*dropout from one epilogue
+        const EpiOp act{kEpiGeluOut, S.g, nullptr, d.Mp, site_drop(*shape, i, kSiteMlp1)};
+        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st, no_drop(), act));
+      } else {
+        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st));
+        V1T_TRY(gelu_forward(S.u, S.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));
+      }
     }
-    V1T_TRY(gelu_forward(S.u, sc.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));
     {
       v1t_gemm_desc g = gd((int)d.R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = 1; g.b_n = d.M; g.c_m = d.Ep; g.r_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, sc.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2)));
+      V1T_TRY(gemm_any(d.impl, g, S.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2)));
     }
   }
   return V1T_OK;
@@ -323,20 +329,23 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteMlp2), st));
       dm = sc.dh;
     }
-    V1T_TRY(gelu_forward(S.u, sc.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // recompute g
     if (GW.w2) {  // dW2[e,m] = sum_r dm[r,e] g[r,m]
       v1t_gemm_desc g = gd(d.E, d.M, R);
       g.a_m = 1; g.a_k = d.Ep; g.b_k = d.Mp; g.b_n = 1; g.c_m = d.M;
-      V1T_TRY(gemm_any_splitk(d.impl, g, dm, sc.g, GW.w2, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, dm, S.g, GW.w2, sc.partials, kPartialBytes, st));
     }
     if (GW.b2) V1T_TRY(colsum(dm, GW.b2, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
     {  // dg[r,m] = sum_e dm[r,e] W2[e,m]   -> sc.g (g no longer needed)
       v1t_gemm_desc g = gd(R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.M; g.b_n = 1; g.c_m = d.Mp;
-      // dW2 above reads sc.g: stream order keeps it safe (same stream)
-      V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st));
+      if (gemm_uses_tc(d.impl, g)) {  // du = (dm W2) * gelu'(u) * dropout in the epilogue
+        const EpiOp act{kEpiGeluGrad, nullptr, S.u, d.Mp, site_drop(*shape, i, kSiteMlp1)};
+        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st, no_drop(), act));
+      } else {
+        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st));
+        V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
+      }
     }
-    V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
     V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
     if (GW.w1) {  // dW1[m,e] = sum_r du[r,m] h2[r,e]
       v1t_gemm_desc g = gd(d.M, d.E, R);

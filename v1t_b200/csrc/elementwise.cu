@@ -64,7 +64,7 @@ __global__ void dropout_rows_kernel(const float* __restrict__ src, float* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols;
     const int c = (int)(i % cols);
-    dst[r * ld + c] = src[r * ld + c] * dropout_mult(dr.seed, dr.site, i, dr.p, inv_keep);
+    dst[r * ld + c] = src[r * ld + c] * dropout_mult(dr.seed, dr.site, (uint64_t)r * ((cols + 3) & ~3) + c, dr.p, inv_keep);
   }
 }
 
@@ -296,10 +296,6 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(float* __restrict
 }
 
 // ---------------------------------------------------------------- GELU ---------------------------------
-__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_df(float u) {
-  return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * expf(-0.5f * u * u);
-}
 
 __global__ void gelu_forward_kernel(const float* __restrict__ u, float* __restrict__ g, int64_t rows, int cols,
                                     int64_t ld, DropSpec dr) {
@@ -311,7 +307,7 @@ __global__ void gelu_forward_kernel(const float* __restrict__ u, float* __restri
     float v = 0.f;
     if (c < cols) {
       v = gelu_f(u[i]);
-      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * cols + c, dr.p, inv_keep);
+      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * ((cols + 3) & ~3) + c, dr.p, inv_keep);
     }
     g[i] = v;
   }
@@ -327,7 +323,7 @@ __global__ void gelu_backward_kernel(float* __restrict__ dg, const float* __rest
     float v = 0.f;
     if (c < cols) {
       v = dg[i] * gelu_df(u[i]);
-      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * cols + c, dr.p, inv_keep);
+      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * ((cols + 3) & ~3) + c, dr.p, inv_keep);
     }
     dg[i] = v;
   }

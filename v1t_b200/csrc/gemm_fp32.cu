@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) sgemm_kernel(GemmArgs g) {
       float v = g.d.alpha * acc[i][j];
       if (g.bias) v += __ldg(g.bias + n);
       if (g.drop.p > 0.f)
-        v *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * g.d.n + n, g.drop.p, 1.f / (1.f - g.drop.p));
+        v *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * ((g.d.n + 3) & ~3) + n, g.drop.p, 1.f / (1.f - g.drop.p));
       if (R) v += __ldg(R + (int64_t)m * g.d.r_m + n);
       float* c = C + (int64_t)m * g.d.c_m + n;
       if (g.d.accumulate) v += *c;
@@ -175,6 +175,7 @@ int gemm_fp32(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   g.d = d;
   g.A = A; g.B = B; g.C = C; g.bias = bias; g.R = R;
   g.drop = drop;
+  g.epi = no_epi();
   g.splits = 1; g.k_chunk = d.k; g.c_split = 0;
   dim3 grid(cdiv(d.n, BN), cdiv(d.m, BM), d.batch1 * d.batch2);
   V1T_CHECK_ARG(grid.z <= 65535 && grid.y <= 65535, "gemm: grid too large");
@@ -205,6 +206,7 @@ int gemm_fp32_splitk(const v1t_gemm_desc& d, const float* A, const float* B, flo
   g.d.c_m = d.n;
   g.A = A; g.B = B; g.C = partials; g.bias = nullptr; g.R = nullptr;
   g.drop = no_drop();
+  g.epi = no_epi();
   g.splits = splits; g.k_chunk = k_chunk; g.c_split = (int64_t)d.m * d.n;
   dim3 grid(cdiv(d.n, BN), cdiv(d.m, BM), splits);
   sgemm_kernel<<<grid, kThreads, 0, st>>>(g);

@@ -323,7 +323,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     uint32_t tl_i = 0;
     const int quarter = warp & 3, half = warp >> 2;
     const float inv_keep = g.drop.p > 0.f ? 1.f / (1.f - g.drop.p) : 1.f;
-    const bool plain = !(g.drop.p > 0.f) && !g.d.accumulate;
+    const bool plain = !g.d.accumulate;
+    const int64_t drop_ld = (g.d.n + 3) & ~3;
+    const float inv_keep2 = g.epi.drop.p > 0.f ? 1.f / (1.f - g.epi.drop.p) : 1.f;
     const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
       const Tile tl = decode_tile(a, t);
@@ -360,13 +362,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             const int mm = tl.m0 + quarter * 32 + r;
             const float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
             if (mm < g.d.m) {
-              float4 o = make_float4(fmaf(g.d.alpha, x.x, bv.x), fmaf(g.d.alpha, x.y, bv.y), fmaf(g.d.alpha, x.z, bv.z),
-                                     fmaf(g.d.alpha, x.w, bv.w));
+              float o[4] = {fmaf(g.d.alpha, x.x, bv.x), fmaf(g.d.alpha, x.y, bv.y), fmaf(g.d.alpha, x.z, bv.z),
+                            fmaf(g.d.alpha, x.w, bv.w)};
+              const int n4 = nb + 4 * cq;
+              if (g.drop.p > 0.f) {
+                float mk[4];
+                dropout_mult4(g.drop.seed, g.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.drop.p, inv_keep, mk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] *= mk[e];
+              }
+              float mk2[4] = {1.f, 1.f, 1.f, 1.f};
+              if (g.epi.kind != kEpiNone && g.epi.drop.p > 0.f)
+                dropout_mult4(g.epi.drop.seed, g.epi.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.epi.drop.p, inv_keep2, mk2);
+              if (g.epi.kind == kEpiGeluGrad) {
+                const float4 uv = __ldg(reinterpret_cast<const float4*>(g.epi.u + (int64_t)mm * g.epi.ld + n4));
+                o[0] *= gelu_df(uv.x) * mk2[0]; o[1] *= gelu_df(uv.y) * mk2[1];
+                o[2] *= gelu_df(uv.z) * mk2[2]; o[3] *= gelu_df(uv.w) * mk2[3];
+              }
               if (g.R) {
                 const float4 rv = __ldg(reinterpret_cast<const float4*>(g.R + tl.r_off + (int64_t)mm * g.d.r_m + nb) + cq);
-                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
               }
-              *(reinterpret_cast<float4*>(g.C + tl.c_off + (int64_t)mm * g.d.c_m + nb) + cq) = o;
+              *(reinterpret_cast<float4*>(g.C + tl.c_off + (int64_t)mm * g.d.c_m + nb) + cq) = make_float4(o[0], o[1], o[2], o[3]);
+              if (g.epi.kind == kEpiGeluOut)
+                *reinterpret_cast<float4*>(g.epi.aux + (int64_t)mm * g.epi.ld + n4) =
+                    make_float4(gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]);
             }
           }
           __syncwarp();
@@ -378,9 +398,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
               float x = g.d.alpha * __uint_as_float(v[j]);
               if (g.bias) x += __ldg(g.bias + n);
               if (g.drop.p > 0.f)
-                x *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * g.d.n + n, g.drop.p, inv_keep);
+                x *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * drop_ld + n, g.drop.p, inv_keep);
+              float m2 = 1.f;
+              if (g.epi.kind != kEpiNone && g.epi.drop.p > 0.f)
+                m2 = dropout_mult(g.epi.drop.seed, g.epi.drop.site, (uint64_t)m * drop_ld + n, g.epi.drop.p, inv_keep2);
+              if (g.epi.kind == kEpiGeluGrad) x *= gelu_df(__ldg(g.epi.u + (int64_t)m * g.epi.ld + n)) * m2;
               if (rrow) x += __ldg(rrow + n);
               if (g.d.accumulate) x += crow[n];
+              if (g.epi.kind == kEpiGeluOut) g.epi.aux[(int64_t)m * g.epi.ld + n] = gelu_f(x) * m2;
               crow[n] = x;
             }
           }
@@ -403,7 +428,7 @@ int g_use_mn_major = 1;  // stage M/N-contiguous operands un-transposed (vector 
 namespace {
 
 int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
-              DropSpec drop, int x3, int splits, int k_chunk, int64_t c_split, cudaStream_t st) {
+              DropSpec drop, int x3, int splits, int k_chunk, int64_t c_split, cudaStream_t st, EpiOp epi = no_epi()) {
   static bool attr_set = false;
   if (!attr_set) {
     V1T_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -413,6 +438,7 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.g.d = d;
   a.g.A = A; a.g.B = B; a.g.C = C; a.g.bias = bias; a.g.R = R;
   a.g.drop = drop;
+  a.g.epi = epi;
   a.g.splits = splits; a.g.k_chunk = k_chunk; a.g.c_split = c_split;
   const int nt = cdiv(d.n, BN_MAX);
   a.bn = (int)round_up(cdiv(d.n, nt), 16);
@@ -441,11 +467,15 @@ bool tc_supported(const v1t_gemm_desc& d) {
 }  // namespace
 
 int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
-            cudaStream_t st, DropSpec drop, int x3) {
+            cudaStream_t st, DropSpec drop, int x3, EpiOp epi) {
   V1T_CHECK_ARG(d.m >= 0 && d.n >= 0 && d.k >= 0 && d.batch1 >= 1 && d.batch2 >= 1, "gemm: bad sizes");
   if (d.m == 0 || d.n == 0) return V1T_OK;
   if (!tc_supported(d)) return gemm_fp32(d, A, B, C, bias, R, st, drop);
-  return launch_tc(d, A, B, C, bias, R, drop, x3, 1, (int)round_up(d.k, BK), 0, st);
+  if (epi.kind != kEpiNone) {
+    V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && epi.ld % 4 == 0 && aligned16(epi.kind == kEpiGeluOut ? (const void*)epi.aux : (const void*)epi.u),
+                  "gemm_tc: fused activation needs an unbatched problem and 16-byte aligned rows");
+  }
+  return launch_tc(d, A, B, C, bias, R, drop, x3, 1, (int)round_up(d.k, BK), 0, st, epi);
 }
 
 int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,

@@ -11,9 +11,21 @@ struct DropSpec {  // inverted dropout; p == 0 -> disabled
 };
 static inline DropSpec no_drop() { return DropSpec{0, 0, 0.f}; }
 
+// optional fused element-wise stage of the tensor-core GEMM epilogue (MLP of the ViT block, vit.py:144-148)
+enum { kEpiNone = 0, kEpiGeluOut = 1, kEpiGeluGrad = 2 };
+struct EpiOp {
+  int kind;           // kEpiGeluOut: aux = gelu(C) * dropout ;  kEpiGeluGrad: C *= gelu'(u) * dropout
+  float* aux;         // [m, ld] second output (kEpiGeluOut)
+  const float* u;     // [m, ld] pre-activation (kEpiGeluGrad)
+  int64_t ld;
+  DropSpec drop;      // dropout of the activation (element index m * roundup(n,4) + n)
+};
+static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}}; }
+
 struct GemmArgs {
   v1t_gemm_desc d;
-  DropSpec drop;    // applied to alpha*acc + bias (element index m*n_cols + n), before the residual add
+  DropSpec drop;    // applied to alpha*acc + bias (element index m*roundup(n_cols,4) + n), before the residual add
+  EpiOp epi;
   const float* A;
   const float* B;
   float* C;
@@ -37,16 +49,20 @@ int reduce_partials_ld(const float* partials, float* out, int parts, int64_t row
 
 // gemm_tc.cu (tcgen05): same contract; x3 = 1 -> bf16 hi/lo split (3 MMAs), 0 -> plain bf16 operands
 int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
-            cudaStream_t st, DropSpec drop, int x3);
+            cudaStream_t st, DropSpec drop, int x3, EpiOp epi = no_epi());
 int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
                    size_t partial_bytes, cudaStream_t st, int x3);
 
 // impl dispatch used by the orchestrator
-inline int gemm_any(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias,
-                    const float* R, cudaStream_t st, DropSpec drop = no_drop()) {
+inline bool gemm_uses_tc(int impl, const v1t_gemm_desc& d) {
   const int64_t work = (int64_t)d.m * d.n * (d.k > 0 ? d.k : 1) * d.batch1 * d.batch2;
-  if (impl == V1T_IMPL_FP32 || work < (1ll << 22)) return gemm_fp32(d, A, B, C, bias, R, st, drop);
-  return gemm_tc(d, A, B, C, bias, R, st, drop, impl == V1T_IMPL_BF16X3);
+  return impl != V1T_IMPL_FP32 && work >= (1ll << 22) && d.k > 0 && (d.a_k == 1 || d.a_m == 1) &&
+         (d.b_k == 1 || d.b_n == 1);
+}
+inline int gemm_any(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias,
+                    const float* R, cudaStream_t st, DropSpec drop = no_drop(), EpiOp epi = no_epi()) {
+  if (!gemm_uses_tc(impl, d)) return gemm_fp32(d, A, B, C, bias, R, st, drop);  // caller applies `epi` separately
+  return gemm_tc(d, A, B, C, bias, R, st, drop, impl == V1T_IMPL_BF16X3, epi);
 }
 inline int gemm_any_splitk(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C,
                            float* partials, size_t partial_bytes, cudaStream_t st) {
