@@ -72,6 +72,7 @@ struct Carver {
 
 struct BlockSaved {
   float *x1, *st1, *qkv, *o, *x2, *st2, *u, *g, *bhid, *blat, *lse;
+  uint8_t *qp[2], *kp[2], *vp[2];  // bf16 hi/lo operand planes of Q, K, V (fused attention), reused by the backward
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -89,6 +90,12 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
   b.bhid = c.take((int64_t)d.B * d.hid + 1);
   b.blat = c.take((int64_t)d.B * d.E);
   b.lse = c.take(d.fused ? (int64_t)d.B * d.heads * d.Tq : 1);
+  const int64_t pf = d.fused ? (int64_t)(plane_bytes(d.B, d.heads, d.Tq, d.Ep) / sizeof(float)) : 1;
+  for (int i = 0; i < 2; ++i) {
+    b.qp[i] = (uint8_t*)c.take(pf);
+    b.kp[i] = (uint8_t*)c.take(pf);
+    b.vp[i] = (uint8_t*)c.take(pf);
+  }
 }
 Saved carve_saved(const Dims& d, void* base) {
   Carver c(base);
@@ -249,14 +256,15 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);
       const int x3 = d.impl == V1T_IMPL_BF16X3;
       const AttnPlanes& pl = sc.planes;
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.q[0], x3 ? pl.q[1] : nullptr,
+      // Q, K, V planes go to the per-block saved area (the backward reuses them); V^T is transient
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.qp[0], x3 ? S.qp[1] : nullptr,
                           nullptr, nullptr, st));
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.k[0], x3 ? pl.k[1] : nullptr,
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.kp[0], x3 ? S.kp[1] : nullptr,
                           nullptr, nullptr, st));
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, nullptr, nullptr, pl.vt[0],
-                          x3 ? pl.vt[1] : nullptr, st));
+      V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.vp[0], x3 ? S.vp[1] : nullptr,
+                          pl.vt[0], x3 ? pl.vt[1] : nullptr, st));
       AttnFwdArgs fa{};
-      fa.q_hi = pl.q[0]; fa.q_lo = pl.q[1]; fa.k_hi = pl.k[0]; fa.k_lo = pl.k[1]; fa.vt_hi = pl.vt[0]; fa.vt_lo = pl.vt[1];
+      fa.q_hi = S.qp[0]; fa.q_lo = S.qp[1]; fa.k_hi = S.kp[0]; fa.k_lo = S.kp[1]; fa.vt_hi = pl.vt[0]; fa.vt_lo = pl.vt[1];
       fa.O = S.o; fa.o_ld = d.I; fa.lse = S.lse;
       fa.B = d.B; fa.H = d.heads; fa.T = d.T; fa.Tp = d.Tq; fa.E = d.E; fa.Dp = d.Ep;
       fa.scale_log2 = (1.0f / sqrtf((float)d.E)) * 1.4426950408889634f;
@@ -383,17 +391,11 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       ProfScope prof(V1T_PHASE_ATTN_BWD, st);
       const int x3 = d.impl == V1T_IMPL_BF16X3;
       const AttnPlanes& pl = sc.planes;
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.q[0], x3 ? pl.q[1] : nullptr,
-                          nullptr, nullptr, st));
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.k[0], x3 ? pl.k[1] : nullptr,
-                          nullptr, nullptr, st));
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.v[0], x3 ? pl.v[1] : nullptr,
-                          nullptr, nullptr, st));
       V1T_TRY(make_planes(sc.dO, d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.dO[0], x3 ? pl.dO[1] : nullptr,
                           nullptr, nullptr, st));
       V1T_TRY(attn_delta(S.o, sc.dO, pl.delta, d.B, d.heads, d.T, d.Tq, d.E, d.I, st));
       AttnBwdArgs ba{};
-      ba.q_hi = pl.q[0]; ba.q_lo = pl.q[1]; ba.k_hi = pl.k[0]; ba.k_lo = pl.k[1]; ba.v_hi = pl.v[0]; ba.v_lo = pl.v[1];
+      ba.q_hi = S.qp[0]; ba.q_lo = S.qp[1]; ba.k_hi = S.kp[0]; ba.k_lo = S.kp[1]; ba.v_hi = S.vp[0]; ba.v_lo = S.vp[1];
       ba.do_hi = pl.dO[0]; ba.do_lo = pl.dO[1];
       ba.lse = S.lse; ba.delta = pl.delta; ba.dqkv = sc.dqkv;
       ba.B = d.B; ba.H = d.heads; ba.T = d.T; ba.Tp = d.Tq; ba.E = d.E; ba.Dp = d.Ep;

@@ -222,18 +222,24 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
   }
 }
 
-// dgamma[c] = sum_p partials[p][0][c], dbeta[c] = sum_p partials[p][1][c]   (fixed order: deterministic)
+// dgamma[c] = sum_p partials[p][0][c], dbeta[c] = sum_p partials[p][1][c]: one warp per column, lanes stride over
+// the partials, fixed shuffle tree (deterministic)
 __global__ void ln_finish_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
                                  float* __restrict__ dbeta, int parts, int E) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= E) return;
   float a = 0.f, b = 0.f;
-  for (int p = 0; p < parts; ++p) {
+  for (int p = lane; p < parts; p += 32) {
     a += partials[((int64_t)p * 2) * E + c];
     b += partials[((int64_t)p * 2 + 1) * E + c];
   }
-  if (dgamma) dgamma[c] = a;
-  if (dbeta) dbeta[c] = b;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    if (dgamma) dgamma[c] = a;
+    if (dbeta) dbeta[c] = b;
+  }
 }
 
 // ---------------------------------------------------------------- softmax ------------------------------
@@ -456,7 +462,7 @@ int ln_backward(const float* dh, const float* x, const float* stats, const float
   V1T_LN_DISPATCH(8, ln_backward_kernel, dh, x, stats, gamma, dx_accum, partials, rows, E, ld)
   { ln_backward_kernel<16><<<grid, 256, 0, st>>>(dh, x, stats, gamma, dx_accum, partials, rows, E, ld); }
   V1T_LAUNCH_CHECK();
-  ln_finish_kernel<<<cdiv(E, 128), 128, 0, st>>>(partials, dgamma, dbeta, grid, E);
+  ln_finish_kernel<<<cdiv(E, 8), 256, 0, st>>>(partials, dgamma, dbeta, grid, E);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
