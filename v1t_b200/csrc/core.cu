@@ -73,6 +73,7 @@ struct Carver {
 struct BlockSaved {
   float *x1, *st1, *qkv, *o, *x2, *st2, *u, *g, *bhid, *blat, *lse;
   uint8_t *qp[2], *kp[2], *vp[2];  // bf16 hi/lo operand planes of Q, K, V (fused attention), reused by the backward
+  uint8_t* wpl[4][2];              // GEMM-operand planes of Wqkv, Wproj, W1, W2 (converted once per step)
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -96,6 +97,17 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
     b.kp[i] = (uint8_t*)c.take(pf);
     b.vp[i] = (uint8_t*)c.take(pf);
   }
+  const int64_t wr[4] = {3 * d.I, d.E, d.M, d.E}, wc[4] = {d.E, d.I, d.E, d.M};
+  for (int w = 0; w < 4; ++w)
+    for (int i = 0; i < 2; ++i)
+      b.wpl[w][i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(wr[w], wc[w]) / sizeof(float)) : 1);
+}
+enum { kWqkv = 0, kWproj = 1, kW1 = 2, kW2 = 3 };
+// plane operand of weight `w` ([rows, cols] = torch Linear [out, in]); none in fp32 mode
+PlaneOp wplane(const Dims& d, const BlockSaved& S, int w) {
+  if (d.impl == V1T_IMPL_FP32) return no_plane();
+  const int64_t wr[4] = {3 * d.I, d.E, d.M, d.E}, wc[4] = {d.E, d.I, d.E, d.M};
+  return PlaneOp{S.wpl[w][0], d.impl == V1T_IMPL_BF16X3 ? S.wpl[w][1] : nullptr, (int)round_up(wr[w], 32), cdiv(wc[w], 32)};
 }
 Saved carve_saved(const Dims& d, void* base) {
   Carver c(base);
@@ -243,13 +255,22 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       V1T_TRY(bmlp_forward(behaviors, W.bw0, W.bb0, W.bw3, W.bb3, S.bhid, S.blat, d.B, d.bdim, d.hid, d.E, st));
       lat = S.blat;
     }
+    if (d.impl != V1T_IMPL_FP32) {  // weights -> bf16 hi/lo operand planes, shared by the forward and backward GEMMs
+      const bool x3 = d.impl == V1T_IMPL_BF16X3;
+      PlaneOp tmp;
+      V1T_TRY(matrix_planes(W.wqkv, d.E, 3 * d.I, d.E, S.wpl[kWqkv][0], x3 ? S.wpl[kWqkv][1] : nullptr, &tmp, st));
+      V1T_TRY(matrix_planes(W.wproj, d.I, d.E, d.I, S.wpl[kWproj][0], x3 ? S.wpl[kWproj][1] : nullptr, &tmp, st));
+      V1T_TRY(matrix_planes(W.w1, d.E, d.M, d.E, S.wpl[kW1][0], x3 ? S.wpl[kW1][1] : nullptr, &tmp, st));
+      V1T_TRY(matrix_planes(W.w2, d.M, d.E, d.M, S.wpl[kW2][0], x3 ? S.wpl[kW2][1] : nullptr, &tmp, st));
+    }
     // ---- Attention.mha (vit.py:267-275)
     V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st));
     {
       v1t_gemm_desc g = gd((int)d.R, 3 * d.I, d.E);
       V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = 3 * d.I;
-      V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
+                       wplane(d, S, kWqkv)));
     }
     }
     if (d.fused) {  // tcgen05 fused attention: qkv -> bf16 operand planes -> O, lse (nothing T x T in HBM)
@@ -288,7 +309,8 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       ProfScope prof(V1T_PHASE_PROJ, st);
       v1t_gemm_desc g = gd((int)d.R, d.E, d.I);
       g.a_m = d.I; g.a_k = 1; g.b_k = 1; g.b_n = d.I; g.c_m = d.Ep; g.r_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj)));
+      V1T_TRY(gemm_any(d.impl, g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj), no_epi(),
+                       no_plane(), wplane(d, S, kWproj)));
     }
     // ---- MLP (vit.py:143-150)
     ProfScope prof_mlp(V1T_PHASE_MLP, st);
@@ -298,7 +320,7 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = d.Mp;
       if (gemm_uses_tc(d.impl, g)) {  // u and gelu(u)*dropout from one epilogue
         const EpiOp act{kEpiGeluOut, S.g, nullptr, d.Mp, site_drop(*shape, i, kSiteMlp1)};
-        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st, no_drop(), act));
+        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st, no_drop(), act, no_plane(), wplane(d, S, kW1)));
       } else {
         V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st));
         V1T_TRY(gelu_forward(S.u, S.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));
@@ -307,7 +329,8 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     {
       v1t_gemm_desc g = gd((int)d.R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = 1; g.b_n = d.M; g.c_m = d.Ep; g.r_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, S.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2)));
+      V1T_TRY(gemm_any(d.impl, g, S.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2), no_epi(), no_plane(),
+                       wplane(d, S, kW2)));
     }
   }
   return V1T_OK;
@@ -348,7 +371,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.M; g.b_n = 1; g.c_m = d.Mp;
       if (gemm_uses_tc(d.impl, g)) {  // du = (dm W2) * gelu'(u) * dropout in the epilogue
         const EpiOp act{kEpiGeluGrad, nullptr, S.u, d.Mp, site_drop(*shape, i, kSiteMlp1)};
-        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st, no_drop(), act));
+        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st, no_drop(), act, no_plane(), wplane(d, S, kW2)));
       } else {
         V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st));
         V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
@@ -364,7 +387,8 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     {  // dh2[r,e] = sum_m du[r,m] W1[m,e]
       v1t_gemm_desc g = gd(R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, sc.g, W.w1, sc.dh, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, sc.g, W.w1, sc.dh, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
+                       wplane(d, S, kW1)));
     }
     V1T_TRY(ln_backward(sc.dh, S.x2, S.st2, W.ln2_w, dx, GW.ln2_w, GW.ln2_b, sc.partials, kPartialBytes, d.R, d.E,
                         d.Ep, st));
@@ -383,7 +407,8 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     {  // dO[r,i] = sum_e da[r,e] Wp[e,i]
       v1t_gemm_desc g = gd(R, d.I, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
-      V1T_TRY(gemm_any(d.impl, g, da, W.wproj, sc.dO, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, da, W.wproj, sc.dO, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
+                       wplane(d, S, kWproj)));
     }
     const int64_t ld = 3 * d.I;
     lin1.reset();
@@ -457,7 +482,8 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
       v1t_gemm_desc g = gd(R, d.E, 3 * d.I);
       g.a_m = ld; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, sc.dqkv, W.wqkv, sc.dh, nullptr, nullptr, st));
+      V1T_TRY(gemm_any(d.impl, g, sc.dqkv, W.wqkv, sc.dh, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
+                       wplane(d, S, kWqkv)));
     }
     V1T_TRY(ln_backward(sc.dh, S.x1, S.st1, W.ln1_w, dx, GW.ln1_w, GW.ln1_b, sc.partials, kPartialBytes, d.R, d.E,
                         d.Ep, st));

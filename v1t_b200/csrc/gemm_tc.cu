@@ -8,8 +8,9 @@
 // mode.  Accumulators are double-buffered in TMEM (2 x 256 columns) so the EPILOGUE warps (tcgen05.ld -> bias /
 // dropout / residual -> global) overlap the next tile's main loop.  Persistent CTAs, one per SM.
 //
-// Warp roles (544 threads): warps 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), warp 8
-// TMEM alloc + MMA issue, warps 9-16 producers.  Pipelines: full/empty mbarriers per smem stage (4 stages x 48 KB), tmem_full/tmem_empty
+// Warp roles (576 threads): warps 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2), warp 8
+// TMEM alloc + MMA issue, warps 9-16 converting producers, warp 17 bulk-copy loader for operands that arrive as
+// pre-swizzled bf16 planes (PlaneOp: weights converted once per step, see planes.cu).  Pipelines: full/empty mbarriers per smem stage (4 stages x 48 KB), tmem_full/tmem_empty
 // per accumulator buffer.
 #include <algorithm>
 
@@ -25,7 +26,8 @@ using namespace tc;
 
 constexpr int BM = 128, BK = 32, STAGES = 2, RAW = 2, BN_MAX = 256;  // UMMA stages, raw fp32 staging slots
 constexpr int kEpiWarps = 8, kProdWarps = 8;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 544
+constexpr int kLoaderWarp = kEpiWarps + 1 + kProdWarps;       // bulk-copies plane operands (PlaneOp) into the stages
+constexpr int kThreads = (kLoaderWarp + 1) * 32;              // 576
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int A_PLANE = BM * 64;       // bytes of one bf16 plane of the A stage (128 rows x 32 k)
 constexpr int B_PLANE = BN_MAX * 64;
@@ -40,7 +42,16 @@ struct TcArgs {
   int x3;        // 1: hi*hi + lo*hi + hi*lo, 0: hi*hi
   int mn_a, mn_b;  // operand is M/N-contiguous in memory and staged un-transposed (MN-major UMMA descriptor)
   int a_vec, b_vec, c_vec, r_vec;  // 128-bit access allowed
+  PlaneOp pa, pb;  // operands supplied as pre-swizzled bf16 planes (bulk-copied, not converted)
+  int a_pl, b_pl;
 };
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 struct Tile {
   int m0, n0, k_begin, k_end;
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], kProdThreads);
+      mbar_init(&full[s], ((a.a_pl && a.b_pl) ? 0 : kProdThreads) + ((a.a_pl || a.b_pl) ? 1 : 0));
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -116,7 +127,62 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 
   const int total_tiles = g.d.batch1 * g.d.batch2 * g.splits * a.tiles_m * a.tiles_n;
 
-  if (warp > kEpiWarps) {
+  if (warp == kLoaderWarp) {
+    // ============================== PLANE LOADER ==============================
+    // One thread: per k-block, wait for the stage to drain, then bulk-copy the plane operand tiles (already in
+    // the swizzled UMMA layout) from global memory; the copies complete on the stage's full barrier.
+    if ((a.a_pl || a.b_pl) && lane == 0) {
+      uint32_t it = 0;
+      const uint32_t nplanes = a.x3 ? 2u : 1u;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(a, t);
+        const int num_kb = (tl.k_end - tl.k_begin + BK - 1) / BK;
+        // tile-constant geometry.  K-major: `rows` consecutive plane rows of atom k0/32 (one copy);  MN-major: 32
+        // plane rows (k) of each of `atoms` consecutive column atoms (2 KB each)
+        const int a_rows = min(BM, a.pa.rows_p - tl.m0), a_atoms = max(0, min(BM / 32, a.pa.catoms - tl.m0 / 32));
+        const int b_rows = min(a.bn, a.pb.rows_p - tl.n0), b_atoms = max(0, min(a.bn / 32, a.pb.catoms - tl.n0 / 32));
+        uint32_t bytes = 0;
+        if (a.a_pl) bytes += a.mn_a ? a_atoms * 2048 : a_rows * 64;
+        if (a.b_pl) bytes += a.mn_b ? b_atoms * 2048 : b_rows * 64;
+        bytes *= nplanes;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int stage = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[stage], ph ^ 1);
+          const int k0 = tl.k_begin + kb * BK;
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + 2 * A_PLANE;
+          mbar_expect_tx(&full[stage], bytes);
+          if (a.a_pl) {
+            if (a.mn_a) {
+              for (int j = 0; j < a_atoms; ++j) {
+                const int64_t src = ((int64_t)(tl.m0 / 32 + j) * a.pa.rows_p + k0) * 64;
+                bulk_g2s(sa + j * 2048, a.pa.hi + src, 2048, &full[stage]);
+                if (a.x3) bulk_g2s(sa + A_PLANE + j * 2048, a.pa.lo + src, 2048, &full[stage]);
+              }
+            } else {
+              const int64_t src = ((int64_t)(k0 >> 5) * a.pa.rows_p + tl.m0) * 64;
+              bulk_g2s(sa, a.pa.hi + src, a_rows * 64, &full[stage]);
+              if (a.x3) bulk_g2s(sa + A_PLANE, a.pa.lo + src, a_rows * 64, &full[stage]);
+            }
+          }
+          if (a.b_pl) {
+            if (a.mn_b) {
+              for (int j = 0; j < b_atoms; ++j) {
+                const int64_t src = ((int64_t)(tl.n0 / 32 + j) * a.pb.rows_p + k0) * 64;
+                bulk_g2s(sb + j * 2048, a.pb.hi + src, 2048, &full[stage]);
+                if (a.x3) bulk_g2s(sb + B_PLANE + j * 2048, a.pb.lo + src, 2048, &full[stage]);
+              }
+            } else {
+              const int64_t src = ((int64_t)(k0 >> 5) * a.pb.rows_p + tl.n0) * 64;
+              bulk_g2s(sb, a.pb.hi + src, b_rows * 64, &full[stage]);
+              if (a.x3) bulk_g2s(sb + B_PLANE, a.pb.lo + src, b_rows * 64, &full[stage]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp > kEpiWarps && !(a.a_pl && a.b_pl)) {
     // ============================== PRODUCERS ==============================
     // Two-level pipeline.  (1) cp.async copies the raw fp32 operand chunks of k-block i+RAW into a per-thread
     // staging slot (each thread later reads only what it copied itself, so no cross-thread synchronisation is
@@ -125,7 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     // UMMA stage.  Thread -> chunk assignment is fixed per launch.
     const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;
     const bool a_kc = (g.d.a_k == 1), b_kc = (g.d.b_k == 1);
-    const int b_chunks = a.bn * 4;
+    const int b_chunks = a.b_pl ? 0 : a.bn * 4;  // plane operands are not converted here
+    const bool a_on = !a.a_pl;
     uint8_t* raw = smem + STAGES * STAGE_BYTES;
 
     // ---- per-thread chunk geometry (constant for the whole launch: no divisions in the k loop) ----
@@ -211,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const float* base = g.A + pf_tl.a_off + (int64_t)l0 * a_sl + (int64_t)c0 * a_sc;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-          copy_chunk(rbase + i * (kProdThreads * 32), base + ca[i].goff, l0 + (ca[i].lc >> 12) < l_lim,
+          if (a_on) copy_chunk(rbase + i * (kProdThreads * 32), base + ca[i].goff, l0 + (ca[i].lc >> 12) < l_lim,
                      c_lim - (c0 + (ca[i].lc & 4095)), a_sc, a_vec);
       }
       {
@@ -227,42 +294,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     };
 
     pf_load();
-#pragma unroll
-    for (int s = 0; s < RAW; ++s) {
-      if (pf_t < total_tiles) {
-        issue_stage(s);
-        pf_next();
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    for (int it = 0; it < total_iters; ++it) {
-      asm volatile("cp.async.wait_group %0;" ::"n"(RAW - 1) : "memory");
-      const int rs = it % RAW, stage = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      const uint8_t* rbase = raw + rs * STAGE_BYTES + ptid * 32;
-      mbar_wait(&empty[stage], ph ^ 1);
-      uint8_t* sa_hi = smem + stage * STAGE_BYTES;
-      uint8_t* sa_lo = sa_hi + A_PLANE;
-      uint8_t* sb_hi = sa_hi + 2 * A_PLANE;
-      uint8_t* sb_lo = sb_hi + B_PLANE;
-      // chunk by chunk: staging slot -> registers -> bf16 hi/lo -> swizzled UMMA stage
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        if (i < 2 || ptid + (i - 2) * kProdThreads < b_chunks) {
-          const float4 x = *reinterpret_cast<const float4*>(rbase + i * (kProdThreads * 32));
-          const float4 y = *reinterpret_cast<const float4*>(rbase + i * (kProdThreads * 32) + 16);
-          const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          const uint32_t soff = i < 2 ? ca[i].soff : cb[i - 2].soff;
-          uint8_t* dh = (i < 2 ? sa_hi : sb_hi) + soff;
-          uint8_t* dl = (i < 2 ? sa_lo : sb_lo) + soff;
-          *reinterpret_cast<uint4*>(dh) = hi;
-          if (a.x3) *reinterpret_cast<uint4*>(dl) = lo;
+    // iterations -RAW..-1 only prefetch (fill the raw slots); iteration `it` converts k-block it and refills its slot
+    for (int it = -RAW; it < total_iters; ++it) {
+      const int rs = (it + RAW) % RAW;
+      if (it >= 0) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RAW - 1) : "memory");
+        const int stage = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const uint8_t* rbase = raw + rs * STAGE_BYTES + ptid * 32;
+        mbar_wait(&empty[stage], ph ^ 1);
+        const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb_hi = sa_hi + 2 * A_PLANE;
+        const uint32_t rb = smem_u32(rbase);
+        // chunk by chunk: staging slot -> registers -> bf16 hi/lo -> swizzled UMMA stage
+  #pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          if (i < 2 || ptid + (i - 2) * kProdThreads < b_chunks) {
+            const uint4 x = lds128(rb + i * (kProdThreads * 32));
+            const uint4 y = lds128(rb + i * (kProdThreads * 32) + 16);
+            const float v[8] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w),
+                                __uint_as_float(y.x), __uint_as_float(y.y), __uint_as_float(y.z), __uint_as_float(y.w)};
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const uint32_t dst = (i < 2 ? sa_hi + ca[i].soff : sb_hi + cb[i - 2].soff);
+            sts128(dst, hi);
+            if (a.x3) sts128(dst + (i < 2 ? A_PLANE : B_PLANE), lo);
+          }
         }
+        fence_proxy_async();
+        mbar_arrive(&full[stage]);
       }
-      fence_proxy_async();
-      mbar_arrive(&full[stage]);
       // refill this raw slot with k-block it + RAW (after its contents were consumed above)
       if (pf_t < total_tiles) {
         issue_stage(rs);
@@ -271,6 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp > kEpiWarps) {
+    // both operands are planes: the conversion warps have nothing to do
   } else if (warp == kEpiWarps) {
     // ============================== MMA ISSUER ==============================
     const uint32_t idesc = idesc_bf16(BM, a.bn, a.mn_a, a.mn_b);
@@ -317,99 +380,112 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     }
   } else {
     // ============================== EPILOGUE ==============================
-    // 8 warps: TMEM lane quarter = warp & 3 (row block), column half = warp >> 2 (alternate 16-column chunks).
-    // Fast path (full, aligned chunk): 4 x 128-bit stores per 16 columns with bias / residual fetched as vectors;
-    // dropout, accumulate and ragged chunks take the element-wise path.
+    // 8 warps: TMEM lane quarter = warp & 3 (row block), column half = warp >> 2 (alternate 32-column groups).
+    // Every 32 x 32 group is transposed through a warp-private smem tile, so that a lane owns 4 adjacent columns
+    // of one row and each 128-bit store instruction writes four full 128-byte row segments.  Ragged edges and
+    // unaligned operands use the same path with element-wise memory accesses.  The row loop is deliberately NOT
+    // unrolled: with dropout (Philox) and GELU inlined, an unrolled body overflowed the instruction cache and the
+    // epilogue became fetch-bound ("no_instructions" stalls, profiles/r1_gemm_epilogue_icache.txt).
     uint32_t tl_i = 0;
     const int quarter = warp & 3, half = warp >> 2;
     const float inv_keep = g.drop.p > 0.f ? 1.f / (1.f - g.drop.p) : 1.f;
-    const bool plain = !g.d.accumulate;
     const int64_t drop_ld = (g.d.n + 3) & ~3;
     const float inv_keep2 = g.epi.drop.p > 0.f ? 1.f / (1.f - g.epi.drop.p) : 1.f;
     const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+    const uint32_t stg = smem_u32(stage_base + warp * 4096);
+    const int cq = lane & 7;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
       const Tile tl = decode_tile(a, t);
       const uint32_t buf = tl_i & 1, tph = (tl_i >> 1) & 1;
       mbar_wait(&tfull[buf], tph);
       tc_fence_after();
-      const int m = tl.m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + buf * BN_MAX + ((uint32_t)(quarter * 32) << 16);
-      float* crow = g.C + tl.c_off + (int64_t)m * g.d.c_m;
-      const float* rrow = g.R ? g.R + tl.r_off + (int64_t)m * g.d.r_m : nullptr;
-      // 32-column groups alternate between the two column halves
+      const int n_lim = min(g.d.n, tl.n0 + a.bn);
+      // 32-column groups alternate between the two column halves (columns past bn are never stored)
       for (int c0 = half * 32; c0 < a.bn; c0 += 64) {
         const int nb = tl.n0 + c0;
-        const int width = min(32, a.bn - c0);  // 16 or 32 (bn is a multiple of 16)
-        uint32_t v[32];
-        tmem_ld16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(v[0]));
-        if (width > 16) tmem_ld16(taddr + c0 + 16, reinterpret_cast<uint32_t(&)[16]>(v[16]));
-        tmem_ld_wait();
-        if (plain && a.c_vec && width == 32 && nb + 32 <= g.d.n && (!g.bias || bias_vec) && (!g.R || a.r_vec)) {
-          // ---- coalesced path: transpose the 32 x 32 block through a private smem tile so that every
-          // 128-bit store instruction writes four full 128-byte row segments (instead of 32 scattered 16 B pieces)
-          float* stg = reinterpret_cast<float*>(stage_base + warp * 4096);
+        {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) =
-                make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          __syncwarp();
-          const int cq = lane & 7;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g.bias) bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + cq);
+            sts128(stg + lane * 128 + ((c ^ (lane & 7)) << 4), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        }
+        __syncwarp();
+        const int n4 = nb + 4 * cq;
+        const int nv = min(4, n_lim - n4);  // valid columns of this lane's quad
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (g.bias && nv > 0) {
+          if (bias_vec && nv == 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n4));
+            bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
-            const int mm = tl.m0 + quarter * 32 + r;
-            const float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
-            if (mm < g.d.m) {
-              float o[4] = {fmaf(g.d.alpha, x.x, bv.x), fmaf(g.d.alpha, x.y, bv.y), fmaf(g.d.alpha, x.z, bv.z),
-                            fmaf(g.d.alpha, x.w, bv.w)};
-              const int n4 = nb + 4 * cq;
-              if (g.drop.p > 0.f) {
-                float mk[4];
-                dropout_mult4(g.drop.seed, g.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.drop.p, inv_keep, mk);
+            for (int e = 0; e < 4; ++e) if (e < nv) bv[e] = __ldg(g.bias + n4 + e);
+          }
+        }
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + (lane >> 3);
+          const int mm = tl.m0 + quarter * 32 + r;
+          if (mm >= g.d.m || nv <= 0) continue;
+          const uint4 xr = lds128(stg + r * 128 + ((cq ^ (r & 7)) << 4));
+          float o[4] = {fmaf(g.d.alpha, __uint_as_float(xr.x), bv[0]), fmaf(g.d.alpha, __uint_as_float(xr.y), bv[1]),
+                        fmaf(g.d.alpha, __uint_as_float(xr.z), bv[2]), fmaf(g.d.alpha, __uint_as_float(xr.w), bv[3])};
+          const bool full4 = (nv == 4);
+          if (g.drop.p > 0.f) {
+            float mk[4];
+            dropout_mult4(g.drop.seed, g.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.drop.p, inv_keep, mk);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] *= mk[e];
-              }
-              float mk2[4] = {1.f, 1.f, 1.f, 1.f};
-              if (g.epi.kind != kEpiNone && g.epi.drop.p > 0.f)
-                dropout_mult4(g.epi.drop.seed, g.epi.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.epi.drop.p, inv_keep2, mk2);
-              if (g.epi.kind == kEpiGeluGrad) {
-                const float4 uv = __ldg(reinterpret_cast<const float4*>(g.epi.u + (int64_t)mm * g.epi.ld + n4));
-                o[0] *= gelu_df(uv.x) * mk2[0]; o[1] *= gelu_df(uv.y) * mk2[1];
-                o[2] *= gelu_df(uv.z) * mk2[2]; o[3] *= gelu_df(uv.w) * mk2[3];
-              }
-              if (g.R) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(g.R + tl.r_off + (int64_t)mm * g.d.r_m + nb) + cq);
-                o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-              }
-              *(reinterpret_cast<float4*>(g.C + tl.c_off + (int64_t)mm * g.d.c_m + nb) + cq) = make_float4(o[0], o[1], o[2], o[3]);
-              if (g.epi.kind == kEpiGeluOut)
-                *reinterpret_cast<float4*>(g.epi.aux + (int64_t)mm * g.epi.ld + n4) =
-                    make_float4(gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]);
+            for (int e = 0; e < 4; ++e) o[e] *= mk[e];
+          }
+          float mk2[4] = {1.f, 1.f, 1.f, 1.f};
+          if (g.epi.kind != kEpiNone && g.epi.drop.p > 0.f)
+            dropout_mult4(g.epi.drop.seed, g.epi.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.epi.drop.p, inv_keep2, mk2);
+          if (g.epi.kind == kEpiGeluGrad) {
+            // epi.ld % 4 == 0 and 16-byte aligned rows are checked on the host: the quad is always readable
+            const float4 uv = __ldg(reinterpret_cast<const float4*>(g.epi.u + (int64_t)mm * g.epi.ld + n4));
+            o[0] *= gelu_df(uv.x) * mk2[0]; o[1] *= gelu_df(uv.y) * mk2[1];
+            o[2] *= gelu_df(uv.z) * mk2[2]; o[3] *= gelu_df(uv.w) * mk2[3];
+          }
+          if (g.R) {
+            const float* rp = g.R + tl.r_off + (int64_t)mm * g.d.r_m + n4;
+            if (a.r_vec && full4) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rp));
+              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (e < nv) o[e] += __ldg(rp + e);
             }
           }
-          __syncwarp();
-        } else if (m < g.d.m) {
-#pragma unroll 4
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (j < width && n < g.d.n) {
-              float x = g.d.alpha * __uint_as_float(v[j]);
-              if (g.bias) x += __ldg(g.bias + n);
-              if (g.drop.p > 0.f)
-                x *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * drop_ld + n, g.drop.p, inv_keep);
-              float m2 = 1.f;
-              if (g.epi.kind != kEpiNone && g.epi.drop.p > 0.f)
-                m2 = dropout_mult(g.epi.drop.seed, g.epi.drop.site, (uint64_t)m * drop_ld + n, g.epi.drop.p, inv_keep2);
-              if (g.epi.kind == kEpiGeluGrad) x *= gelu_df(__ldg(g.epi.u + (int64_t)m * g.epi.ld + n)) * m2;
-              if (rrow) x += __ldg(rrow + n);
-              if (g.d.accumulate) x += crow[n];
-              if (g.epi.kind == kEpiGeluOut) g.epi.aux[(int64_t)m * g.epi.ld + n] = gelu_f(x) * m2;
-              crow[n] = x;
+          float* cp = g.C + tl.c_off + (int64_t)mm * g.d.c_m + n4;
+          if (a.c_vec && full4) {
+            if (g.d.accumulate) {
+              const float4 cv = *reinterpret_cast<const float4*>(cp);
+              o[0] += cv.x; o[1] += cv.y; o[2] += cv.z; o[3] += cv.w;
+            }
+            *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nv) {
+                if (g.d.accumulate) o[e] += cp[e];
+                cp[e] = o[e];
+              }
+          }
+          if (g.epi.kind == kEpiGeluOut) {
+            float* ap = g.epi.aux + (int64_t)mm * g.epi.ld + n4;
+            const float4 gv = make_float4(gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]);
+            if (full4) *reinterpret_cast<float4*>(ap) = gv;
+            else {
+              const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (e < nv) ap[e] = ge[e];
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
@@ -427,8 +503,15 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 int g_use_mn_major = 1;  // stage M/N-contiguous operands un-transposed (vector loads) with MN-major descriptors
 namespace {
 
+// N tile: an MN-major plane B operand is copied in whole 32-column atoms
+int pick_bn(const v1t_gemm_desc& d, const PlaneOp& pb) {
+  const int nt = cdiv(d.n, BN_MAX);
+  return (int)round_up(cdiv(d.n, nt), (pb.hi && d.b_k != 1) ? 32 : 16);
+}
+
 int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
-              DropSpec drop, int x3, int splits, int k_chunk, int64_t c_split, cudaStream_t st, EpiOp epi = no_epi()) {
+              DropSpec drop, int x3, int splits, int k_chunk, int64_t c_split, cudaStream_t st, EpiOp epi = no_epi(),
+              PlaneOp pa = no_plane(), PlaneOp pb = no_plane()) {
   static bool attr_set = false;
   if (!attr_set) {
     V1T_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -440,13 +523,18 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.g.drop = drop;
   a.g.epi = epi;
   a.g.splits = splits; a.g.k_chunk = k_chunk; a.g.c_split = c_split;
-  const int nt = cdiv(d.n, BN_MAX);
-  a.bn = (int)round_up(cdiv(d.n, nt), 16);
+  a.pa = pa; a.pb = pb;
+  a.a_pl = pa.hi != nullptr; a.b_pl = pb.hi != nullptr;
+  if (a.a_pl || a.b_pl)
+    V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && (!x3 || ((!a.a_pl || pa.lo) && (!a.b_pl || pb.lo))),
+                  "tc gemm: plane operands need an unbatched problem and, in bf16x3 mode, the lo plane");
+  a.bn = pick_bn(d, pb);
   a.tiles_n = cdiv(d.n, a.bn);
   a.tiles_m = cdiv(d.m, BM);
   a.x3 = x3;
-  a.mn_a = g_use_mn_major && d.a_k != 1 && d.a_m == 1;
-  a.mn_b = g_use_mn_major && d.b_k != 1 && d.b_n == 1 && a.bn % 32 == 0;
+  // plane operands cannot be transposed while staging: their orientation follows the problem
+  a.mn_a = a.a_pl ? (d.a_k != 1) : (g_use_mn_major && d.a_k != 1 && d.a_m == 1);
+  a.mn_b = a.b_pl ? (d.b_k != 1) : (g_use_mn_major && d.b_k != 1 && d.b_n == 1 && a.bn % 32 == 0);
   // row stride of the staged rows: a_m / b_n for K-contiguous sources, a_k / b_k for MN-major staging
   a.a_vec = aligned16(A) && (a.mn_a ? d.a_k : d.a_m) % 4 == 0 && d.a_b1 % 4 == 0 && d.a_b2 % 4 == 0;
   a.b_vec = aligned16(B) && (a.mn_b ? d.b_k : d.b_n) % 4 == 0 && d.b_b1 % 4 == 0 && d.b_b2 % 4 == 0;
@@ -467,7 +555,7 @@ bool tc_supported(const v1t_gemm_desc& d) {
 }  // namespace
 
 int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
-            cudaStream_t st, DropSpec drop, int x3, EpiOp epi) {
+            cudaStream_t st, DropSpec drop, int x3, EpiOp epi, PlaneOp pa, PlaneOp pb) {
   V1T_CHECK_ARG(d.m >= 0 && d.n >= 0 && d.k >= 0 && d.batch1 >= 1 && d.batch2 >= 1, "gemm: bad sizes");
   if (d.m == 0 || d.n == 0) return V1T_OK;
   if (!tc_supported(d)) return gemm_fp32(d, A, B, C, bias, R, st, drop);
@@ -475,29 +563,29 @@ int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, co
     V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && epi.ld % 4 == 0 && aligned16(epi.kind == kEpiGeluOut ? (const void*)epi.aux : (const void*)epi.u),
                   "gemm_tc: fused activation needs an unbatched problem and 16-byte aligned rows");
   }
-  return launch_tc(d, A, B, C, bias, R, drop, x3, 1, (int)round_up(d.k, BK), 0, st, epi);
+  return launch_tc(d, A, B, C, bias, R, drop, x3, 1, (int)round_up(d.k, BK), 0, st, epi, pa, pb);
 }
 
 int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
-                   size_t partial_bytes, cudaStream_t st, int x3) {
+                   size_t partial_bytes, cudaStream_t st, int x3, PlaneOp pa, PlaneOp pb) {
   V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1, "splitk gemm: no batch");
   if (d.m == 0 || d.n == 0) return V1T_OK;
   if (!tc_supported(d)) return gemm_fp32_splitk(d, A, B, C, partials, partial_bytes, st);
-  const int nt = cdiv(d.n, BN_MAX);
-  const int bn = (int)round_up(cdiv(d.n, nt), 16);
+  const int bn = pick_bn(d, pb);
   const int tiles = cdiv(d.n, bn) * cdiv(d.m, BM);
   const int64_t n_ld = round_up(d.n, 4);
   const int64_t per = (int64_t)d.m * n_ld * (int64_t)sizeof(float);
   int splits = (2 * kNumSMs + tiles - 1) / tiles;
   splits = std::min(splits, cdiv(d.k, 4 * BK));
   splits = (int)std::min<int64_t>(splits, (int64_t)partial_bytes / per);
-  if (splits <= 1) return gemm_tc(d, A, B, C, nullptr, nullptr, st, no_drop(), x3);
+  if (splits <= 1) return gemm_tc(d, A, B, C, nullptr, nullptr, st, no_drop(), x3, no_epi(), pa, pb);
   const int k_chunk = (int)round_up(cdiv(d.k, splits), BK);
   splits = cdiv(d.k, k_chunk);
   v1t_gemm_desc p = d;
   p.accumulate = 0;
   p.c_m = n_ld;
-  V1T_TRY(launch_tc(p, A, B, partials, nullptr, nullptr, no_drop(), x3, splits, k_chunk, (int64_t)d.m * n_ld, st));
+  V1T_TRY(launch_tc(p, A, B, partials, nullptr, nullptr, no_drop(), x3, splits, k_chunk, (int64_t)d.m * n_ld, st, no_epi(),
+                    pa, pb));
   return reduce_partials_ld(partials, C, splits, d.m, d.n, n_ld, d.c_m, d.accumulate, st);
 }
 

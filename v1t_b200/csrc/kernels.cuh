@@ -22,6 +22,17 @@ struct EpiOp {
 };
 static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}}; }
 
+// Pre-swizzled bf16 hi/lo planes of a row-major matrix X[rows, cols] (planes.cu: matrix_planes): 32-column atoms,
+// [catoms][rows_p][64 B], rows 64 B apart, 16-byte chunks XOR-swizzled with ((row >> 1) & 3), zero padded.  A GEMM
+// operand given as planes is bulk-copied straight into the UMMA stage (no conversion work in the GEMM): K-major
+// when the contraction runs over X's columns, MN-major when it runs over X's rows.
+struct PlaneOp {
+  const uint8_t* hi;
+  const uint8_t* lo;
+  int rows_p, catoms;
+};
+static inline PlaneOp no_plane() { return PlaneOp{nullptr, nullptr, 0, 0}; }
+
 struct GemmArgs {
   v1t_gemm_desc d;
   DropSpec drop;    // applied to alpha*acc + bias (element index m*roundup(n_cols,4) + n), before the residual add
@@ -49,9 +60,10 @@ int reduce_partials_ld(const float* partials, float* out, int parts, int64_t row
 
 // gemm_tc.cu (tcgen05): same contract; x3 = 1 -> bf16 hi/lo split (3 MMAs), 0 -> plain bf16 operands
 int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
-            cudaStream_t st, DropSpec drop, int x3, EpiOp epi = no_epi());
+            cudaStream_t st, DropSpec drop, int x3, EpiOp epi = no_epi(), PlaneOp pa = no_plane(),
+            PlaneOp pb = no_plane());
 int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
-                   size_t partial_bytes, cudaStream_t st, int x3);
+                   size_t partial_bytes, cudaStream_t st, int x3, PlaneOp pa = no_plane(), PlaneOp pb = no_plane());
 
 // impl dispatch used by the orchestrator
 inline bool gemm_uses_tc(int impl, const v1t_gemm_desc& d) {
@@ -60,19 +72,25 @@ inline bool gemm_uses_tc(int impl, const v1t_gemm_desc& d) {
          (d.b_k == 1 || d.b_n == 1);
 }
 inline int gemm_any(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias,
-                    const float* R, cudaStream_t st, DropSpec drop = no_drop(), EpiOp epi = no_epi()) {
+                    const float* R, cudaStream_t st, DropSpec drop = no_drop(), EpiOp epi = no_epi(),
+                    PlaneOp pa = no_plane(), PlaneOp pb = no_plane()) {
   if (!gemm_uses_tc(impl, d)) return gemm_fp32(d, A, B, C, bias, R, st, drop);  // caller applies `epi` separately
-  return gemm_tc(d, A, B, C, bias, R, st, drop, impl == V1T_IMPL_BF16X3, epi);
+  return gemm_tc(d, A, B, C, bias, R, st, drop, impl == V1T_IMPL_BF16X3, epi, pa, pb);
 }
 inline int gemm_any_splitk(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C,
-                           float* partials, size_t partial_bytes, cudaStream_t st) {
+                           float* partials, size_t partial_bytes, cudaStream_t st, PlaneOp pa = no_plane(),
+                           PlaneOp pb = no_plane()) {
   const int64_t work = (int64_t)d.m * d.n * (d.k > 0 ? d.k : 1);
   if (impl == V1T_IMPL_FP32 || work < (1ll << 22)) return gemm_fp32_splitk(d, A, B, C, partials, partial_bytes, st);
-  return gemm_tc_splitk(d, A, B, C, partials, partial_bytes, st, impl == V1T_IMPL_BF16X3);
+  return gemm_tc_splitk(d, A, B, C, partials, partial_bytes, st, impl == V1T_IMPL_BF16X3, pa, pb);
 }
 
 // planes.cu / attn_tc.cu (fused attention on tcgen05)
 size_t plane_bytes(int B, int H, int Tp, int Dp);
+// planes of a plain row-major matrix (GEMM operands, see PlaneOp): bytes of ONE plane, and the converter
+size_t matrix_plane_bytes(int64_t rows, int64_t cols);
+int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, PlaneOp* out,
+                  cudaStream_t st);
 int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tp, int E, int Dp, void* rm_hi,
                 void* rm_lo, void* tr_hi, void* tr_lo, cudaStream_t st);
 int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int T, int Tp, int E, int64_t ld,

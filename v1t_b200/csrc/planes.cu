@@ -72,6 +72,25 @@ __global__ void __launch_bounds__(256) make_planes_kernel(const float* __restric
   }
 }
 
+// GEMM-operand planes of a row-major matrix X[rows, cols]: one thread per 16-byte chunk (8 columns of one row)
+__global__ void matrix_planes_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int64_t cols,
+                                     int64_t rows_p, int64_t chunks, uint8_t* __restrict__ hi,
+                                     uint8_t* __restrict__ lo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= chunks) return;
+  const int c = (int)(idx & 3);
+  const int64_t r = (idx >> 2) % rows_p, a = (idx >> 2) / rows_p;
+  const int64_t col0 = a * 32 + c * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = (r < rows && col0 + e < cols) ? __ldg(X + r * ld + col0 + e) : 0.f;
+  uint4 h, l;
+  split8(v, h, l);
+  const int64_t off = (a * rows_p + r) * 64 + ((c ^ (int)((r >> 1) & 3)) << 4);
+  *reinterpret_cast<uint4*>(hi + off) = h;
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
+}
+
 // delta[b,h,t] = sum_d O[b,t,h*E+d] * dO[b,t,h*E+d]   (softmax backward row term); one warp per (b,t,h)
 __global__ void attn_delta_kernel(const float* __restrict__ O, const float* __restrict__ dO, float* __restrict__ delta,
                                   int B, int H, int T, int Tp, int E, int64_t ld) {
@@ -93,6 +112,22 @@ __global__ void attn_delta_kernel(const float* __restrict__ O, const float* __re
 }  // namespace
 
 size_t plane_bytes(int B, int H, int Tp, int Dp) { return (size_t)B * H * Tp * Dp * 2; }
+
+size_t matrix_plane_bytes(int64_t rows, int64_t cols) {
+  return (size_t)cdiv(cols, 32) * (size_t)round_up(rows, 32) * 64;
+}
+
+int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, PlaneOp* out,
+                  cudaStream_t st) {
+  const int64_t rows_p = round_up(rows, 32), catoms = cdiv(cols, 32);
+  const int64_t chunks = catoms * rows_p * 4;
+  V1T_CHECK_ARG(X && hi && out && catoms * rows_p < (1ll << 31), "matrix_planes: bad argument");
+  matrix_planes_kernel<<<(unsigned)cdiv(chunks, 256), 256, 0, st>>>(X, ld, rows, cols, rows_p, chunks, (uint8_t*)hi,
+                                                                      (uint8_t*)lo);
+  V1T_LAUNCH_CHECK();
+  out->hi = (const uint8_t*)hi; out->lo = (const uint8_t*)lo; out->rows_p = (int)rows_p; out->catoms = (int)catoms;
+  return V1T_OK;
+}
 
 int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tp, int E, int Dp, void* rm_hi,
                 void* rm_lo, void* tr_hi, void* tr_lo, cudaStream_t st) {
