@@ -201,6 +201,19 @@ int v1t_gemm_tc_set_mn_major(int on);
 int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
                 const float* R, int impl, void* stream);
 
+/* GEMM operands as pre-swizzled bf16 planes.  A row-major matrix X[rows, cols] (leading dim ld) is converted once
+ * into a hi plane (and a lo plane, x ~= hi + lo) laid out like the shared-memory tiles tcgen05.mma reads: 32-column
+ * atoms, [ceil(cols/32)][round_up(rows,32)][64 B], 16-byte chunks XOR-swizzled with ((row >> 1) & 3), zero padded.
+ * v1t_gemm_tc_planes is v1t_gemm_tc with either operand optionally replaced by the planes of the matrix it views
+ * (a_hi/b_hi NULL = use the fp32 pointer): the planes are bulk-copied into the MMA stages without conversion work.
+ * The operand must be the whole matrix the planes were made from (K-major when d->a_k / d->b_k == 1, else
+ * M/N-major); unbatched problems only.  This is how the core feeds weights (nn.Linear, vit.py:146,221,230). */
+size_t v1t_matrix_plane_bytes(int64_t rows, int64_t cols);
+int v1t_matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, void* stream);
+int v1t_gemm_tc_planes(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
+                       const float* R, int impl, const void* a_hi, const void* a_lo, int64_t a_rows, int64_t a_cols,
+                       const void* b_hi, const void* b_lo, int64_t b_rows, int64_t b_cols, void* stream);
+
 /* measurement helper: cycles for iters*8 tcgen05.mma (M=128, K=16, bf16) of width N on all SMs; ts=1: A operand
  * from tensor memory, mn_b=1: MN-major B.  out_dev: 148 int64 cycle counts (device memory). */
 int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long* out_dev, void* stream);

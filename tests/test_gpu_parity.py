@@ -349,6 +349,85 @@ def test_gemm_tc_bf16x3_matches_fp64(shape, mn_major):
     assert rel_err(got, ref) < 2e-5, rel_err(got, ref)
 
 
+def _planes_of(lib, X, x3=True):
+    """bf16 hi/lo operand planes of a row-major 2-D matrix (v1t_matrix_planes); returns (hi, lo) byte tensors"""
+    from v1t_b200 import _lib
+    rows, cols = X.shape
+    nbytes = lib.v1t_matrix_plane_bytes(rows, cols)
+    hi = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    lo = torch.empty(nbytes, dtype=torch.uint8, device=DEV) if x3 else None
+    rc = lib.v1t_matrix_planes(X.data_ptr(), X.stride(0), rows, cols, hi.data_ptr(), lo.data_ptr() if x3 else None,
+                               torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    return hi, lo
+
+
+def test_matrix_planes_layout():
+    """v1t_matrix_planes: 32-column atoms, 64-byte rows, 16-byte chunks XOR-swizzled by (row >> 1) & 3; hi + lo
+    reproduces the fp32 value to ~2^-16; pads are zero."""
+    from v1t_b200 import _lib
+    lib = _lib.load()
+    rows, cols = 70, 45
+    X = torch.randn(rows, cols + 3, device=DEV)[:, :cols]
+    hi, lo = _planes_of(lib, X)
+    rows_p, catoms = 96, 2
+    assert hi.numel() == rows_p * catoms * 64
+    hi16 = hi.view(torch.bfloat16).view(catoms, rows_p, 4, 8).float().cpu()
+    lo16 = lo.view(torch.bfloat16).view(catoms, rows_p, 4, 8).float().cpu()
+    full = torch.zeros(rows_p, catoms * 32)
+    full[:rows, :cols] = X.cpu()
+    for a in range(catoms):
+        for r in range(rows_p):
+            for cc in range(4):
+                phys = cc ^ ((r >> 1) & 3)
+                want = full[r, a * 32 + cc * 8:a * 32 + cc * 8 + 8]
+                got_hi = hi16[a, r, phys]
+                assert torch.equal(got_hi, want.bfloat16().float())
+                assert (got_hi + lo16[a, r, phys] - want).abs().max() <= 2.0 ** -15 * max(1.0, want.abs().max())
+
+
+@pytest.mark.parametrize("impl_name,tol", [("bf16x3", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("which", ["b", "a", "ab"])
+@pytest.mark.parametrize("m,n,k", [(300, 155, 155), (1000, 620, 488), (155, 488, 3000)])
+def test_gemm_tc_plane_operands(m, n, k, ta, tb, which, impl_name, tol):
+    """Operands supplied as pre-swizzled bf16 planes (bulk-copied into the MMA stages) in every orientation:
+    K-major (contraction over the matrix' columns) and M/N-major (over its rows), ragged sizes."""
+    import ctypes as C
+    from v1t_b200 import _lib
+    lib = _lib.load()
+    impl = {"bf16x3": _lib.IMPL_BF16X3, "bf16": _lib.IMPL_BF16}[impl_name]
+    rng = torch.Generator(device=DEV).manual_seed(m + 3 * n + 7 * k)
+    A = torch.randn((k, m) if ta else (m, k), device=DEV, generator=rng)
+    Bm = torch.randn((n, k) if tb else (k, n), device=DEV, generator=rng)
+    bias = torch.randn(n, device=DEV, generator=rng)
+    ldc = n + 1
+    Cm = torch.full((m, ldc), float("nan"), device=DEV)
+    d = _lib.GemmDesc(m=m, n=n, k=k, batch1=1, batch2=1, alpha=1.0, accumulate=0)
+    d.a_m, d.a_k = (1, m) if ta else (k, 1)
+    d.b_k, d.b_n = (1, k) if tb else (n, 1)
+    d.c_m = ldc
+    x3 = impl_name == "bf16x3"
+    ah, al = _planes_of(lib, A, x3) if "a" in which else (None, None)
+    bh, bl = _planes_of(lib, Bm, x3) if "b" in which else (None, None)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    rc = lib.v1t_gemm_tc_planes(C.byref(d), None if ah is not None else A.data_ptr(),
+                                None if bh is not None else Bm.data_ptr(), Cm.data_ptr(), bias.data_ptr(), None, impl,
+                                ptr(ah), ptr(al), A.shape[0], A.shape[1], ptr(bh), ptr(bl), Bm.shape[0], Bm.shape[1],
+                                torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    Am = A.t() if ta else A
+    Bn = Bm.t() if tb else Bm
+    if not x3:
+        Am, Bn = Am.bfloat16().float(), Bn.bfloat16().float()
+    ref = (Am.double() @ Bn.double() + bias.double()).cpu().numpy()
+    got = Cm[:, :n].cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) < (2e-5 if x3 else 1e-5), rel_err(got, ref)
+    assert torch.isnan(Cm[:, n:]).all()  # nothing written past column n
+
+
 @pytest.mark.parametrize("shape", TC_SHAPES[:4])
 def test_gemm_tc_bf16_matches_bf16_rounded_reference(shape):
     """Plain bf16 operands: agrees with an fp64 product of bf16-ROUNDED inputs (exact operand semantics)."""

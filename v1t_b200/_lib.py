@@ -88,6 +88,10 @@ SYMBOLS = {
     "v1t_gemm_fp32": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "v1t_gemm_tc_set_mn_major": (C.c_int, [C.c_int]),
     "v1t_gemm_tc": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "v1t_matrix_plane_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "v1t_matrix_planes": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp]),
+    "v1t_gemm_tc_planes": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int64,
+                                     C.c_int64, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "v1t_attn_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "v1t_attn_forward": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f, C.c_uint64, C.c_uint32,
                                    _vp, _vp, _vp, _vp]),

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (STAGES + RAW) * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* pfull = empty + STAGES;  // plane-operand bulk copies landed (expect_tx, loader warp)
+  uint64_t* tfull = pfull + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* stage_base = smem + (STAGES + RAW) * STAGE_BYTES + 256;
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], ((a.a_pl && a.b_pl) ? 0 : kProdThreads) + ((a.a_pl || a.b_pl) ? 1 : 0));
+      mbar_init(&full[s], kProdThreads);
+      mbar_init(&pfull[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -152,31 +154,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           const int k0 = tl.k_begin + kb * BK;
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + 2 * A_PLANE;
-          mbar_expect_tx(&full[stage], bytes);
+          mbar_expect_tx(&pfull[stage], bytes);
           if (a.a_pl) {
             if (a.mn_a) {
               for (int j = 0; j < a_atoms; ++j) {
                 const int64_t src = ((int64_t)(tl.m0 / 32 + j) * a.pa.rows_p + k0) * 64;
-                bulk_g2s(sa + j * 2048, a.pa.hi + src, 2048, &full[stage]);
-                if (a.x3) bulk_g2s(sa + A_PLANE + j * 2048, a.pa.lo + src, 2048, &full[stage]);
+                bulk_g2s(sa + j * 2048, a.pa.hi + src, 2048, &pfull[stage]);
+                if (a.x3) bulk_g2s(sa + A_PLANE + j * 2048, a.pa.lo + src, 2048, &pfull[stage]);
               }
             } else {
               const int64_t src = ((int64_t)(k0 >> 5) * a.pa.rows_p + tl.m0) * 64;
-              bulk_g2s(sa, a.pa.hi + src, a_rows * 64, &full[stage]);
-              if (a.x3) bulk_g2s(sa + A_PLANE, a.pa.lo + src, a_rows * 64, &full[stage]);
+              bulk_g2s(sa, a.pa.hi + src, a_rows * 64, &pfull[stage]);
+              if (a.x3) bulk_g2s(sa + A_PLANE, a.pa.lo + src, a_rows * 64, &pfull[stage]);
             }
           }
           if (a.b_pl) {
             if (a.mn_b) {
               for (int j = 0; j < b_atoms; ++j) {
                 const int64_t src = ((int64_t)(tl.n0 / 32 + j) * a.pb.rows_p + k0) * 64;
-                bulk_g2s(sb + j * 2048, a.pb.hi + src, 2048, &full[stage]);
-                if (a.x3) bulk_g2s(sb + B_PLANE + j * 2048, a.pb.lo + src, 2048, &full[stage]);
+                bulk_g2s(sb + j * 2048, a.pb.hi + src, 2048, &pfull[stage]);
+                if (a.x3) bulk_g2s(sb + B_PLANE + j * 2048, a.pb.lo + src, 2048, &pfull[stage]);
               }
             } else {
               const int64_t src = ((int64_t)(k0 >> 5) * a.pb.rows_p + tl.n0) * 64;
-              bulk_g2s(sb, a.pb.hi + src, b_rows * 64, &full[stage]);
-              if (a.x3) bulk_g2s(sb + B_PLANE, a.pb.lo + src, b_rows * 64, &full[stage]);
+              bulk_g2s(sb, a.pb.hi + src, b_rows * 64, &pfull[stage]);
+              if (a.x3) bulk_g2s(sb + B_PLANE, a.pb.lo + src, b_rows * 64, &pfull[stage]);
             }
           }
         }
@@ -307,9 +309,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const uint32_t sb_hi = sa_hi + 2 * A_PLANE;
         const uint32_t rb = smem_u32(rbase);
         // chunk by chunk: staging slot -> registers -> bf16 hi/lo -> swizzled UMMA stage
-  #pragma unroll
+#pragma unroll
         for (int i = 0; i < 6; ++i) {
-          if (i < 2 || ptid + (i - 2) * kProdThreads < b_chunks) {
+          if (i < 2 ? a_on : ptid + (i - 2) * kProdThreads < b_chunks) {
             const uint4 x = lds128(rb + i * (kProdThreads * 32));
             const uint4 y = lds128(rb + i * (kProdThreads * 32) + 16);
             const float v[8] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w),
@@ -349,7 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int stage = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[stage], ph);
+        if (!(a.a_pl && a.b_pl)) mbar_wait(&full[stage], ph);   // converted operands stored
+        if (a.a_pl || a.b_pl) mbar_wait(&pfull[stage], ph);      // plane operands landed
         tc_fence_after();
         {
           const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
@@ -601,4 +604,38 @@ extern "C" int v1t_gemm_tc(const v1t_gemm_desc* d, const float* A, const float* 
   V1T_CHECK_ARG(d && A && B && C, "v1t_gemm_tc: null argument");
   V1T_CHECK_ARG(impl == V1T_IMPL_BF16X3 || impl == V1T_IMPL_BF16, "v1t_gemm_tc: impl must be BF16X3 or BF16");
   return v1t::gemm_tc(*d, A, B, C, bias, R, (cudaStream_t)stream, v1t::no_drop(), impl == V1T_IMPL_BF16X3);
+}
+
+extern "C" size_t v1t_matrix_plane_bytes(int64_t rows, int64_t cols) {
+  return (rows > 0 && cols > 0) ? v1t::matrix_plane_bytes(rows, cols) : 0;
+}
+
+extern "C" int v1t_matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo,
+                                 void* stream) {
+  V1T_CHECK_ARG(X && hi && rows > 0 && cols > 0 && ld >= cols, "v1t_matrix_planes: bad argument");
+  v1t::PlaneOp out;
+  return v1t::matrix_planes(X, ld, rows, cols, hi, lo, &out, (cudaStream_t)stream);
+}
+
+extern "C" int v1t_gemm_tc_planes(const v1t_gemm_desc* d, const float* A, const float* B, float* C, const float* bias,
+                                  const float* R, int impl, const void* a_hi, const void* a_lo, int64_t a_rows,
+                                  int64_t a_cols, const void* b_hi, const void* b_lo, int64_t b_rows, int64_t b_cols,
+                                  void* stream) {
+  using namespace v1t;
+  V1T_CHECK_ARG(d && C && (A || a_hi) && (B || b_hi), "v1t_gemm_tc_planes: null argument");
+  V1T_CHECK_ARG(impl == V1T_IMPL_BF16X3 || impl == V1T_IMPL_BF16, "v1t_gemm_tc_planes: impl must be BF16X3 or BF16");
+  V1T_CHECK_ARG(d->k > 0 && (d->a_k == 1 || d->a_m == 1) && (d->b_k == 1 || d->b_n == 1),
+                "v1t_gemm_tc_planes: operands must be contiguous along k or along m/n");
+  PlaneOp pa = no_plane(), pb = no_plane();
+  if (a_hi) {  // the planes' matrix is A itself (k = columns) or A^T (k = rows)
+    V1T_CHECK_ARG(d->a_k == 1 ? (a_rows == d->m && a_cols == d->k) : (a_rows == d->k && a_cols == d->m),
+                  "v1t_gemm_tc_planes: A planes do not match the problem");
+    pa = PlaneOp{(const uint8_t*)a_hi, (const uint8_t*)a_lo, (int)round_up(a_rows, 32), cdiv(a_cols, 32)};
+  }
+  if (b_hi) {
+    V1T_CHECK_ARG(d->b_k == 1 ? (b_rows == d->n && b_cols == d->k) : (b_rows == d->k && b_cols == d->n),
+                  "v1t_gemm_tc_planes: B planes do not match the problem");
+    pb = PlaneOp{(const uint8_t*)b_hi, (const uint8_t*)b_lo, (int)round_up(b_rows, 32), cdiv(b_cols, 32)};
+  }
+  return gemm_tc(*d, A, B, C, bias, R, (cudaStream_t)stream, no_drop(), impl == V1T_IMPL_BF16X3, no_epi(), pa, pb);
 }
