@@ -24,6 +24,10 @@ namespace {
 
 using namespace tc;
 
+#ifndef EPI_UNROLL
+#define EPI_UNROLL 1
+#endif
+constexpr int kEpiUnroll = EPI_UNROLL;  // rows of a 32 x 32 group in flight per epilogue warp (ILP vs code size)
 constexpr int BM = 128, BK = 32, STAGES = 2, RAW = 2, BN_MAX = 256;  // UMMA stages, raw fp32 staging slots
 constexpr int kEpiWarps = 8, kProdWarps = 8;
 constexpr int kLoaderWarp = kEpiWarps + 1 + kProdWarps;       // bulk-copies plane operands (PlaneOp) into the stages
@@ -76,26 +80,14 @@ __device__ __forceinline__ Tile decode_tile(const TcArgs& a, int t) {
   return tl;
 }
 
-// 8 consecutive k of one row (zero-filled outside [0,rows) x [.,k_end))
-__device__ __forceinline__ void load8(const float* __restrict__ base, int64_t s_row, int64_t s_k, bool vec, int row,
-                                      int rows, int k, int k_end, float (&v)[8]) {
-  if (row >= rows || k >= k_end) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    return;
-  }
-  const float* p = base + (int64_t)row * s_row + (int64_t)k * s_k;
-  if (vec && k + 8 <= k_end) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 y = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (k + j < k_end) ? __ldg(p + (int64_t)j * s_k) : 0.f;
-  }
-}
-
+// Template parameters strip everything a launch does not need (the three warp roles share one instruction cache
+// and the kernel is fetch-sensitive): EPI bit 0 = dropout on the main output, bits 1.. = EpiOp kind; ACONV / BCONV =
+// the operand is converted from fp32 by the producer warps (false: it arrives as planes through the loader warp).
+template <int EPI, bool ACONV, bool BCONV>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
+  constexpr bool kDrop = (EPI & 1) != 0;
+  constexpr int kKind = EPI >> 1;
+  constexpr bool kConv = ACONV || BCONV, kPlanes = !ACONV || !BCONV;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (STAGES + RAW) * STAGE_BYTES);
@@ -133,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     // ============================== PLANE LOADER ==============================
     // One thread: per k-block, wait for the stage to drain, then bulk-copy the plane operand tiles (already in
     // the swizzled UMMA layout) from global memory; the copies complete on the stage's full barrier.
-    if ((a.a_pl || a.b_pl) && lane == 0) {
+    if (kPlanes && lane == 0) {
       uint32_t it = 0;
       const uint32_t nplanes = a.x3 ? 2u : 1u;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -144,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const int a_rows = min(BM, a.pa.rows_p - tl.m0), a_atoms = max(0, min(BM / 32, a.pa.catoms - tl.m0 / 32));
         const int b_rows = min(a.bn, a.pb.rows_p - tl.n0), b_atoms = max(0, min(a.bn / 32, a.pb.catoms - tl.n0 / 32));
         uint32_t bytes = 0;
-        if (a.a_pl) bytes += a.mn_a ? a_atoms * 2048 : a_rows * 64;
-        if (a.b_pl) bytes += a.mn_b ? b_atoms * 2048 : b_rows * 64;
+        if (!ACONV) bytes += a.mn_a ? a_atoms * 2048 : a_rows * 64;
+        if (!BCONV) bytes += a.mn_b ? b_atoms * 2048 : b_rows * 64;
         bytes *= nplanes;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int stage = it % STAGES;
@@ -155,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + 2 * A_PLANE;
           mbar_expect_tx(&pfull[stage], bytes);
-          if (a.a_pl) {
+          if constexpr (!ACONV) {
             if (a.mn_a) {
               for (int j = 0; j < a_atoms; ++j) {
                 const int64_t src = ((int64_t)(tl.m0 / 32 + j) * a.pa.rows_p + k0) * 64;
@@ -168,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
               if (a.x3) bulk_g2s(sa + A_PLANE, a.pa.lo + src, a_rows * 64, &pfull[stage]);
             }
           }
-          if (a.b_pl) {
+          if constexpr (!BCONV) {
             if (a.mn_b) {
               for (int j = 0; j < b_atoms; ++j) {
                 const int64_t src = ((int64_t)(tl.n0 / 32 + j) * a.pb.rows_p + k0) * 64;
@@ -184,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         }
       }
     }
-  } else if (warp > kEpiWarps && !(a.a_pl && a.b_pl)) {
+  } else if (warp > kEpiWarps && kConv) {
     // ============================== PRODUCERS ==============================
     // Two-level pipeline.  (1) cp.async copies the raw fp32 operand chunks of k-block i+RAW into a per-thread
     // staging slot (each thread later reads only what it copied itself, so no cross-thread synchronisation is
@@ -193,8 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     // UMMA stage.  Thread -> chunk assignment is fixed per launch.
     const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;
     const bool a_kc = (g.d.a_k == 1), b_kc = (g.d.b_k == 1);
-    const int b_chunks = a.b_pl ? 0 : a.bn * 4;  // plane operands are not converted here
-    const bool a_on = !a.a_pl;
+    const int b_chunks = BCONV ? a.bn * 4 : 0;  // plane operands are not converted here
     uint8_t* raw = smem + STAGES * STAGE_BYTES;
 
     // ---- per-thread chunk geometry (constant for the whole launch: no divisions in the k loop) ----
@@ -280,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const float* base = g.A + pf_tl.a_off + (int64_t)l0 * a_sl + (int64_t)c0 * a_sc;
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-          if (a_on) copy_chunk(rbase + i * (kProdThreads * 32), base + ca[i].goff, l0 + (ca[i].lc >> 12) < l_lim,
+          if (ACONV) copy_chunk(rbase + i * (kProdThreads * 32), base + ca[i].goff, l0 + (ca[i].lc >> 12) < l_lim,
                      c_lim - (c0 + (ca[i].lc & 4095)), a_sc, a_vec);
       }
       {
@@ -289,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const float* base = g.B + pf_tl.b_off + (int64_t)l0 * b_sl + (int64_t)c0 * b_sc;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (ptid + i * kProdThreads < b_chunks)
+          if (BCONV && ptid + i * kProdThreads < b_chunks)
             copy_chunk(rbase + (2 + i) * (kProdThreads * 32), base + cb[i].goff, l0 + (cb[i].lc >> 12) < l_lim,
                        c_lim - (c0 + (cb[i].lc & 4095)), b_sc, b_vec);
       }
@@ -311,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         // chunk by chunk: staging slot -> registers -> bf16 hi/lo -> swizzled UMMA stage
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          if (i < 2 ? a_on : ptid + (i - 2) * kProdThreads < b_chunks) {
+          if (i < 2 ? ACONV : (BCONV && ptid + (i - 2) * kProdThreads < b_chunks)) {
             const uint4 x = lds128(rb + i * (kProdThreads * 32));
             const uint4 y = lds128(rb + i * (kProdThreads * 32) + 16);
             const float v[8] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w),
@@ -351,8 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int stage = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        if (!(a.a_pl && a.b_pl)) mbar_wait(&full[stage], ph);   // converted operands stored
-        if (a.a_pl || a.b_pl) mbar_wait(&pfull[stage], ph);      // plane operands landed
+        if (kConv) mbar_wait(&full[stage], ph);     // converted operands stored
+        if (kPlanes) mbar_wait(&pfull[stage], ph);  // plane operands landed
         tc_fence_after();
         {
           const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
@@ -391,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     // epilogue became fetch-bound ("no_instructions" stalls, profiles/r1_gemm_epilogue_icache.txt).
     uint32_t tl_i = 0;
     const int quarter = warp & 3, half = warp >> 2;
-    const float inv_keep = g.drop.p > 0.f ? 1.f / (1.f - g.drop.p) : 1.f;
+    const float inv_keep = (kDrop && g.drop.p > 0.f) ? 1.f / (1.f - g.drop.p) : 1.f;
     const int64_t drop_ld = (g.d.n + 3) & ~3;
     const float inv_keep2 = g.epi.drop.p > 0.f ? 1.f / (1.f - g.epi.drop.p) : 1.f;
     const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
@@ -428,36 +419,51 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             for (int e = 0; e < 4; ++e) if (e < nv) bv[e] = __ldg(g.bias + n4 + e);
           }
         }
-#pragma unroll 1
+        // The pre-activation (GELU gradient) and residual quads of row-iteration i + 1 are fetched while iteration
+        // i computes: with the loop rolled, an un-prefetched global load would stall every iteration for its full
+        // latency (8 epilogue warps cannot hide it).
+        const int row0 = tl.m0 + quarter * 32 + (lane >> 3);
+        const bool pre_u = kKind == kEpiGeluGrad && nv > 0;
+        const bool pre_r = g.R && a.r_vec && nv == 4;
+        float4 u_nx = make_float4(0.f, 0.f, 0.f, 0.f), r_nx = u_nx;
+        auto prefetch = [&](int i) {
+          const int mm = row0 + 4 * i;
+          if (mm < g.d.m) {
+            if (pre_u) u_nx = __ldg(reinterpret_cast<const float4*>(g.epi.u + (int64_t)mm * g.epi.ld + n4));
+            if (pre_r) r_nx = __ldg(reinterpret_cast<const float4*>(g.R + tl.r_off + (int64_t)mm * g.d.r_m + n4));
+          }
+        };
+        prefetch(0);
+#pragma unroll kEpiUnroll
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + (lane >> 3);
           const int mm = tl.m0 + quarter * 32 + r;
+          const float4 uv = u_nx, rv = r_nx;
+          if (i + 1 < 8) prefetch(i + 1);
           if (mm >= g.d.m || nv <= 0) continue;
           const uint4 xr = lds128(stg + r * 128 + ((cq ^ (r & 7)) << 4));
           float o[4] = {fmaf(g.d.alpha, __uint_as_float(xr.x), bv[0]), fmaf(g.d.alpha, __uint_as_float(xr.y), bv[1]),
                         fmaf(g.d.alpha, __uint_as_float(xr.z), bv[2]), fmaf(g.d.alpha, __uint_as_float(xr.w), bv[3])};
           const bool full4 = (nv == 4);
-          if (g.drop.p > 0.f) {
+          if (kDrop && g.drop.p > 0.f) {
             float mk[4];
             dropout_mult4(g.drop.seed, g.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.drop.p, inv_keep, mk);
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] *= mk[e];
           }
           float mk2[4] = {1.f, 1.f, 1.f, 1.f};
-          if (g.epi.kind != kEpiNone && g.epi.drop.p > 0.f)
+          if (kKind != kEpiNone && g.epi.drop.p > 0.f)
             dropout_mult4(g.epi.drop.seed, g.epi.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.epi.drop.p, inv_keep2, mk2);
-          if (g.epi.kind == kEpiGeluGrad) {
+          if constexpr (kKind == kEpiGeluGrad) {
             // epi.ld % 4 == 0 and 16-byte aligned rows are checked on the host: the quad is always readable
-            const float4 uv = __ldg(reinterpret_cast<const float4*>(g.epi.u + (int64_t)mm * g.epi.ld + n4));
             o[0] *= gelu_df(uv.x) * mk2[0]; o[1] *= gelu_df(uv.y) * mk2[1];
             o[2] *= gelu_df(uv.z) * mk2[2]; o[3] *= gelu_df(uv.w) * mk2[3];
           }
           if (g.R) {
-            const float* rp = g.R + tl.r_off + (int64_t)mm * g.d.r_m + n4;
-            if (a.r_vec && full4) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(rp));
+            if (pre_r) {
               o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
             } else {
+              const float* rp = g.R + tl.r_off + (int64_t)mm * g.d.r_m + n4;
 #pragma unroll
               for (int e = 0; e < 4; ++e) if (e < nv) o[e] += __ldg(rp + e);
             }
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
                 cp[e] = o[e];
               }
           }
-          if (g.epi.kind == kEpiGeluOut) {
+          if constexpr (kKind == kEpiGeluOut) {
             float* ap = g.epi.aux + (int64_t)mm * g.epi.ld + n4;
             const float4 gv = make_float4(gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]);
             if (full4) *reinterpret_cast<float4*>(ap) = gv;
@@ -515,11 +521,6 @@ int pick_bn(const v1t_gemm_desc& d, const PlaneOp& pb) {
 int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
               DropSpec drop, int x3, int splits, int k_chunk, int64_t c_split, cudaStream_t st, EpiOp epi = no_epi(),
               PlaneOp pa = no_plane(), PlaneOp pb = no_plane()) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    V1T_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   TcArgs a;
   a.g.d = d;
   a.g.A = A; a.g.B = B; a.g.C = C; a.g.bias = bias; a.g.R = R;
@@ -546,7 +547,23 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   const int64_t total = (int64_t)d.batch1 * d.batch2 * splits * a.tiles_m * a.tiles_n;
   V1T_CHECK_ARG(total < (1ll << 31), "tc gemm: too many tiles");
   const int grid = (int)std::min<int64_t>(total, kNumSMs);
-  tc_gemm_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(a);
+  // instantiation table: [epilogue variant][A converted][B converted]
+  using Kern = void (*)(const TcArgs);
+#define V1T_TC_ROW(E) {{tc_gemm_kernel<E, false, false>, tc_gemm_kernel<E, false, true>}, \
+                       {tc_gemm_kernel<E, true, false>, tc_gemm_kernel<E, true, true>}}
+  static const Kern table[4][2][2] = {V1T_TC_ROW(0), V1T_TC_ROW(1), V1T_TC_ROW(kEpiGeluOut << 1),
+                                      V1T_TC_ROW(kEpiGeluGrad << 1)};
+#undef V1T_TC_ROW
+  static bool attr_set[4][2][2] = {};
+  V1T_CHECK_ARG(epi.kind == kEpiNone || drop.p <= 0.f, "tc gemm: a fused activation excludes dropout on the main output");
+  const int ev = epi.kind == kEpiGeluOut ? 2 : epi.kind == kEpiGeluGrad ? 3 : (drop.p > 0.f ? 1 : 0);
+  const int ac = a.a_pl ? 0 : 1, bc = a.b_pl ? 0 : 1;
+  Kern kern = table[ev][ac][bc];
+  if (!attr_set[ev][ac][bc]) {
+    V1T_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[ev][ac][bc] = true;
+  }
+  kern<<<grid, kThreads, SMEM_BYTES, st>>>(a);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
