@@ -74,6 +74,7 @@ struct BlockSaved {
   float *x1, *st1, *qkv, *o, *x2, *st2, *u, *g, *bhid, *blat, *lse;
   uint8_t *qp[2], *kp[2], *vp[2];  // bf16 hi/lo operand planes of Q, K, V (fused attention), reused by the backward
   uint8_t* wpl[4][2];              // GEMM-operand planes of Wqkv, Wproj, W1, W2 (converted once per step)
+  uint8_t* gpl[2];                 // operand planes of gelu(u) * dropout (emitted by the MLP GEMM epilogue)
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -101,8 +102,19 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
   for (int w = 0; w < 4; ++w)
     for (int i = 0; i < 2; ++i)
       b.wpl[w][i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(wr[w], wc[w]) / sizeof(float)) : 1);
+  for (int i = 0; i < 2; ++i)
+    b.gpl[i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
 }
 enum { kWqkv = 0, kWproj = 1, kW1 = 2, kW2 = 3 };
+// activation planes: the [R, cols] matrix as GEMM operand / as destination of the kernel producing it
+PlaneOp act_plane(const Dims& d, uint8_t* const (&pl)[2], int64_t cols) {
+  if (d.impl == V1T_IMPL_FP32) return no_plane();
+  return PlaneOp{pl[0], d.impl == V1T_IMPL_BF16X3 ? pl[1] : nullptr, (int)round_up(d.R, 32), cdiv(cols, 32)};
+}
+PlaneOut act_plane_out(const Dims& d, uint8_t* const (&pl)[2]) {
+  if (d.impl == V1T_IMPL_FP32) return no_plane_out();
+  return PlaneOut{pl[0], d.impl == V1T_IMPL_BF16X3 ? pl[1] : nullptr, (int)round_up(d.R, 32)};
+}
 // plane operand of weight `w` ([rows, cols] = torch Linear [out, in]); none in fp32 mode
 PlaneOp wplane(const Dims& d, const BlockSaved& S, int w) {
   if (d.impl == V1T_IMPL_FP32) return no_plane();
@@ -122,6 +134,7 @@ constexpr size_t kPartialBytes = 64u << 20;
 struct Scratch {
   BlockSaved tmp;    // one block of "saved" space for inference (keep_for_backward == 0)
   float *h, *dh, *g, *dqkv, *dO, *patches, *P1, *P2, *partials, *dlat, *dz3, *dhid, *dpos;
+  uint8_t *hpl[2], *dpl[2], *dupl[2];  // operand planes of the LayerNorm output, of dropout(dx) and of du (backward)
   AttnPlanes planes;
   int chunk;         // attention batch chunk
   size_t total;
@@ -154,6 +167,12 @@ Scratch carve_scratch(const Dims& d, void* base) {
     s.planes = carve_attn_planes(pbase, d.B, d.heads, d.Tq, d.Ep, true);
   } else {
     s.planes = AttnPlanes{};
+  }
+  for (int i = 0; i < 2; ++i) {
+    const bool tc = d.impl != V1T_IMPL_FP32;
+    s.hpl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
+    s.dpl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
+    s.dupl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
   }
   s.partials = c.take(kPartialBytes / sizeof(float));
   s.dlat = c.take((int64_t)d.B * d.E);
@@ -264,13 +283,13 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       V1T_TRY(matrix_planes(W.w2, d.M, d.E, d.M, S.wpl[kW2][0], x3 ? S.wpl[kW2][1] : nullptr, &tmp, st));
     }
     // ---- Attention.mha (vit.py:267-275)
-    V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st));
+    V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st, act_plane_out(d, sc.hpl)));
     {
       v1t_gemm_desc g = gd((int)d.R, 3 * d.I, d.E);
       V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = 3 * d.I;
-      V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
-                       wplane(d, S, kWqkv)));
+      V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st, no_drop(), no_epi(),
+                       act_plane(d, sc.hpl, d.E), wplane(d, S, kWqkv)));
     }
     }
     if (d.fused) {  // tcgen05 fused attention: qkv -> bf16 operand planes -> O, lse (nothing T x T in HBM)
@@ -314,13 +333,15 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     }
     // ---- MLP (vit.py:143-150)
     ProfScope prof_mlp(V1T_PHASE_MLP, st);
-    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, S.st2, d.R, d.E, d.Ep, st));
+    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, S.st2, d.R, d.E, d.Ep, st, act_plane_out(d, sc.hpl)));
     {
       v1t_gemm_desc g = gd((int)d.R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = d.Mp;
       if (gemm_uses_tc(d.impl, g)) {  // u and gelu(u)*dropout from one epilogue
-        const EpiOp act{kEpiGeluOut, S.g, nullptr, d.Mp, site_drop(*shape, i, kSiteMlp1)};
-        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st, no_drop(), act, no_plane(), wplane(d, S, kW1)));
+        // gelu(u) * dropout leaves the epilogue as operand planes only (consumers: W2 GEMM and its weight gradient)
+        const EpiOp act{kEpiGeluOut, nullptr, nullptr, d.Mp, site_drop(*shape, i, kSiteMlp1), act_plane_out(d, S.gpl)};
+        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st, no_drop(), act, act_plane(d, sc.hpl, d.E),
+                         wplane(d, S, kW1)));
       } else {
         V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st));
         V1T_TRY(gelu_forward(S.u, S.g, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));
@@ -329,8 +350,9 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     {
       v1t_gemm_desc g = gd((int)d.R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = 1; g.b_n = d.M; g.c_m = d.Ep; g.r_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, S.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2), no_epi(), no_plane(),
-                       wplane(d, S, kW2)));
+      const bool gp = gemm_uses_tc(d.impl, g);  // then the MLP GEMM above emitted planes instead of fp32 g
+      V1T_TRY(gemm_any(d.impl, g, S.g, W.w2, x, W.b2, S.x2, st, site_drop(*shape, i, kSiteMlp2), no_epi(),
+                       gp ? act_plane(d, S.gpl, d.M) : no_plane(), wplane(d, S, kW2)));
     }
   }
   return V1T_OK;
@@ -356,59 +378,67 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     // ================= MLP branch: x_out = x2 + drop(g W2^T + b2) =================
     std::unique_ptr<ProfScope> lin1(new ProfScope(V1T_PHASE_LINEAR_BWD, st));
     const float* dm = dx;
+    PlaneOp dmp = no_plane();  // operand planes of dm (emitted by the dropout kernel)
     if (drop) {
-      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteMlp2), st));
+      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteMlp2), st, act_plane_out(d, sc.dpl)));
       dm = sc.dh;
+      dmp = act_plane(d, sc.dpl, d.E);
     }
+    // whether the forward MLP GEMM ran on the tensor cores (then gelu(u)*dropout exists as planes only)
+    const bool mlp_tc = [&] { v1t_gemm_desc g = gd(R, d.M, d.E); g.a_k = 1; g.b_k = 1; return gemm_uses_tc(d.impl, g); }();
     if (GW.w2) {  // dW2[e,m] = sum_r dm[r,e] g[r,m]
       v1t_gemm_desc g = gd(d.E, d.M, R);
       g.a_m = 1; g.a_k = d.Ep; g.b_k = d.Mp; g.b_n = 1; g.c_m = d.M;
-      V1T_TRY(gemm_any_splitk(d.impl, g, dm, S.g, GW.w2, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, dm, S.g, GW.w2, sc.partials, kPartialBytes, st, dmp,
+                              mlp_tc ? act_plane(d, S.gpl, d.M) : no_plane()));
     }
     if (GW.b2) V1T_TRY(colsum(dm, GW.b2, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
     {  // dg[r,m] = sum_e dm[r,e] W2[e,m]   -> sc.g (g no longer needed)
       v1t_gemm_desc g = gd(R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.M; g.b_n = 1; g.c_m = d.Mp;
       if (gemm_uses_tc(d.impl, g)) {  // du = (dm W2) * gelu'(u) * dropout in the epilogue
-        const EpiOp act{kEpiGeluGrad, nullptr, S.u, d.Mp, site_drop(*shape, i, kSiteMlp1)};
-        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st, no_drop(), act, no_plane(), wplane(d, S, kW2)));
+        const EpiOp act{kEpiGeluGrad, nullptr, S.u, d.Mp, site_drop(*shape, i, kSiteMlp1), act_plane_out(d, sc.dupl)};
+        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st, no_drop(), act, dmp, wplane(d, S, kW2)));
       } else {
         V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st));
         V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
       }
     }
-    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
+    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, nullptr, d.R, d.E, d.Ep, st,
+                       act_plane_out(d, sc.hpl)));
+    const PlaneOp dup = mlp_tc ? act_plane(d, sc.dupl, d.M) : no_plane();  // du planes from the epilogue above
     if (GW.w1) {  // dW1[m,e] = sum_r du[r,m] h2[r,e]
       v1t_gemm_desc g = gd(d.M, d.E, R);
       g.a_m = 1; g.a_k = d.Mp; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
-      V1T_TRY(gemm_any_splitk(d.impl, g, sc.g, sc.h, GW.w1, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, sc.g, sc.h, GW.w1, sc.partials, kPartialBytes, st, dup,
+                              act_plane(d, sc.hpl, d.E)));
     }
     if (GW.b1) V1T_TRY(colsum(sc.g, GW.b1, 1, d.R, d.M, 0, d.Mp, 0, sc.partials, kPartialBytes, st));
     {  // dh2[r,e] = sum_m du[r,m] W1[m,e]
       v1t_gemm_desc g = gd(R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, sc.g, W.w1, sc.dh, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
-                       wplane(d, S, kW1)));
+      V1T_TRY(gemm_any(d.impl, g, sc.g, W.w1, sc.dh, nullptr, nullptr, st, no_drop(), no_epi(), dup, wplane(d, S, kW1)));
     }
     V1T_TRY(ln_backward(sc.dh, S.x2, S.st2, W.ln2_w, dx, GW.ln2_w, GW.ln2_b, sc.partials, kPartialBytes, d.R, d.E,
                         d.Ep, st));
     // ================= attention branch: x2 = x1 + drop(o Wproj^T + b) =================
     const float* da = dx;
+    PlaneOp dap = no_plane();
     if (drop) {
-      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteProj), st));
+      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteProj), st, act_plane_out(d, sc.dpl)));
       da = sc.dh;
+      dap = act_plane(d, sc.dpl, d.E);
     }
     if (GW.wproj) {  // dWp[e,i] = sum_r da[r,e] o[r,i]
       v1t_gemm_desc g = gd(d.E, d.I, R);
       g.a_m = 1; g.a_k = d.Ep; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
-      V1T_TRY(gemm_any_splitk(d.impl, g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st, dap));
     }
     if (GW.bproj) V1T_TRY(colsum(da, GW.bproj, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
     {  // dO[r,i] = sum_e da[r,e] Wp[e,i]
       v1t_gemm_desc g = gd(R, d.I, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
-      V1T_TRY(gemm_any(d.impl, g, da, W.wproj, sc.dO, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
-                       wplane(d, S, kWproj)));
+      V1T_TRY(gemm_any(d.impl, g, da, W.wproj, sc.dO, nullptr, nullptr, st, no_drop(), no_epi(), dap, wplane(d, S, kWproj)));
     }
     const int64_t ld = 3 * d.I;
     lin1.reset();
@@ -473,11 +503,13 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       }
     }
     ProfScope lin2(V1T_PHASE_LINEAR_BWD, st);
-    V1T_TRY(ln_forward(S.x1, nullptr, d.T, nullptr, W.ln1_w, W.ln1_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
+    V1T_TRY(ln_forward(S.x1, nullptr, d.T, nullptr, W.ln1_w, W.ln1_b, sc.h, nullptr, d.R, d.E, d.Ep, st,
+                       act_plane_out(d, sc.hpl)));
     if (GW.wqkv) {  // dWqkv[n,e] = sum_r dqkv[r,n] h1[r,e]
       v1t_gemm_desc g = gd(3 * d.I, d.E, R);
       g.a_m = 1; g.a_k = ld; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
-      V1T_TRY(gemm_any_splitk(d.impl, g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st));
+      V1T_TRY(gemm_any_splitk(d.impl, g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st, no_plane(),
+                              act_plane(d, sc.hpl, d.E)));
     }
     {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
       v1t_gemm_desc g = gd(R, d.E, 3 * d.I);

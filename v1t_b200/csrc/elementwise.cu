@@ -5,6 +5,7 @@
 // bias / LayerNorm-affine / pos-embedding gradients.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 #include <algorithm>
 
 namespace v1t {
@@ -68,6 +69,49 @@ __global__ void dropout_rows_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// 8 columns (one 16-byte plane chunk) per thread: two Philox calls, 128-bit accesses, optional operand planes of
+// the result (zero in the pad columns)
+__global__ void dropout_rows8_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int cols,
+                                     int64_t ld, int chunks, DropSpec dr, PlaneOut pl) {
+  const float inv_keep = 1.f / (1.f - dr.p);
+  const int64_t total = (pl.hi ? (int64_t)pl.rows_p : rows) * chunks;  // plane pad rows are zero-filled too
+  const int64_t drop_ld = (cols + 3) & ~3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    const int ch = (int)(i % chunks);
+    const int c0 = ch * 8;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = c0 + 4 * q;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c < cols && r < rows) {
+        float m[4];
+        dropout_mult4(dr.seed, dr.site, ((uint64_t)r * drop_ld + c) >> 2, dr.p, inv_keep, m);
+        if (c + 4 <= cols) {
+          const float4 s4 = *reinterpret_cast<const float4*>(src + r * ld + c);
+          x[0] = s4.x * m[0]; x[1] = s4.y * m[1]; x[2] = s4.z * m[2]; x[3] = s4.w * m[3];
+          *reinterpret_cast<float4*>(dst + r * ld + c) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+          for (int e = 0; e < 4 && c + e < cols; ++e) {
+            x[e] = src[r * ld + c + e] * m[e];
+            dst[r * ld + c + e] = x[e];
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[4 * q + e] = x[e];
+    }
+    if (pl.hi) {
+      uint4 hi, lo;
+      tc::split8(v, hi, lo);
+      const int64_t off = tc::plane_chunk_off(ch >> 2, pl.rows_p, r, ch & 3);
+      *reinterpret_cast<uint4*>(pl.hi + off) = hi;
+      if (pl.lo) *reinterpret_cast<uint4*>(pl.lo + off) = lo;
+    }
+  }
+}
+
 __global__ void dropout_mask_kernel(float* __restrict__ out, int64_t n, DropSpec dr) {
   const float inv_keep = 1.f / (1.f - dr.p);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -112,7 +156,8 @@ __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict
                                                          int rows_per_batch, float* __restrict__ x_out,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ h,
-                                                         float* __restrict__ stats, int64_t rows, int E, int ld) {
+                                                         float* __restrict__ stats, int64_t rows, int E, int ld,
+                                                         PlaneOut pl) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -122,6 +167,16 @@ __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict
     const int c = lane + 32 * i;
     g[i] = c < E ? gamma[c] : 0.f;
     bt[i] = c < E ? beta[c] : 0.f;
+  }
+  for (int64_t r = rows + warp; pl.hi && r < pl.rows_p; r += nwarps) {  // zero rows padding the planes
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < 32 * ((E + 31) / 32)) {
+        const int64_t off = tc::plane_chunk_off(i, pl.rows_p, r, lane >> 3) + (lane & 7) * 2;
+        *reinterpret_cast<uint16_t*>(pl.hi + off) = 0;
+        if (pl.lo) *reinterpret_cast<uint16_t*>(pl.lo + off) = 0;
+      }
+    }
   }
   for (int64_t r = warp; r < rows; r += nwarps) {
     float v[NV];
@@ -152,6 +207,14 @@ __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict
         const bool in = c < E;
         if (x_out) x_out[r * ld + c] = in ? v[i] : 0.f;
         if (h) h[r * ld + c] = in ? (v[i] - mean) * rstd * g[i] + bt[i] : 0.f;
+      }
+      // GEMM-operand planes of the normalised row: lane = column within atom i, 8 lanes per 16-byte chunk
+      if (pl.hi && c < 32 * ((E + 31) / 32)) {
+        const float y = c < E ? (v[i] - mean) * rstd * g[i] + bt[i] : 0.f;
+        const __nv_bfloat16 hb = __float2bfloat16_rn(y);
+        const int64_t off = tc::plane_chunk_off(i, pl.rows_p, r, lane >> 3) + (lane & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(pl.hi + off) = hb;
+        if (pl.lo) *reinterpret_cast<__nv_bfloat16*>(pl.lo + off) = __float2bfloat16_rn(y - __bfloat162float(hb));
       }
     }
     if (lane == 0 && stats) {
@@ -405,7 +468,15 @@ int cls_rows(const float* cls, const float* pos, float* x, int B, int T, int E, 
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
-int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st) {
+int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st,
+                 PlaneOut pl) {
+  if (ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const int chunks = cdiv(cols, 32) * 4;  // 16-byte plane chunks (8 columns) per row
+    dropout_rows8_kernel<<<ew_grid(rows * chunks), 256, 0, st>>>(src, dst, rows, cols, ld, chunks, dr, pl);
+    V1T_LAUNCH_CHECK();
+    return V1T_OK;
+  }
+  V1T_CHECK_ARG(!pl.hi, "dropout_rows: plane output needs 16-byte aligned rows");
   dropout_rows_kernel<<<ew_grid(rows * cols), 256, 0, st>>>(src, dst, rows, cols, ld, dr);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
@@ -433,16 +504,16 @@ int tanh_grad(const float* dy, const float* y, float* dz, int64_t n, cudaStream_
   } else
 
 int ln_forward(const float* x_in, const float* add, int rows_per_batch, float* x_out, const float* gamma,
-               const float* beta, float* h, float* stats, int64_t rows, int E, int ld, cudaStream_t st) {
+               const float* beta, float* h, float* stats, int64_t rows, int E, int ld, cudaStream_t st, PlaneOut pl) {
   const int nv = cdiv(ld, 32);
   V1T_CHECK_ARG(nv <= 32 && ld >= E, "layer norm: emb dim %d (ld %d) unsupported (max 1024)", E, ld);
   const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMs * 8);
-  V1T_LN_DISPATCH(1, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
-  V1T_LN_DISPATCH(2, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
-  V1T_LN_DISPATCH(5, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
-  V1T_LN_DISPATCH(8, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
-  V1T_LN_DISPATCH(16, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld)
-  { ln_forward_kernel<32><<<grid, 256, 0, st>>>(x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld); }
+  V1T_LN_DISPATCH(1, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld, pl)
+  V1T_LN_DISPATCH(2, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld, pl)
+  V1T_LN_DISPATCH(5, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld, pl)
+  V1T_LN_DISPATCH(8, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld, pl)
+  V1T_LN_DISPATCH(16, ln_forward_kernel, x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld, pl)
+  { ln_forward_kernel<32><<<grid, 256, 0, st>>>(x_in, add, rows_per_batch, x_out, gamma, beta, h, stats, rows, E, ld, pl); }
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

@@ -88,12 +88,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
   constexpr bool kDrop = (EPI & 1) != 0;
   constexpr int kKind = EPI >> 1;
   constexpr bool kConv = ACONV || BCONV, kPlanes = !ACONV || !BCONV;
+  // with no operand to convert, the raw staging slots become two more UMMA stages (bulk copies need the depth)
+  constexpr int kNS = kConv ? STAGES : STAGES + RAW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (STAGES + RAW) * STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* pfull = empty + STAGES;  // plane-operand bulk copies landed (expect_tx, loader warp)
-  uint64_t* tfull = pfull + STAGES;
+  uint64_t* empty = full + (STAGES + RAW);
+  uint64_t* pfull = empty + (STAGES + RAW);  // plane-operand bulk copies landed (expect_tx, loader warp)
+  uint64_t* tfull = pfull + (STAGES + RAW);
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* stage_base = smem + (STAGES + RAW) * STAGE_BYTES + 256;
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
   const GemmArgs& g = a.g;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < kNS; ++s) {
       mbar_init(&full[s], kProdThreads);
       mbar_init(&pfull[s], 1);
       mbar_init(&empty[s], 1);
@@ -123,55 +125,45 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
 
   if (warp == kLoaderWarp) {
     // ============================== PLANE LOADER ==============================
-    // One thread: per k-block, wait for the stage to drain, then bulk-copy the plane operand tiles (already in
-    // the swizzled UMMA layout) from global memory; the copies complete on the stage's full barrier.
-    if (kPlanes && lane == 0) {
+    // Per k-block: wait for the stage to drain, then bulk-copy the plane operand tiles (already in the swizzled
+    // UMMA layout) from global memory; the copies complete on the stage's pfull barrier.  K-major operand: `rows`
+    // consecutive plane rows of column atom k0/32 (one copy per plane).  MN-major: 32 plane rows (k) of each of
+    // `atoms` consecutive column atoms (2 KB each).  One copy per lane, so a stage's copies are issued in parallel.
+    if (kPlanes) {
       uint32_t it = 0;
-      const uint32_t nplanes = a.x3 ? 2u : 1u;
+      const int np = a.x3 ? 2 : 1;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const Tile tl = decode_tile(a, t);
         const int num_kb = (tl.k_end - tl.k_begin + BK - 1) / BK;
-        // tile-constant geometry.  K-major: `rows` consecutive plane rows of atom k0/32 (one copy);  MN-major: 32
-        // plane rows (k) of each of `atoms` consecutive column atoms (2 KB each)
         const int a_rows = min(BM, a.pa.rows_p - tl.m0), a_atoms = max(0, min(BM / 32, a.pa.catoms - tl.m0 / 32));
         const int b_rows = min(a.bn, a.pb.rows_p - tl.n0), b_atoms = max(0, min(a.bn / 32, a.pb.catoms - tl.n0 / 32));
+        const int a_items = ACONV ? 0 : (a.mn_a ? a_atoms : 1) * np;
+        const int b_items = BCONV ? 0 : (a.mn_b ? b_atoms : 1) * np;
         uint32_t bytes = 0;
-        if (!ACONV) bytes += a.mn_a ? a_atoms * 2048 : a_rows * 64;
-        if (!BCONV) bytes += a.mn_b ? b_atoms * 2048 : b_rows * 64;
-        bytes *= nplanes;
+        if (!ACONV) bytes += (a.mn_a ? a_atoms * 2048 : a_rows * 64) * np;
+        if (!BCONV) bytes += (a.mn_b ? b_atoms * 2048 : b_rows * 64) * np;
+        // this lane's copy (constant over the k loop except for the k offset)
+        const bool mine = lane < a_items + b_items;
+        const bool is_b = lane >= a_items;
+        const int idx = is_b ? lane - a_items : lane;
+        const int plane = idx % np, atom = idx / np;
+        const bool mn = is_b ? a.mn_b : a.mn_a;
+        const PlaneOp& po = is_b ? a.pb : a.pa;
+        const uint8_t* src_base = plane ? po.lo : po.hi;
+        const int row0 = is_b ? tl.n0 : tl.m0;
+        const uint32_t dst_off = (is_b ? 2 * A_PLANE : 0) + plane * (is_b ? B_PLANE : A_PLANE) + (mn ? atom * 2048 : 0);
+        const uint32_t cbytes = mn ? 2048u : (uint32_t)((is_b ? b_rows : a_rows) * 64);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int stage = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+          const int stage = it % kNS;
+          const uint32_t ph = (it / kNS) & 1;
           mbar_wait(&empty[stage], ph ^ 1);
           const int k0 = tl.k_begin + kb * BK;
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + 2 * A_PLANE;
-          mbar_expect_tx(&pfull[stage], bytes);
-          if constexpr (!ACONV) {
-            if (a.mn_a) {
-              for (int j = 0; j < a_atoms; ++j) {
-                const int64_t src = ((int64_t)(tl.m0 / 32 + j) * a.pa.rows_p + k0) * 64;
-                bulk_g2s(sa + j * 2048, a.pa.hi + src, 2048, &pfull[stage]);
-                if (a.x3) bulk_g2s(sa + A_PLANE + j * 2048, a.pa.lo + src, 2048, &pfull[stage]);
-              }
-            } else {
-              const int64_t src = ((int64_t)(k0 >> 5) * a.pa.rows_p + tl.m0) * 64;
-              bulk_g2s(sa, a.pa.hi + src, a_rows * 64, &pfull[stage]);
-              if (a.x3) bulk_g2s(sa + A_PLANE, a.pa.lo + src, a_rows * 64, &pfull[stage]);
-            }
-          }
-          if constexpr (!BCONV) {
-            if (a.mn_b) {
-              for (int j = 0; j < b_atoms; ++j) {
-                const int64_t src = ((int64_t)(tl.n0 / 32 + j) * a.pb.rows_p + k0) * 64;
-                bulk_g2s(sb + j * 2048, a.pb.hi + src, 2048, &pfull[stage]);
-                if (a.x3) bulk_g2s(sb + B_PLANE + j * 2048, a.pb.lo + src, 2048, &pfull[stage]);
-              }
-            } else {
-              const int64_t src = ((int64_t)(k0 >> 5) * a.pb.rows_p + tl.n0) * 64;
-              bulk_g2s(sb, a.pb.hi + src, b_rows * 64, &pfull[stage]);
-              if (a.x3) bulk_g2s(sb + B_PLANE, a.pb.lo + src, b_rows * 64, &pfull[stage]);
-            }
+          if (lane == 0) mbar_expect_tx(&pfull[stage], bytes);
+          __syncwarp();
+          if (mine) {
+            const int64_t src = mn ? ((int64_t)(row0 / 32 + atom) * po.rows_p + k0) * 64
+                                   : ((int64_t)(k0 >> 5) * po.rows_p + row0) * 64;
+            bulk_g2s(smem + stage * STAGE_BYTES + dst_off, src_base + src, cbytes, &pfull[stage]);
           }
         }
       }
@@ -340,8 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN_MAX;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int stage = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+        const int stage = it % kNS;
+        const uint32_t ph = (it / kNS) & 1;
         if (kConv) mbar_wait(&full[stage], ph);     // converted operands stored
         if (kPlanes) mbar_wait(&pfull[stage], ph);  // plane operands landed
         tc_fence_after();
@@ -440,7 +432,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           const int mm = tl.m0 + quarter * 32 + r;
           const float4 uv = u_nx, rv = r_nx;
           if (i + 1 < 8) prefetch(i + 1);
-          if (mm >= g.d.m || nv <= 0) continue;
+          if (mm >= g.d.m || nv <= 0) {  // past the last row / column: only the zero padding of the emitted planes
+            if (kKind != kEpiNone && g.epi.pl.hi && mm < g.epi.pl.rows_p && n4 < 32 * ((g.d.n + 31) / 32)) {
+              const int64_t off = plane_chunk_off(n4 >> 5, g.epi.pl.rows_p, mm, cq >> 1) + (cq & 1) * 8;
+              *reinterpret_cast<uint2*>(g.epi.pl.hi + off) = make_uint2(0u, 0u);
+              if (g.epi.pl.lo) *reinterpret_cast<uint2*>(g.epi.pl.lo + off) = make_uint2(0u, 0u);
+            }
+            continue;
+          }
           const uint4 xr = lds128(stg + r * 128 + ((cq ^ (r & 7)) << 4));
           float o[4] = {fmaf(g.d.alpha, __uint_as_float(xr.x), bv[0]), fmaf(g.d.alpha, __uint_as_float(xr.y), bv[1]),
                         fmaf(g.d.alpha, __uint_as_float(xr.z), bv[2]), fmaf(g.d.alpha, __uint_as_float(xr.w), bv[3])};
@@ -484,14 +483,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
               }
           }
           if constexpr (kKind == kEpiGeluOut) {
-            float* ap = g.epi.aux + (int64_t)mm * g.epi.ld + n4;
-            const float4 gv = make_float4(gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]);
-            if (full4) *reinterpret_cast<float4*>(ap) = gv;
-            else {
-              const float ge[4] = {gv.x, gv.y, gv.z, gv.w};
+            const float ge[4] = {gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) if (e < nv) ap[e] = ge[e];
+            for (int e = 0; e < 4; ++e) o[e] = ge[e];  // o now holds the activation (what the planes carry)
+            if (g.epi.aux) {
+              float* ap = g.epi.aux + (int64_t)mm * g.epi.ld + n4;
+              if (full4) *reinterpret_cast<float4*>(ap) = make_float4(ge[0], ge[1], ge[2], ge[3]);
+              else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (e < nv) ap[e] = ge[e];
+              }
             }
+          }
+          if (kKind != kEpiNone && g.epi.pl.hi) {  // operand planes of the activation-side result
+            const float pv[4] = {o[0], nv > 1 ? o[1] : 0.f, nv > 2 ? o[2] : 0.f, nv > 3 ? o[3] : 0.f};
+            uint2 ph, plo;
+            split4(pv, ph, plo);
+            const int64_t off = plane_chunk_off(n4 >> 5, g.epi.pl.rows_p, mm, cq >> 1) + (cq & 1) * 8;
+            *reinterpret_cast<uint2*>(g.epi.pl.hi + off) = ph;
+            if (g.epi.pl.lo) *reinterpret_cast<uint2*>(g.epi.pl.lo + off) = plo;
           }
         }
         __syncwarp();
@@ -582,6 +592,11 @@ int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, co
   if (epi.kind != kEpiNone) {
     V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && epi.ld % 4 == 0 && aligned16(epi.kind == kEpiGeluOut ? (const void*)epi.aux : (const void*)epi.u),
                   "gemm_tc: fused activation needs an unbatched problem and 16-byte aligned rows");
+    V1T_CHECK_ARG(epi.kind != kEpiGeluOut || epi.aux || epi.pl.hi, "gemm_tc: GELU output has no destination");
+    // emitted planes must be covered by the N tiling (whole 32-column atoms) and by the rows of the problem
+    V1T_CHECK_ARG(!epi.pl.hi || (cdiv(d.n, pick_bn(d, pb)) * pick_bn(d, pb) >= 32 * cdiv(d.n, 32) && epi.pl.rows_p >= d.m &&
+                                 d.n % 4 == 0),
+                  "gemm_tc: plane output does not fit the tiling");
   }
   return launch_tc(d, A, B, C, bias, R, drop, x3, 1, (int)round_up(d.k, BK), 0, st, epi, pa, pb);
 }

@@ -13,14 +13,24 @@ static inline DropSpec no_drop() { return DropSpec{0, 0, 0.f}; }
 
 // optional fused element-wise stage of the tensor-core GEMM epilogue (MLP of the ViT block, vit.py:144-148)
 enum { kEpiNone = 0, kEpiGeluOut = 1, kEpiGeluGrad = 2 };
+// Destination for operand planes (see PlaneOp below) emitted by the kernel that PRODUCES an activation, so that the
+// GEMMs consuming it never convert: hi/lo plane base pointers and the padded row count of the [rows, cols] matrix.
+struct PlaneOut {
+  uint8_t* hi;
+  uint8_t* lo;
+  int rows_p;
+};
+static inline PlaneOut no_plane_out() { return PlaneOut{nullptr, nullptr, 0}; }
+
 struct EpiOp {
   int kind;           // kEpiGeluOut: aux = gelu(C) * dropout ;  kEpiGeluGrad: C *= gelu'(u) * dropout
   float* aux;         // [m, ld] second output (kEpiGeluOut)
   const float* u;     // [m, ld] pre-activation (kEpiGeluGrad)
   int64_t ld;
   DropSpec drop;      // dropout of the activation (element index m * roundup(n,4) + n)
+  PlaneOut pl;        // optional planes of the activation-side result (aux for kEpiGeluOut, C for kEpiGeluGrad)
 };
-static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}}; }
+static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}, no_plane_out()}; }
 
 // Pre-swizzled bf16 hi/lo planes of a row-major matrix X[rows, cols] (planes.cu: matrix_planes): 32-column atoms,
 // [catoms][rows_p][64 B], rows 64 B apart, 16-byte chunks XOR-swizzled with ((row >> 1) & 3), zero padded.  A GEMM
@@ -135,12 +145,14 @@ int im2col(const float* img, float* patches, int B, int C, int H, int W, int p, 
 int col2im(const float* dpatches, float* dimg, int B, int C, int H, int W, int p, int s, int gh, int gw,
            cudaStream_t st);
 int cls_rows(const float* cls, const float* pos, float* x, int B, int T, int E, int ld, cudaStream_t st);
-int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st);
+int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st,
+                 PlaneOut pl = no_plane_out());
 int bmlp_forward(const float* beh, const float* w0, const float* b0, const float* w3, const float* b3, float* hid,
                  float* lat, int B, int bdim, int H, int E, cudaStream_t st);
 int tanh_grad(const float* dy, const float* y, float* dz, int64_t n, cudaStream_t st);  // dz = dy*(1-y^2)
 int ln_forward(const float* x_in, const float* add, int rows_per_batch, float* x_out, const float* gamma,
-               const float* beta, float* h, float* stats, int64_t rows, int E, int ld, cudaStream_t st);
+               const float* beta, float* h, float* stats, int64_t rows, int E, int ld, cudaStream_t st,
+               PlaneOut pl = no_plane_out());
 int ln_backward(const float* dh, const float* x, const float* stats, const float* gamma, float* dx_accum,
                 float* dgamma, float* dbeta, float* partials, size_t partial_bytes, int64_t rows, int E, int ld,
                 cudaStream_t st);

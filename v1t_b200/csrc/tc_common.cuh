@@ -218,6 +218,25 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// byte offset of 16-byte chunk `chunk` of row `row` in column atom `atom` of a matrix plane ([atoms][rows_p][64 B])
+__device__ __forceinline__ int64_t plane_chunk_off(int64_t atom, int64_t rows_p, int64_t row, int chunk) {
+  return (atom * rows_p + row) * 64 + ((chunk ^ (int)((row >> 1) & 3)) << 4);
+}
+// 4 adjacent values -> 8 bytes of the hi plane and 8 bytes of the lo plane
+__device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
+  uint32_t h[2], l[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hb);
+    const __nv_bfloat162 lb = __floats2bfloat162_rn(x[2 * i] - hf.x, x[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+    l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+  }
+  hi = make_uint2(h[0], h[1]);
+  lo = make_uint2(l[0], l[1]);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
