@@ -1,7 +1,9 @@
 // Attention forward, second generation: Q (the 128-row resident operand) and P (the A operand of P V) live in
 // TENSOR MEMORY, so every tcgen05.mma runs in its TS form (~10 + N/2 cycles instead of 43 + N/2, measured by
-// scripts/mma_microbench.py) and shared memory only holds the streamed K and V^T tiles, each in its own
-// double-buffered ring (K(j) is free after S(j), V(j) after P V(j)), which hides the bulk-copy latency.
+// scripts/mma_microbench.py) and shared memory only holds the streamed K and V tiles, each in its own
+// double-buffered ring (K(j) is free after S(j), V(j) after P V(j)), which hides the bulk-copy latency.  V comes
+// from the same token-major planes as K and is read through an MN-major descriptor (N = head dim is the
+// contiguous direction), so no transposed copy of V is ever made.
 // Same two-pass softmax as generation 1 (attn_tc.cu): pass 1 = row maxima from the hi planes, pass 2 = exact.
 //
 // TMEM columns (Dp = 160): Q_hi[80] | Q_lo[80] | S[2][64] | P_hi[32] | P_lo[32] | O[160]  = 512.
@@ -34,7 +36,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <int AD>
 struct FSmem {
   static constexpr uint32_t kKTile = AD * BKEY * 64;       // one plane of a K tile (64 keys x Dp)
-  static constexpr uint32_t kVTile = 2 * AD * 32 * 64;     // one plane of a V^T tile (Dp rows x 64 keys)
+  static constexpr uint32_t kVTile = AD * BKEY * 64;       // one plane of a V tile (64 keys x Dp, MN-major operand)
   static constexpr uint32_t k_ring = 0;                    // 2 slots x (hi, lo); pass 1: 4 hi-only slots
   static constexpr uint32_t v_ring = 4 * kKTile;           // 2 slots x (hi, lo)
   static constexpr uint32_t bars = v_ring + 4 * kVTile;
@@ -136,10 +138,10 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
         mbar_expect_tx(&v_full[s], a.x3 ? 2 * L::kVTile : L::kVTile);
         uint8_t* base = smem + L::v_ring + s * 2 * L::kVTile;
 #pragma unroll
-        for (int ka = 0; ka < 2; ++ka) {
-          const int64_t src = (((int64_t)bh * at + (j * 2 + ka)) * Dp) * 64;
-          bulk_g2s(base + ka * Dp * 64, a.vt_hi + src, Dp * 64, &v_full[s]);
-          if (a.x3) bulk_g2s(base + L::kVTile + ka * Dp * 64, a.vt_lo + src, Dp * 64, &v_full[s]);
+        for (int at_i = 0; at_i < AD; ++at_i) {  // head-dim atom at_i: 64 key rows of 64 bytes, contiguous in the plane
+          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + j * BKEY) * 64;
+          bulk_g2s(base + at_i * BKEY * 64, a.v_hi + src, BKEY * 64, &v_full[s]);
+          if (a.x3) bulk_g2s(base + L::kVTile + at_i * BKEY * 64, a.v_lo + src, BKEY * 64, &v_full[s]);
         }
       }
     }
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     // ============================== MMA ISSUER ==============================
     const bool leader = elect_one();
     const uint32_t idesc_s = idesc_bf16(BQ, BKEY, 0, 0);
-    const uint32_t idesc_o = idesc_bf16(BQ, Dp, 0, 0);
+    const uint32_t idesc_o = idesc_bf16(BQ, Dp, 0, 1);  // B = V is MN-major (head dim contiguous)
     const uint32_t kr0 = smem_u32(smem + L::k_ring) >> 4, vr0 = smem_u32(smem + L::v_ring) >> 4;
     const uint32_t tQ_hi = tmem_base + cQ_hi, tQ_lo = tmem_base + cQ_lo;
     const uint32_t tP_hi = tmem_base + cP_hi, tP_lo = tmem_base + cP_lo, tO = tmem_base + cO;
@@ -189,11 +191,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       mbar_wait(&v_full[s], (j >> 1) & 1);
       mbar_wait(p_full, j & 1);
       tc_fence_after();
-      const uint64_t vh = kDescK64 | (uint64_t)(vr0 + s * 2 * (L::kVTile >> 4)), vl = vh + (L::kVTile >> 4);
+      // MN-major SWIZZLE_64B: head-dim atoms BKEY*64 bytes apart (LBO), 16 keys = 16 rows of 64 bytes per MMA
+      const uint64_t vh = desc_mn_sw64_base(BKEY * 64) | (uint64_t)(vr0 + s * 2 * (L::kVTile >> 4)), vl = vh + (L::kVTile >> 4);
 #pragma unroll
       for (int ks = 0; ks < BKEY / 16; ++ks) {
-        constexpr uint32_t kVA = Dp * 64 / 16;
-        const uint32_t vo = (ks >> 1) * kVA + (ks & 1) * 2;
+        const uint32_t vo = ks * (16 * 64 / 16);
         if (leader) {
           umma_bf16_ts(tO, tP_hi + ks * 8, vh + vo, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
           if (a.x3) {

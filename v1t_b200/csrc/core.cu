@@ -296,15 +296,15 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);
       const int x3 = d.impl == V1T_IMPL_BF16X3;
       const AttnPlanes& pl = sc.planes;
-      // Q, K, V planes go to the per-block saved area (the backward reuses them); V^T is transient
+      // Q, K, V planes go to the per-block saved area (the backward reuses them)
       V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.qp[0], x3 ? S.qp[1] : nullptr,
                           nullptr, nullptr, st));
       V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.kp[0], x3 ? S.kp[1] : nullptr,
                           nullptr, nullptr, st));
       V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.vp[0], x3 ? S.vp[1] : nullptr,
-                          pl.vt[0], x3 ? pl.vt[1] : nullptr, st));
+                          nullptr, nullptr, st));
       AttnFwdArgs fa{};
-      fa.q_hi = S.qp[0]; fa.q_lo = S.qp[1]; fa.k_hi = S.kp[0]; fa.k_lo = S.kp[1]; fa.vt_hi = pl.vt[0]; fa.vt_lo = pl.vt[1];
+      fa.q_hi = S.qp[0]; fa.q_lo = S.qp[1]; fa.k_hi = S.kp[0]; fa.k_lo = S.kp[1]; fa.v_hi = S.vp[0]; fa.v_lo = S.vp[1];
       fa.O = S.o; fa.o_ld = d.I; fa.lse = S.lse;
       fa.B = d.B; fa.H = d.heads; fa.T = d.T; fa.Tp = d.Tq; fa.E = d.E; fa.Dp = d.Ep;
       fa.scale_log2 = (1.0f / sqrtf((float)d.E)) * 1.4426950408889634f;

@@ -106,7 +106,7 @@ int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int T
 int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int T, int Tp, int E, int64_t ld,
                cudaStream_t st);
 struct AttnFwdArgs {
-  const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo;  // pre-swizzled bf16 planes (planes.cu)
+  const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo;  // pre-swizzled bf16 RM planes (rows = tokens; planes.cu)
   float* O;          // [B, T, o_ld]: O[(b*T+t)*o_ld + h*E + d]
   int64_t o_ld;
   float* lse;        // [B*H, Tp] log2-domain log-sum-exp (may be null)
@@ -115,8 +115,7 @@ struct AttnFwdArgs {
   int x3;
   DropSpec drop;
 };
-int attn_fwd_tc(const AttnFwdArgs& a, cudaStream_t st);   // generation 1: Q and P in shared memory
-int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // generation 2: Q and P in tensor memory
+int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // Q and P in tensor memory (attn_fwd2.cu)
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st);
 struct AttnBwdArgs {
   const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo, *do_hi, *do_lo;  // RM planes (rows = tokens, K = head dim)
@@ -128,12 +127,11 @@ struct AttnBwdArgs {
   int x3;
   DropSpec drop;
 };
-int attn_bwd_tc(const AttnBwdArgs& a, cudaStream_t st);   // generation 1: resident operands in shared memory
-int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st);  // generation 2: resident operands in tensor memory
+int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st);  // resident operands in tensor memory (attn_bwd2.cu)
 int attn_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t st);
 struct AttnPlanes {  // [0] = hi, [1] = lo
-  uint8_t *q[2], *k[2], *vt[2];   // forward (vt: V transposed, rows = head dim)
-  uint8_t *v[2], *dO[2];          // backward (v aliases vt's storage)
+  uint8_t *q[2], *k[2], *v[2];    // RM planes (rows = tokens, K = head dim)
+  uint8_t *dO[2];                 // backward
   float *lse, *delta;                                 // [B*H, Tp]
   size_t total;
 };
