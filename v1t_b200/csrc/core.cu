@@ -75,6 +75,7 @@ struct BlockSaved {
   uint8_t *qp[2], *kp[2], *vp[2];  // bf16 hi/lo operand planes of Q, K, V (fused attention), reused by the backward
   uint8_t* wpl[4][2];              // GEMM-operand planes of Wqkv, Wproj, W1, W2 (converted once per step)
   uint8_t* gpl[2];                 // operand planes of gelu(u) * dropout (emitted by the MLP GEMM epilogue)
+  uint8_t* wqp[2];                 // Wqkv planes with every head's rows padded to Ep (head-aligned QKV GEMM output)
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -102,8 +103,26 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
   for (int w = 0; w < 4; ++w)
     for (int i = 0; i < 2; ++i)
       b.wpl[w][i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(wr[w], wc[w]) / sizeof(float)) : 1);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     b.gpl[i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
+    b.wqp[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(3 * d.heads * d.Ep, d.E) / sizeof(float)) : 1);
+  }
+}
+// the QKV GEMM of the fused-attention path: output columns (q|k|v, head, Ep) written straight into attention planes
+v1t_gemm_desc qkv_planes_desc(const Dims& d) {
+  v1t_gemm_desc g{};
+  g.m = (int)d.R; g.n = 3 * d.heads * d.Ep; g.k = d.E; g.batch1 = 1; g.batch2 = 1; g.alpha = 1.f;
+  g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E;
+  return g;
+}
+bool qkv_to_planes(const Dims& d) { return d.fused && gemm_uses_tc(d.impl, qkv_planes_desc(d)); }
+HeadPlanes head_planes(const Dims& d, const BlockSaved& S) {
+  HeadPlanes hp{};
+  const bool x3 = d.impl == V1T_IMPL_BF16X3;
+  hp.p[0][0] = S.qp[0]; hp.p[1][0] = S.kp[0]; hp.p[2][0] = S.vp[0];
+  hp.p[0][1] = x3 ? S.qp[1] : nullptr; hp.p[1][1] = x3 ? S.kp[1] : nullptr; hp.p[2][1] = x3 ? S.vp[1] : nullptr;
+  hp.T = d.T; hp.Tq = d.Tq; hp.H = d.heads; hp.AD = d.Ep / 32;
+  return hp;
 }
 enum { kWqkv = 0, kWproj = 1, kW1 = 2, kW2 = 3 };
 // activation planes: the [R, cols] matrix as GEMM operand / as destination of the kernel producing it
@@ -281,12 +300,26 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       V1T_TRY(matrix_planes(W.wproj, d.I, d.E, d.I, S.wpl[kWproj][0], x3 ? S.wpl[kWproj][1] : nullptr, &tmp, st));
       V1T_TRY(matrix_planes(W.w1, d.E, d.M, d.E, S.wpl[kW1][0], x3 ? S.wpl[kW1][1] : nullptr, &tmp, st));
       V1T_TRY(matrix_planes(W.w2, d.M, d.E, d.M, S.wpl[kW2][0], x3 ? S.wpl[kW2][1] : nullptr, &tmp, st));
+      if (qkv_to_planes(d))
+        V1T_TRY(matrix_planes(W.wqkv, d.E, 3 * d.I, d.E, S.wqp[0], x3 ? S.wqp[1] : nullptr, &tmp, st, d.E, d.Ep));
     }
     // ---- Attention.mha (vit.py:267-275)
     V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st, act_plane_out(d, sc.hpl)));
-    {
+    V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
+    if (qkv_to_planes(d)) {
+      // q, k, v leave the GEMM epilogue as the attention kernels' operand planes (fp32 qkv is never materialised;
+      // v1t_attention_probs rebuilds it from the planes for the attention-map hooks)
+      const bool x3 = d.impl == V1T_IMPL_BF16X3;
+      EpiOp epi = no_epi();
+      epi.kind = kEpiHeadPlanes;
+      epi.hp = head_planes(d, S);
+      uint8_t* pads[6] = {S.qp[0], S.kp[0], S.vp[0], S.qp[1], S.kp[1], S.vp[1]};
+      V1T_TRY(zero_plane_pad_rows(pads, x3 ? 6 : 3, (int64_t)d.B * d.heads * (d.Ep / 32), d.Tq, d.T, st));
+      const PlaneOp wq{S.wqp[0], x3 ? S.wqp[1] : nullptr, (int)round_up(3 * d.heads * d.Ep, 32), cdiv(d.E, 32)};
+      V1T_TRY(gemm_any(d.impl, qkv_planes_desc(d), sc.h, nullptr, nullptr, nullptr, nullptr, st, no_drop(), epi,
+                       act_plane(d, sc.hpl, d.E), wq));
+    } else {
       v1t_gemm_desc g = gd((int)d.R, 3 * d.I, d.E);
-      V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = 3 * d.I;
       V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st, no_drop(), no_epi(),
                        act_plane(d, sc.hpl, d.E), wplane(d, S, kWqkv)));
@@ -296,13 +329,15 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);
       const int x3 = d.impl == V1T_IMPL_BF16X3;
       const AttnPlanes& pl = sc.planes;
-      // Q, K, V planes go to the per-block saved area (the backward reuses them)
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.qp[0], x3 ? S.qp[1] : nullptr,
-                          nullptr, nullptr, st));
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.kp[0], x3 ? S.kp[1] : nullptr,
-                          nullptr, nullptr, st));
-      V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.vp[0], x3 ? S.vp[1] : nullptr,
-                          nullptr, nullptr, st));
+      // Q, K, V planes live in the per-block saved area (the backward reuses them)
+      if (!qkv_to_planes(d)) {
+        V1T_TRY(make_planes(S.qkv, 3 * d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.qp[0], x3 ? S.qp[1] : nullptr,
+                            nullptr, nullptr, st));
+        V1T_TRY(make_planes(S.qkv, 3 * d.I, d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.kp[0], x3 ? S.kp[1] : nullptr,
+                            nullptr, nullptr, st));
+        V1T_TRY(make_planes(S.qkv, 3 * d.I, 2 * d.I, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, S.vp[0], x3 ? S.vp[1] : nullptr,
+                            nullptr, nullptr, st));
+      }
       AttnFwdArgs fa{};
       fa.q_hi = S.qp[0]; fa.q_lo = S.qp[1]; fa.k_hi = S.kp[0]; fa.k_lo = S.kp[1]; fa.v_hi = S.vp[0]; fa.v_lo = S.vp[1];
       fa.O = S.o; fa.o_ld = d.I; fa.lse = S.lse;
@@ -586,6 +621,8 @@ extern "C" int v1t_attention_probs(const v1t_core_shape* shape, const void* save
   V1T_CHECK_ARG(saved_mem && probs && block >= 0 && block < d.blocks, "attention_probs: bad argument");
   Saved sv = carve_saved(d, const_cast<void*>(saved_mem));
   const int chunk = attn_chunk(d);
+  if (qkv_to_planes(d))  // the forward kept q, k, v only as bf16 hi/lo planes: rebuild fp32 qkv in its (unused) slot
+    V1T_TRY(planes_to_qkv(head_planes(d, sv.blk[block]), d.B, d.E, sv.blk[block].qkv, (cudaStream_t)stream));
   for (int b0 = 0; b0 < d.B; b0 += chunk) {
     const int bc = std::min(chunk, d.B - b0);
     V1T_TRY(attention_probs(d, sv.blk[block].qkv, b0, bc, probs + (int64_t)b0 * d.heads * d.T * d.T, d.T, no_drop(),

@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
   constexpr int kKind = EPI >> 1;
   constexpr bool kConv = ACONV || BCONV, kPlanes = !ACONV || !BCONV;
   // with no operand to convert, the raw staging slots become two more UMMA stages (bulk copies need the depth)
-  constexpr int kNS = kConv ? STAGES : STAGES + RAW;
+  // (three of the four slots; the last one holds the transpose tiles of the extra epilogue warps, see below)
+  constexpr int kNS = kConv ? STAGES : STAGES + RAW - 1;
+  // ... and the idle conversion warps join the epilogue: 16 instead of 8 warps drain the accumulators
+  constexpr int kEpiW = kConv ? kEpiWarps : kEpiWarps + kProdWarps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (STAGES + RAW) * STAGE_BYTES);
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], kEpiWarps * 32);
+      mbar_init(&tempty[b], kEpiW * 32);
     }
     fence_barrier_init();
   }
@@ -317,8 +320,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else if (warp > kEpiWarps) {
-    // both operands are planes: the conversion warps have nothing to do
   } else if (warp == kEpiWarps) {
     // ============================== MMA ISSUER ==============================
     const uint32_t idesc = idesc_bf16(BM, a.bn, a.mn_a, a.mn_b);
@@ -366,19 +367,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     }
   } else {
     // ============================== EPILOGUE ==============================
-    // 8 warps: TMEM lane quarter = warp & 3 (row block), column half = warp >> 2 (alternate 32-column groups).
+    // 8 warps (16 when no operand needs converting: warps 9-16 then drain accumulators too): TMEM lane quarter =
+    // warp & 3 (row block, fixed by the hardware); the warps sharing a quarter take alternate 32-column groups.
     // Every 32 x 32 group is transposed through a warp-private smem tile, so that a lane owns 4 adjacent columns
     // of one row and each 128-bit store instruction writes four full 128-byte row segments.  Ragged edges and
     // unaligned operands use the same path with element-wise memory accesses.  The row loop is deliberately NOT
     // unrolled: with dropout (Philox) and GELU inlined, an unrolled body overflowed the instruction cache and the
     // epilogue became fetch-bound ("no_instructions" stalls, profiles/r1_gemm_epilogue_icache.txt).
     uint32_t tl_i = 0;
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3;
+    // column slot among the warps of this quarter: warps 0-7 -> 0, 1; warps 9-16 -> 2, 3
+    const int slot = warp < kEpiWarps ? (warp >> 2) : 2 + ((warp - kEpiWarps - 1) >> 2);
+    constexpr int kSlots = kEpiW / 4;
     const float inv_keep = (kDrop && g.drop.p > 0.f) ? 1.f / (1.f - g.drop.p) : 1.f;
     const int64_t drop_ld = (g.d.n + 3) & ~3;
     const float inv_keep2 = g.epi.drop.p > 0.f ? 1.f / (1.f - g.epi.drop.p) : 1.f;
     const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
-    const uint32_t stg = smem_u32(stage_base + warp * 4096);
+    const uint32_t stg = warp < kEpiWarps ? smem_u32(stage_base + warp * 4096)
+                                          : smem_u32(smem + (STAGES + RAW - 1) * STAGE_BYTES + (warp - kEpiWarps - 1) * 4096);
     const int cq = lane & 7;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl_i) {
       const Tile tl = decode_tile(a, t);
@@ -387,8 +393,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BN_MAX + ((uint32_t)(quarter * 32) << 16);
       const int n_lim = min(g.d.n, tl.n0 + a.bn);
+      int hp_b0 = 0, hp_t0 = 0;
+      int64_t hp_bstride = 0;
+      if constexpr (kKind == kEpiHeadPlanes) {
+        const int r0 = tl.m0 + quarter * 32 + (lane >> 3);
+        hp_b0 = r0 / g.epi.hp.T;
+        hp_t0 = r0 - hp_b0 * g.epi.hp.T;
+        hp_bstride = (int64_t)g.epi.hp.H * g.epi.hp.AD * g.epi.hp.Tq * 64;
+      }
       // 32-column groups alternate between the two column halves (columns past bn are never stored)
-      for (int c0 = half * 32; c0 < a.bn; c0 += 64) {
+      for (int c0 = slot * 32; c0 < a.bn; c0 += 32 * kSlots) {
         const int nb = tl.n0 + c0;
         {
           uint32_t v[32];
@@ -401,6 +415,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         __syncwarp();
         const int n4 = nb + 4 * cq;
         const int nv = min(4, n_lim - n4);  // valid columns of this lane's quad
+        // kEpiHeadPlanes: this 32-column group is one head-dim atom of q, k or v of one head
+        uint8_t *hp_hi = nullptr, *hp_lo = nullptr;
+        int64_t hp_base = 0;
+        if constexpr (kKind == kEpiHeadPlanes) {
+          const HeadPlanes& hp = g.epi.hp;
+          const int sec = nb >> 5, atom = sec % hp.AD, hh = (sec / hp.AD) % hp.H, s3 = min(sec / (hp.AD * hp.H), 2);
+          hp_hi = hp.p[s3][0]; hp_lo = hp.p[s3][1];
+          hp_base = (int64_t)(hh * hp.AD + atom) * hp.Tq * 64 + (cq & 1) * 8;
+        }
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (g.bias && nv > 0) {
           if (bias_vec && nv == 4) {
@@ -443,6 +466,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           const uint4 xr = lds128(stg + r * 128 + ((cq ^ (r & 7)) << 4));
           float o[4] = {fmaf(g.d.alpha, __uint_as_float(xr.x), bv[0]), fmaf(g.d.alpha, __uint_as_float(xr.y), bv[1]),
                         fmaf(g.d.alpha, __uint_as_float(xr.z), bv[2]), fmaf(g.d.alpha, __uint_as_float(xr.w), bv[3])};
+          if constexpr (kKind == kEpiHeadPlanes) {
+            // this 32-column group is one head-dim atom of q, k or v of one head: row (b, t) of its plane slab
+            // (sample, token) of this row: one division per tile (hp_b0 / hp_t0), then a wrap at sample boundaries
+            int t = hp_t0 + 4 * i, bb = hp_b0;
+            while (t >= g.epi.hp.T) { t -= g.epi.hp.T; ++bb; }
+            const int64_t off = hp_base + (int64_t)bb * hp_bstride + t * 64 + (((cq >> 1) ^ ((t >> 1) & 3)) << 4);
+            uint2 ph, plo;
+            split4(o, ph, plo);
+            *reinterpret_cast<uint2*>(hp_hi + off) = ph;
+            if (hp_lo) *reinterpret_cast<uint2*>(hp_lo + off) = plo;
+            if (!g.C) continue;
+          }
           const bool full4 = (nv == 4);
           if (kDrop && g.drop.p > 0.f) {
             float mk[4];
@@ -523,9 +558,10 @@ int g_use_mn_major = 1;  // stage M/N-contiguous operands un-transposed (vector 
 namespace {
 
 // N tile: an MN-major plane B operand is copied in whole 32-column atoms
-int pick_bn(const v1t_gemm_desc& d, const PlaneOp& pb) {
+int pick_bn(const v1t_gemm_desc& d, const PlaneOp& pb, const EpiOp& epi = no_epi()) {
   const int nt = cdiv(d.n, BN_MAX);
-  return (int)round_up(cdiv(d.n, nt), (pb.hi && d.b_k != 1) ? 32 : 16);
+  const bool whole_atoms = (pb.hi && d.b_k != 1) || epi.pl.hi || epi.kind == kEpiHeadPlanes;
+  return (int)round_up(cdiv(d.n, nt), whole_atoms ? 32 : 16);
 }
 
 int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
@@ -542,7 +578,7 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   if (a.a_pl || a.b_pl)
     V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && (!x3 || ((!a.a_pl || pa.lo) && (!a.b_pl || pb.lo))),
                   "tc gemm: plane operands need an unbatched problem and, in bf16x3 mode, the lo plane");
-  a.bn = pick_bn(d, pb);
+  a.bn = pick_bn(d, pb, epi);
   a.tiles_n = cdiv(d.n, a.bn);
   a.tiles_m = cdiv(d.m, BM);
   a.x3 = x3;
@@ -561,12 +597,12 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   using Kern = void (*)(const TcArgs);
 #define V1T_TC_ROW(E) {{tc_gemm_kernel<E, false, false>, tc_gemm_kernel<E, false, true>}, \
                        {tc_gemm_kernel<E, true, false>, tc_gemm_kernel<E, true, true>}}
-  static const Kern table[4][2][2] = {V1T_TC_ROW(0), V1T_TC_ROW(1), V1T_TC_ROW(kEpiGeluOut << 1),
-                                      V1T_TC_ROW(kEpiGeluGrad << 1)};
+  static const Kern table[5][2][2] = {V1T_TC_ROW(0), V1T_TC_ROW(1), V1T_TC_ROW(kEpiGeluOut << 1),
+                                      V1T_TC_ROW(kEpiGeluGrad << 1), V1T_TC_ROW(kEpiHeadPlanes << 1)};
 #undef V1T_TC_ROW
-  static bool attr_set[4][2][2] = {};
+  static bool attr_set[5][2][2] = {};
   V1T_CHECK_ARG(epi.kind == kEpiNone || drop.p <= 0.f, "tc gemm: a fused activation excludes dropout on the main output");
-  const int ev = epi.kind == kEpiGeluOut ? 2 : epi.kind == kEpiGeluGrad ? 3 : (drop.p > 0.f ? 1 : 0);
+  const int ev = epi.kind == kEpiGeluOut ? 2 : epi.kind == kEpiGeluGrad ? 3 : epi.kind == kEpiHeadPlanes ? 4 : (drop.p > 0.f ? 1 : 0);
   const int ac = a.a_pl ? 0 : 1, bc = a.b_pl ? 0 : 1;
   Kern kern = table[ev][ac][bc];
   if (!attr_set[ev][ac][bc]) {
@@ -589,12 +625,17 @@ int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, co
   V1T_CHECK_ARG(d.m >= 0 && d.n >= 0 && d.k >= 0 && d.batch1 >= 1 && d.batch2 >= 1, "gemm: bad sizes");
   if (d.m == 0 || d.n == 0) return V1T_OK;
   if (!tc_supported(d)) return gemm_fp32(d, A, B, C, bias, R, st, drop);
-  if (epi.kind != kEpiNone) {
+  if (epi.kind == kEpiHeadPlanes) {
+    const HeadPlanes& hp = epi.hp;
+    V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && !bias && !R && !d.accumulate && hp.p[0][0] && hp.p[1][0] && hp.p[2][0] &&
+                      d.n == 3 * hp.H * hp.AD * 32 && hp.T > 0 && d.m % hp.T == 0 && hp.Tq >= hp.T,
+                  "gemm_tc: head-plane output does not match the problem");
+  } else if (epi.kind != kEpiNone) {
     V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && epi.ld % 4 == 0 && aligned16(epi.kind == kEpiGeluOut ? (const void*)epi.aux : (const void*)epi.u),
                   "gemm_tc: fused activation needs an unbatched problem and 16-byte aligned rows");
     V1T_CHECK_ARG(epi.kind != kEpiGeluOut || epi.aux || epi.pl.hi, "gemm_tc: GELU output has no destination");
     // emitted planes must be covered by the N tiling (whole 32-column atoms) and by the rows of the problem
-    V1T_CHECK_ARG(!epi.pl.hi || (cdiv(d.n, pick_bn(d, pb)) * pick_bn(d, pb) >= 32 * cdiv(d.n, 32) && epi.pl.rows_p >= d.m &&
+    V1T_CHECK_ARG(!epi.pl.hi || (cdiv(d.n, pick_bn(d, pb, epi)) * pick_bn(d, pb, epi) >= 32 * cdiv(d.n, 32) && epi.pl.rows_p >= d.m &&
                                  d.n % 4 == 0),
                   "gemm_tc: plane output does not fit the tiling");
   }

@@ -12,7 +12,7 @@ struct DropSpec {  // inverted dropout; p == 0 -> disabled
 static inline DropSpec no_drop() { return DropSpec{0, 0, 0.f}; }
 
 // optional fused element-wise stage of the tensor-core GEMM epilogue (MLP of the ViT block, vit.py:144-148)
-enum { kEpiNone = 0, kEpiGeluOut = 1, kEpiGeluGrad = 2 };
+enum { kEpiNone = 0, kEpiGeluOut = 1, kEpiGeluGrad = 2, kEpiHeadPlanes = 3 };
 // Destination for operand planes (see PlaneOp below) emitted by the kernel that PRODUCES an activation, so that the
 // GEMMs consuming it never convert: hi/lo plane base pointers and the padded row count of the [rows, cols] matrix.
 struct PlaneOut {
@@ -22,15 +22,25 @@ struct PlaneOut {
 };
 static inline PlaneOut no_plane_out() { return PlaneOut{nullptr, nullptr, 0}; }
 
+// Destination of kEpiHeadPlanes: the GEMM output [B*T, 3 * H * AD*32] (q | k | v, every head padded to AD*32
+// columns) leaves the epilogue as the per-(sample, head) attention operand planes of planes.cu
+// ([b*H + h][AD atoms][Tq rows][64 B]) instead of fp32 -- no separate conversion pass over qkv.
+struct HeadPlanes {
+  uint8_t* p[3][2];   // [q, k, v][hi, lo]
+  int T, Tq, H, AD;
+};
+
 struct EpiOp {
   int kind;           // kEpiGeluOut: aux = gelu(C) * dropout ;  kEpiGeluGrad: C *= gelu'(u) * dropout
+                      // kEpiHeadPlanes: alpha * acc -> attention planes `hp` (C may be null)
   float* aux;         // [m, ld] second output (kEpiGeluOut)
   const float* u;     // [m, ld] pre-activation (kEpiGeluGrad)
   int64_t ld;
   DropSpec drop;      // dropout of the activation (element index m * roundup(n,4) + n)
   PlaneOut pl;        // optional planes of the activation-side result (aux for kEpiGeluOut, C for kEpiGeluGrad)
+  HeadPlanes hp;
 };
-static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}, no_plane_out()}; }
+static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}, no_plane_out(), HeadPlanes{}}; }
 
 // Pre-swizzled bf16 hi/lo planes of a row-major matrix X[rows, cols] (planes.cu: matrix_planes): 32-column atoms,
 // [catoms][rows_p][64 B], rows 64 B apart, 16-byte chunks XOR-swizzled with ((row >> 1) & 3), zero padded.  A GEMM
@@ -99,8 +109,14 @@ inline int gemm_any_splitk(int impl, const v1t_gemm_desc& d, const float* A, con
 size_t plane_bytes(int B, int H, int Tp, int Dp);
 // planes of a plain row-major matrix (GEMM operands, see PlaneOp): bytes of ONE plane, and the converter
 size_t matrix_plane_bytes(int64_t rows, int64_t cols);
+// row_gin / row_gout: every group of row_gin source rows becomes row_gout plane rows (zero padded), e.g. the
+// per-head blocks of Wqkv (155 rows) padded to 160 so that the QKV GEMM output is head-aligned.
 int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, PlaneOp* out,
-                  cudaStream_t st);
+                  cudaStream_t st, int row_gin = 0, int row_gout = 0);
+// zero rows [T, Tq) of every (sample, head, atom) slab of up to 6 attention planes
+int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st);
+// fp32 qkv [B*T, 3*H*E] back from the attention planes (hi + lo), for the attention-map hooks
+int planes_to_qkv(const HeadPlanes& hp, int B, int E, float* qkv, cudaStream_t st);
 int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tp, int E, int Dp, void* rm_hi,
                 void* rm_lo, void* tr_hi, void* tr_lo, cudaStream_t st);
 int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int T, int Tp, int E, int64_t ld,

@@ -11,6 +11,8 @@
 //   TR plane  rows = head dim, K = tokens   [B*H][Tp/32 atoms][Dp rows][64 B]     (V^T, Q^T, K^T, dO^T: operands
 //                                                                                  contracted over tokens)
 // Pad rows / columns (t >= T, d >= E) are written as zeros.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -75,20 +77,52 @@ __global__ void __launch_bounds__(256) make_planes_kernel(const float* __restric
 // GEMM-operand planes of a row-major matrix X[rows, cols]: one thread per 16-byte chunk (8 columns of one row)
 __global__ void matrix_planes_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int64_t cols,
                                      int64_t rows_p, int64_t chunks, uint8_t* __restrict__ hi,
-                                     uint8_t* __restrict__ lo) {
+                                     uint8_t* __restrict__ lo, int gin, int gout) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= chunks) return;
   const int c = (int)(idx & 3);
   const int64_t r = (idx >> 2) % rows_p, a = (idx >> 2) / rows_p;
   const int64_t col0 = a * 32 + c * 8;
+  int64_t sr = r;  // source row (-1: padding)
+  if (gout > 0) sr = (r % gout < gin) ? (r / gout) * gin + r % gout : -1;
   float v[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = (r < rows && col0 + e < cols) ? __ldg(X + r * ld + col0 + e) : 0.f;
+  for (int e = 0; e < 8; ++e) v[e] = (sr >= 0 && sr < rows && col0 + e < cols) ? __ldg(X + sr * ld + col0 + e) : 0.f;
   uint4 h, l;
   split8(v, h, l);
   const int64_t off = (a * rows_p + r) * 64 + ((c ^ (int)((r >> 1) & 3)) << 4);
   *reinterpret_cast<uint4*>(hi + off) = h;
   if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
+}
+
+struct PadPlanes { uint8_t* p[6]; };
+// zero the pad rows t in [T, Tq) of every slab ((sample, head, atom): Tq rows of 64 bytes) of each plane
+__global__ void zero_pad_rows_kernel(PadPlanes pp, int n_planes, int64_t slabs, int Tq, int T) {
+  const int pad = Tq - T;
+  const int64_t total = slabs * pad * 4;  // 16-byte pieces per plane
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int piece = (int)(i & 3);
+    const int64_t row = (i >> 2) % pad, slab = (i >> 2) / pad;
+    const int64_t off = (slab * Tq + T + row) * 64 + piece * 16;
+    for (int p = 0; p < n_planes; ++p) *reinterpret_cast<uint4*>(pp.p[p] + off) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// qkv[(b*T+t), (s*H+h)*E + d] = hi + lo of the attention planes (attention-map hooks only)
+__global__ void planes_to_qkv_kernel(HeadPlanes hp, int B, int E, float* __restrict__ qkv) {
+  const int64_t total = (int64_t)B * hp.T * 3 * hp.H * E;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % E);
+    int64_t r = i / E;
+    const int h = (int)(r % hp.H); r /= hp.H;
+    const int s = (int)(r % 3); r /= 3;
+    const int t = (int)(r % hp.T), b = (int)(r / hp.T);
+    const int64_t off = ((((int64_t)b * hp.H + h) * hp.AD + d / 32) * hp.Tq + t) * 64 +
+                        ((((d & 31) >> 3) ^ ((t >> 1) & 3)) << 4) + (d & 7) * 2;
+    float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(hp.p[s][0] + off));
+    if (hp.p[s][1]) v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(hp.p[s][1] + off));
+    qkv[i] = v;
+  }
 }
 
 // delta[b,h,t] = sum_d O[b,t,h*E+d] * dO[b,t,h*E+d]   (softmax backward row term); one warp per (b,t,h)
@@ -118,14 +152,35 @@ size_t matrix_plane_bytes(int64_t rows, int64_t cols) {
 }
 
 int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, PlaneOp* out,
-                  cudaStream_t st) {
-  const int64_t rows_p = round_up(rows, 32), catoms = cdiv(cols, 32);
+                  cudaStream_t st, int row_gin, int row_gout) {
+  V1T_CHECK_ARG(row_gout == 0 || (row_gin > 0 && row_gout >= row_gin && rows % row_gin == 0),
+                "matrix_planes: bad row grouping");
+  const int64_t prow = row_gout ? rows / row_gin * row_gout : rows;
+  const int64_t rows_p = round_up(prow, 32), catoms = cdiv(cols, 32);
   const int64_t chunks = catoms * rows_p * 4;
   V1T_CHECK_ARG(X && hi && out && catoms * rows_p < (1ll << 31), "matrix_planes: bad argument");
   matrix_planes_kernel<<<(unsigned)cdiv(chunks, 256), 256, 0, st>>>(X, ld, rows, cols, rows_p, chunks, (uint8_t*)hi,
-                                                                      (uint8_t*)lo);
+                                                                      (uint8_t*)lo, row_gin, row_gout);
   V1T_LAUNCH_CHECK();
   out->hi = (const uint8_t*)hi; out->lo = (const uint8_t*)lo; out->rows_p = (int)rows_p; out->catoms = (int)catoms;
+  return V1T_OK;
+}
+
+int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st) {
+  V1T_CHECK_ARG(n_planes >= 0 && n_planes <= 6 && Tq >= T, "zero_plane_pad_rows: bad argument");
+  if (n_planes == 0 || Tq == T) return V1T_OK;
+  PadPlanes pp{};
+  for (int i = 0; i < n_planes; ++i) pp.p[i] = planes[i];
+  const int64_t total = slabs * (Tq - T) * 4;
+  zero_pad_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv(total, 256), 4096), 256, 0, st>>>(pp, n_planes, slabs, Tq, T);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+int planes_to_qkv(const HeadPlanes& hp, int B, int E, float* qkv, cudaStream_t st) {
+  const int64_t total = (int64_t)B * hp.T * 3 * hp.H * E;
+  planes_to_qkv_kernel<<<(unsigned)std::min<int64_t>(cdiv(total, 256), 65535), 256, 0, st>>>(hp, B, E, qkv);
+  V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
 
