@@ -409,8 +409,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
     tc_fence_after();
     const int I = a.H * a.E;
     // MODE_V: dV (col block 2I);  MODE_S/KV: dK (col block I, scaled);  MODE_S/!KV: dQ (col block 0, scaled)
-    float* dst = a.dqkv + ((int64_t)b * a.T + ri) * (3 * I) + h * a.E + (MODE == MODE_V ? 2 * I : (KV ? I : 0));
+    constexpr int kSec = MODE == MODE_V ? 2 : (KV ? 1 : 0);
+    float* dst = a.dqkv ? a.dqkv + ((int64_t)b * a.T + ri) * (3 * I) + h * a.E + kSec * I : nullptr;
     const float sc = MODE == MODE_V ? 1.f : a.scale;
+    const int64_t prow = (int64_t)b * a.T + ri;            // row of the [B*T, 3*H*Dp] gradient matrix
+    const int atom0 = (kSec * a.H + h) * AD;                // first column atom of this head's slice
 #pragma unroll
     for (int cc = 0; cc < AD; ++cc) {
       const int d0 = half * (AD * 16) + cc * 16;
@@ -418,9 +421,24 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
       tmem_ld16(tmem_base + lane_off + cOut + d0, v);
       tmem_ld_wait();
       if (ri < a.T) {
+        if (dst) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-          if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
+          for (int c = 0; c < 16; ++c)
+            if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
+        }
+        if (a.dq_pl.hi) {  // operand planes for the Wqkv weight-gradient and input-gradient GEMMs (pad columns are 0)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[8 * q + e]) * sc;
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int64_t off = plane_chunk_off(atom0 + (d0 >> 5), a.dq_pl.rows_p, prow, ((d0 & 31) >> 3) + q);
+            *reinterpret_cast<uint4*>(a.dq_pl.hi + off) = hi;
+            if (a.dq_pl.lo) *reinterpret_cast<uint4*>(a.dq_pl.lo + off) = lo;
+          }
+        }
       }
     }
     tc_fence_before();

@@ -154,6 +154,7 @@ struct Scratch {
   BlockSaved tmp;    // one block of "saved" space for inference (keep_for_backward == 0)
   float *h, *dh, *g, *dqkv, *dO, *patches, *P1, *P2, *partials, *dlat, *dz3, *dhid, *dpos;
   uint8_t *hpl[2], *dpl[2], *dupl[2];  // operand planes of the LayerNorm output, of dropout(dx) and of du (backward)
+  uint8_t* dqpl[2];                    // operand planes of the head-padded dqkv (from the attention backward)
   AttnPlanes planes;
   int chunk;         // attention batch chunk
   size_t total;
@@ -192,6 +193,7 @@ Scratch carve_scratch(const Dims& d, void* base) {
     s.hpl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
     s.dpl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
     s.dupl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
+    s.dqpl[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(d.R, 3 * d.heads * d.Ep) / sizeof(float)) : 1);
   }
   s.partials = c.take(kPartialBytes / sizeof(float));
   s.dlat = c.take((int64_t)d.B * d.E);
@@ -487,7 +489,15 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       AttnBwdArgs ba{};
       ba.q_hi = S.qp[0]; ba.q_lo = S.qp[1]; ba.k_hi = S.kp[0]; ba.k_lo = S.kp[1]; ba.v_hi = S.vp[0]; ba.v_lo = S.vp[1];
       ba.do_hi = pl.dO[0]; ba.do_lo = pl.dO[1];
-      ba.lse = S.lse; ba.delta = pl.delta; ba.dqkv = sc.dqkv;
+      ba.lse = S.lse; ba.delta = pl.delta;
+      if (qkv_to_planes(d)) {  // dQ | dK | dV leave the kernels as operand planes of the head-padded gradient only
+        ba.dqkv = nullptr;
+        ba.dq_pl = act_plane_out(d, sc.dqpl);
+        uint8_t* pads[2] = {sc.dqpl[0], sc.dqpl[1]};  // rows past B*T of the planes (contracted by the weight gradient)
+        V1T_TRY(zero_plane_pad_rows(pads, x3 ? 2 : 1, 3 * d.heads * (d.Ep / 32), (int)round_up(d.R, 32), (int)d.R, st));
+      } else {
+        ba.dqkv = sc.dqkv;
+      }
       ba.B = d.B; ba.H = d.heads; ba.T = d.T; ba.Tp = d.Tq; ba.E = d.E; ba.Dp = d.Ep;
       ba.scale = scale; ba.scale_log2 = scale * 1.4426950408889634f;
       ba.x3 = x3;
@@ -540,17 +550,37 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     ProfScope lin2(V1T_PHASE_LINEAR_BWD, st);
     V1T_TRY(ln_forward(S.x1, nullptr, d.T, nullptr, W.ln1_w, W.ln1_b, sc.h, nullptr, d.R, d.E, d.Ep, st,
                        act_plane_out(d, sc.hpl)));
-    if (GW.wqkv) {  // dWqkv[n,e] = sum_r dqkv[r,n] h1[r,e]
-      v1t_gemm_desc g = gd(3 * d.I, d.E, R);
-      g.a_m = 1; g.a_k = ld; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
-      V1T_TRY(gemm_any_splitk(d.impl, g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st, no_plane(),
-                              act_plane(d, sc.hpl, d.E)));
-    }
-    {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
-      v1t_gemm_desc g = gd(R, d.E, 3 * d.I);
-      g.a_m = ld; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, sc.dqkv, W.wqkv, sc.dh, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
-                       wplane(d, S, kWqkv)));
+    if (qkv_to_planes(d)) {
+      // head-padded problem (every head's 155 columns sit in a 160-column group): both GEMMs read dqkv from the
+      // planes written by the attention backward; the weight gradient drops the padded rows while reducing
+      const int NP = 3 * d.heads * d.Ep;
+      const PlaneOp dqp = act_plane(d, sc.dqpl, NP);
+      const bool x3 = d.impl == V1T_IMPL_BF16X3;
+      if (GW.wqkv) {  // dWqkv[n,e] = sum_r dqkv[r,n] h1[r,e]
+        v1t_gemm_desc g = gd(NP, d.E, R);
+        g.a_m = 1; g.a_k = NP; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
+        V1T_TRY(gemm_any_splitk(d.impl, g, nullptr, sc.h, GW.wqkv, sc.partials, kPartialBytes, st, dqp,
+                                act_plane(d, sc.hpl, d.E), GroupMap{d.E, d.Ep, 0, 0}));
+      }
+      {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
+        v1t_gemm_desc g = gd(R, d.E, NP);
+        g.a_m = NP; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
+        const PlaneOp wq{S.wqp[0], x3 ? S.wqp[1] : nullptr, (int)round_up(NP, 32), cdiv(d.E, 32)};
+        V1T_TRY(gemm_any(d.impl, g, nullptr, nullptr, sc.dh, nullptr, nullptr, st, no_drop(), no_epi(), dqp, wq));
+      }
+    } else {
+      if (GW.wqkv) {  // dWqkv[n,e] = sum_r dqkv[r,n] h1[r,e]
+        v1t_gemm_desc g = gd(3 * d.I, d.E, R);
+        g.a_m = 1; g.a_k = ld; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
+        V1T_TRY(gemm_any_splitk(d.impl, g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st, no_plane(),
+                                act_plane(d, sc.hpl, d.E)));
+      }
+      {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
+        v1t_gemm_desc g = gd(R, d.E, 3 * d.I);
+        g.a_m = ld; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
+        V1T_TRY(gemm_any(d.impl, g, sc.dqkv, W.wqkv, sc.dh, nullptr, nullptr, st, no_drop(), no_epi(), no_plane(),
+                         wplane(d, S, kWqkv)));
+      }
     }
     V1T_TRY(ln_backward(sc.dh, S.x1, S.st1, W.ln1_w, dx, GW.ln1_w, GW.ln1_b, sc.partials, kPartialBytes, d.R, d.E,
                         d.Ep, st));

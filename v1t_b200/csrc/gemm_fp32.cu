@@ -135,25 +135,32 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, float
   *o = accumulate ? *o + s : s;
 }
 
+// un-pad a grouped index: groups of `gout` (padded) hold `gin` real entries; -1 for padding
+__device__ __forceinline__ int64_t ungroup(int64_t i, int gin, int gout) {
+  if (gout <= 0) return i;
+  return (i % gout < gin) ? (i / gout) * gin + i % gout : -1;
+}
 __global__ void reduce_partials_ld_kernel(const float* __restrict__ partials, float* __restrict__ out, int parts,
                                           int64_t rows, int64_t cols, int64_t in_ld, int64_t out_ld,
-                                          int accumulate) {
+                                          int accumulate, GroupMap gm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int64_t r = i / cols, c = i % cols;
+  const int64_t ro = ungroup(r, gm.row_gin, gm.row_gout), co = ungroup(c, gm.col_gin, gm.col_gout);
+  if (ro < 0 || co < 0) return;  // padded row / column of a head-padded product
   float s = 0.f;
   for (int p = 0; p < parts; ++p) s += partials[((int64_t)p * rows + r) * in_ld + c];
-  float* o = out + r * out_ld + c;
+  float* o = out + ro * out_ld + co;
   *o = accumulate ? *o + s : s;
 }
 
 }  // namespace
 
 int reduce_partials_ld(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t in_ld,
-                       int64_t out_ld, int accumulate, cudaStream_t st) {
+                       int64_t out_ld, int accumulate, cudaStream_t st, GroupMap gm) {
   if (rows * cols == 0) return V1T_OK;
   reduce_partials_ld_kernel<<<cdiv(rows * cols, 256), 256, 0, st>>>(partials, out, parts, rows, cols, in_ld, out_ld,
-                                                                    accumulate);
+                                                                    accumulate, gm);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

@@ -643,7 +643,7 @@ int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, co
 }
 
 int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
-                   size_t partial_bytes, cudaStream_t st, int x3, PlaneOp pa, PlaneOp pb) {
+                   size_t partial_bytes, cudaStream_t st, int x3, PlaneOp pa, PlaneOp pb, GroupMap gm) {
   V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1, "splitk gemm: no batch");
   if (d.m == 0 || d.n == 0) return V1T_OK;
   if (!tc_supported(d)) return gemm_fp32_splitk(d, A, B, C, partials, partial_bytes, st);
@@ -654,7 +654,9 @@ int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float
   int splits = (2 * kNumSMs + tiles - 1) / tiles;
   splits = std::min(splits, cdiv(d.k, 4 * BK));
   splits = (int)std::min<int64_t>(splits, (int64_t)partial_bytes / per);
-  if (splits <= 1) return gemm_tc(d, A, B, C, nullptr, nullptr, st, no_drop(), x3, no_epi(), pa, pb);
+  const bool mapped = gm.row_gout > 0 || gm.col_gout > 0;  // a remapped product always goes through the partials
+  if (splits <= 1 && !mapped) return gemm_tc(d, A, B, C, nullptr, nullptr, st, no_drop(), x3, no_epi(), pa, pb);
+  splits = std::max(splits, 1);
   const int k_chunk = (int)round_up(cdiv(d.k, splits), BK);
   splits = cdiv(d.k, k_chunk);
   v1t_gemm_desc p = d;
@@ -662,7 +664,7 @@ int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float
   p.c_m = n_ld;
   V1T_TRY(launch_tc(p, A, B, partials, nullptr, nullptr, no_drop(), x3, splits, k_chunk, (int64_t)d.m * n_ld, st, no_epi(),
                     pa, pb));
-  return reduce_partials_ld(partials, C, splits, d.m, d.n, n_ld, d.c_m, d.accumulate, st);
+  return reduce_partials_ld(partials, C, splits, d.m, d.n, n_ld, d.c_m, d.accumulate, st, gm);
 }
 
 }  // namespace v1t

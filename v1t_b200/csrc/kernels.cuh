@@ -75,15 +75,20 @@ int gemm_fp32_splitk(const v1t_gemm_desc& d, const float* A, const float* B, flo
 int reduce_partials(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t ld_out,
                     int accumulate, cudaStream_t st);
 
+// GroupMap: the product was computed with head-padded rows / columns (groups of *_gout holding *_gin real
+// entries); the reduction writes only the real ones, compacted, into `out`
+struct GroupMap { int row_gin, row_gout, col_gin, col_gout; };
+static inline GroupMap no_group_map() { return GroupMap{0, 0, 0, 0}; }
 int reduce_partials_ld(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t in_ld,
-                       int64_t out_ld, int accumulate, cudaStream_t st);
+                       int64_t out_ld, int accumulate, cudaStream_t st, GroupMap gm = no_group_map());
 
 // gemm_tc.cu (tcgen05): same contract; x3 = 1 -> bf16 hi/lo split (3 MMAs), 0 -> plain bf16 operands
 int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, const float* bias, const float* R,
             cudaStream_t st, DropSpec drop, int x3, EpiOp epi = no_epi(), PlaneOp pa = no_plane(),
             PlaneOp pb = no_plane());
 int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float* C, float* partials,
-                   size_t partial_bytes, cudaStream_t st, int x3, PlaneOp pa = no_plane(), PlaneOp pb = no_plane());
+                   size_t partial_bytes, cudaStream_t st, int x3, PlaneOp pa = no_plane(), PlaneOp pb = no_plane(),
+                   GroupMap gm = no_group_map());
 
 // impl dispatch used by the orchestrator
 inline bool gemm_uses_tc(int impl, const v1t_gemm_desc& d) {
@@ -99,10 +104,10 @@ inline int gemm_any(int impl, const v1t_gemm_desc& d, const float* A, const floa
 }
 inline int gemm_any_splitk(int impl, const v1t_gemm_desc& d, const float* A, const float* B, float* C,
                            float* partials, size_t partial_bytes, cudaStream_t st, PlaneOp pa = no_plane(),
-                           PlaneOp pb = no_plane()) {
+                           PlaneOp pb = no_plane(), GroupMap gm = no_group_map()) {
   const int64_t work = (int64_t)d.m * d.n * (d.k > 0 ? d.k : 1);
   if (impl == V1T_IMPL_FP32 || work < (1ll << 22)) return gemm_fp32_splitk(d, A, B, C, partials, partial_bytes, st);
-  return gemm_tc_splitk(d, A, B, C, partials, partial_bytes, st, impl == V1T_IMPL_BF16X3, pa, pb);
+  return gemm_tc_splitk(d, A, B, C, partials, partial_bytes, st, impl == V1T_IMPL_BF16X3, pa, pb, gm);
 }
 
 // planes.cu / attn_tc.cu (fused attention on tcgen05)
@@ -137,7 +142,8 @@ struct AttnBwdArgs {
   const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo, *do_hi, *do_lo;  // RM planes (rows = tokens, K = head dim)
   const float* lse;    // [B*H, Tp] base-2 log-sum-exp saved by the forward
   const float* delta;  // [B*H, Tp] rowsum(dO * O)
-  float* dqkv;         // [B, T, 3*H*E] packed like to_qkv's output: dQ | dK | dV
+  float* dqkv;         // [B, T, 3*H*E] packed like to_qkv's output: dQ | dK | dV (may be null when dq_pl is given)
+  PlaneOut dq_pl;      // optional: GEMM-operand planes of the head-padded [B*T, 3*H*Dp] gradient (dQ | dK | dV)
   int B, H, T, Tp, E, Dp;
   float scale_log2, scale;
   int x3;
