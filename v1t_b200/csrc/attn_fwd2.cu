@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv_l = 1.f / l;
-    float* orow = a.O + ((int64_t)b * a.T + qi) * a.o_ld + h * a.E;
+    float* orow = a.O ? a.O + ((int64_t)b * a.T + qi) * a.o_ld + h * a.E : nullptr;
+    const int64_t prow = (int64_t)b * a.T + qi;  // row of the head-padded [B*T, H*Dp] output matrix
 #pragma unroll
     for (int cc = 0; cc < AD; ++cc) {
       const int c0 = half * (AD * 16) + cc * 16;
@@ -354,9 +355,24 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       tmem_ld16(tmem_base + lane_off + cO + c0, v);
       tmem_ld_wait();
       if (qi < a.T) {
+        if (orow) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-          if (c0 + c < a.E) orow[c0 + c] = __uint_as_float(v[c]) * inv_l;
+          for (int c = 0; c < 16; ++c)
+            if (c0 + c < a.E) orow[c0 + c] = __uint_as_float(v[c]) * inv_l;
+        }
+        if (a.o_pl.hi) {  // operand planes for the projection GEMM and its weight gradient (pad columns are 0)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[8 * q + e]) * inv_l;
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int64_t off = plane_chunk_off(h * AD + (c0 >> 5), a.o_pl.rows_p, prow, ((c0 & 31) >> 3) + q);
+            *reinterpret_cast<uint4*>(a.o_pl.hi + off) = hi;
+            if (a.o_pl.lo) *reinterpret_cast<uint4*>(a.o_pl.lo + off) = lo;
+          }
+        }
       }
     }
     // padded query rows get +inf so that the backward's exp2(S*c - lse) vanishes there without bounds checks

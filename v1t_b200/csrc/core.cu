@@ -76,6 +76,8 @@ struct BlockSaved {
   uint8_t* wpl[4][2];              // GEMM-operand planes of Wqkv, Wproj, W1, W2 (converted once per step)
   uint8_t* gpl[2];                 // operand planes of gelu(u) * dropout (emitted by the MLP GEMM epilogue)
   uint8_t* wqp[2];                 // Wqkv planes with every head's rows padded to Ep (head-aligned QKV GEMM output)
+  uint8_t* wpp[2];                 // Wproj planes with every head's columns padded to Ep
+  uint8_t* opl[2];                 // operand planes of the head-padded attention output [R, H*Ep]
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -106,6 +108,8 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
   for (int i = 0; i < 2; ++i) {
     b.gpl[i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
     b.wqp[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(3 * d.heads * d.Ep, d.E) / sizeof(float)) : 1);
+    b.wpp[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(d.E, d.heads * d.Ep) / sizeof(float)) : 1);
+    b.opl[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(d.R, d.heads * d.Ep) / sizeof(float)) : 1);
   }
 }
 // the QKV GEMM of the fused-attention path: output columns (q|k|v, head, Ep) written straight into attention planes
@@ -302,8 +306,10 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       V1T_TRY(matrix_planes(W.wproj, d.I, d.E, d.I, S.wpl[kWproj][0], x3 ? S.wpl[kWproj][1] : nullptr, &tmp, st));
       V1T_TRY(matrix_planes(W.w1, d.E, d.M, d.E, S.wpl[kW1][0], x3 ? S.wpl[kW1][1] : nullptr, &tmp, st));
       V1T_TRY(matrix_planes(W.w2, d.M, d.E, d.M, S.wpl[kW2][0], x3 ? S.wpl[kW2][1] : nullptr, &tmp, st));
-      if (qkv_to_planes(d))
+      if (qkv_to_planes(d)) {
         V1T_TRY(matrix_planes(W.wqkv, d.E, 3 * d.I, d.E, S.wqp[0], x3 ? S.wqp[1] : nullptr, &tmp, st, d.E, d.Ep));
+        V1T_TRY(matrix_planes(W.wproj, d.I, d.E, d.I, S.wpp[0], x3 ? S.wpp[1] : nullptr, &tmp, st, 0, 0, d.E, d.Ep));
+      }
     }
     // ---- Attention.mha (vit.py:267-275)
     V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st, act_plane_out(d, sc.hpl)));
@@ -343,6 +349,12 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       AttnFwdArgs fa{};
       fa.q_hi = S.qp[0]; fa.q_lo = S.qp[1]; fa.k_hi = S.kp[0]; fa.k_lo = S.kp[1]; fa.v_hi = S.vp[0]; fa.v_lo = S.vp[1];
       fa.O = S.o; fa.o_ld = d.I; fa.lse = S.lse;
+      if (qkv_to_planes(d)) {  // O leaves the kernel only as operand planes of the head-padded [R, H*Ep] matrix
+        fa.O = nullptr;
+        fa.o_pl = act_plane_out(d, S.opl);
+        uint8_t* pads[2] = {S.opl[0], S.opl[1]};  // rows past B*T (contracted by the Wproj weight gradient)
+        V1T_TRY(zero_plane_pad_rows(pads, x3 ? 2 : 1, d.heads * (d.Ep / 32), (int)round_up(d.R, 32), (int)d.R, st));
+      }
       fa.B = d.B; fa.H = d.heads; fa.T = d.T; fa.Tp = d.Tq; fa.E = d.E; fa.Dp = d.Ep;
       fa.scale_log2 = (1.0f / sqrtf((float)d.E)) * 1.4426950408889634f;
       fa.x3 = x3;
@@ -363,10 +375,19 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     }
     {  // x2 = x1 + dropout(o Wproj^T + b)
       ProfScope prof(V1T_PHASE_PROJ, st);
-      v1t_gemm_desc g = gd((int)d.R, d.E, d.I);
-      g.a_m = d.I; g.a_k = 1; g.b_k = 1; g.b_n = d.I; g.c_m = d.Ep; g.r_m = d.Ep;
-      V1T_TRY(gemm_any(d.impl, g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj), no_epi(),
-                       no_plane(), wplane(d, S, kWproj)));
+      if (qkv_to_planes(d)) {  // head-padded contraction (K = H*Ep), both operands from planes
+        const int KP = d.heads * d.Ep;
+        v1t_gemm_desc g = gd((int)d.R, d.E, KP);
+        g.a_m = KP; g.a_k = 1; g.b_k = 1; g.b_n = KP; g.c_m = d.Ep; g.r_m = d.Ep;
+        const PlaneOp wp{S.wpp[0], d.impl == V1T_IMPL_BF16X3 ? S.wpp[1] : nullptr, (int)round_up(d.E, 32), cdiv(KP, 32)};
+        V1T_TRY(gemm_any(d.impl, g, nullptr, nullptr, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj), no_epi(),
+                         act_plane(d, S.opl, KP), wp));
+      } else {
+        v1t_gemm_desc g = gd((int)d.R, d.E, d.I);
+        g.a_m = d.I; g.a_k = 1; g.b_k = 1; g.b_n = d.I; g.c_m = d.Ep; g.r_m = d.Ep;
+        V1T_TRY(gemm_any(d.impl, g, S.o, W.wproj, S.x2, W.bproj, S.x1, st, site_drop(*shape, i, kSiteProj), no_epi(),
+                         no_plane(), wplane(d, S, kWproj)));
+      }
     }
     // ---- MLP (vit.py:143-150)
     ProfScope prof_mlp(V1T_PHASE_MLP, st);
@@ -466,13 +487,34 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       da = sc.dh;
       dap = act_plane(d, sc.dpl, d.E);
     }
+    const bool hp_path = qkv_to_planes(d);  // head-padded plane dataflow through the attention branch
+    const int KP = d.heads * d.Ep;
+    const PlaneOp wpp{S.wpp[0], d.impl == V1T_IMPL_BF16X3 ? S.wpp[1] : nullptr, (int)round_up(d.E, 32), cdiv(KP, 32)};
     if (GW.wproj) {  // dWp[e,i] = sum_r da[r,e] o[r,i]
-      v1t_gemm_desc g = gd(d.E, d.I, R);
-      g.a_m = 1; g.a_k = d.Ep; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
-      V1T_TRY(gemm_any_splitk(d.impl, g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st, dap));
+      if (hp_path) {  // o from the planes the attention forward wrote; padded columns dropped by the reduction
+        v1t_gemm_desc g = gd(d.E, KP, R);
+        g.a_m = 1; g.a_k = d.Ep; g.b_k = KP; g.b_n = 1; g.c_m = d.I;
+        V1T_TRY(gemm_any_splitk(d.impl, g, da, nullptr, GW.wproj, sc.partials, kPartialBytes, st, dap,
+                                act_plane(d, S.opl, KP), GroupMap{0, 0, d.E, d.Ep}));
+      } else {
+        v1t_gemm_desc g = gd(d.E, d.I, R);
+        g.a_m = 1; g.a_k = d.Ep; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
+        V1T_TRY(gemm_any_splitk(d.impl, g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st, dap));
+      }
     }
     if (GW.bproj) V1T_TRY(colsum(da, GW.bproj, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
-    {  // dO[r,i] = sum_e da[r,e] Wp[e,i]
+    if (hp_path) {  // dO[r, (h, d)] = sum_e da[r,e] Wp[e, h*E + d]  -> straight into the attention kernels' dO planes
+      v1t_gemm_desc g = gd(R, KP, d.E);
+      g.a_m = d.Ep; g.a_k = 1; g.b_k = KP; g.b_n = 1;
+      EpiOp epi = no_epi();
+      epi.kind = kEpiHeadPlanes;
+      epi.hp.p[0][0] = sc.planes.dO[0];
+      epi.hp.p[0][1] = d.impl == V1T_IMPL_BF16X3 ? sc.planes.dO[1] : nullptr;
+      epi.hp.T = d.T; epi.hp.Tq = d.Tq; epi.hp.H = d.heads; epi.hp.AD = d.Ep / 32;
+      uint8_t* pads[2] = {sc.planes.dO[0], sc.planes.dO[1]};
+      V1T_TRY(zero_plane_pad_rows(pads, d.impl == V1T_IMPL_BF16X3 ? 2 : 1, (int64_t)d.B * d.heads * (d.Ep / 32), d.Tq, d.T, st));
+      V1T_TRY(gemm_any(d.impl, g, da, nullptr, nullptr, nullptr, nullptr, st, no_drop(), epi, dap, wpp));
+    } else {  // dO[r,i] = sum_e da[r,e] Wp[e,i]
       v1t_gemm_desc g = gd(R, d.I, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.I; g.b_n = 1; g.c_m = d.I;
       V1T_TRY(gemm_any(d.impl, g, da, W.wproj, sc.dO, nullptr, nullptr, st, no_drop(), no_epi(), dap, wplane(d, S, kWproj)));
@@ -483,9 +525,14 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       ProfScope prof(V1T_PHASE_ATTN_BWD, st);
       const int x3 = d.impl == V1T_IMPL_BF16X3;
       const AttnPlanes& pl = sc.planes;
-      V1T_TRY(make_planes(sc.dO, d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.dO[0], x3 ? pl.dO[1] : nullptr,
-                          nullptr, nullptr, st));
-      V1T_TRY(attn_delta(S.o, sc.dO, pl.delta, d.B, d.heads, d.T, d.Tq, d.E, d.I, st));
+      if (hp_path) {  // dO planes came out of the GEMM above; delta = rowsum(O * dO) from the planes
+        V1T_TRY(attn_delta_planes(act_plane(d, S.opl, KP), pl.dO[0], x3 ? pl.dO[1] : nullptr, pl.delta, d.B, d.heads, d.T,
+                                  d.Tq, d.Ep / 32, st));
+      } else {
+        V1T_TRY(make_planes(sc.dO, d.I, 0, d.B, d.heads, d.T, d.Tq, d.E, d.Ep, pl.dO[0], x3 ? pl.dO[1] : nullptr,
+                            nullptr, nullptr, st));
+        V1T_TRY(attn_delta(S.o, sc.dO, pl.delta, d.B, d.heads, d.T, d.Tq, d.E, d.I, st));
+      }
       AttnBwdArgs ba{};
       ba.q_hi = S.qp[0]; ba.q_lo = S.qp[1]; ba.k_hi = S.kp[0]; ba.k_lo = S.kp[1]; ba.v_hi = S.vp[0]; ba.v_lo = S.vp[1];
       ba.do_hi = pl.dO[0]; ba.do_lo = pl.dO[1];

@@ -627,8 +627,10 @@ int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, co
   if (!tc_supported(d)) return gemm_fp32(d, A, B, C, bias, R, st, drop);
   if (epi.kind == kEpiHeadPlanes) {
     const HeadPlanes& hp = epi.hp;
-    V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && !bias && !R && !d.accumulate && hp.p[0][0] && hp.p[1][0] && hp.p[2][0] &&
-                      d.n == 3 * hp.H * hp.AD * 32 && hp.T > 0 && d.m % hp.T == 0 && hp.Tq >= hp.T,
+    const int per = hp.H * hp.AD * 32;
+    V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && !bias && !R && !d.accumulate && hp.p[0][0] && per > 0 &&
+                      (d.n == per || (d.n == 3 * per && hp.p[1][0] && hp.p[2][0])) && hp.T > 0 && d.m % hp.T == 0 &&
+                      hp.Tq >= hp.T,
                   "gemm_tc: head-plane output does not match the problem");
   } else if (epi.kind != kEpiNone) {
     V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && epi.ld % 4 == 0 && aligned16(epi.kind == kEpiGeluOut ? (const void*)epi.aux : (const void*)epi.u),

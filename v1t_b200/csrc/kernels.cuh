@@ -22,7 +22,7 @@ struct PlaneOut {
 };
 static inline PlaneOut no_plane_out() { return PlaneOut{nullptr, nullptr, 0}; }
 
-// Destination of kEpiHeadPlanes: the GEMM output [B*T, 3 * H * AD*32] (q | k | v, every head padded to AD*32
+// Destination of kEpiHeadPlanes: the GEMM output [B*T, S * H * AD*32] (S = 3: q | k | v, S = 1: dO; every head padded to AD*32
 // columns) leaves the epilogue as the per-(sample, head) attention operand planes of planes.cu
 // ([b*H + h][AD atoms][Tq rows][64 B]) instead of fp32 -- no separate conversion pass over qkv.
 struct HeadPlanes {
@@ -117,7 +117,9 @@ size_t matrix_plane_bytes(int64_t rows, int64_t cols);
 // row_gin / row_gout: every group of row_gin source rows becomes row_gout plane rows (zero padded), e.g. the
 // per-head blocks of Wqkv (155 rows) padded to 160 so that the QKV GEMM output is head-aligned.
 int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, PlaneOp* out,
-                  cudaStream_t st, int row_gin = 0, int row_gout = 0);
+                  cudaStream_t st, int row_gin = 0, int row_gout = 0, int col_gin = 0, int col_gout = 0);
+int attn_delta_planes(const PlaneOp& o, const void* do_hi, const void* do_lo, float* delta, int B, int H, int T, int Tp,
+                      int AD, cudaStream_t st);
 // zero rows [T, Tq) of every (sample, head, atom) slab of up to 6 attention planes
 int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st);
 // fp32 qkv [B*T, 3*H*E] back from the attention planes (hi + lo), for the attention-map hooks
@@ -128,7 +130,8 @@ int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int 
                cudaStream_t st);
 struct AttnFwdArgs {
   const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo;  // pre-swizzled bf16 RM planes (rows = tokens; planes.cu)
-  float* O;          // [B, T, o_ld]: O[(b*T+t)*o_ld + h*E + d]
+  float* O;          // [B, T, o_ld]: O[(b*T+t)*o_ld + h*E + d] (may be null when o_pl is given)
+  PlaneOut o_pl;     // optional: GEMM-operand planes of the head-padded [B*T, H*Dp] output
   int64_t o_ld;
   float* lse;        // [B*H, Tp] log2-domain log-sum-exp (may be null)
   int B, H, T, Tp, E, Dp;

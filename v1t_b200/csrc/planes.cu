@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) make_planes_kernel(const float* __restric
 // GEMM-operand planes of a row-major matrix X[rows, cols]: one thread per 16-byte chunk (8 columns of one row)
 __global__ void matrix_planes_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int64_t cols,
                                      int64_t rows_p, int64_t chunks, uint8_t* __restrict__ hi,
-                                     uint8_t* __restrict__ lo, int gin, int gout) {
+                                     uint8_t* __restrict__ lo, int gin, int gout, int cgin, int cgout) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= chunks) return;
   const int c = (int)(idx & 3);
@@ -87,7 +87,11 @@ __global__ void matrix_planes_kernel(const float* __restrict__ X, int64_t ld, in
   if (gout > 0) sr = (r % gout < gin) ? (r / gout) * gin + r % gout : -1;
   float v[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = (sr >= 0 && sr < rows && col0 + e < cols) ? __ldg(X + sr * ld + col0 + e) : 0.f;
+  for (int e = 0; e < 8; ++e) {
+    int64_t sc = col0 + e;  // source column (-1: padding)
+    if (cgout > 0) sc = (sc % cgout < cgin) ? (sc / cgout) * cgin + sc % cgout : -1;
+    v[e] = (sr >= 0 && sr < rows && sc >= 0 && sc < cols) ? __ldg(X + sr * ld + sc) : 0.f;
+  }
   uint4 h, l;
   split8(v, h, l);
   const int64_t off = (a * rows_p + r) * 64 + ((c ^ (int)((r >> 1) & 3)) << 4);
@@ -152,15 +156,18 @@ size_t matrix_plane_bytes(int64_t rows, int64_t cols) {
 }
 
 int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, PlaneOp* out,
-                  cudaStream_t st, int row_gin, int row_gout) {
+                  cudaStream_t st, int row_gin, int row_gout, int col_gin, int col_gout) {
   V1T_CHECK_ARG(row_gout == 0 || (row_gin > 0 && row_gout >= row_gin && rows % row_gin == 0),
                 "matrix_planes: bad row grouping");
+  V1T_CHECK_ARG(col_gout == 0 || (col_gin > 0 && col_gout >= col_gin && cols % col_gin == 0),
+                "matrix_planes: bad column grouping");
   const int64_t prow = row_gout ? rows / row_gin * row_gout : rows;
-  const int64_t rows_p = round_up(prow, 32), catoms = cdiv(cols, 32);
+  const int64_t pcol = col_gout ? cols / col_gin * col_gout : cols;
+  const int64_t rows_p = round_up(prow, 32), catoms = cdiv(pcol, 32);
   const int64_t chunks = catoms * rows_p * 4;
   V1T_CHECK_ARG(X && hi && out && catoms * rows_p < (1ll << 31), "matrix_planes: bad argument");
   matrix_planes_kernel<<<(unsigned)cdiv(chunks, 256), 256, 0, st>>>(X, ld, rows, cols, rows_p, chunks, (uint8_t*)hi,
-                                                                      (uint8_t*)lo, row_gin, row_gout);
+                                                                      (uint8_t*)lo, row_gin, row_gout, col_gin, col_gout);
   V1T_LAUNCH_CHECK();
   out->hi = (const uint8_t*)hi; out->lo = (const uint8_t*)lo; out->rows_p = (int)rows_p; out->catoms = (int)catoms;
   return V1T_OK;
@@ -192,6 +199,40 @@ int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int T
   const size_t smem = sizeof(float) * 32 * (Dp + 1);
   make_planes_kernel<<<grid, 256, smem, st>>>(X, ld, col0, B, H, T, Tp, E, Dp, (uint8_t*)rm_hi, (uint8_t*)rm_lo,
                                               (uint8_t*)tr_hi, (uint8_t*)tr_lo);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+// delta from the planes alone: O as operand planes of the head-padded [B*T, H*Dp] matrix (attention forward
+// epilogue), dO as attention planes ([b*H+h][atoms][Tp][64 B]); one warp per (b, t, h), lane = column within an atom
+__global__ void attn_delta_planes_kernel(PlaneOp o, const uint8_t* __restrict__ do_hi, const uint8_t* __restrict__ do_lo,
+                                         float* __restrict__ delta, int B, int H, int T, int Tp, int AD) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)B * T * H) return;
+  const int h = (int)(w % H);
+  const int64_t r = w / H;  // b*T + t
+  const int b = (int)(r / T), t = (int)(r % T);
+  float s = 0.f;
+  for (int a = 0; a < AD; ++a) {
+    const int64_t oo = tc::plane_chunk_off(h * AD + a, o.rows_p, r, lane >> 3) + (lane & 7) * 2;
+    const int64_t go = ((((int64_t)b * H + h) * AD + a) * Tp + t) * 64 + (((lane >> 3) ^ ((t >> 1) & 3)) << 4) + (lane & 7) * 2;
+    float ov = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(o.hi + oo));
+    float gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(do_hi + go));
+    if (o.lo) ov += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(o.lo + oo));
+    if (do_lo) gv += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(do_lo + go));
+    s = fmaf(ov, gv, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) delta[((int64_t)b * H + h) * Tp + t] = s;
+}
+
+int attn_delta_planes(const PlaneOp& o, const void* do_hi, const void* do_lo, float* delta, int B, int H, int T, int Tp,
+                      int AD, cudaStream_t st) {
+  const int64_t warps = (int64_t)B * T * H;
+  V1T_CUDA(cudaMemsetAsync(delta, 0, sizeof(float) * (size_t)B * H * Tp, st));  // zero the padded rows
+  attn_delta_planes_kernel<<<cdiv(warps, 8), 256, 0, st>>>(o, (const uint8_t*)do_hi, (const uint8_t*)do_lo, delta, B, H, T,
+                                                          Tp, AD);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
