@@ -148,8 +148,8 @@ def test_dropout_masks_replay_exactly_against_oracle():
     d = g.mice["A"]
     cfg = g.core_config()
     B, T, E, H, M = d["images"].shape[0], cfg.num_tokens, cfg.emb_dim, cfg.num_heads, cfg.mlp_dim
-    def mk(site, shape, p):  # rows of every mask are indexed with a 4-aligned stride (one Philox call = 4 columns)
-        padded = tuple(shape[:-1]) + ((shape[-1] + 3) // 4 * 4,)
+    def mk(site, shape, p):  # rows of every mask are indexed with an 8-aligned stride (one Philox call = 8 columns)
+        padded = tuple(shape[:-1]) + ((shape[-1] + 7) // 8 * 8,)
         full = VF.dropout_mask(int(np.prod(padded)), seed, site, p, DEV).cpu().numpy().reshape(padded)
         return full[..., :shape[-1]].astype(np.float64)
     masks = {"tokens": mk(0, (B, T, E), p_tok)}
@@ -500,7 +500,7 @@ def test_fused_attention_forward_dropout_replay():
     rc = lib.v1t_attn_forward(qkv.data_ptr(), B, H, T, E, _lib.IMPL_BF16X3, p, seed, site, out.data_ptr(), None,
                               scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0, _lib.last_error()
-    Tc = (T + 3) // 4 * 4
+    Tc = (T + 7) // 8 * 8
     mask = VF.dropout_mask(B * H * T * Tc, seed, site, p, DEV).view(B, H, T, Tc)[..., :T].double()
     ref, _ = _attn_ref(qkv, H, E, mask)
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 3e-5
@@ -530,7 +530,7 @@ def test_fused_attention_backward(B, H, T, E, p, impl, tol):
                                _lib.IMPL_NAMES[impl], p, seed, site, d_qkv.data_ptr(), scratch.data_ptr(), st)
     assert rc == 0, _lib.last_error()
     torch.cuda.synchronize()
-    Tc = (T + 3) // 4 * 4
+    Tc = (T + 7) // 8 * 8
     mask = VF.dropout_mask(B * H * T * Tc, seed, site, p, DEV).view(B, H, T, Tc)[..., :T].double() if p > 0 else None
     q64 = qkv.double().requires_grad_(True)
     ref, _ = _attn_ref(q64, H, E, mask)

@@ -59,8 +59,9 @@ struct Smem2 {
   static constexpr uint32_t x_ring = MODE == MODE_S ? kYlo : 0;
   static constexpr uint32_t y_ring = x_ring + kXS * kSlot;
   static constexpr uint32_t bars = y_ring + kYS * kSlot;
-  static constexpr uint32_t mask = bars + 256;        // dropout multipliers, [warp][N/2][32] floats
-  static constexpr uint32_t total = mask + kSmWarps * (N / 2) * 32 * 4 + 1024;
+  static constexpr int kMaskLd = 36;                  // floats per column of the mask tile (32 keys + 4: conflict-free)
+  static constexpr uint32_t mask = bars + 256;        // dropout multipliers, [warp][N/2][kMaskLd] floats
+  static constexpr uint32_t total = mask + kSmWarps * (N / 2) * kMaskLd * 4 + 1024;
 };
 
 template <int MODE, bool KV, int N, int AD>
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
     }
 
     const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
-    const int Tc = (a.T + 3) & ~3;
+    const int Tc = (int)drop_stride(a.T);
     const float* lse = a.lse + (int64_t)bh * a.Tp;
     const float* delta = a.delta + (int64_t)bh * a.Tp;
     float lse_r = 0.f, delta_r = 0.f;
@@ -341,32 +342,33 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
       for (int c = 0; c < NH; ++c) mult[c] = 1.f;
       if (a.drop.p > 0.f) {
         if constexpr (kv_roles) {
-          // thread = key row, columns = queries.  One Philox call covers 4 adjacent KEYS of one query, i.e. 4
-          // adjacent lanes: lane (kg = lane/4, cq = lane%4) generates the calls of key-group kg for the columns
-          // c = 4i + cq and the warp transposes them through a private smem tile [column][lane].
-          float* mt = reinterpret_cast<float*>(smem + L::mask) + warp * (NH * 32);
-          const int kg = lane >> 2, cq = lane & 3;
-          const int key0 = r0 + quarter * 32 + kg * 4;
+          // thread = key row, columns = queries.  One Philox call covers 8 adjacent KEYS of one query, i.e. 8
+          // adjacent lanes: lane (kg = lane/8, cq = lane%8) generates the calls of key-group kg for the columns
+          // c = 8i + cq and the warp transposes them through a private smem tile [column][lane].
+          float* mt = reinterpret_cast<float*>(smem + L::mask) + warp * (NH * L::kMaskLd);
+          const int kg = lane >> 3, cq = lane & 7;
+          const int key0 = r0 + quarter * 32 + kg * 8;
 #pragma unroll
-          for (int i = 0; i < NH / 4; ++i) {
-            const int c = 4 * i + cq;
-            float mk[4];
+          for (int i = 0; i < NH / 8; ++i) {
+            const int c = 8 * i + cq;
+            float mk[8];
             const uint64_t idx = ((uint64_t)bh * a.T + (uint64_t)min(c0 + c, a.T - 1)) * (uint64_t)Tc + key0;
-            dropout_mult4(a.drop.seed, a.drop.site, idx >> 2, a.drop.p, inv_keep, mk);
-            *reinterpret_cast<float4*>(mt + c * 32 + kg * 4) = make_float4(mk[0], mk[1], mk[2], mk[3]);
+            dropout_mult8(a.drop.seed, a.drop.site, idx >> 3, a.drop.p, inv_keep, mk);
+            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8) = make_float4(mk[0], mk[1], mk[2], mk[3]);
+            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8 + 4) = make_float4(mk[4], mk[5], mk[6], mk[7]);
           }
           __syncwarp();
 #pragma unroll
-          for (int c = 0; c < NH; ++c) mult[c] = mt[c * 32 + lane];
+          for (int c = 0; c < NH; ++c) mult[c] = mt[c * L::kMaskLd + lane];
           __syncwarp();
-        } else {                   // thread = query row, columns = keys: 4 adjacent keys share one Philox call
+        } else {                   // thread = query row, columns = keys: 8 adjacent keys share one Philox call
           const uint64_t rowb = ((uint64_t)bh * a.T + (uint64_t)min(ri, a.T - 1)) * (uint64_t)Tc;
 #pragma unroll
-          for (int g = 0; g < NH / 4; ++g) {
-            float mk[4];
-            dropout_mult4(a.drop.seed, a.drop.site, (rowb + (uint64_t)(c0 + 4 * g)) >> 2, a.drop.p, inv_keep, mk);
+          for (int g = 0; g < NH / 8; ++g) {
+            float mk[8];
+            dropout_mult8(a.drop.seed, a.drop.site, (rowb + (uint64_t)(c0 + 8 * g)) >> 3, a.drop.p, inv_keep, mk);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) mult[4 * g + e] = mk[e];
+            for (int e = 0; e < 8; ++e) mult[8 * g + e] = mk[e];
           }
         }
       }

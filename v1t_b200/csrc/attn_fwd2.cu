@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     const float m2 = m * a.scale_log2;
     float l = 0.f;
     const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
-    const int Tc = (a.T + 3) & ~3;
+    const int Tc = (int)drop_stride(a.T);
     const uint64_t drop_row = ((uint64_t)bh * a.T + (uint64_t)min(qi, a.T - 1)) * (uint64_t)Tc;
     // ---- pass 2
     for (int j = 0; j < nk; ++j, ++its) {
@@ -315,11 +315,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       }
       if (a.drop.p > 0.f) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float mk[4];
-          dropout_mult4(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 4 * g)) >> 2, a.drop.p, inv_keep, mk);
+        for (int g = 0; g < 4; ++g) {  // one Philox call per 8 adjacent keys
+          float mk[8];
+          dropout_mult8(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 8 * g)) >> 3, a.drop.p, inv_keep, mk);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) p[4 * g + e] *= mk[e];
+          for (int e = 0; e < 8; ++e) p[8 * g + e] *= mk[e];
         }
       }
       mbar_wait(p_empty, (j & 1) ^ 1);  // P V of the previous tile has consumed the operand

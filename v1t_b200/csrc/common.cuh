@@ -69,12 +69,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- counter-based RNG for dropout masks (Philox4x32-10); replayable in backward -----------------------
+// ---- counter-based RNG for dropout masks; replayable in backward -------------------------------------
+// Philox4x32 with 7 rounds (the fewest that Salmon et al. 2011 report as Crush-resistant): one call yields 128 bits =
+// EIGHT 16-bit uniforms, i.e. the keep decisions of 8 adjacent elements (keep iff u16 >= round(p * 65536)).  The
+// masks cost 11 % of the training step with the 10-round / 4-elements-per-call version; every site indexes its
+// elements with a row stride rounded up to 8 (drop_stride) so that a call never straddles two rows.
+__host__ __device__ inline int64_t drop_stride(int64_t cols) { return (cols + 7) & ~(int64_t)7; }
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr_hi0, uint32_t ctr_hi1) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = ctr_hi0, c3 = ctr_hi1;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0;
@@ -87,14 +92,26 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint
   return make_uint4(c0, c1, c2, c3);
 }
 
-// keep-multiplier of inverted dropout for element `idx` of dropout site `site`: 0 or 1/(1-p).
-// One Philox call yields 4 lanes; element idx uses call idx>>2, lane idx&3.
+__device__ __forceinline__ uint32_t dropout_thr16(float p) { return (uint32_t)(p * 65536.0f + 0.5f); }
+// keep-multipliers (0 or 1/(1-p)) of the aligned group `group` (elements 8*group .. 8*group+7): ONE Philox call
+__device__ __forceinline__ void dropout_mult8(uint64_t seed, uint32_t site, uint64_t group, float p, float inv_keep,
+                                              float (&m)[8]) {
+  const uint4 r = philox4x32(seed, group, site, 0x5eedu);
+  const uint32_t thr = dropout_thr16(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[2 * i] = (w[i] & 0xffffu) >= thr ? inv_keep : 0.0f;
+    m[2 * i + 1] = (w[i] >> 16) >= thr ? inv_keep : 0.0f;
+  }
+}
+// keep-multiplier of element `idx` of dropout site `site`: call idx >> 3, 16-bit lane idx & 7
 __device__ __forceinline__ float dropout_mult(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
-  uint4 r = philox4x32(seed, idx >> 2, site, 0x5eedu);
-  uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-  // uniform in [0,1): keep iff u >= p  (matches "bernoulli(1-p)")
-  float u = (float)(w >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.0f;
+  const uint4 r = philox4x32(seed, idx >> 3, site, 0x5eedu);
+  const uint32_t l = (uint32_t)idx & 7u;
+  const uint32_t w = (l >> 1) == 0 ? r.x : (l >> 1) == 1 ? r.y : (l >> 1) == 2 ? r.z : r.w;
+  const uint32_t u = (l & 1) ? (w >> 16) : (w & 0xffffu);
+  return u >= dropout_thr16(p) ? inv_keep : 0.0f;
 }
 
 
@@ -103,14 +120,16 @@ __device__ __forceinline__ float gelu_df(float u) {
   return 0.5f * (1.f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * expf(-0.5f * u * u);
 }
 
-// 4 multipliers of the aligned group `group` (elements 4*group .. 4*group+3) with ONE Philox call
-__device__ __forceinline__ void dropout_mult4(uint64_t seed, uint32_t site, uint64_t group, float p, float inv_keep,
+// 4 multipliers of the aligned quad `quad` (elements 4*quad .. 4*quad+3): half of the Philox call quad >> 1
+__device__ __forceinline__ void dropout_mult4(uint64_t seed, uint32_t site, uint64_t quad, float p, float inv_keep,
                                               float (&m)[4]) {
-  const uint4 r = philox4x32(seed, group, site, 0x5eedu);
-  m[0] = (float)(r.x >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
-  m[1] = (float)(r.y >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
-  m[2] = (float)(r.z >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
-  m[3] = (float)(r.w >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
+  const uint4 r = philox4x32(seed, quad >> 1, site, 0x5eedu);
+  const uint32_t thr = dropout_thr16(p);
+  const uint32_t w0 = (quad & 1) ? r.z : r.x, w1 = (quad & 1) ? r.w : r.y;
+  m[0] = (w0 & 0xffffu) >= thr ? inv_keep : 0.0f;
+  m[1] = (w0 >> 16) >= thr ? inv_keep : 0.0f;
+  m[2] = (w1 & 0xffffu) >= thr ? inv_keep : 0.0f;
+  m[3] = (w1 >> 16) >= thr ? inv_keep : 0.0f;
 }
 
 }  // namespace v1t

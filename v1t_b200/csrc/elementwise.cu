@@ -65,7 +65,7 @@ __global__ void dropout_rows_kernel(const float* __restrict__ src, float* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols;
     const int c = (int)(i % cols);
-    dst[r * ld + c] = src[r * ld + c] * dropout_mult(dr.seed, dr.site, (uint64_t)r * ((cols + 3) & ~3) + c, dr.p, inv_keep);
+    dst[r * ld + c] = src[r * ld + c] * dropout_mult(dr.seed, dr.site, (uint64_t)r * drop_stride(cols) + c, dr.p, inv_keep);
   }
 }
 
@@ -75,19 +75,19 @@ __global__ void dropout_rows8_kernel(const float* __restrict__ src, float* __res
                                      int64_t ld, int chunks, DropSpec dr, PlaneOut pl) {
   const float inv_keep = 1.f / (1.f - dr.p);
   const int64_t total = (pl.hi ? (int64_t)pl.rows_p : rows) * chunks;  // plane pad rows are zero-filled too
-  const int64_t drop_ld = (cols + 3) & ~3;
+  const int64_t drop_ld = drop_stride(cols);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / chunks;
     const int ch = (int)(i % chunks);
     const int c0 = ch * 8;
-    float v[8];
+    float v[8], m8[8];
+    if (c0 < cols && r < rows) dropout_mult8(dr.seed, dr.site, ((uint64_t)r * drop_ld + c0) >> 3, dr.p, inv_keep, m8);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int c = c0 + 4 * q;
       float x[4] = {0.f, 0.f, 0.f, 0.f};
       if (c < cols && r < rows) {
-        float m[4];
-        dropout_mult4(dr.seed, dr.site, ((uint64_t)r * drop_ld + c) >> 2, dr.p, inv_keep, m);
+        const float m[4] = {m8[4 * q], m8[4 * q + 1], m8[4 * q + 2], m8[4 * q + 3]};
         if (c + 4 <= cols) {
           const float4 s4 = *reinterpret_cast<const float4*>(src + r * ld + c);
           x[0] = s4.x * m[0]; x[1] = s4.y * m[1]; x[2] = s4.z * m[2]; x[3] = s4.w * m[3];
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S
     const float inv = 1.f / warp_sum(sum);
     for (int c = lane; c < cols; c += 32) {
       float p = row[c] * inv;
-      if (dr.p > 0.f) p *= dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * ((cols + 3) & ~3) + c, dr.p, inv_keep);
+      if (dr.p > 0.f) p *= dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * drop_stride(cols) + c, dr.p, inv_keep);
       row[c] = p;
     }
   }
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(float* __restrict
     for (int c = lane; c < cols; c += 32) {
       float dv = d[c];
       if (dr.p > 0.f) {
-        const float m = dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * ((cols + 3) & ~3) + c, dr.p, inv_keep);
+        const float m = dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * drop_stride(cols) + c, dr.p, inv_keep);
         dv *= m;
         d[c] = dv;
       }
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(float* __restrict
       const float pv = p[c];
       d[c] = pv * (d[c] - dot);
       if (dr.p > 0.f)
-        p[c] = pv * dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * ((cols + 3) & ~3) + c, dr.p, inv_keep);
+        p[c] = pv * dropout_mult(dr.seed, dr.site, (uint64_t)(row_offset + r) * drop_stride(cols) + c, dr.p, inv_keep);
     }
   }
 }
@@ -376,7 +376,7 @@ __global__ void gelu_forward_kernel(const float* __restrict__ u, float* __restri
     float v = 0.f;
     if (c < cols) {
       v = gelu_f(u[i]);
-      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * ((cols + 3) & ~3) + c, dr.p, inv_keep);
+      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * drop_stride(cols) + c, dr.p, inv_keep);
     }
     g[i] = v;
   }
@@ -392,7 +392,7 @@ __global__ void gelu_backward_kernel(float* __restrict__ dg, const float* __rest
     float v = 0.f;
     if (c < cols) {
       v = dg[i] * gelu_df(u[i]);
-      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * ((cols + 3) & ~3) + c, dr.p, inv_keep);
+      if (dr.p > 0.f) v *= dropout_mult(dr.seed, dr.site, (uint64_t)r * drop_stride(cols) + c, dr.p, inv_keep);
     }
     dg[i] = v;
   }

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads) sgemm_kernel(GemmArgs g) {
       float v = g.d.alpha * acc[i][j];
       if (g.bias) v += __ldg(g.bias + n);
       if (g.drop.p > 0.f)
-        v *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * ((g.d.n + 3) & ~3) + n, g.drop.p, 1.f / (1.f - g.drop.p));
+        v *= dropout_mult(g.drop.seed, g.drop.site, (uint64_t)m * drop_stride(g.d.n) + n, g.drop.p, 1.f / (1.f - g.drop.p));
       if (R) v += __ldg(R + (int64_t)m * g.d.r_m + n);
       float* c = C + (int64_t)m * g.d.c_m + n;
       if (g.d.accumulate) v += *c;

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     const int slot = warp < kEpiWarps ? (warp >> 2) : 2 + ((warp - kEpiWarps - 1) >> 2);
     constexpr int kSlots = kEpiW / 4;
     const float inv_keep = (kDrop && g.drop.p > 0.f) ? 1.f / (1.f - g.drop.p) : 1.f;
-    const int64_t drop_ld = (g.d.n + 3) & ~3;
+    const int64_t drop_ld = drop_stride(g.d.n);
     const float inv_keep2 = g.epi.drop.p > 0.f ? 1.f / (1.f - g.epi.drop.p) : 1.f;
     const bool bias_vec = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     const uint32_t stg = warp < kEpiWarps ? smem_u32(stage_base + warp * 4096)
