@@ -17,8 +17,9 @@
 // TMEM columns (HC = Dp/2 columns per 128 x Dp bf16 plane):
 //   MODE_S: X_hi | X_lo | Y_hi | S'[N] | dP'[N] | dS'_hi[N/2] | dS'_lo[N/2] | out[Dp]     = 3 HC + 3 N + Dp  (496 @ N=32)
 //   MODE_V: X_hi | X_lo | S'[2][N] | Pd'_hi[N/2] | Pd'_lo[N/2] | out[Dp]                  = 2 HC + 3 N + Dp  (512 @ N=64)
-// Warp roles (320 threads): warps 0-7 softmax-backward/epilogue (lane quarter = warp & 3, column half = warp >> 2),
-// warp 8 MMA issue + TMEM alloc, warp 9 bulk-copy producer.
+// Warp roles (608 threads): warps 0-15 softmax-backward/epilogue (lane quarter = warp & 3, column slot = warp >> 2:
+// each warp owns a quarter of a tile's columns; with 8 warps the element-wise work was latency-bound at ~0.4 IPC and
+// the tensor pipe sat at 35-45 %), warp 16 MMA issue + TMEM alloc, warps 17-18 bulk-copy producers (one per ring).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -32,7 +33,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int kSmWarps = 8;
+constexpr int kSmWarps = 16;
+constexpr int kSlots = kSmWarps / 4;  // column slots per TMEM lane quarter
 constexpr int kSmThreads = kSmWarps * 32;
 constexpr int kThreadsAttn = (kSmWarps + 3) * 32;
 constexpr int kMmaWarp = kSmWarps, kLoadWarpX = kSmWarps + 1, kLoadWarpY = kSmWarps + 2;
@@ -60,13 +62,15 @@ struct Smem2 {
   static constexpr uint32_t y_ring = x_ring + kXS * kSlot;
   static constexpr uint32_t bars = y_ring + kYS * kSlot;
   static constexpr int kMaskLd = 36;                  // floats per column of the mask tile (32 keys + 4: conflict-free)
-  static constexpr uint32_t mask = bars + 256;        // dropout multipliers, [warp][N/2][kMaskLd] floats
-  static constexpr uint32_t total = mask + kSmWarps * (N / 2) * kMaskLd * 4 + 1024;
+  static constexpr uint32_t mask = bars + 256;        // dropout multipliers, [warp][N/kSlots][kMaskLd] floats
+  static constexpr uint32_t total = mask + kSmWarps * (N / kSlots) * kMaskLd * 4 + 1024;
 };
 
 template <int MODE, bool KV, int N, int AD>
 __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a) {
-  constexpr int Dp = AD * 32, HC = AD * 16, NH = N / 2;
+  constexpr int Dp = AD * 32, HC = AD * 16;
+  constexpr int NH = N / kSlots;  // tile columns per softmax warp
+  constexpr int OPC = N / 2;      // TMEM columns of one bf16 plane of the Pd' / dS' operand
   using L = Smem2<MODE, N, AD>;
   constexpr int kXS = L::kXS, kYS = L::kYS;
   extern __shared__ uint8_t smem_raw[];
@@ -122,8 +126,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
   constexpr uint32_t cY_hi = 2 * HC;                                     // MODE_S only
   constexpr uint32_t cS = MODE == MODE_S ? 3 * HC : 2 * HC;              // S' (MODE_V: two buffers of N)
   constexpr uint32_t cDP = cS + N;                                       // MODE_S: dP'
-  constexpr uint32_t cPS_hi = cS + 2 * N, cPS_lo = cPS_hi + NH;          // A operand of the output MMA
-  constexpr uint32_t cOut = cPS_lo + NH;
+  constexpr uint32_t cPS_hi = cS + 2 * N, cPS_lo = cPS_hi + OPC;         // A operand of the output MMA
+  constexpr uint32_t cOut = cPS_lo + OPC;
   static_assert(cOut + Dp <= 512, "TMEM budget exceeded");
 
   if (warp == kLoadWarpX || warp == kLoadWarpY) {
@@ -255,13 +259,13 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
     issue_out(nt - 1, true);
   } else {
     // ============================== SOFTMAX-BACKWARD / EPILOGUE ==============================
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, slot = warp >> 2;
     const int row = quarter * 32 + lane;
     const int ri = r0 + row;  // key index (kv_roles) or query index
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int b = bh / a.H, h = bh % a.H;
 
-    // ---- resident operands: plane rows -> TMEM (thread = row; half 0 = hi plane, half 1 = lo plane)
+    // ---- resident operands: plane rows -> TMEM (thread = row; slot 0: X hi, slot 1: X lo, slot 2: Y hi)
     {
       const int sw = (ri >> 1) & 3;
       auto load_plane_row = [&](const uint8_t* plane, uint32_t tcol) {
@@ -278,12 +282,9 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
           }
         }
       };
-      if (half == 0) {
-        load_plane_row(X_hi, cX_hi);
-      } else {
-        if (a.x3) load_plane_row(X_lo, cX_lo);
-        if (MODE == MODE_S) load_plane_row(Y_hi, cY_hi);
-      }
+      if (slot == 0) load_plane_row(X_hi, cX_hi);
+      if (slot == 1 && a.x3) load_plane_row(X_lo, cX_lo);
+      if (slot == 2 && MODE == MODE_S) load_plane_row(Y_hi, cY_hi);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(res_full);
@@ -301,8 +302,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
       // per-column softmax statistics of this tile, fetched before the scores arrive
       float lsv[kv_roles ? NH : 1], dlv[(kv_roles && MODE == MODE_S) ? NH : 1];
       if constexpr (kv_roles) {
-        const float4* l4 = reinterpret_cast<const float4*>(lse + j * N + half * NH);
-        const float4* d4 = reinterpret_cast<const float4*>(delta + j * N + half * NH);
+        const float4* l4 = reinterpret_cast<const float4*>(lse + j * N + slot * NH);
+        const float4* d4 = reinterpret_cast<const float4*>(delta + j * N + slot * NH);
 #pragma unroll
         for (int g = 0; g < NH / 4; ++g) {
           const float4 lv = __ldg(l4 + g);
@@ -318,12 +319,12 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
       float sv[NH], dv[NH];
       {
         uint32_t v1[NH];
-        if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cS + buf * N + half * NH, v1);
-        else tmem_ld32(tmem_base + lane_off + cS + buf * N + half * NH, v1);
+        if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
+        else tmem_ld8(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
         if constexpr (MODE == MODE_S) {
           uint32_t v2[NH];
-          if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cDP + half * NH, v2);
-          else tmem_ld32(tmem_base + lane_off + cDP + half * NH, v2);
+          if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cDP + slot * NH, v2);
+          else tmem_ld8(tmem_base + lane_off + cDP + slot * NH, v2);
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < NH; ++c) dv[c] = __uint_as_float(v2[c]);
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
       tc_fence_before();
       mbar_arrive(&sp_empty[buf]);
 
-      const int c0 = j * N + half * NH;
+      const int c0 = j * N + slot * NH;
       float mult[NH];
 #pragma unroll
       for (int c = 0; c < NH; ++c) mult[c] = 1.f;
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
         for (int e = 0; e < 8; ++e) x[e] = sv[ch * 8 + e];
         uint32_t hw[4], lw[4];
         split8_words(x, hw, lw);
-        const uint32_t col = (half * NH + ch * 8) / 2;
+        const uint32_t col = (slot * NH + ch * 8) / 2;
         tmem_st4(tmem_base + lane_off + cPS_hi + col, hw[0], hw[1], hw[2], hw[3]);
         if (a.x3) tmem_st4(tmem_base + lane_off + cPS_lo + col, lw[0], lw[1], lw[2], lw[3]);
       }
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
       tc_fence_before();
       mbar_arrive(ps_full);
     }
-    // ---- epilogue: accumulator -> d_qkv (fp32, packed [B,T,3*H*E]); each half writes AD*16 columns
+    // ---- epilogue: accumulator -> d_qkv (fp32, packed [B,T,3*H*E]) and / or operand planes; each slot: AD*8 columns
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int I = a.H * a.E;
@@ -418,28 +419,25 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
     const int atom0 = (kSec * a.H + h) * AD;                // first column atom of this head's slice
 #pragma unroll
     for (int cc = 0; cc < AD; ++cc) {
-      const int d0 = half * (AD * 16) + cc * 16;
-      uint32_t v[16];
-      tmem_ld16(tmem_base + lane_off + cOut + d0, v);
+      const int d0 = slot * (AD * 8) + cc * 8;
+      uint32_t v[8];
+      tmem_ld8(tmem_base + lane_off + cOut + d0, v);
       tmem_ld_wait();
       if (ri < a.T) {
         if (dst) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
+          for (int c = 0; c < 8; ++c)
             if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
         }
         if (a.dq_pl.hi) {  // operand planes for the Wqkv weight-gradient and input-gradient GEMMs (pad columns are 0)
+          float x[8];
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[8 * q + e]) * sc;
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int64_t off = plane_chunk_off(atom0 + (d0 >> 5), a.dq_pl.rows_p, prow, ((d0 & 31) >> 3) + q);
-            *reinterpret_cast<uint4*>(a.dq_pl.hi + off) = hi;
-            if (a.dq_pl.lo) *reinterpret_cast<uint4*>(a.dq_pl.lo + off) = lo;
-          }
+          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[e]) * sc;
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const int64_t off = plane_chunk_off(atom0 + (d0 >> 5), a.dq_pl.rows_p, prow, (d0 & 31) >> 3);
+          *reinterpret_cast<uint4*>(a.dq_pl.hi + off) = hi;
+          if (a.dq_pl.lo) *reinterpret_cast<uint4*>(a.dq_pl.lo + off) = lo;
         }
       }
     }
