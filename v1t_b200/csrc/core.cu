@@ -75,6 +75,7 @@ struct BlockSaved {
   uint8_t *qp[2], *kp[2], *vp[2];  // bf16 hi/lo operand planes of Q, K, V (fused attention), reused by the backward
   uint8_t* wpl[4][2];              // GEMM-operand planes of Wqkv, Wproj, W1, W2 (converted once per step)
   uint8_t* gpl[2];                 // operand planes of gelu(u) * dropout (emitted by the MLP GEMM epilogue)
+  uint8_t *h1pl[2], *h2pl[2];      // operand planes of the two LayerNorm outputs (kept: no recompute in the backward)
   uint8_t* wqp[2];                 // Wqkv planes with every head's rows padded to Ep (head-aligned QKV GEMM output)
   uint8_t* wpp[2];                 // Wproj planes with every head's columns padded to Ep
   uint8_t* opl[2];                 // operand planes of the head-padded attention output [R, H*Ep]
@@ -107,6 +108,8 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
       b.wpl[w][i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(wr[w], wc[w]) / sizeof(float)) : 1);
   for (int i = 0; i < 2; ++i) {
     b.gpl[i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
+    b.h1pl[i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
+    b.h2pl[i] = (uint8_t*)c.take(d.impl != V1T_IMPL_FP32 ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
     b.wqp[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(3 * d.heads * d.Ep, d.E) / sizeof(float)) : 1);
     b.wpp[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(d.E, d.heads * d.Ep) / sizeof(float)) : 1);
     b.opl[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(d.R, d.heads * d.Ep) / sizeof(float)) : 1);
@@ -157,7 +160,7 @@ constexpr size_t kPartialBytes = 64u << 20;
 struct Scratch {
   BlockSaved tmp;    // one block of "saved" space for inference (keep_for_backward == 0)
   float *h, *dh, *g, *dqkv, *dO, *patches, *P1, *P2, *partials, *dlat, *dz3, *dhid, *dpos;
-  uint8_t *hpl[2], *dpl[2], *dupl[2];  // operand planes of the LayerNorm output, of dropout(dx) and of du (backward)
+  uint8_t *dpl[2], *dupl[2];           // operand planes of dropout(dx) and of du (backward)
   uint8_t* dqpl[2];                    // operand planes of the head-padded dqkv (from the attention backward)
   AttnPlanes planes;
   int chunk;         // attention batch chunk
@@ -194,7 +197,6 @@ Scratch carve_scratch(const Dims& d, void* base) {
   }
   for (int i = 0; i < 2; ++i) {
     const bool tc = d.impl != V1T_IMPL_FP32;
-    s.hpl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
     s.dpl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
     s.dupl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
     s.dqpl[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(d.R, 3 * d.heads * d.Ep) / sizeof(float)) : 1);
@@ -312,7 +314,7 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       }
     }
     // ---- Attention.mha (vit.py:267-275)
-    V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st, act_plane_out(d, sc.hpl)));
+    V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st, act_plane_out(d, S.h1pl)));
     V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
     if (qkv_to_planes(d)) {
       // q, k, v leave the GEMM epilogue as the attention kernels' operand planes (fp32 qkv is never materialised;
@@ -325,12 +327,12 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       V1T_TRY(zero_plane_pad_rows(pads, x3 ? 6 : 3, (int64_t)d.B * d.heads * (d.Ep / 32), d.Tq, d.T, st));
       const PlaneOp wq{S.wqp[0], x3 ? S.wqp[1] : nullptr, (int)round_up(3 * d.heads * d.Ep, 32), cdiv(d.E, 32)};
       V1T_TRY(gemm_any(d.impl, qkv_planes_desc(d), sc.h, nullptr, nullptr, nullptr, nullptr, st, no_drop(), epi,
-                       act_plane(d, sc.hpl, d.E), wq));
+                       act_plane(d, S.h1pl, d.E), wq));
     } else {
       v1t_gemm_desc g = gd((int)d.R, 3 * d.I, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = 3 * d.I;
       V1T_TRY(gemm_any(d.impl, g, sc.h, W.wqkv, S.qkv, nullptr, nullptr, st, no_drop(), no_epi(),
-                       act_plane(d, sc.hpl, d.E), wplane(d, S, kWqkv)));
+                       act_plane(d, S.h1pl, d.E), wplane(d, S, kWqkv)));
     }
     }
     if (d.fused) {  // tcgen05 fused attention: qkv -> bf16 operand planes -> O, lse (nothing T x T in HBM)
@@ -391,14 +393,14 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     }
     // ---- MLP (vit.py:143-150)
     ProfScope prof_mlp(V1T_PHASE_MLP, st);
-    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, S.st2, d.R, d.E, d.Ep, st, act_plane_out(d, sc.hpl)));
+    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, S.st2, d.R, d.E, d.Ep, st, act_plane_out(d, S.h2pl)));
     {
       v1t_gemm_desc g = gd((int)d.R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = d.Mp;
       if (gemm_uses_tc(d.impl, g)) {  // u and gelu(u)*dropout from one epilogue
         // gelu(u) * dropout leaves the epilogue as operand planes only (consumers: W2 GEMM and its weight gradient)
         const EpiOp act{kEpiGeluOut, nullptr, nullptr, d.Mp, site_drop(*shape, i, kSiteMlp1), act_plane_out(d, S.gpl)};
-        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st, no_drop(), act, act_plane(d, sc.hpl, d.E),
+        V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st, no_drop(), act, act_plane(d, S.h2pl, d.E),
                          wplane(d, S, kW1)));
       } else {
         V1T_TRY(gemm_any(d.impl, g, sc.h, W.w1, S.u, W.b1, nullptr, st));
@@ -462,14 +464,17 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
         V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
       }
     }
-    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, nullptr, d.R, d.E, d.Ep, st,
-                       act_plane_out(d, sc.hpl)));
+    // the weight gradients read the LayerNorm outputs from the planes the forward kept; only the CUDA-core path
+    // (fp32 impl or tiny problems) recomputes them in fp32
+    auto wgrad_tc = [&](int64_t m, int64_t n) { return d.impl != V1T_IMPL_FP32 && m * n * (int64_t)R >= (1ll << 22); };
+    if (!wgrad_tc(d.M, d.E))
+      V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
     const PlaneOp dup = mlp_tc ? act_plane(d, sc.dupl, d.M) : no_plane();  // du planes from the epilogue above
     if (GW.w1) {  // dW1[m,e] = sum_r du[r,m] h2[r,e]
       v1t_gemm_desc g = gd(d.M, d.E, R);
       g.a_m = 1; g.a_k = d.Mp; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
       V1T_TRY(gemm_any_splitk(d.impl, g, sc.g, sc.h, GW.w1, sc.partials, kPartialBytes, st, dup,
-                              act_plane(d, sc.hpl, d.E)));
+                              act_plane(d, S.h2pl, d.E)));
     }
     if (GW.b1) V1T_TRY(colsum(sc.g, GW.b1, 1, d.R, d.M, 0, d.Mp, 0, sc.partials, kPartialBytes, st));
     {  // dh2[r,e] = sum_m du[r,m] W1[m,e]
@@ -595,8 +600,8 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       }
     }
     ProfScope lin2(V1T_PHASE_LINEAR_BWD, st);
-    V1T_TRY(ln_forward(S.x1, nullptr, d.T, nullptr, W.ln1_w, W.ln1_b, sc.h, nullptr, d.R, d.E, d.Ep, st,
-                       act_plane_out(d, sc.hpl)));
+    if (!wgrad_tc(3 * d.I, d.E))
+      V1T_TRY(ln_forward(S.x1, nullptr, d.T, nullptr, W.ln1_w, W.ln1_b, sc.h, nullptr, d.R, d.E, d.Ep, st));
     if (qkv_to_planes(d)) {
       // head-padded problem (every head's 155 columns sit in a 160-column group): both GEMMs read dqkv from the
       // planes written by the attention backward; the weight gradient drops the padded rows while reducing
@@ -607,7 +612,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
         v1t_gemm_desc g = gd(NP, d.E, R);
         g.a_m = 1; g.a_k = NP; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
         V1T_TRY(gemm_any_splitk(d.impl, g, nullptr, sc.h, GW.wqkv, sc.partials, kPartialBytes, st, dqp,
-                                act_plane(d, sc.hpl, d.E), GroupMap{d.E, d.Ep, 0, 0}));
+                                act_plane(d, S.h1pl, d.E), GroupMap{d.E, d.Ep, 0, 0}));
       }
       {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
         v1t_gemm_desc g = gd(R, d.E, NP);
@@ -620,7 +625,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
         v1t_gemm_desc g = gd(3 * d.I, d.E, R);
         g.a_m = 1; g.a_k = ld; g.b_k = d.Ep; g.b_n = 1; g.c_m = d.E;
         V1T_TRY(gemm_any_splitk(d.impl, g, sc.dqkv, sc.h, GW.wqkv, sc.partials, kPartialBytes, st, no_plane(),
-                                act_plane(d, sc.hpl, d.E)));
+                                act_plane(d, S.h1pl, d.E)));
       }
       {  // dh1[r,e] = sum_n dqkv[r,n] Wqkv[n,e]
         v1t_gemm_desc g = gd(R, d.E, 3 * d.I);

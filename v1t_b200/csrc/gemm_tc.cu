@@ -653,7 +653,9 @@ int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float
   const int tiles = cdiv(d.n, bn) * cdiv(d.m, BM);
   const int64_t n_ld = round_up(d.n, 4);
   const int64_t per = (int64_t)d.m * n_ld * (int64_t)sizeof(float);
-  int splits = (2 * kNumSMs + tiles - 1) / tiles;
+  // one wave of the persistent grid: as many K chunks as fit the SMs (tiles * splits <= 148), so that no CTA gets a
+  // second work item while others idle, and the partials stay small
+  int splits = std::max(1, kNumSMs / tiles);
   splits = std::min(splits, cdiv(d.k, 4 * BK));
   splits = (int)std::min<int64_t>(splits, (int64_t)partial_bytes / per);
   const bool mapped = gm.row_gout > 0 || gm.col_gout > 0;  // a remapped product always goes through the partials

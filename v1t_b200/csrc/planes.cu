@@ -214,14 +214,26 @@ __global__ void attn_delta_planes_kernel(PlaneOp o, const uint8_t* __restrict__ 
   const int64_t r = w / H;  // b*T + t
   const int b = (int)(r / T), t = (int)(r % T);
   float s = 0.f;
-  for (int a = 0; a < AD; ++a) {
-    const int64_t oo = tc::plane_chunk_off(h * AD + a, o.rows_p, r, lane >> 3) + (lane & 7) * 2;
-    const int64_t go = ((((int64_t)b * H + h) * AD + a) * Tp + t) * 64 + (((lane >> 3) ^ ((t >> 1) & 3)) << 4) + (lane & 7) * 2;
-    float ov = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(o.hi + oo));
-    float gv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(do_hi + go));
-    if (o.lo) ov += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(o.lo + oo));
-    if (do_lo) gv += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(do_lo + go));
-    s = fmaf(ov, gv, s);
+  if (lane < AD * 4) {  // one 16-byte chunk (8 head-dim columns) per lane, 128-bit loads from all four planes
+    const int a = lane >> 2, ch = lane & 3;
+    const int64_t oo = tc::plane_chunk_off(h * AD + a, o.rows_p, r, ch);
+    const int64_t go = ((((int64_t)b * H + h) * AD + a) * Tp + t) * 64 + ((ch ^ ((t >> 1) & 3)) << 4);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4 oh = __ldg(reinterpret_cast<const uint4*>(o.hi + oo));
+    const uint4 ol = o.lo ? __ldg(reinterpret_cast<const uint4*>(o.lo + oo)) : z;
+    const uint4 gh = __ldg(reinterpret_cast<const uint4*>(do_hi + go));
+    const uint4 gl = do_lo ? __ldg(reinterpret_cast<const uint4*>(do_lo + go)) : z;
+    const uint32_t ohw[4] = {oh.x, oh.y, oh.z, oh.w}, olw[4] = {ol.x, ol.y, ol.z, ol.w};
+    const uint32_t ghw[4] = {gh.x, gh.y, gh.z, gh.w}, glw[4] = {gl.x, gl.y, gl.z, gl.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {  // a bf16 is the upper half of the fp32 with the same value
+      const float o0 = __uint_as_float(ohw[e] << 16) + __uint_as_float(olw[e] << 16);
+      const float o1 = __uint_as_float(ohw[e] & 0xffff0000u) + __uint_as_float(olw[e] & 0xffff0000u);
+      const float g0 = __uint_as_float(ghw[e] << 16) + __uint_as_float(glw[e] << 16);
+      const float g1 = __uint_as_float(ghw[e] & 0xffff0000u) + __uint_as_float(glw[e] & 0xffff0000u);
+      s = fmaf(o0, g0, s);
+      s = fmaf(o1, g1, s);
+    }
   }
   s = warp_sum(s);
   if (lane == 0) delta[((int64_t)b * H + h) * Tp + t] = s;
