@@ -304,7 +304,11 @@ def run_b200(args):
     achieved = attn_flops / (attn_ms / 1e3) / 1e12 if attn_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "kernel": "attention fwd+bwd phases", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": attention_traffic(),
+                "traffic_note": "DRAM read+write bytes of the attention kernels of ONE block, fwd+bwd (ncu, profiles/)",
+                "peak_source": peaks["source"] + " (sustained)",
+                "flops_note": "algorithmic FLOPs 4*B*H*T^2*E (x3 for fwd+bwd); the bf16x3 mode executes 3 MMAs per "
+                              "product and the backward recomputes S, so the tensor pipe does ~8x this",
                 "share_of_step": attn_ms / max(sum(p["ms_per_step"] for p in phases.values()), 1e-9)}
     ro_ms = phases["readout_fwd"]["ms_per_step"] + phases["readout_bwd"]["ms_per_step"]
     L, E = 1653, 155
@@ -337,6 +341,22 @@ def run_b200(args):
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+def attention_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the attention kernels of one block (forward + the three
+    backward launches + delta), from the committed ncu launch list of this workload (profiles/); None if absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_kernel_traffic.json")
+    try:
+        with open(path) as fh:
+            kernels = json.load(fh)["kernels"]
+    except (OSError, ValueError, KeyError):
+        return None
+    total = 0.0
+    for name, k in kernels.items():
+        if "attn_fwd2" in name or "attn_bwd2" in name or "attn_delta" in name:
+            total += k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"]
+    return total or None
 
 
 def main():
