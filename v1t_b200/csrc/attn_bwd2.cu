@@ -67,7 +67,7 @@ struct Smem2 {
 };
 
 template <int MODE, bool KV, int N, int AD>
-__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a) {
+__device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
   constexpr int Dp = AD * 32, HC = AD * 16;
   constexpr int NH = N / kSlots;  // tile columns per softmax warp
   constexpr int OPC = N / 2;      // TMEM columns of one bf16 plane of the Pd' / dS' operand
@@ -448,22 +448,24 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
-template <int MODE, bool KV, int N, int AD>
-int launch_bwd2(const AttnBwdArgs& a, cudaStream_t st) {
-  using L = Smem2<MODE, N, AD>;
-  static_assert(L::total <= 232448, "shared memory budget exceeded");
-  V1T_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<MODE, KV, N, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
-  dim3 grid(cdiv(a.T, 128), a.B * a.H);
-  attn_bwd2_kernel<MODE, KV, N, AD><<<grid, kThreadsAttn, L::total, st>>>(a);
-  V1T_LAUNCH_CHECK();
-  return V1T_OK;
+// The three launches (dV, dK, dQ) are independent: ONE grid runs them back to back (blockIdx.z = which) so that the
+// 5.6-wave tails of three separate launches (832 CTAs on 148 SMs each) become one 16.9-wave launch.
+template <int AD>
+__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a) {
+  if (blockIdx.z == 0) attn_bwd2_body<MODE_V, true, 64, AD>(a);        // dV
+  else if (blockIdx.z == 1) attn_bwd2_body<MODE_S, true, 32, AD>(a);   // dK
+  else attn_bwd2_body<MODE_S, false, 32, AD>(a);                       // dQ
 }
 
 template <int AD>
 int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
-  V1T_TRY((launch_bwd2<MODE_V, true, 64, AD>(a, st)));   // dV
-  V1T_TRY((launch_bwd2<MODE_S, true, 32, AD>(a, st)));   // dK
-  return launch_bwd2<MODE_S, false, 32, AD>(a, st);      // dQ
+  constexpr uint32_t smem = std::max({Smem2<MODE_V, 64, AD>::total, Smem2<MODE_S, 32, AD>::total});
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  V1T_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(a.T, 128), a.B * a.H, 3);
+  attn_bwd2_kernel<AD><<<grid, kThreadsAttn, smem, st>>>(a);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
 }
 
 }  // namespace

@@ -303,15 +303,20 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     }
     if (d.impl != V1T_IMPL_FP32) {  // weights -> bf16 hi/lo operand planes, shared by the forward and backward GEMMs
       const bool x3 = d.impl == V1T_IMPL_BF16X3;
-      PlaneOp tmp;
-      V1T_TRY(matrix_planes(W.wqkv, d.E, 3 * d.I, d.E, S.wpl[kWqkv][0], x3 ? S.wpl[kWqkv][1] : nullptr, &tmp, st));
-      V1T_TRY(matrix_planes(W.wproj, d.I, d.E, d.I, S.wpl[kWproj][0], x3 ? S.wpl[kWproj][1] : nullptr, &tmp, st));
-      V1T_TRY(matrix_planes(W.w1, d.E, d.M, d.E, S.wpl[kW1][0], x3 ? S.wpl[kW1][1] : nullptr, &tmp, st));
-      V1T_TRY(matrix_planes(W.w2, d.M, d.E, d.M, S.wpl[kW2][0], x3 ? S.wpl[kW2][1] : nullptr, &tmp, st));
-      if (qkv_to_planes(d)) {
-        V1T_TRY(matrix_planes(W.wqkv, d.E, 3 * d.I, d.E, S.wqp[0], x3 ? S.wqp[1] : nullptr, &tmp, st, d.E, d.Ep));
-        V1T_TRY(matrix_planes(W.wproj, d.I, d.E, d.I, S.wpp[0], x3 ? S.wpp[1] : nullptr, &tmp, st, 0, 0, d.E, d.Ep));
+      PlaneJobs jobs{};
+      auto add = [&](const float* X, int64_t ld, int64_t rows, int64_t cols, uint8_t* const (&pl)[2], int rgi = 0,
+                     int rgo = 0, int cgi = 0, int cgo = 0) {
+        jobs.job[jobs.n++] = PlaneJob{X, ld, rows, cols, 0, pl[0], x3 ? pl[1] : nullptr, rgi, rgo, cgi, cgo};
+      };
+      add(W.wqkv, d.E, 3 * d.I, d.E, S.wpl[kWqkv]);
+      add(W.wproj, d.I, d.E, d.I, S.wpl[kWproj]);
+      add(W.w1, d.E, d.M, d.E, S.wpl[kW1]);
+      add(W.w2, d.M, d.E, d.M, S.wpl[kW2]);
+      if (qkv_to_planes(d)) {  // head-padded variants for the attention branch
+        add(W.wqkv, d.E, 3 * d.I, d.E, S.wqp, d.E, d.Ep);
+        add(W.wproj, d.I, d.E, d.I, S.wpp, 0, 0, d.E, d.Ep);
       }
+      V1T_TRY(matrix_planes_batch(jobs, st));
     }
     // ---- Attention.mha (vit.py:267-275)
     V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st, act_plane_out(d, S.h1pl)));
@@ -639,6 +644,11 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     // ================= behaviour MLP: x1 = x_in + lat[b] =================
     if (d.bdim > 0 && (GW.bw0 || GW.bb0 || GW.bw3 || GW.bb3)) {
       V1T_TRY(colsum(dx, sc.dlat, d.B, d.T, d.E, (int64_t)d.T * d.Ep, d.Ep, d.E, sc.partials, kPartialBytes, st));
+      if (bmlp_backward_smem(d.B, d.hid, d.E) <= 200 * 1024) {  // the rest of this backward is one small CTA
+        V1T_TRY(bmlp_backward(sc.dlat, S.blat, S.bhid, behaviors, W.bw3, GW.bw0, GW.bb0, GW.bw3, GW.bb3, d.B, d.bdim,
+                              d.hid, d.E, st));
+        continue;
+      }
       V1T_TRY(tanh_grad(sc.dlat, S.blat, sc.dz3, (int64_t)d.B * d.E, st));
       if (GW.bw3) {  // dW3[e,j] = sum_b dz3[b,e] hid[b,j]
         v1t_gemm_desc g = gd(d.E, d.hid, d.B);

@@ -149,6 +149,55 @@ __global__ void tanh_grad_kernel(const float* __restrict__ dy, const float* __re
   }
 }
 
+// Backward of BehaviorMLP (vit.py:181-202) in ONE CTA (the whole problem is B x 155 x 77): given dlat[b,e] (the
+// gradient of the latent added to every token), dz3 = dlat * (1 - lat^2); dW3[e,j] = sum_b dz3[b,e] hid[b,j];
+// db3 = colsum(dz3); dhid = dz3 W3; dz0 = dhid * (1 - hid^2); dW0[j,i] = sum_b dz0[b,j] beh[b,i]; db0 = colsum(dz0).
+// Fixed summation order (deterministic).  Replaces 8 latency-bound launches per block.
+__global__ void __launch_bounds__(256) bmlp_backward_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
+                                                            const float* __restrict__ hid, const float* __restrict__ beh,
+                                                            const float* __restrict__ w3, float* __restrict__ dw0,
+                                                            float* __restrict__ db0, float* __restrict__ dw3,
+                                                            float* __restrict__ db3, int B, int bdim, int H, int E) {
+  extern __shared__ float sh[];
+  float* dz3 = sh;            // [B][E]
+  float* dz0 = sh + B * E;    // [B][H]
+  for (int i = threadIdx.x; i < B * E; i += blockDim.x) {
+    const float y = lat[i];
+    dz3[i] = dlat[i] * (1.f - y * y);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E * H; i += blockDim.x) {
+    const int e = i / H, j = i % H;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dz3[b * E + e], hid[b * H + j], s);
+    if (dw3) dw3[i] = s;
+  }
+  for (int e = threadIdx.x; e < E && db3; e += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dz3[b * E + e];
+    db3[e] = s;
+  }
+  for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
+    const int b = i / H, j = i % H;
+    float s = 0.f;
+    for (int e = 0; e < E; ++e) s = fmaf(dz3[b * E + e], __ldg(w3 + e * H + j), s);
+    const float y = hid[i];
+    dz0[i] = s * (1.f - y * y);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * bdim && dw0; i += blockDim.x) {
+    const int j = i / bdim, k = i % bdim;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dz0[b * H + j], beh[b * bdim + k], s);
+    dw0[i] = s;
+  }
+  for (int j = threadIdx.x; j < H && db0; j += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dz0[b * H + j];
+    db0[j] = s;
+  }
+}
+
 // ---------------------------------------------------------------- LayerNorm ----------------------------
 // one warp per row; lane owns columns lane + 32*i.  NV = ceil(E/32) rounded to a compiled size.
 template <int NV>
@@ -489,6 +538,20 @@ int dropout_mask(float* out, int64_t n, DropSpec dr, cudaStream_t st) {
 int bmlp_forward(const float* beh, const float* w0, const float* b0, const float* w3, const float* b3, float* hid,
                  float* lat, int B, int bdim, int H, int E, cudaStream_t st) {
   bmlp_forward_kernel<<<B, 128, H * sizeof(float), st>>>(beh, w0, b0, w3, b3, hid, lat, bdim, H, E);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+size_t bmlp_backward_smem(int B, int H, int E) { return sizeof(float) * (size_t)B * (E + H); }
+int bmlp_backward(const float* dlat, const float* lat, const float* hid, const float* beh, const float* w3, float* dw0,
+                  float* db0, float* dw3, float* db3, int B, int bdim, int H, int E, cudaStream_t st) {
+  const size_t smem = bmlp_backward_smem(B, H, E);
+  V1T_CHECK_ARG(smem <= 200 * 1024, "bmlp_backward: batch too large for the single-CTA kernel");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    V1T_CUDA(cudaFuncSetAttribute(bmlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  bmlp_backward_kernel<<<1, 256, smem, st>>>(dlat, lat, hid, beh, w3, dw0, db0, dw3, db3, B, bdim, H, E);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

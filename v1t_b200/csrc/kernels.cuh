@@ -120,6 +120,20 @@ int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* 
                   cudaStream_t st, int row_gin = 0, int row_gout = 0, int col_gin = 0, int col_gout = 0);
 int attn_delta_planes(const PlaneOp& o, const void* do_hi, const void* do_lo, float* delta, int B, int H, int T, int Tp,
                       int AD, cudaStream_t st);
+// the same for several matrices in ONE launch (all weights of a block)
+struct PlaneJob {
+  const float* X;
+  int64_t ld, rows, cols, rows_p;  // rows_p is filled in by matrix_planes_batch
+  uint8_t *hi, *lo;
+  int row_gin, row_gout, col_gin, col_gout;
+};
+struct PlaneJobs {
+  static constexpr int kMax = 8;
+  PlaneJob job[kMax];
+  int64_t first[kMax + 1];
+  int n;
+};
+int matrix_planes_batch(PlaneJobs& jobs, cudaStream_t st);
 // zero rows [T, Tq) of every (sample, head, atom) slab of up to 6 attention planes
 int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st);
 // fp32 qkv [B*T, 3*H*E] back from the attention planes (hi + lo), for the attention-map hooks
@@ -173,6 +187,9 @@ int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t l
 int bmlp_forward(const float* beh, const float* w0, const float* b0, const float* w3, const float* b3, float* hid,
                  float* lat, int B, int bdim, int H, int E, cudaStream_t st);
 int tanh_grad(const float* dy, const float* y, float* dz, int64_t n, cudaStream_t st);  // dz = dy*(1-y^2)
+size_t bmlp_backward_smem(int B, int H, int E);
+int bmlp_backward(const float* dlat, const float* lat, const float* hid, const float* beh, const float* w3, float* dw0,
+                  float* db0, float* dw3, float* db3, int B, int bdim, int H, int E, cudaStream_t st);
 int ln_forward(const float* x_in, const float* add, int rows_per_batch, float* x_out, const float* gamma,
                const float* beta, float* h, float* stats, int64_t rows, int E, int ld, cudaStream_t st,
                PlaneOut pl = no_plane_out());

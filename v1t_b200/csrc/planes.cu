@@ -75,11 +75,9 @@ __global__ void __launch_bounds__(256) make_planes_kernel(const float* __restric
 }
 
 // GEMM-operand planes of a row-major matrix X[rows, cols]: one thread per 16-byte chunk (8 columns of one row)
-__global__ void matrix_planes_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int64_t cols,
-                                     int64_t rows_p, int64_t chunks, uint8_t* __restrict__ hi,
-                                     uint8_t* __restrict__ lo, int gin, int gout, int cgin, int cgout) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= chunks) return;
+__device__ __forceinline__ void matrix_planes_chunk(int64_t idx, const float* __restrict__ X, int64_t ld, int64_t rows,
+                                                    int64_t cols, int64_t rows_p, uint8_t* __restrict__ hi,
+                                                    uint8_t* __restrict__ lo, int gin, int gout, int cgin, int cgout) {
   const int c = (int)(idx & 3);
   const int64_t r = (idx >> 2) % rows_p, a = (idx >> 2) / rows_p;
   const int64_t col0 = a * 32 + c * 8;
@@ -97,6 +95,22 @@ __global__ void matrix_planes_kernel(const float* __restrict__ X, int64_t ld, in
   const int64_t off = (a * rows_p + r) * 64 + ((c ^ (int)((r >> 1) & 3)) << 4);
   *reinterpret_cast<uint4*>(hi + off) = h;
   if (lo) *reinterpret_cast<uint4*>(lo + off) = l;
+}
+__global__ void matrix_planes_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int64_t cols,
+                                     int64_t rows_p, int64_t chunks, uint8_t* __restrict__ hi,
+                                     uint8_t* __restrict__ lo, int gin, int gout, int cgin, int cgout) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < chunks) matrix_planes_chunk(idx, X, ld, rows, cols, rows_p, hi, lo, gin, gout, cgin, cgout);
+}
+// several matrices in one launch (the weights of a block): job j owns chunk indices [first[j], first[j+1])
+__global__ void matrix_planes_batch_kernel(const PlaneJobs jobs) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= jobs.first[jobs.n]) return;
+  int j = 0;
+  while (idx >= jobs.first[j + 1]) ++j;
+  const PlaneJob& q = jobs.job[j];
+  matrix_planes_chunk(idx - jobs.first[j], q.X, q.ld, q.rows, q.cols, q.rows_p, q.hi, q.lo, q.row_gin, q.row_gout,
+                      q.col_gin, q.col_gout);
 }
 
 struct PadPlanes { uint8_t* p[6]; };
@@ -170,6 +184,22 @@ int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* 
                                                                       (uint8_t*)lo, row_gin, row_gout, col_gin, col_gout);
   V1T_LAUNCH_CHECK();
   out->hi = (const uint8_t*)hi; out->lo = (const uint8_t*)lo; out->rows_p = (int)rows_p; out->catoms = (int)catoms;
+  return V1T_OK;
+}
+
+int matrix_planes_batch(PlaneJobs& jobs, cudaStream_t st) {
+  V1T_CHECK_ARG(jobs.n >= 0 && jobs.n <= PlaneJobs::kMax, "matrix_planes_batch: too many jobs");
+  jobs.first[0] = 0;
+  for (int j = 0; j < jobs.n; ++j) {
+    PlaneJob& q = jobs.job[j];
+    const int64_t prow = q.row_gout ? q.rows / q.row_gin * q.row_gout : q.rows;
+    const int64_t pcol = q.col_gout ? q.cols / q.col_gin * q.col_gout : q.cols;
+    q.rows_p = round_up(prow, 32);
+    jobs.first[j + 1] = jobs.first[j] + (int64_t)cdiv(pcol, 32) * q.rows_p * 4;
+  }
+  if (jobs.first[jobs.n] == 0) return V1T_OK;
+  matrix_planes_batch_kernel<<<(unsigned)cdiv(jobs.first[jobs.n], 256), 256, 0, st>>>(jobs);
+  V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
 
