@@ -153,7 +153,7 @@ __global__ void tanh_grad_kernel(const float* __restrict__ dy, const float* __re
 // gradient of the latent added to every token), dz3 = dlat * (1 - lat^2); dW3[e,j] = sum_b dz3[b,e] hid[b,j];
 // db3 = colsum(dz3); dhid = dz3 W3; dz0 = dhid * (1 - hid^2); dW0[j,i] = sum_b dz0[b,j] beh[b,i]; db0 = colsum(dz0).
 // Fixed summation order (deterministic).  Replaces 8 latency-bound launches per block.
-__global__ void __launch_bounds__(256) bmlp_backward_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
+__global__ void __launch_bounds__(1024) bmlp_backward_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
                                                             const float* __restrict__ hid, const float* __restrict__ beh,
                                                             const float* __restrict__ w3, float* __restrict__ dw0,
                                                             float* __restrict__ db0, float* __restrict__ dw3,
@@ -551,7 +551,7 @@ int bmlp_backward(const float* dlat, const float* lat, const float* hid, const f
     V1T_CUDA(cudaFuncSetAttribute(bmlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  bmlp_backward_kernel<<<1, 256, smem, st>>>(dlat, lat, hid, beh, w3, dw0, db0, dw3, db3, B, bdim, H, E);
+  bmlp_backward_kernel<<<1, 1024, smem, st>>>(dlat, lat, hid, beh, w3, dw0, db0, dw3, db3, B, bdim, H, E);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
@@ -586,7 +586,7 @@ int ln_backward(const float* dh, const float* x, const float* stats, const float
                 cudaStream_t st) {
   const int nv = cdiv(ld, 32);
   V1T_CHECK_ARG(nv <= 16 && ld >= E, "layer norm backward: emb dim %d unsupported (max 512)", E);
-  int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMs * 2);
+  int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)kNumSMs * 6);  // 48 warps per SM hide the load latency
   const int64_t max_grid = (int64_t)(partial_bytes / (2 * (size_t)E * sizeof(float)));
   V1T_CHECK_ARG(max_grid >= 1, "layer norm backward: partials workspace too small");
   if (grid > max_grid) grid = (int)max_grid;

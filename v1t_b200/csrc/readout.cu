@@ -18,7 +18,7 @@ namespace v1t {
 namespace {
 
 constexpr int kNeuronsPerCta = 32;
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;  // 2 neurons per warp: 27 warps/SM at N=8000 (one warp walks a neuron over the batch: latency-bound)
 constexpr int kBatchTile = 32;  // samples staged per output tile
 constexpr float kEpsF32 = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (losses.py:22)
 
