@@ -457,8 +457,15 @@ __global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ p
   const int64_t per = (rows + strips - 1) / strips;
   const int64_t r0 = strip * per, r1 = min(rows, r0 + per);
   float s = 0.f;
-  if (c < cols)
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += X[b * xb + r * ld + c];
+  if (c < cols) {
+    const float* p = X + b * xb + c;
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {  // four independent loads in flight per thread (fixed summation order)
+      const float v0 = p[r * ld], v1 = p[(r + 8) * ld], v2 = p[(r + 16) * ld], v3 = p[(r + 24) * ld];
+      s += (v0 + v1) + (v2 + v3);
+    }
+    for (; r < r1; r += 8) s += p[r * ld];
+  }
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
@@ -469,15 +476,17 @@ __global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ p
   }
 }
 
-// out[b*out_ld + c] = sum_strip partials[(b*strips+strip)*cols + c]
+// out[b*out_ld + c] = sum_strip partials[(b*strips+strip)*cols + c]: one warp per output, lanes stride over the strips
 __global__ void colsum_finish_kernel(const float* __restrict__ partials, float* __restrict__ out, int batch, int cols,
                                      int strips, int64_t out_ld) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= (int64_t)batch * cols) return;
   const int b = (int)(i / cols), c = (int)(i % cols);
   float s = 0.f;
-  for (int k = 0; k < strips; ++k) s += partials[((int64_t)b * strips + k) * cols + c];
-  out[b * out_ld + c] = s;
+  for (int k = lane; k < strips; k += 32) s += partials[((int64_t)b * strips + k) * cols + c];
+  s = warp_sum(s);
+  if (lane == 0) out[b * out_ld + c] = s;
 }
 
 __global__ void batchsum_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int64_t rows, int cols,
@@ -629,13 +638,13 @@ int gelu_backward(float* dg_inout, const float* u, int64_t rows, int cols, int64
 int colsum(const float* X, float* out, int batch, int64_t rows, int cols, int64_t xb, int64_t ld, int64_t out_ld,
            float* partials, size_t partial_bytes, cudaStream_t st) {
   if (cols == 0 || batch == 0) return V1T_OK;
-  int strips = (int)std::min<int64_t>(64, std::max<int64_t>(1, rows / 64));
+  int strips = (int)std::min<int64_t>(256, std::max<int64_t>(1, rows / 64));
   while (strips > 1 && (size_t)batch * strips * cols * sizeof(float) > partial_bytes) strips /= 2;
   V1T_CHECK_ARG((size_t)batch * strips * cols * sizeof(float) <= partial_bytes, "colsum: partials workspace too small");
   dim3 grid(cdiv(cols, 32), strips, batch), block(32, 8);
   colsum_kernel<<<grid, block, 0, st>>>(X, partials, rows, cols, xb, ld, strips);
   V1T_LAUNCH_CHECK();
-  colsum_finish_kernel<<<cdiv((int64_t)batch * cols, 256), 256, 0, st>>>(partials, out, batch, cols, strips, out_ld);
+  colsum_finish_kernel<<<cdiv((int64_t)batch * cols, 8), 256, 0, st>>>(partials, out, batch, cols, strips, out_ld);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

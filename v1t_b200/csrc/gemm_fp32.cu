@@ -149,7 +149,14 @@ __global__ void reduce_partials_ld_kernel(const float* __restrict__ partials, fl
   const int64_t ro = ungroup(r, gm.row_gin, gm.row_gout), co = ungroup(c, gm.col_gin, gm.col_gout);
   if (ro < 0 || co < 0) return;  // padded row / column of a head-padded product
   float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += partials[((int64_t)p * rows + r) * in_ld + c];
+  const float* pp = partials + r * in_ld + c;
+  const int64_t ps = rows * in_ld;
+  int p = 0;
+  for (; p + 3 < parts; p += 4) {  // four loads in flight; fixed order
+    const float v0 = pp[p * ps], v1 = pp[(p + 1) * ps], v2 = pp[(p + 2) * ps], v3 = pp[(p + 3) * ps];
+    s += (v0 + v1) + (v2 + v3);
+  }
+  for (; p < parts; ++p) s += pp[p * ps];
   float* o = out + ro * out_ld + co;
   *o = accumulate ? *o + s : s;
 }
