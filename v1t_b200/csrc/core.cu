@@ -445,7 +445,9 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     const float* dm = dx;
     PlaneOp dmp = no_plane();  // operand planes of dm (emitted by the dropout kernel)
     if (drop) {
-      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteMlp2), st, act_plane_out(d, sc.dpl)));
+      // dm = dropout(dx) as fp32 + operand planes, and db2 = colsum(dm) from the same pass
+      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteMlp2), st, act_plane_out(d, sc.dpl), GW.b2,
+                           sc.partials, kPartialBytes));
       dm = sc.dh;
       dmp = act_plane(d, sc.dpl, d.E);
     }
@@ -457,13 +459,16 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       V1T_TRY(gemm_any_splitk(d.impl, g, dm, S.g, GW.w2, sc.partials, kPartialBytes, st, dmp,
                               mlp_tc ? act_plane(d, S.gpl, d.M) : no_plane()));
     }
-    if (GW.b2) V1T_TRY(colsum(dm, GW.b2, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
+    if (GW.b2 && !drop) V1T_TRY(colsum(dm, GW.b2, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
     {  // dg[r,m] = sum_e dm[r,e] W2[e,m]   -> sc.g (g no longer needed)
       v1t_gemm_desc g = gd(R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = d.M; g.b_n = 1; g.c_m = d.Mp;
       if (gemm_uses_tc(d.impl, g)) {  // du = (dm W2) * gelu'(u) * dropout in the epilogue
-        const EpiOp act{kEpiGeluGrad, nullptr, S.u, d.Mp, site_drop(*shape, i, kSiteMlp1), act_plane_out(d, sc.dupl)};
-        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st, no_drop(), act, dmp, wplane(d, S, kW2)));
+        // du leaves the epilogue as operand planes (for dW1 and dh2) plus 32-row partial column sums (db1): no fp32 du
+        EpiOp act{kEpiGeluGrad, nullptr, S.u, d.Mp, site_drop(*shape, i, kSiteMlp1), act_plane_out(d, sc.dupl)};
+        act.cs_part = GW.b1 ? sc.partials : nullptr;
+        V1T_TRY(gemm_any(d.impl, g, dm, W.w2, nullptr, nullptr, nullptr, st, no_drop(), act, dmp, wplane(d, S, kW2)));
+        if (GW.b1) V1T_TRY(colsum_finish(sc.partials, GW.b1, d.M, 4 * cdiv(R, 128), st));
       } else {
         V1T_TRY(gemm_any(d.impl, g, dm, W.w2, sc.g, nullptr, nullptr, st));
         V1T_TRY(gelu_backward(sc.g, S.u, d.R, d.M, d.Mp, site_drop(*shape, i, kSiteMlp1), st));  // du in sc.g
@@ -481,7 +486,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       V1T_TRY(gemm_any_splitk(d.impl, g, sc.g, sc.h, GW.w1, sc.partials, kPartialBytes, st, dup,
                               act_plane(d, S.h2pl, d.E)));
     }
-    if (GW.b1) V1T_TRY(colsum(sc.g, GW.b1, 1, d.R, d.M, 0, d.Mp, 0, sc.partials, kPartialBytes, st));
+    if (GW.b1 && !mlp_tc) V1T_TRY(colsum(sc.g, GW.b1, 1, d.R, d.M, 0, d.Mp, 0, sc.partials, kPartialBytes, st));
     {  // dh2[r,e] = sum_m du[r,m] W1[m,e]
       v1t_gemm_desc g = gd(R, d.E, d.M);
       g.a_m = d.Mp; g.a_k = 1; g.b_k = d.E; g.b_n = 1; g.c_m = d.Ep;
@@ -493,7 +498,8 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
     const float* da = dx;
     PlaneOp dap = no_plane();
     if (drop) {
-      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteProj), st, act_plane_out(d, sc.dpl)));
+      V1T_TRY(dropout_rows(dx, sc.dh, d.R, d.E, d.Ep, site_drop(*shape, i, kSiteProj), st, act_plane_out(d, sc.dpl),
+                           GW.bproj, sc.partials, kPartialBytes));
       da = sc.dh;
       dap = act_plane(d, sc.dpl, d.E);
     }
@@ -512,7 +518,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
         V1T_TRY(gemm_any_splitk(d.impl, g, da, S.o, GW.wproj, sc.partials, kPartialBytes, st, dap));
       }
     }
-    if (GW.bproj) V1T_TRY(colsum(da, GW.bproj, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
+    if (GW.bproj && !drop) V1T_TRY(colsum(da, GW.bproj, 1, d.R, d.E, 0, d.Ep, 0, sc.partials, kPartialBytes, st));
     if (hp_path) {  // dO[r, (h, d)] = sum_e da[r,e] Wp[e, h*E + d]  -> straight into the attention kernels' dO planes
       v1t_gemm_desc g = gd(R, KP, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = KP; g.b_n = 1;

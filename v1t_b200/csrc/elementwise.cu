@@ -112,6 +112,61 @@ __global__ void dropout_rows8_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// The same, plus the column sums of the result (the bias gradient of the Linear whose output gradient this is):
+// a thread keeps ONE chunk (8 columns) and walks rows, so the sums stay in registers; per-CTA partials, fixed order.
+// block = 256 threads = (256 / chunks) row lanes x chunks.
+__global__ void __launch_bounds__(256) dropout_rows8_colsum_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                   int64_t rows, int cols, int64_t ld, int chunks,
+                                                                   DropSpec dr, PlaneOut pl, float* __restrict__ partials) {
+  extern __shared__ float red[];  // [row lanes][chunks * 8]
+  const float inv_keep = 1.f / (1.f - dr.p);
+  const int rpp = 256 / chunks;
+  const int ch = threadIdx.x % chunks, ty = threadIdx.x / chunks;
+  const int64_t rows_all = pl.hi ? (int64_t)pl.rows_p : rows;
+  const int64_t drop_ld = drop_stride(cols);
+  const int c0 = ch * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ty < rpp) {
+    for (int64_t r = (int64_t)blockIdx.x * rpp + ty; r < rows_all; r += (int64_t)gridDim.x * rpp) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (c0 < cols && r < rows) {
+        float m8[8];
+        dropout_mult8(dr.seed, dr.site, ((uint64_t)r * drop_ld + c0) >> 3, dr.p, inv_keep, m8);
+        if (c0 + 8 <= cols) {
+          const float4 a = *reinterpret_cast<const float4*>(src + r * ld + c0);
+          const float4 b = *reinterpret_cast<const float4*>(src + r * ld + c0 + 4);
+          v[0] = a.x * m8[0]; v[1] = a.y * m8[1]; v[2] = a.z * m8[2]; v[3] = a.w * m8[3];
+          v[4] = b.x * m8[4]; v[5] = b.y * m8[5]; v[6] = b.z * m8[6]; v[7] = b.w * m8[7];
+          *reinterpret_cast<float4*>(dst + r * ld + c0) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(dst + r * ld + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          for (int e = 0; e < 8 && c0 + e < cols; ++e) {
+            v[e] = src[r * ld + c0 + e] * m8[e];
+            dst[r * ld + c0 + e] = v[e];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+      if (pl.hi) {
+        uint4 hi, lo;
+        tc::split8(v, hi, lo);
+        const int64_t off = tc::plane_chunk_off(ch >> 2, pl.rows_p, r, ch & 3);
+        *reinterpret_cast<uint4*>(pl.hi + off) = hi;
+        if (pl.lo) *reinterpret_cast<uint4*>(pl.lo + off) = lo;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[ty * chunks * 8 + c0 + e] = acc[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float s = 0.f;
+    for (int y = 0; y < rpp; ++y) s += red[y * chunks * 8 + c];
+    partials[(int64_t)blockIdx.x * cols + c] = s;
+  }
+}
+
 __global__ void dropout_mask_kernel(float* __restrict__ out, int64_t n, DropSpec dr) {
   const float inv_keep = 1.f / (1.f - dr.p);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -527,8 +582,24 @@ int cls_rows(const float* cls, const float* pos, float* x, int B, int T, int E, 
   return V1T_OK;
 }
 int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st,
-                 PlaneOut pl) {
-  if (ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+                 PlaneOut pl, float* colsum_out, float* partials, size_t partial_bytes) {
+  const bool aligned = ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  if (colsum_out) {  // fused bias gradient
+    const int chunks = cdiv(cols, 32) * 4;
+    V1T_CHECK_ARG(aligned && chunks <= 256 && partials, "dropout_rows: fused column sums need aligned rows and <= 2048 columns");
+    const int rpp = 256 / chunks;
+    const int64_t rows_all = pl.hi ? (int64_t)pl.rows_p : rows;
+    int grid = (int)std::min<int64_t>(cdiv(rows_all, rpp), (int64_t)kNumSMs * 4);
+    grid = (int)std::min<int64_t>(grid, (int64_t)(partial_bytes / (sizeof(float) * (size_t)cols)));
+    V1T_CHECK_ARG(grid >= 1, "dropout_rows: partials workspace too small");
+    dropout_rows8_colsum_kernel<<<grid, 256, sizeof(float) * rpp * chunks * 8, st>>>(src, dst, rows, cols, ld, chunks, dr,
+                                                                                     pl, partials);
+    V1T_LAUNCH_CHECK();
+    colsum_finish_kernel<<<cdiv((int64_t)cols, 8), 256, 0, st>>>(partials, colsum_out, 1, cols, grid, 0);
+    V1T_LAUNCH_CHECK();
+    return V1T_OK;
+  }
+  if (aligned) {
     const int chunks = cdiv(cols, 32) * 4;  // 16-byte plane chunks (8 columns) per row
     dropout_rows8_kernel<<<ew_grid(rows * chunks), 256, 0, st>>>(src, dst, rows, cols, ld, chunks, dr, pl);
     V1T_LAUNCH_CHECK();
@@ -645,6 +716,12 @@ int colsum(const float* X, float* out, int batch, int64_t rows, int cols, int64_
   colsum_kernel<<<grid, block, 0, st>>>(X, partials, rows, cols, xb, ld, strips);
   V1T_LAUNCH_CHECK();
   colsum_finish_kernel<<<cdiv((int64_t)batch * cols, 8), 256, 0, st>>>(partials, out, batch, cols, strips, out_ld);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+int colsum_finish(const float* partials, float* out, int cols, int strips, cudaStream_t st) {
+  colsum_finish_kernel<<<cdiv((int64_t)cols, 8), 256, 0, st>>>(partials, out, 1, cols, strips, 0);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           }
         };
         prefetch(0);
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll kEpiUnroll
         for (int i = 0; i < 8; ++i) {
           const int r = 4 * i + (lane >> 3);
@@ -502,20 +503,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
               for (int e = 0; e < 4; ++e) if (e < nv) o[e] += __ldg(rp + e);
             }
           }
-          float* cp = g.C + tl.c_off + (int64_t)mm * g.d.c_m + n4;
-          if (a.c_vec && full4) {
-            if (g.d.accumulate) {
-              const float4 cv = *reinterpret_cast<const float4*>(cp);
-              o[0] += cv.x; o[1] += cv.y; o[2] += cv.z; o[3] += cv.w;
-            }
-            *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
+          if constexpr (kKind == kEpiGeluGrad) {  // column sums of the result (bias gradient), registers per lane
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (e < nv) {
-                if (g.d.accumulate) o[e] += cp[e];
-                cp[e] = o[e];
+            for (int e = 0; e < 4; ++e) cs[e] += (e < nv) ? o[e] : 0.f;
+          }
+          if (g.C) {
+            float* cp = g.C + tl.c_off + (int64_t)mm * g.d.c_m + n4;
+            if (a.c_vec && full4) {
+              if (g.d.accumulate) {
+                const float4 cv = *reinterpret_cast<const float4*>(cp);
+                o[0] += cv.x; o[1] += cv.y; o[2] += cv.z; o[3] += cv.w;
               }
+              *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < nv) {
+                  if (g.d.accumulate) o[e] += cp[e];
+                  cp[e] = o[e];
+                }
+            }
           }
           if constexpr (kKind == kEpiGeluOut) {
             const float ge[4] = {gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]};
@@ -537,6 +544,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             const int64_t off = plane_chunk_off(n4 >> 5, g.epi.pl.rows_p, mm, cq >> 1) + (cq & 1) * 8;
             *reinterpret_cast<uint2*>(g.epi.pl.hi + off) = ph;
             if (g.epi.pl.lo) *reinterpret_cast<uint2*>(g.epi.pl.lo + off) = plo;
+          }
+        }
+        if constexpr (kKind == kEpiGeluGrad) {
+          if (g.epi.cs_part) {  // 32-row partial column sums of this group -> [tile_m * 4 + quarter][n]
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+            }
+            if (lane < 8 && nv > 0) {
+              float* pp = g.epi.cs_part + (int64_t)((tl.m0 / BM) * 4 + quarter) * g.d.n + n4;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (e < nv) pp[e] = cs[e];
+            }
           }
         }
         __syncwarp();

@@ -39,8 +39,9 @@ struct EpiOp {
   DropSpec drop;      // dropout of the activation (element index m * roundup(n,4) + n)
   PlaneOut pl;        // optional planes of the activation-side result (aux for kEpiGeluOut, C for kEpiGeluGrad)
   HeadPlanes hp;
+  float* cs_part;     // kEpiGeluGrad: optional [4 * ceil(m/128)][n] partial column sums of C (32-row groups, 0 past m)
 };
-static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}, no_plane_out(), HeadPlanes{}}; }
+static inline EpiOp no_epi() { return EpiOp{kEpiNone, nullptr, nullptr, 0, DropSpec{0, 0, 0.f}, no_plane_out(), HeadPlanes{}, nullptr}; }
 
 // Pre-swizzled bf16 hi/lo planes of a row-major matrix X[rows, cols] (planes.cu: matrix_planes): 32-column atoms,
 // [catoms][rows_p][64 B], rows 64 B apart, 16-byte chunks XOR-swizzled with ((row >> 1) & 3), zero padded.  A GEMM
@@ -182,8 +183,10 @@ int im2col(const float* img, float* patches, int B, int C, int H, int W, int p, 
 int col2im(const float* dpatches, float* dimg, int B, int C, int H, int W, int p, int s, int gh, int gw,
            cudaStream_t st);
 int cls_rows(const float* cls, const float* pos, float* x, int B, int T, int E, int ld, cudaStream_t st);
+// colsum_out (optional): also out[c] = sum_r dst[r, c] (fixed-order reduction through `partials`)
 int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t ld, DropSpec dr, cudaStream_t st,
-                 PlaneOut pl = no_plane_out());
+                 PlaneOut pl = no_plane_out(), float* colsum_out = nullptr, float* partials = nullptr,
+                 size_t partial_bytes = 0);
 int bmlp_forward(const float* beh, const float* w0, const float* b0, const float* w3, const float* b3, float* hid,
                  float* lat, int B, int bdim, int H, int E, cudaStream_t st);
 int tanh_grad(const float* dy, const float* y, float* dz, int64_t n, cudaStream_t st);  // dz = dy*(1-y^2)
@@ -203,6 +206,8 @@ int gelu_forward(const float* u, float* g, int64_t rows, int cols, int64_t ld, D
 int gelu_backward(float* dg_inout, const float* u, int64_t rows, int cols, int64_t ld, DropSpec dr,
                   cudaStream_t st);
 // out[b, c] = sum_r X[b, r, c]   (X element strides: batch xb, row ld, col 1)
+// out[c] = sum over `strips` rows of partials[strip * cols + c] (the finishing pass of colsum, for fused producers)
+int colsum_finish(const float* partials, float* out, int cols, int strips, cudaStream_t st);
 int colsum(const float* X, float* out, int batch, int64_t rows, int cols, int64_t xb, int64_t ld,
            int64_t out_ld, float* partials, size_t partial_bytes, cudaStream_t st);
 // out[t, c] = sum_b X[b, t, c]
