@@ -491,8 +491,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             dropout_mult4(g.epi.drop.seed, g.epi.drop.site, ((uint64_t)mm * drop_ld + n4) >> 2, g.epi.drop.p, inv_keep2, mk2);
           if constexpr (kKind == kEpiGeluGrad) {
             // epi.ld % 4 == 0 and 16-byte aligned rows are checked on the host: the quad is always readable
-            o[0] *= gelu_df(uv.x) * mk2[0]; o[1] *= gelu_df(uv.y) * mk2[1];
-            o[2] *= gelu_df(uv.z) * mk2[2]; o[3] *= gelu_df(uv.w) * mk2[3];
+            o[0] *= gelu_fast_df(uv.x) * mk2[0]; o[1] *= gelu_fast_df(uv.y) * mk2[1];
+            o[2] *= gelu_fast_df(uv.z) * mk2[2]; o[3] *= gelu_fast_df(uv.w) * mk2[3];
           }
           if (g.R) {
             if (pre_r) {
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             }
           }
           if constexpr (kKind == kEpiGeluOut) {
-            const float ge[4] = {gelu_f(o[0]) * mk2[0], gelu_f(o[1]) * mk2[1], gelu_f(o[2]) * mk2[2], gelu_f(o[3]) * mk2[3]};
+            const float ge[4] = {gelu_fast_f(o[0]) * mk2[0], gelu_fast_f(o[1]) * mk2[1], gelu_fast_f(o[2]) * mk2[2], gelu_fast_f(o[3]) * mk2[3]};
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = ge[e];  // o now holds the activation (what the planes carry)
             if (g.epi.aux) {
