@@ -417,6 +417,7 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
     const float sc = MODE == MODE_V ? 1.f : a.scale;
     const int64_t prow = (int64_t)b * a.T + ri;            // row of the [B*T, 3*H*Dp] gradient matrix
     const int atom0 = (kSec * a.H + h) * AD;                // first column atom of this head's slice
+    const uint32_t stage = smem_u32(smem + L::x_ring);
 #pragma unroll
     for (int cc = 0; cc < AD; ++cc) {
       const int d0 = slot * (AD * 8) + cc * 8;
@@ -429,15 +430,34 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
           for (int c = 0; c < 8; ++c)
             if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
         }
-        if (a.dq_pl.hi) {  // operand planes for the Wqkv weight-gradient and input-gradient GEMMs (pad columns are 0)
-          float x[8];
+      }
+      if (a.dq_pl.hi) {
+        // operand planes for the Wqkv weight-gradient and input-gradient GEMMs (pad columns are 0): staged in the idle
+        // x ring in plane layout, then one bulk store per (head-dim atom, plane) writes 128 consecutive plane rows
+        float x[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[e]) * sc;
-          uint4 hi, lo;
-          split8(x, hi, lo);
-          const int64_t off = plane_chunk_off(atom0 + (d0 >> 5), a.dq_pl.rows_p, prow, (d0 & 31) >> 3);
-          *reinterpret_cast<uint4*>(a.dq_pl.hi + off) = hi;
-          if (a.dq_pl.lo) *reinterpret_cast<uint4*>(a.dq_pl.lo + off) = lo;
+        for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[e]) * sc;
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t so = (uint32_t)(d0 >> 5) * (128 * 64) + row * 64 + ((((d0 & 31) >> 3) ^ (int)((prow >> 1) & 3)) << 4);
+        sts128(stage + so, hi);
+        if (a.dq_pl.lo) sts128(stage + AD * 128 * 64 + so, lo);
+      }
+    }
+    if (a.dq_pl.hi) {
+      fence_proxy_async();
+      named_bar_sync(1, kSmThreads);
+      const int rows_valid = min(128, a.T - r0);  // rows past T belong to the next sample of the flat matrix
+      if (threadIdx.x < AD * 2 && rows_valid > 0) {
+        const int at_i = threadIdx.x >> 1, pln = threadIdx.x & 1;
+        uint8_t* dstp = pln ? a.dq_pl.lo : a.dq_pl.hi;
+        if (dstp) {
+          const int64_t off = ((int64_t)(atom0 + at_i) * a.dq_pl.rows_p + ((int64_t)b * a.T + r0)) * 64;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp + off),
+                       "r"(stage + (uint32_t)(pln * AD + at_i) * (128 * 64)), "r"(rows_valid * 64)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
       }
     }

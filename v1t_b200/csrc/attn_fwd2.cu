@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     const float inv_l = 1.f / l;
     float* orow = a.O ? a.O + ((int64_t)b * a.T + qi) * a.o_ld + h * a.E : nullptr;
     const int64_t prow = (int64_t)b * a.T + qi;  // row of the head-padded [B*T, H*Dp] output matrix
+    const uint32_t stage = smem_u32(smem + L::k_ring);
 #pragma unroll
     for (int cc = 0; cc < AD; ++cc) {
       const int c0 = half * (AD * 16) + cc * 16;
@@ -360,18 +361,39 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
           for (int c = 0; c < 16; ++c)
             if (c0 + c < a.E) orow[c0 + c] = __uint_as_float(v[c]) * inv_l;
         }
-        if (a.o_pl.hi) {  // operand planes for the projection GEMM and its weight gradient (pad columns are 0)
+      }
+      if (a.o_pl.hi) {
+        // operand planes for the projection GEMM and its weight gradient (pad columns are 0): staged in the (now
+        // idle) K ring in plane layout -- rows are consecutive plane rows, so each head-dim atom of the tile is ONE
+        // contiguous block that a bulk store writes out (full lines instead of 16-byte pieces at a 64-byte stride)
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float x[8];
+        for (int q = 0; q < 2; ++q) {
+          float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[8 * q + e]) * inv_l;
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int64_t off = plane_chunk_off(h * AD + (c0 >> 5), a.o_pl.rows_p, prow, ((c0 & 31) >> 3) + q);
-            *reinterpret_cast<uint4*>(a.o_pl.hi + off) = hi;
-            if (a.o_pl.lo) *reinterpret_cast<uint4*>(a.o_pl.lo + off) = lo;
-          }
+          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[8 * q + e]) * inv_l;
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          const uint32_t so = (uint32_t)(c0 >> 5) * (BQ * 64) + row * 64 +
+                              (((((c0 & 31) >> 3) + q) ^ (int)((prow >> 1) & 3)) << 4);
+          sts128(stage + so, hi);
+          if (a.o_pl.lo) sts128(stage + AD * BQ * 64 + so, lo);
+        }
+      }
+    }
+    if (a.o_pl.hi) {
+      fence_proxy_async();              // generic-proxy stores above -> visible to the bulk (async proxy) store
+      named_bar_sync(1, kSmThreads);
+      const int rows_valid = min(BQ, a.T - q0);  // rows past T belong to the next sample of the flat matrix
+      if (threadIdx.x < AD * 2 && rows_valid > 0) {
+        const int at_i = threadIdx.x >> 1, pln = threadIdx.x & 1;
+        uint8_t* dstp = pln ? a.o_pl.lo : a.o_pl.hi;
+        if (dstp) {
+          const int64_t off = ((int64_t)(h * AD + at_i) * a.o_pl.rows_p + ((int64_t)b * a.T + q0)) * 64;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp + off),
+                       "r"(stage + (uint32_t)(pln * AD + at_i) * (BQ * 64)), "r"(rows_valid * 64)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must stay intact until it was read
         }
       }
     }
