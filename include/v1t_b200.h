@@ -218,6 +218,12 @@ int v1t_gemm_tc_planes(const v1t_gemm_desc* d, const float* A, const float* B, f
  * from tensor memory, mn_b=1: MN-major B.  out_dev: 148 int64 cycle counts (device memory). */
 int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long* out_dev, void* stream);
 
+/* measurement helper: every SM streams iters rounds of `copies` cp.async.bulk copies of `bytes` bytes from a global
+ * buffer (span bytes, wrapped) into a ring of `slots` shared-memory slots; out_dev: 148 int64 cycle counts.  Measures
+ * the per-SM global->shared fill ceiling that bounds the bf16x3 main loops. */
+int v1t_bulk_microbench(const void* src, long long span, int bytes, int copies, int slots, int iters,
+                        long long* out_dev, void* stream);
+
 /* self-test of the tensor-memory A operand (tcgen05.st + TS-form tcgen05.mma): C[128,N] = bf16(A[128,K]) bf16(B[N,K])^T */
 int v1t_ts_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
 

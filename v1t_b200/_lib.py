@@ -98,6 +98,7 @@ SYMBOLS = {
     "v1t_attn_backward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f, C.c_uint64,
                                     C.c_uint32, _vp, _vp, _vp]),
     "v1t_mma_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "v1t_bulk_microbench": (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "v1t_ts_selftest": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "v1t_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint32, _f, _vp]),
 }

@@ -7,8 +7,9 @@
 // Same two-pass softmax as generation 1 (attn_tc.cu): pass 1 = row maxima from the hi planes, pass 2 = exact.
 //
 // TMEM columns (Dp = 160): Q_hi[80] | Q_lo[80] | S[2][64] | P_hi[32] | P_lo[32] | O[160]  = 512.
-// Warp roles (352 threads): warps 0-7 softmax/epilogue (lane quarter = warp & 3, column half = warp >> 2),
-// warp 8 MMA issue + TMEM alloc, warp 9 K-ring producer, warp 10 V-ring producer.
+// Warp roles (608 threads): warps 0-15 softmax/epilogue (lane quarter = warp & 3, column slot = warp >> 2: 16 of a
+// tile's 64 key columns each -- with 8 warps the exp/dropout/split chain of a tile did not fit under the MMAs of the
+// next one), warp 16 MMA issue + TMEM alloc, warp 17 K-ring producer, warp 18 V-ring producer.
 #include <algorithm>
 
 #include "common.cuh"
@@ -21,7 +22,9 @@ namespace {
 using namespace tc;
 
 constexpr int BQ = 128, BKEY = 64;
-constexpr int kSmWarps = 8;
+constexpr int kSmWarps = 16;
+constexpr int kSlots = kSmWarps / 4;   // column slots per TMEM lane quarter
+constexpr int NW = BKEY / kSlots;      // key columns of a tile per softmax warp
 constexpr int kSmThreads = kSmWarps * 32;
 constexpr int kThreadsAttn = (kSmWarps + 3) * 32;
 constexpr int kMmaWarp = kSmWarps, kLoadWarpK = kSmWarps + 1, kLoadWarpV = kSmWarps + 2;
@@ -37,11 +40,14 @@ template <int AD>
 struct FSmem {
   static constexpr uint32_t kKTile = AD * BKEY * 64;       // one plane of a K tile (64 keys x Dp)
   static constexpr uint32_t kVTile = AD * BKEY * 64;       // one plane of a V tile (64 keys x Dp, MN-major operand)
-  static constexpr uint32_t k_ring = 0;                    // 2 slots x (hi, lo); pass 1: 4 hi-only slots
-  static constexpr uint32_t v_ring = 4 * kKTile;           // 2 slots x (hi, lo)
+  // K ring depth: 3 slots were tried (more bytes in flight) and were not faster than 2 -- the copies are not
+  // latency-bound
+  static constexpr int kKS = 2;
+  static constexpr uint32_t k_ring = 0;                    // kKS slots x (hi, lo); pass 1: 4 hi-only slots
+  static constexpr uint32_t v_ring = 2 * kKS * kKTile;     // 2 slots x (hi, lo)
   static constexpr uint32_t bars = v_ring + 4 * kVTile;
   static constexpr uint32_t xch = bars + 256;              // cross-half exchange of row max / row sum
-  static constexpr uint32_t total = xch + 2 * BQ * 4 + 1024;
+  static constexpr uint32_t total = xch + kSlots * BQ * 4 + 1024;
 };
 
 template <int AD>
@@ -55,15 +61,16 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
   uint64_t* p_full = bars + 1;
   uint64_t* p_empty = bars + 2;
   uint64_t* o_full = bars + 3;
-  uint64_t* k_full = bars + 4;    // [2]
-  uint64_t* k_empty = bars + 6;   // [2]
-  uint64_t* v_full = bars + 8;    // [2]
-  uint64_t* v_empty = bars + 10;  // [2]
-  uint64_t* s_full = bars + 12;   // [2]
-  uint64_t* s_empty = bars + 14;  // [2]
-  uint64_t* r_full = bars + 16;   // [4] pass-1 ring
-  uint64_t* r_empty = bars + 20;  // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* k_full = bars + 4;    // [kKS <= 4]
+  uint64_t* k_empty = bars + 8;   // [kKS <= 4]
+  uint64_t* v_full = bars + 12;   // [2]
+  uint64_t* v_empty = bars + 14;  // [2]
+  uint64_t* s_full = bars + 16;   // [2]
+  uint64_t* s_empty = bars + 18;  // [2]
+  uint64_t* r_full = bars + 20;   // [4] pass-1 ring
+  uint64_t* r_empty = bars + 24;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  constexpr int kKS = L::kKS;
   float* xch = reinterpret_cast<float*>(smem + L::xch);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,8 +85,6 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
@@ -88,6 +93,10 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     for (int i = 0; i < 4; ++i) {
       mbar_init(&r_full[i], 1);
       mbar_init(&r_empty[i], 1);
+    }
+    for (int i = 0; i < kKS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -124,8 +133,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       }
       // pass 2: 2 slots of (hi, lo)
       for (int j = 0; j < nk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+        const int s = j % kKS;
+        mbar_wait(&k_empty[s], ((j / kKS) & 1) ^ 1);
         load_k(L::k_ring + s * 2 * L::kKTile, L::k_ring + s * 2 * L::kKTile + L::kKTile, j, a.x3 != 0, &k_full[s]);
       }
     }
@@ -182,9 +191,9 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       ++its;
     };
     auto issue_s2 = [&](int j) {
-      const int s = j & 1;
+      const int s = j % kKS;
       const uint64_t kh = kDescK64 | (uint64_t)(kr0 + s * 2 * (L::kKTile >> 4));
-      issue_s(kh, kh + (L::kKTile >> 4), a.x3 != 0, &k_full[s], (j >> 1) & 1, &k_empty[s]);
+      issue_s(kh, kh + (L::kKTile >> 4), a.x3 != 0, &k_full[s], (j / kKS) & 1, &k_empty[s]);
     };
     auto issue_pv = [&](int j, bool last) {
       const int s = j & 1;
@@ -226,16 +235,16 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     issue_pv(nk - 1, true);
   } else {
     // ============================== SOFTMAX / EPILOGUE ==============================
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, slot = warp >> 2;
     const int row = quarter * 32 + lane;
     const int qi = q0 + row;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int b = bh / a.H, h = bh % a.H;
-    // ---- Q rows -> TMEM (half 0: hi plane, half 1: lo plane)
+    // ---- Q rows -> TMEM (slot 0: hi plane, slot 1: lo plane)
     {
       const int sw = (qi >> 1) & 3;
-      const uint8_t* plane = half == 0 ? a.q_hi : a.q_lo;
-      if (half == 0 || a.x3) {
+      const uint8_t* plane = slot == 0 ? a.q_hi : a.q_lo;
+      if (slot == 0 || (slot == 1 && a.x3)) {
 #pragma unroll
         for (int at_i = 0; at_i < AD; ++at_i) {
           const uint4* src = reinterpret_cast<const uint4*>(plane + (((int64_t)bh * AD + at_i) * a.Tp + qi) * 64);
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 v = ph[c ^ sw];
-            tmem_st4(tmem_base + lane_off + (half == 0 ? cQ_hi : cQ_lo) + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
+            tmem_st4(tmem_base + lane_off + (slot == 0 ? cQ_hi : cQ_lo) + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
           }
         }
       }
@@ -255,29 +264,30 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     }
     uint32_t its = 0;
     float m = -INFINITY;
-    // ---- pass 1: row max over this warp's 32 of the 64 key columns
+    // ---- pass 1: row max over this warp's NW of the 64 key columns
     for (int j = 0; j < nk; ++j, ++its) {
       const uint32_t buf = its & 1;
       mbar_wait(&s_full[buf], (its >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem_base + lane_off + cS + buf * BKEY + half * 32, v);
+      uint32_t v[NW];
+      tmem_ld16(tmem_base + lane_off + cS + buf * BKEY + slot * NW, v);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_empty[buf]);
-      const int jb = j * BKEY + half * 32;
-      if (jb + 32 <= a.T) {
+      const int jb = j * BKEY + slot * NW;
+      if (jb + NW <= a.T) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
+        for (int c = 0; c < NW; ++c) m = fmaxf(m, __uint_as_float(v[c]));
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
+        for (int c = 0; c < NW; ++c)
           if (jb + c < a.T) m = fmaxf(m, __uint_as_float(v[c]));
       }
     }
-    xch[half * BQ + row] = m;
+    xch[slot * BQ + row] = m;
     named_bar_sync(1, kSmThreads);
-    m = fmaxf(xch[row], xch[BQ + row]);
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) m = fmaxf(m, xch[s * BQ + row]);
     named_bar_sync(1, kSmThreads);
     const float m2 = m * a.scale_log2;
     float l = 0.f;
@@ -289,33 +299,33 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       const uint32_t buf = its & 1;
       mbar_wait(&s_full[buf], (its >> 1) & 1);
       tc_fence_after();
-      float p[32];
+      float p[NW];
       {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + cS + buf * BKEY + half * 32, v);
+        uint32_t v[NW];
+        tmem_ld16(tmem_base + lane_off + cS + buf * BKEY + slot * NW, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) p[c] = __uint_as_float(v[c]);
+        for (int c = 0; c < NW; ++c) p[c] = __uint_as_float(v[c]);
       }
       tc_fence_before();
       mbar_arrive(&s_empty[buf]);
-      const int jb = j * BKEY + half * 32;
-      if (jb + 32 <= a.T) {
+      const int jb = j * BKEY + slot * NW;
+      if (jb + NW <= a.T) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < NW; ++c) {
           p[c] = fast_exp2(fmaf(p[c], a.scale_log2, -m2));
           l += p[c];
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < NW; ++c) {
           p[c] = (jb + c < a.T) ? fast_exp2(fmaf(p[c], a.scale_log2, -m2)) : 0.f;
           l += p[c];
         }
       }
       if (a.drop.p > 0.f) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // one Philox call per 8 adjacent keys
+        for (int g = 0; g < NW / 8; ++g) {  // one Philox call per 8 adjacent keys
           float mk[8];
           dropout_mult8(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 8 * g)) >> 3, a.drop.p, inv_keep, mk);
 #pragma unroll
@@ -325,13 +335,13 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       mbar_wait(p_empty, (j & 1) ^ 1);  // P V of the previous tile has consumed the operand
       tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < NW / 8; ++ch) {
         float x[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = p[ch * 8 + e];
         uint32_t hw[4], lw[4];
         split8_words(x, hw, lw);
-        const uint32_t col = (half * 32 + ch * 8) / 2;
+        const uint32_t col = (slot * NW + ch * 8) / 2;
         tmem_st4(tmem_base + lane_off + cP_hi + col, hw[0], hw[1], hw[2], hw[3]);
         if (a.x3) tmem_st4(tmem_base + lane_off + cP_lo + col, lw[0], lw[1], lw[2], lw[3]);
       }
@@ -339,9 +349,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    xch[half * BQ + row] = l;
+    xch[slot * BQ + row] = l;
     named_bar_sync(1, kSmThreads);
-    l = xch[row] + xch[BQ + row];
+    l = 0.f;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) l += xch[s * BQ + row];
     // ---- epilogue
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -351,33 +363,27 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     const uint32_t stage = smem_u32(smem + L::k_ring);
 #pragma unroll
     for (int cc = 0; cc < AD; ++cc) {
-      const int c0 = half * (AD * 16) + cc * 16;
-      uint32_t v[16];
-      tmem_ld16(tmem_base + lane_off + cO + c0, v);
+      const int c0 = slot * (AD * 8) + cc * 8;  // each slot drains AD*8 of the Dp output columns
+      uint32_t v[8];
+      tmem_ld8(tmem_base + lane_off + cO + c0, v);
       tmem_ld_wait();
-      if (qi < a.T) {
-        if (orow) {
+      if (qi < a.T && orow) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c0 + c < a.E) orow[c0 + c] = __uint_as_float(v[c]) * inv_l;
-        }
+        for (int c = 0; c < 8; ++c)
+          if (c0 + c < a.E) orow[c0 + c] = __uint_as_float(v[c]) * inv_l;
       }
       if (a.o_pl.hi) {
         // operand planes for the projection GEMM and its weight gradient (pad columns are 0): staged in the (now
         // idle) K ring in plane layout -- rows are consecutive plane rows, so each head-dim atom of the tile is ONE
         // contiguous block that a bulk store writes out (full lines instead of 16-byte pieces at a 64-byte stride)
+        float x[8];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float x[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[8 * q + e]) * inv_l;
-          uint4 hi, lo;
-          split8(x, hi, lo);
-          const uint32_t so = (uint32_t)(c0 >> 5) * (BQ * 64) + row * 64 +
-                              (((((c0 & 31) >> 3) + q) ^ (int)((prow >> 1) & 3)) << 4);
-          sts128(stage + so, hi);
-          if (a.o_pl.lo) sts128(stage + AD * BQ * 64 + so, lo);
-        }
+        for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[e]) * inv_l;
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t so = (uint32_t)(c0 >> 5) * (BQ * 64) + row * 64 + ((((c0 & 31) >> 3) ^ (int)((prow >> 1) & 3)) << 4);
+        sts128(stage + so, hi);
+        if (a.o_pl.lo) sts128(stage + AD * BQ * 64 + so, lo);
       }
     }
     if (a.o_pl.hi) {
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       }
     }
     // padded query rows get +inf so that the backward's exp2(S*c - lse) vanishes there without bounds checks
-    if (half == 0 && a.lse) a.lse[(int64_t)bh * a.Tp + qi] = qi < a.T ? m2 + log2f(l) : INFINITY;
+    if (slot == 0 && a.lse) a.lse[(int64_t)bh * a.Tp + qi] = qi < a.T ? m2 + log2f(l) : INFINITY;
     tc_fence_before();
   }
 

@@ -149,3 +149,61 @@ extern "C" int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long*
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// cp.async.bulk fill-rate microbenchmark: every SM streams `iters` rounds of `copies` copies of `bytes` bytes from a
+// global buffer (`span` bytes, wrapped) into a ring of `slots` shared-memory slots; a slot is re-filled as soon as
+// its previous contents landed (nothing consumes the data).  out_dev[sm] = cycles.  Answers "how many GB/s can one
+// SM pull in, as a function of the copy size and the bytes in flight" -- the bound of the bf16x3 attention / GEMM
+// main loops.
+namespace v1t {
+namespace {
+__global__ void __launch_bounds__(32, 1) bulk_microbench_kernel(const uint8_t* __restrict__ src, int64_t span, int bytes,
+                                                                int copies, int slots, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[8];
+  using namespace tc;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < slots; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const int64_t slot_bytes = (int64_t)bytes * copies;
+  const int64_t per_cta = slot_bytes * iters;
+  long long t0 = 0;
+  if (threadIdx.x == 0) {
+    t0 = clock64();
+    for (int it = 0; it < iters + slots; ++it) {
+      const int s = it % slots;
+      if (it >= slots) mbar_wait(&full[s], ((it / slots) - 1) & 1);  // previous fill of this slot has landed
+      if (it < iters) {
+        mbar_expect_tx(&full[s], (uint32_t)slot_bytes);
+        int64_t off = ((int64_t)blockIdx.x * per_cta + (int64_t)it * slot_bytes) % (span - slot_bytes);
+        off &= ~(int64_t)127;
+        for (int cidx = 0; cidx < copies; ++cidx) {
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_u32(smem + (int64_t)s * slot_bytes + (int64_t)cidx * bytes)),
+                       "l"(src + off + (int64_t)cidx * bytes), "r"(bytes), "r"(smem_u32(&full[s]))
+                       : "memory");
+        }
+      }
+    }
+    out[blockIdx.x] = clock64() - t0;
+  }
+}
+}  // namespace
+}  // namespace v1t
+
+extern "C" int v1t_bulk_microbench(const void* src, long long span, int bytes, int copies, int slots, int iters,
+                                   long long* out_dev, void* stream) {
+  using namespace v1t;
+  V1T_CHECK_ARG(src && out_dev && bytes > 0 && bytes % 16 == 0 && copies >= 1 && slots >= 1 && slots <= 8 && iters >= 1 &&
+                    (long long)bytes * copies * slots <= 200 * 1024 && span >= 2ll * bytes * copies,
+                "bulk_microbench: bad argument");
+  V1T_CUDA(cudaFuncSetAttribute(bulk_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024 + 1024));
+  bulk_microbench_kernel<<<kNumSMs, 32, 201 * 1024 + 1024, (cudaStream_t)stream>>>((const uint8_t*)src, span, bytes, copies,
+                                                                                    slots, iters, out_dev);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
