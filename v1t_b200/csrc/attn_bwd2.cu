@@ -138,9 +138,9 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
         if (MODE == MODE_S && a.x3) {
           mbar_expect_tx(res_full, L::kYlo);
 #pragma unroll
-          for (int at_i = 0; at_i < AD; ++at_i) {
-            const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + r0) * 64;
-            bulk_g2s(smem + L::y_lo + at_i * 8192, Y_lo + src, 8192, res_full);
+          for (int at_i = 0; at_i < AD; ++at_i) {  // resident layout [atom][128 rows][64 B] from two 64-row plane tiles
+            bulk_g2s(smem + L::y_lo + at_i * 8192, Y_lo + attn_plane_off(bh, at_i, r0, a.Tp, AD), 4096, res_full);
+            bulk_g2s(smem + L::y_lo + at_i * 8192 + 4096, Y_lo + attn_plane_off(bh, at_i, r0 + 64, a.Tp, AD), 4096, res_full);
           }
         } else {
           mbar_arrive(res_full);
@@ -158,11 +158,17 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
         mbar_wait(&emptyb[s], ((j / slots) & 1) ^ 1);
         uint8_t* base = ring + s * L::kSlot;
         mbar_expect_tx(&fullb[s], (a.x3 ? 2 : 1) * L::kTile);
+        if constexpr (N == 64) {  // a whole 64-row plane tile: its AD atoms are contiguous, one copy per plane
+          const int64_t src = attn_plane_off(bh, 0, j * N, a.Tp, AD);
+          bulk_g2s(base, src_hi + src, L::kTile, &fullb[s]);
+          if (a.x3) bulk_g2s(base + L::kTile, src_lo + src, L::kTile, &fullb[s]);
+        } else {
 #pragma unroll
-        for (int at_i = 0; at_i < AD; ++at_i) {
-          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + (int64_t)j * N) * 64;
-          bulk_g2s(base + at_i * tb, src_hi + src, tb, &fullb[s]);
-          if (a.x3) bulk_g2s(base + L::kTile + at_i * tb, src_lo + src, tb, &fullb[s]);
+          for (int at_i = 0; at_i < AD; ++at_i) {
+            const int64_t src = attn_plane_off(bh, at_i, j * N, a.Tp, AD);
+            bulk_g2s(base + at_i * tb, src_hi + src, tb, &fullb[s]);
+            if (a.x3) bulk_g2s(base + L::kTile + at_i * tb, src_lo + src, tb, &fullb[s]);
+          }
         }
       }
     }
@@ -271,7 +277,7 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
       auto load_plane_row = [&](const uint8_t* plane, uint32_t tcol) {
 #pragma unroll
         for (int at_i = 0; at_i < AD; ++at_i) {
-          const uint4* src = reinterpret_cast<const uint4*>(plane + (((int64_t)bh * AD + at_i) * a.Tp + ri) * 64);
+          const uint4* src = reinterpret_cast<const uint4*>(plane + attn_plane_off(bh, at_i, ri, a.Tp, AD));
           uint4 ph[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);

@@ -114,12 +114,10 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     if (lane == 0) {
       auto load_k = [&](uint32_t dst_hi, uint32_t dst_lo, int j, bool lo, uint64_t* bar) {
         mbar_expect_tx(bar, lo ? 2 * L::kKTile : L::kKTile);
-#pragma unroll
-        for (int at_i = 0; at_i < AD; ++at_i) {
-          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + j * BKEY) * 64;
-          bulk_g2s(smem + dst_hi + at_i * BKEY * 64, a.k_hi + src, BKEY * 64, bar);
-          if (lo) bulk_g2s(smem + dst_lo + at_i * BKEY * 64, a.k_lo + src, BKEY * 64, bar);
-        }
+        // the AD atoms of a 64-key tile are contiguous in the plane: ONE copy per plane ([atom][64 keys][64 B])
+        const int64_t src = attn_plane_off(bh, 0, j * BKEY, a.Tp, AD);
+        bulk_g2s(smem + dst_hi, a.k_hi + src, L::kKTile, bar);
+        if (lo) bulk_g2s(smem + dst_lo, a.k_lo + src, L::kKTile, bar);
       };
       // pass 1: hi planes only, 4-slot ring over the K region
       for (int j = 0; j < nk; ++j) {
@@ -146,12 +144,9 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
         mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[s], a.x3 ? 2 * L::kVTile : L::kVTile);
         uint8_t* base = smem + L::v_ring + s * 2 * L::kVTile;
-#pragma unroll
-        for (int at_i = 0; at_i < AD; ++at_i) {  // head-dim atom at_i: 64 key rows of 64 bytes, contiguous in the plane
-          const int64_t src = (((int64_t)bh * AD + at_i) * a.Tp + j * BKEY) * 64;
-          bulk_g2s(base + at_i * BKEY * 64, a.v_hi + src, BKEY * 64, &v_full[s]);
-          if (a.x3) bulk_g2s(base + L::kVTile + at_i * BKEY * 64, a.v_lo + src, BKEY * 64, &v_full[s]);
-        }
+        const int64_t src = attn_plane_off(bh, 0, j * BKEY, a.Tp, AD);  // [atom][64 keys][64 B], one copy per plane
+        bulk_g2s(base, a.v_hi + src, L::kVTile, &v_full[s]);
+        if (a.x3) bulk_g2s(base + L::kVTile, a.v_lo + src, L::kVTile, &v_full[s]);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -247,7 +242,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       if (slot == 0 || (slot == 1 && a.x3)) {
 #pragma unroll
         for (int at_i = 0; at_i < AD; ++at_i) {
-          const uint4* src = reinterpret_cast<const uint4*>(plane + (((int64_t)bh * AD + at_i) * a.Tp + qi) * 64);
+          const uint4* src = reinterpret_cast<const uint4*>(plane + attn_plane_off(bh, at_i, qi, a.Tp, AD));
           uint4 ph[4];
 #pragma unroll
           for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);

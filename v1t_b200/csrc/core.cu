@@ -329,7 +329,7 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       epi.kind = kEpiHeadPlanes;
       epi.hp = head_planes(d, S);
       uint8_t* pads[6] = {S.qp[0], S.kp[0], S.vp[0], S.qp[1], S.kp[1], S.vp[1]};
-      V1T_TRY(zero_plane_pad_rows(pads, x3 ? 6 : 3, (int64_t)d.B * d.heads * (d.Ep / 32), d.Tq, d.T, st));
+      V1T_TRY(zero_plane_pad_rows(pads, x3 ? 6 : 3, (int64_t)d.B * d.heads * (d.Ep / 32), d.Tq, d.T, st, d.Ep / 32));
       const PlaneOp wq{S.wqp[0], x3 ? S.wqp[1] : nullptr, (int)round_up(3 * d.heads * d.Ep, 32), cdiv(d.E, 32)};
       V1T_TRY(gemm_any(d.impl, qkv_planes_desc(d), sc.h, nullptr, nullptr, nullptr, nullptr, st, no_drop(), epi,
                        act_plane(d, S.h1pl, d.E), wq));
@@ -528,7 +528,8 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       epi.hp.p[0][1] = d.impl == V1T_IMPL_BF16X3 ? sc.planes.dO[1] : nullptr;
       epi.hp.T = d.T; epi.hp.Tq = d.Tq; epi.hp.H = d.heads; epi.hp.AD = d.Ep / 32;
       uint8_t* pads[2] = {sc.planes.dO[0], sc.planes.dO[1]};
-      V1T_TRY(zero_plane_pad_rows(pads, d.impl == V1T_IMPL_BF16X3 ? 2 : 1, (int64_t)d.B * d.heads * (d.Ep / 32), d.Tq, d.T, st));
+      V1T_TRY(zero_plane_pad_rows(pads, d.impl == V1T_IMPL_BF16X3 ? 2 : 1, (int64_t)d.B * d.heads * (d.Ep / 32), d.Tq, d.T, st,
+                                  d.Ep / 32));
       V1T_TRY(gemm_any(d.impl, g, da, nullptr, nullptr, nullptr, nullptr, st, no_drop(), epi, dap, wpp));
     } else {  // dO[r,i] = sum_e da[r,e] Wp[e,i]
       v1t_gemm_desc g = gd(R, d.I, d.E);

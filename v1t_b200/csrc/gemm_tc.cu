@@ -394,12 +394,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       const uint32_t taddr = tmem_base + buf * BN_MAX + ((uint32_t)(quarter * 32) << 16);
       const int n_lim = min(g.d.n, tl.n0 + a.bn);
       int hp_b0 = 0, hp_t0 = 0;
-      int64_t hp_bstride = 0;
       if constexpr (kKind == kEpiHeadPlanes) {
         const int r0 = tl.m0 + quarter * 32 + (lane >> 3);
         hp_b0 = r0 / g.epi.hp.T;
         hp_t0 = r0 - hp_b0 * g.epi.hp.T;
-        hp_bstride = (int64_t)g.epi.hp.H * g.epi.hp.AD * g.epi.hp.Tq * 64;
       }
       // 32-column groups alternate between the two column halves (columns past bn are never stored)
       for (int c0 = slot * 32; c0 < a.bn; c0 += 32 * kSlots) {
@@ -417,12 +415,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const int nv = min(4, n_lim - n4);  // valid columns of this lane's quad
         // kEpiHeadPlanes: this 32-column group is one head-dim atom of q, k or v of one head
         uint8_t *hp_hi = nullptr, *hp_lo = nullptr;
-        int64_t hp_base = 0;
+        int hp_atom = 0, hp_head = 0;
         if constexpr (kKind == kEpiHeadPlanes) {
           const HeadPlanes& hp = g.epi.hp;
-          const int sec = nb >> 5, atom = sec % hp.AD, hh = (sec / hp.AD) % hp.H, s3 = min(sec / (hp.AD * hp.H), 2);
+          const int sec = nb >> 5, s3 = min(sec / (hp.AD * hp.H), 2);
+          hp_atom = sec % hp.AD;
+          hp_head = (sec / hp.AD) % hp.H;
           hp_hi = hp.p[s3][0]; hp_lo = hp.p[s3][1];
-          hp_base = (int64_t)(hh * hp.AD + atom) * hp.Tq * 64 + (cq & 1) * 8;
         }
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (g.bias && nv > 0) {
@@ -472,7 +471,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             // (sample, token) of this row: one division per tile (hp_b0 / hp_t0), then a wrap at sample boundaries
             int t = hp_t0 + 4 * i, bb = hp_b0;
             while (t >= g.epi.hp.T) { t -= g.epi.hp.T; ++bb; }
-            const int64_t off = hp_base + (int64_t)bb * hp_bstride + t * 64 + (((cq >> 1) ^ ((t >> 1) & 3)) << 4);
+            const int64_t off = attn_plane_off((int64_t)bb * g.epi.hp.H + hp_head, hp_atom, t, g.epi.hp.Tq, g.epi.hp.AD) +
+                                (((cq >> 1) ^ ((t >> 1) & 3)) << 4) + (cq & 1) * 8;
             uint2 ph, plo;
             split4(o, ph, plo);
             *reinterpret_cast<uint2*>(hp_hi + off) = ph;

@@ -136,7 +136,9 @@ struct PlaneJobs {
 };
 int matrix_planes_batch(PlaneJobs& jobs, cudaStream_t st);
 // zero rows [T, Tq) of every (sample, head, atom) slab of up to 6 attention planes
-int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st);
+// attn_ad > 0: the planes are attention planes with attn_ad atoms per head (slabs = B*H*attn_ad), else matrix planes
+int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st,
+                        int attn_ad = 0);
 // fp32 qkv [B*T, 3*H*E] back from the attention planes (hi + lo), for the attention-map hooks
 int planes_to_qkv(const HeadPlanes& hp, int B, int E, float* qkv, cudaStream_t st);
 int make_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tp, int E, int Dp, void* rm_hi,

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) make_planes_kernel(const float* __restric
       for (int e = 0; e < 8; ++e) v[e] = tile[tl * pitch + a * 32 + c * 8 + e];
       uint4 hi, lo;
       split8(v, hi, lo);
-      const int64_t off = (((int64_t)bh * atoms_d + a) * Tp + t) * 64 + ((c ^ ((t >> 1) & 3)) << 4);
+      const int64_t off = attn_plane_off(bh, a, t, Tp, atoms_d) + ((c ^ ((t >> 1) & 3)) << 4);
       *reinterpret_cast<uint4*>(rm_hi + off) = hi;
       if (rm_lo) *reinterpret_cast<uint4*>(rm_lo + off) = lo;
     }
@@ -114,14 +114,16 @@ __global__ void matrix_planes_batch_kernel(const PlaneJobs jobs) {
 }
 
 struct PadPlanes { uint8_t* p[6]; };
-// zero the pad rows t in [T, Tq) of every slab ((sample, head, atom): Tq rows of 64 bytes) of each plane
-__global__ void zero_pad_rows_kernel(PadPlanes pp, int n_planes, int64_t slabs, int Tq, int T) {
+// zero the pad rows t in [T, Tq) of every slab of each plane.  attn_ad == 0: matrix planes, slab = column atom (Tq
+// rows of 64 bytes each);  attn_ad > 0: attention planes, slab = (sample*head) * attn_ad + atom (attn_plane_off)
+__global__ void zero_pad_rows_kernel(PadPlanes pp, int n_planes, int64_t slabs, int Tq, int T, int attn_ad) {
   const int pad = Tq - T;
   const int64_t total = slabs * pad * 4;  // 16-byte pieces per plane
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int piece = (int)(i & 3);
     const int64_t row = (i >> 2) % pad, slab = (i >> 2) / pad;
-    const int64_t off = (slab * Tq + T + row) * 64 + piece * 16;
+    const int64_t off = (attn_ad > 0 ? tc::attn_plane_off(slab / attn_ad, (int)(slab % attn_ad), T + (int)row, Tq, attn_ad)
+                                     : (slab * Tq + T + row) * 64) + piece * 16;
     for (int p = 0; p < n_planes; ++p) *reinterpret_cast<uint4*>(pp.p[p] + off) = make_uint4(0, 0, 0, 0);
   }
 }
@@ -135,7 +137,7 @@ __global__ void planes_to_qkv_kernel(HeadPlanes hp, int B, int E, float* __restr
     const int h = (int)(r % hp.H); r /= hp.H;
     const int s = (int)(r % 3); r /= 3;
     const int t = (int)(r % hp.T), b = (int)(r / hp.T);
-    const int64_t off = ((((int64_t)b * hp.H + h) * hp.AD + d / 32) * hp.Tq + t) * 64 +
+    const int64_t off = tc::attn_plane_off((int64_t)b * hp.H + h, d / 32, t, hp.Tq, hp.AD) +
                         ((((d & 31) >> 3) ^ ((t >> 1) & 3)) << 4) + (d & 7) * 2;
     float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(hp.p[s][0] + off));
     if (hp.p[s][1]) v += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(hp.p[s][1] + off));
@@ -203,13 +205,14 @@ int matrix_planes_batch(PlaneJobs& jobs, cudaStream_t st) {
   return V1T_OK;
 }
 
-int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st) {
+int zero_plane_pad_rows(uint8_t* const* planes, int n_planes, int64_t slabs, int Tq, int T, cudaStream_t st, int attn_ad) {
   V1T_CHECK_ARG(n_planes >= 0 && n_planes <= 6 && Tq >= T, "zero_plane_pad_rows: bad argument");
   if (n_planes == 0 || Tq == T) return V1T_OK;
   PadPlanes pp{};
   for (int i = 0; i < n_planes; ++i) pp.p[i] = planes[i];
   const int64_t total = slabs * (Tq - T) * 4;
-  zero_pad_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv(total, 256), 4096), 256, 0, st>>>(pp, n_planes, slabs, Tq, T);
+  zero_pad_rows_kernel<<<(unsigned)std::min<int64_t>(cdiv(total, 256), 4096), 256, 0, st>>>(pp, n_planes, slabs, Tq, T,
+                                                                                            attn_ad);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
@@ -247,7 +250,7 @@ __global__ void attn_delta_planes_kernel(PlaneOp o, const uint8_t* __restrict__ 
   if (lane < AD * 4) {  // one 16-byte chunk (8 head-dim columns) per lane, 128-bit loads from all four planes
     const int a = lane >> 2, ch = lane & 3;
     const int64_t oo = tc::plane_chunk_off(h * AD + a, o.rows_p, r, ch);
-    const int64_t go = ((((int64_t)b * H + h) * AD + a) * Tp + t) * 64 + ((ch ^ ((t >> 1) & 3)) << 4);
+    const int64_t go = tc::attn_plane_off((int64_t)b * H + h, a, t, Tp, AD) + ((ch ^ ((t >> 1) & 3)) << 4);
     const uint4 z = make_uint4(0, 0, 0, 0);
     const uint4 oh = __ldg(reinterpret_cast<const uint4*>(o.hi + oo));
     const uint4 ol = o.lo ? __ldg(reinterpret_cast<const uint4*>(o.lo + oo)) : z;

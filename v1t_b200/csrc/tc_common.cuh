@@ -218,6 +218,14 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Attention planes (Q, K, V, dO per (sample, head)): [b*H + h][Tq/64 key/query tiles][AD atoms][64 rows][64 B], i.e. the
+// AD head-dim atoms of a 64-token tile are CONTIGUOUS (AD * 4 KB): a streamed K / V / Q / dO tile is one bulk copy
+// per plane that lands in shared memory exactly as [atom][64 rows][64 B].  (Bulk copies cost ~90 cycles each on
+// top of the bytes -- scripts/bulk_microbench.py: 4 KB copies cap an SM at 68 GB/s, 20 KB copies at 105-114 -- and
+// the forward needs 67 GB/s.)  Returns the byte offset of row t of atom `atom`; Tq is a multiple of 128.
+__host__ __device__ __forceinline__ int64_t attn_plane_off(int64_t bh, int atom, int t, int Tq, int AD) {
+  return ((((bh * (Tq >> 6) + (t >> 6)) * AD + atom) << 6) + (t & 63)) << 6;
+}
 // byte offset of 16-byte chunk `chunk` of row `row` in column atom `atom` of a matrix plane ([atoms][rows_p][64 B])
 __device__ __forceinline__ int64_t plane_chunk_off(int64_t atom, int64_t rows_p, int64_t row, int chunk) {
   return (atom * rows_p + row) * 64 + ((chunk ^ (int)((row >> 1) & 3)) << 4);
