@@ -320,29 +320,8 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
           }
         }
       }
-      mbar_wait(&sp_full[buf], MODE == MODE_V ? ((j >> 1) & 1) : (j & 1));
-      tc_fence_after();
-      float sv[NH], dv[NH];
-      {
-        uint32_t v1[NH];
-        if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
-        else tmem_ld8(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
-        if constexpr (MODE == MODE_S) {
-          uint32_t v2[NH];
-          if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cDP + slot * NH, v2);
-          else tmem_ld8(tmem_base + lane_off + cDP + slot * NH, v2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < NH; ++c) dv[c] = __uint_as_float(v2[c]);
-        } else {
-          tmem_ld_wait();
-        }
-#pragma unroll
-        for (int c = 0; c < NH; ++c) sv[c] = __uint_as_float(v1[c]);
-      }
-      tc_fence_before();
-      mbar_arrive(&sp_empty[buf]);
-
+      // dropout multipliers of this tile: independent of the scores, so they are drawn before the wait below and
+      // stay off the S' -> dS' critical path that the output MMA waits for
       const int c0 = j * N + slot * NH;
       float mult[NH];
 #pragma unroll
@@ -379,6 +358,29 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
           }
         }
       }
+      mbar_wait(&sp_full[buf], MODE == MODE_V ? ((j >> 1) & 1) : (j & 1));
+      tc_fence_after();
+      float sv[NH], dv[NH];
+      {
+        uint32_t v1[NH];
+        if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
+        else tmem_ld8(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
+        if constexpr (MODE == MODE_S) {
+          uint32_t v2[NH];
+          if constexpr (NH == 16) tmem_ld16(tmem_base + lane_off + cDP + slot * NH, v2);
+          else tmem_ld8(tmem_base + lane_off + cDP + slot * NH, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NH; ++c) dv[c] = __uint_as_float(v2[c]);
+        } else {
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int c = 0; c < NH; ++c) sv[c] = __uint_as_float(v1[c]);
+      }
+      tc_fence_before();
+      mbar_arrive(&sp_empty[buf]);
+
       // No bounds checks: the forward stores lse = +inf for padded queries (so P' = exp2(-inf) = 0 there), delta
       // is zero-padded, and padded KEY rows only pollute accumulator rows that are never stored.
       if constexpr (kv_roles) {

@@ -292,6 +292,19 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     // ---- pass 2
     for (int j = 0; j < nk; ++j, ++its) {
       const uint32_t buf = its & 1;
+      const int jb = j * BKEY + slot * NW;
+      // the dropout multipliers do not depend on S: draw them BEFORE waiting for the scores, so that the chain from
+      // "S(j) complete" to "P(j) in TMEM" (which the P V MMA waits for) holds no Philox latency
+      float mk[NW];
+      if (a.drop.p > 0.f) {
+#pragma unroll
+        for (int g = 0; g < NW / 8; ++g) {  // one Philox call per 8 adjacent keys
+          float m8[8];
+          dropout_mult8(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 8 * g)) >> 3, a.drop.p, inv_keep, m8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) mk[8 * g + e] = m8[e];
+        }
+      }
       mbar_wait(&s_full[buf], (its >> 1) & 1);
       tc_fence_after();
       float p[NW];
@@ -304,7 +317,6 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       }
       tc_fence_before();
       mbar_arrive(&s_empty[buf]);
-      const int jb = j * BKEY + slot * NW;
       if (jb + NW <= a.T) {
 #pragma unroll
         for (int c = 0; c < NW; ++c) {
@@ -320,12 +332,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       }
       if (a.drop.p > 0.f) {
 #pragma unroll
-        for (int g = 0; g < NW / 8; ++g) {  // one Philox call per 8 adjacent keys
-          float mk[8];
-          dropout_mult8(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 8 * g)) >> 3, a.drop.p, inv_keep, mk);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) p[8 * g + e] *= mk[e];
-        }
+        for (int c = 0; c < NW; ++c) p[c] *= mk[c];
       }
       mbar_wait(p_empty, (j & 1) ^ 1);  // P V of the previous tile has consumed the operand
       tc_fence_after();
