@@ -36,6 +36,12 @@ constexpr int kProdThreads = kProdWarps * 32;
 constexpr int A_PLANE = BM * 64;       // bytes of one bf16 plane of the A stage (128 rows x 32 k)
 constexpr int B_PLANE = BN_MAX * 64;
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // hi + lo planes of A and B
+// "wide" stages of all-plane launches with N <= 160: BK = 64 (bulk copies cost ~90 cycles each regardless of size, and
+// MN-major operands arrive in per-atom pieces of BK * 64 bytes: 2 KB pieces capped an SM at 45 GB/s, see
+// scripts/bulk_microbench.py).  Two stages fill exactly the three 48 KB slots.
+constexpr int WBK = 64, W_BN = 160, W_A_PLANE = BM * WBK * 2, W_B_PLANE = W_BN * WBK * 2;
+constexpr int W_STAGE = 2 * W_A_PLANE + 2 * W_B_PLANE;
+static_assert(2 * W_STAGE <= 3 * (2 * (BM * 64) + 2 * (BN_MAX * 64)), "wide stages must fit the first three slots");
 constexpr int kEpiStage = 8 * 4096;  // per-warp 32 x 32 fp32 transpose tiles of the epilogue
 constexpr int SMEM_BYTES = (STAGES + RAW) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + kEpiStage;
 
@@ -48,6 +54,7 @@ struct TcArgs {
   int a_vec, b_vec, c_vec, r_vec;  // 128-bit access allowed
   PlaneOp pa, pb;  // operands supplied as pre-swizzled bf16 planes (bulk-copied, not converted)
   int a_pl, b_pl;
+  int wide;        // all-plane launch with bn <= 160: 64-deep k-blocks in two 72 KB stages (half as many bulk copies)
 };
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -132,7 +139,50 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
     // UMMA layout) from global memory; the copies complete on the stage's pfull barrier.  K-major operand: `rows`
     // consecutive plane rows of column atom k0/32 (one copy per plane).  MN-major: 32 plane rows (k) of each of
     // `atoms` consecutive column atoms (2 KB each).  One copy per lane, so a stage's copies are issued in parallel.
-    if (kPlanes) {
+    if (!kConv && a.wide) {
+      // ---- wide stages (BK = 64): per k-block the K-major operand is two atoms (two copies per plane), the
+      // MN-major operand `atoms` pieces of klen * 64 bytes at a 4 KB pitch; klen = 32 for a ragged last block
+      uint32_t it = 0;
+      const int np = a.x3 ? 2 : 1;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(a, t);
+        const int kend_p = (tl.k_end + 31) & ~31;
+        const int num_kb = (tl.k_end - tl.k_begin + WBK - 1) / WBK;
+        const int a_rows = min(BM, a.pa.rows_p - tl.m0), a_atoms = max(0, min(BM / 32, a.pa.catoms - tl.m0 / 32));
+        const int b_rows = min(a.bn, a.pb.rows_p - tl.n0), b_atoms = max(0, min(a.bn / 32, a.pb.catoms - tl.n0 / 32));
+        const int a_items = (a.mn_a ? a_atoms : 2) * np, b_items = (a.mn_b ? b_atoms : 2) * np;
+        const bool mine = lane < a_items + b_items;
+        const bool is_b = lane >= a_items;
+        const int idx = is_b ? lane - a_items : lane;
+        const int plane = idx % np, atom = idx / np;  // atom: MN atom (MN-major) or k atom 0/1 (K-major)
+        const bool mn = is_b ? a.mn_b : a.mn_a;
+        const PlaneOp& po = is_b ? a.pb : a.pa;
+        const uint8_t* src_base = plane ? po.lo : po.hi;
+        const int row0 = is_b ? tl.n0 : tl.m0;
+        const int rows = is_b ? b_rows : a_rows;
+        const int pitch_k = (is_b ? a.bn : BM) * 64;  // K-major: bytes between the two k atoms of a stage
+        const uint32_t dst_off = (is_b ? 2 * W_A_PLANE : 0) + plane * (is_b ? W_B_PLANE : W_A_PLANE) +
+                                 (mn ? atom * (WBK * 64) : atom * pitch_k);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int stage = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(&empty[stage], ph ^ 1);
+          const int k0 = tl.k_begin + kb * WBK;
+          const int klen = min(WBK, kend_p - k0);  // 32 or 64
+          if (lane == 0) {
+            const uint32_t ab = a.mn_a ? a_atoms * klen * 64 : (klen >> 5) * a_rows * 64;
+            const uint32_t bb = a.mn_b ? b_atoms * klen * 64 : (klen >> 5) * b_rows * 64;
+            mbar_expect_tx(&pfull[stage], (ab + bb) * np);
+          }
+          __syncwarp();
+          if (mine && (mn || atom * 32 < klen)) {
+            const int64_t src = mn ? ((int64_t)(row0 / 32 + atom) * po.rows_p + k0) * 64
+                                   : ((int64_t)((k0 >> 5) + atom) * po.rows_p + row0) * 64;
+            bulk_g2s(smem + stage * W_STAGE + dst_off, src_base + src, mn ? klen * 64 : rows * 64, &pfull[stage]);
+          }
+        }
+      }
+    } else if (kPlanes) {
       uint32_t it = 0;
       const int np = a.x3 ? 2 : 1;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -332,6 +382,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
       mbar_wait(&tempty[buf], tph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN_MAX;
+      if (!kConv && a.wide) {  // ---- wide stages: up to four 16-deep MMA steps per k-block
+        const int kend_p = (tl.k_end + 31) & ~31;
+        const int nkb = (tl.k_end - tl.k_begin + WBK - 1) / WBK;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int stage = it & 1;
+          mbar_wait(&pfull[stage], (it >> 1) & 1);
+          tc_fence_after();
+          const int klen = min(WBK, kend_p - (tl.k_begin + kb * WBK));
+          const uint32_t sa_hi = smem_u32(smem + stage * W_STAGE);
+          const uint32_t sa_lo = sa_hi + W_A_PLANE, sb_hi = sa_hi + 2 * W_A_PLANE, sb_lo = sb_hi + W_B_PLANE;
+          const uint32_t pitch_b = a.bn * 64;
+#pragma unroll
+          for (int kk = 0; kk < WBK / 16; ++kk) {
+            if (kk * 16 < klen) {
+              const uint32_t ka = (kk >> 1) * (BM * 64) + (kk & 1) * 32, kbo = (kk >> 1) * pitch_b + (kk & 1) * 32;
+              const uint64_t ah = a.mn_a ? desc_mn_sw64(sa_hi + kk * 1024, WBK * 64) : desc_k_sw64(sa_hi + ka);
+              const uint64_t bh = a.mn_b ? desc_mn_sw64(sb_hi + kk * 1024, WBK * 64) : desc_k_sw64(sb_hi + kbo);
+              const uint64_t al = a.mn_a ? desc_mn_sw64(sa_lo + kk * 1024, WBK * 64) : desc_k_sw64(sa_lo + ka);
+              const uint64_t bl = a.mn_b ? desc_mn_sw64(sb_lo + kk * 1024, WBK * 64) : desc_k_sw64(sb_lo + kbo);
+              if (leader) {
+                umma_bf16(d_tmem, ah, bh, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                if (a.x3) {
+                  umma_bf16(d_tmem, al, bh, idesc, 1u);
+                  umma_bf16(d_tmem, ah, bl, idesc, 1u);
+                }
+              }
+            }
+          }
+          if (leader) {
+            umma_commit(&empty[stage]);
+            if (kb == nkb - 1) umma_commit(&tfull[buf]);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int stage = it % kNS;
         const uint32_t ph = (it / kNS) & 1;
@@ -603,6 +689,7 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.tiles_n = cdiv(d.n, a.bn);
   a.tiles_m = cdiv(d.m, BM);
   a.x3 = x3;
+  a.wide = (a.a_pl && a.b_pl && a.bn <= W_BN) ? 1 : 0;
   // plane operands cannot be transposed while staging: their orientation follows the problem
   a.mn_a = a.a_pl ? (d.a_k != 1) : (g_use_mn_major && d.a_k != 1 && d.a_m == 1);
   a.mn_b = a.b_pl ? (d.b_k != 1) : (g_use_mn_major && d.b_k != 1 && d.b_n == 1 && a.bn % 32 == 0);
@@ -682,7 +769,7 @@ int gemm_tc_splitk(const v1t_gemm_desc& d, const float* A, const float* B, float
   const bool mapped = gm.row_gout > 0 || gm.col_gout > 0;  // a remapped product always goes through the partials
   if (splits <= 1 && !mapped) return gemm_tc(d, A, B, C, nullptr, nullptr, st, no_drop(), x3, no_epi(), pa, pb);
   splits = std::max(splits, 1);
-  const int k_chunk = (int)round_up(cdiv(d.k, splits), BK);
+  const int k_chunk = (int)round_up(cdiv(d.k, splits), (pa.hi && pb.hi) ? WBK : BK);  // whole (wide) stages per split
   splits = cdiv(d.k, k_chunk);
   v1t_gemm_desc p = d;
   p.accumulate = 0;
