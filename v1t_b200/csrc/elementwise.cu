@@ -389,23 +389,26 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
   }
 }
 
-// dgamma[c] = sum_p partials[p][0][c], dbeta[c] = sum_p partials[p][1][c]: one warp per column, lanes stride over
-// the partials, fixed shuffle tree (deterministic)
-__global__ void ln_finish_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
-                                 float* __restrict__ dbeta, int parts, int E) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= E) return;
-  float a = 0.f, b = 0.f;
-  for (int p = lane; p < parts; p += 32) {
-    a += partials[((int64_t)p * 2) * E + c];
-    b += partials[((int64_t)p * 2 + 1) * E + c];
-  }
-  a = warp_sum(a);
-  b = warp_sum(b);
-  if (lane == 0) {
-    if (dgamma) dgamma[c] = a;
-    if (dbeta) dbeta[c] = b;
+// dgamma[c] = sum_p partials[p][0][c], dbeta[c] = sum_p partials[p][1][c].  lane = column (coalesced rows of the
+// partials), the 8 warps of a block take every 8th partial, fixed-order smem reduction (deterministic).
+// grid (ceil(E/32), 2): blockIdx.y = 0 -> dgamma, 1 -> dbeta
+__global__ void __launch_bounds__(256) ln_finish_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
+                                                        float* __restrict__ dbeta, int parts, int E) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int which = blockIdx.y;
+  float s = 0.f;
+  if (c < E)
+    for (int p = wid; p < parts; p += 8) s += partials[((int64_t)p * 2 + which) * E + c];
+  red[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && c < E) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    float* out = which == 0 ? dgamma : dbeta;
+    if (out) out[c] = t;
   }
 }
 
@@ -531,17 +534,24 @@ __global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ p
   }
 }
 
-// out[b*out_ld + c] = sum_strip partials[(b*strips+strip)*cols + c]: one warp per output, lanes stride over the strips
-__global__ void colsum_finish_kernel(const float* __restrict__ partials, float* __restrict__ out, int batch, int cols,
-                                     int strips, int64_t out_ld) {
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (i >= (int64_t)batch * cols) return;
-  const int b = (int)(i / cols), c = (int)(i % cols);
+// out[b*out_ld + c] = sum_strip partials[(b*strips+strip)*cols + c].  lane = column (coalesced), the 8 warps of a
+// block take every 8th strip, fixed-order smem reduction.  grid (ceil(cols/32), batch)
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partials, float* __restrict__ out,
+                                                            int batch, int cols, int strips, int64_t out_ld) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane, b = blockIdx.y;
   float s = 0.f;
-  for (int k = lane; k < strips; k += 32) s += partials[((int64_t)b * strips + k) * cols + c];
-  s = warp_sum(s);
-  if (lane == 0) out[b * out_ld + c] = s;
+  if (c < cols)
+    for (int k = wid; k < strips; k += 8) s += partials[((int64_t)b * strips + k) * cols + c];
+  red[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    out[b * out_ld + c] = t;
+  }
 }
 
 __global__ void batchsum_kernel(const float* __restrict__ X, float* __restrict__ out, int B, int64_t rows, int cols,
@@ -595,7 +605,7 @@ int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t l
     dropout_rows8_colsum_kernel<<<grid, 256, sizeof(float) * rpp * chunks * 8, st>>>(src, dst, rows, cols, ld, chunks, dr,
                                                                                      pl, partials);
     V1T_LAUNCH_CHECK();
-    colsum_finish_kernel<<<cdiv((int64_t)cols, 8), 256, 0, st>>>(partials, colsum_out, 1, cols, grid, 0);
+    colsum_finish_kernel<<<dim3(cdiv(cols, 32), 1), 256, 0, st>>>(partials, colsum_out, 1, cols, grid, 0);
     V1T_LAUNCH_CHECK();
     return V1T_OK;
   }
@@ -676,7 +686,7 @@ int ln_backward(const float* dh, const float* x, const float* stats, const float
   V1T_LN_DISPATCH(8, ln_backward_kernel, dh, x, stats, gamma, dx_accum, partials, rows, E, ld)
   { ln_backward_kernel<16><<<grid, 256, 0, st>>>(dh, x, stats, gamma, dx_accum, partials, rows, E, ld); }
   V1T_LAUNCH_CHECK();
-  ln_finish_kernel<<<cdiv(E, 8), 256, 0, st>>>(partials, dgamma, dbeta, grid, E);
+  ln_finish_kernel<<<dim3(cdiv(E, 32), 2), 256, 0, st>>>(partials, dgamma, dbeta, grid, E);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
@@ -715,13 +725,13 @@ int colsum(const float* X, float* out, int batch, int64_t rows, int cols, int64_
   dim3 grid(cdiv(cols, 32), strips, batch), block(32, 8);
   colsum_kernel<<<grid, block, 0, st>>>(X, partials, rows, cols, xb, ld, strips);
   V1T_LAUNCH_CHECK();
-  colsum_finish_kernel<<<cdiv((int64_t)batch * cols, 8), 256, 0, st>>>(partials, out, batch, cols, strips, out_ld);
+  colsum_finish_kernel<<<dim3(cdiv(cols, 32), batch), 256, 0, st>>>(partials, out, batch, cols, strips, out_ld);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
 
 int colsum_finish(const float* partials, float* out, int cols, int strips, cudaStream_t st) {
-  colsum_finish_kernel<<<cdiv((int64_t)cols, 8), 256, 0, st>>>(partials, out, 1, cols, strips, 0);
+  colsum_finish_kernel<<<dim3(cdiv(cols, 32), 1), 256, 0, st>>>(partials, out, 1, cols, strips, 0);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

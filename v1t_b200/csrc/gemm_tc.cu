@@ -668,6 +668,9 @@ namespace {
 int pick_bn(const v1t_gemm_desc& d, const PlaneOp& pb, const EpiOp& epi = no_epi()) {
   const int nt = cdiv(d.n, BN_MAX);
   const bool whole_atoms = (pb.hi && d.b_k != 1) || epi.pl.hi || epi.kind == kEpiHeadPlanes;
+  // plane-emitting epilogues are the bottleneck of their launches and run on 4 column slots per TMEM quarter: keep
+  // the 32-column groups of every tile a multiple of 4 (full 256-wide tiles plus one narrower tail tile)
+  if (nt > 1 && (epi.pl.hi || epi.kind == kEpiHeadPlanes)) return BN_MAX;
   return (int)round_up(cdiv(d.n, nt), whole_atoms ? 32 : 16);
 }
 
