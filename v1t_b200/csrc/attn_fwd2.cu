@@ -4,7 +4,8 @@
 // double-buffered ring (K(j) is free after S(j), V(j) after P V(j)), which hides the bulk-copy latency.  V comes
 // from the same token-major planes as K and is read through an MN-major descriptor (N = head dim is the
 // contiguous direction), so no transposed copy of V is ever made.
-// Same two-pass softmax as generation 1 (attn_tc.cu): pass 1 = row maxima from the hi planes, pass 2 = exact.
+// Two-pass softmax: pass 1 = row maxima from the hi planes only (any value near the true maximum works as the
+// reference point), pass 2 = exact scores, P = exp2, row sums, O += P V (no rescaling of the accumulator in TMEM).
 //
 // TMEM columns (Dp = 160): Q_hi[80] | Q_lo[80] | S[2][64] | P_hi[32] | P_lo[32] | O[160]  = 512.
 // Warp roles (608 threads): warps 0-15 softmax/epilogue (lane quarter = warp & 3, column slot = warp >> 2: 16 of a
