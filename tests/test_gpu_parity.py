@@ -258,6 +258,53 @@ def test_attention_probs_hook_matches_oracle():
         assert np.allclose(a.sum(-1).cpu().numpy(), 1.0, atol=1e-5)
 
 
+def test_attention_probs_hook_from_planes_default_dims():
+    """Same hook contract on the tensor-core path at the default dims, where q, k, v exist only as bf16 hi/lo operand
+    planes written by the QKV GEMM epilogue: v1t_attention_probs rebuilds fp32 qkv from the planes (hi + lo)."""
+    g = Golden("default_dims")
+    model, _ = build(g, b200_impl="bf16x3")
+    model.eval()
+    got = []
+    hooks = [blk["mha"].attend.register_forward_hook(lambda m, i, o: got.append(o.detach().clone()))
+             for blk in model.core.transformer.blocks]
+    d = g.mice["A"]
+    with torch.no_grad():
+        model.core(cu(d["images"]), mouse_id="A", behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]))
+    for h in hooks:
+        h.remove()
+    P = O.params_to_f64(g.sd, "core.")
+    _, cache = O.core_forward(P, g.core_config(), d["images"], d["behaviors"], d["pupil_centers"])
+    assert len(got) == len(cache["blocks"])
+    for a, c in zip(got, cache["blocks"]):
+        assert rel_err(a.cpu().numpy(), c["p"]) < 2e-4
+        assert np.allclose(a.sum(-1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("p", [0.0229, 0.2544, 0.5])
+def test_dropout_mask_statistics(p):
+    """The counter-based masks (Philox4x32-7, eight 16-bit decisions per call) keep 1 - p of the elements (within
+    4 sigma), scale the kept ones by 1/(1-p), differ between sites and seeds, and are reproducible."""
+    from v1t_b200.functional import dropout_mask
+    n = 1 << 22
+    m1 = dropout_mask(n, seed=123, site=5, p=p, device=DEV)
+    m2 = dropout_mask(n, seed=123, site=5, p=p, device=DEV)
+    m3 = dropout_mask(n, seed=123, site=6, p=p, device=DEV)
+    m4 = dropout_mask(n, seed=124, site=5, p=p, device=DEV)
+    assert torch.equal(m1, m2)
+    kept = (m1 > 0).double().mean().item()
+    sigma = (p * (1 - p) / n) ** 0.5
+    assert abs(kept - (1 - p)) < 4 * sigma + 1.0 / 65536  # threshold is quantised to 1/65536
+    vals = torch.unique(m1)
+    assert vals.numel() == 2 and vals[0].item() == 0.0 and abs(vals[1].item() - 1.0 / (1.0 - p)) < 1e-6
+    for other in (m3, m4):  # independent streams: agreement rate ~ p^2 + (1-p)^2
+        agree = ((m1 > 0) == (other > 0)).double().mean().item()
+        assert abs(agree - (p * p + (1 - p) * (1 - p))) < 5e-3
+    # adjacent elements of one Philox call are uncorrelated
+    k = (m1 > 0).double()
+    corr = ((k[:-1] - kept) * (k[1:] - kept)).mean().item() / max(kept * (1 - kept), 1e-12)
+    assert abs(corr) < 5e-3
+
+
 def test_full_size_properties_baseline_config():
     """BASELINE configs[0] size (B=16, 4 blocks, T=1654, N=8000): size-independent properties — run-to-run
     determinism of everything except the atomically-scattered map gradient, batch-split invariance, loss equal to
