@@ -204,52 +204,57 @@ __global__ void tanh_grad_kernel(const float* __restrict__ dy, const float* __re
   }
 }
 
-// Backward of BehaviorMLP (vit.py:181-202) in ONE CTA (the whole problem is B x 155 x 77): given dlat[b,e] (the
-// gradient of the latent added to every token), dz3 = dlat * (1 - lat^2); dW3[e,j] = sum_b dz3[b,e] hid[b,j];
-// db3 = colsum(dz3); dhid = dz3 W3; dz0 = dhid * (1 - hid^2); dW0[j,i] = sum_b dz0[b,j] beh[b,i]; db0 = colsum(dz0).
-// Fixed summation order (deterministic).  Replaces 8 latency-bound launches per block.
-__global__ void __launch_bounds__(1024) bmlp_backward_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
+// Backward of BehaviorMLP (vit.py:181-202), the whole problem is B x 155 x 77: given dlat[b,e] (the gradient of the
+// latent added to every token), dz3 = dlat * (1 - lat^2); dW3[e,j] = sum_b dz3[b,e] hid[b,j]; db3 = colsum(dz3);
+// dhid = dz3 W3; dz0 = dhid * (1 - hid^2); dW0[j,i] = sum_b dz0[b,j] beh[b,i]; db0 = colsum(dz0).
+// gridDim.x CTAs without any cross-CTA dependency: every CTA recomputes dz3 (tiny) and owns a slice of the e rows
+// (dW3, db3) and a slice of the hidden units j (dhid -> dz0 -> dW0, db0).  Fixed summation order (deterministic).
+// Replaces 8 latency-bound launches per block.
+__global__ void __launch_bounds__(256) bmlp_backward_kernel(const float* __restrict__ dlat, const float* __restrict__ lat,
                                                             const float* __restrict__ hid, const float* __restrict__ beh,
                                                             const float* __restrict__ w3, float* __restrict__ dw0,
                                                             float* __restrict__ db0, float* __restrict__ dw3,
                                                             float* __restrict__ db3, int B, int bdim, int H, int E) {
   extern __shared__ float sh[];
   float* dz3 = sh;            // [B][E]
-  float* dz0 = sh + B * E;    // [B][H]
+  float* dz0 = sh + B * E;    // [B][jn] (this CTA's hidden units)
+  const int G = gridDim.x, g = blockIdx.x;
+  const int e0 = (int)((int64_t)E * g / G), e1 = (int)((int64_t)E * (g + 1) / G);
+  const int j0 = (int)((int64_t)H * g / G), j1 = (int)((int64_t)H * (g + 1) / G), jn = j1 - j0;
   for (int i = threadIdx.x; i < B * E; i += blockDim.x) {
     const float y = lat[i];
     dz3[i] = dlat[i] * (1.f - y * y);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < E * H; i += blockDim.x) {
-    const int e = i / H, j = i % H;
+  for (int i = threadIdx.x; i < (e1 - e0) * H && dw3; i += blockDim.x) {
+    const int e = e0 + i / H, j = i % H;
     float s = 0.f;
     for (int b = 0; b < B; ++b) s = fmaf(dz3[b * E + e], hid[b * H + j], s);
-    if (dw3) dw3[i] = s;
+    dw3[e * H + j] = s;
   }
-  for (int e = threadIdx.x; e < E && db3; e += blockDim.x) {
+  for (int e = e0 + threadIdx.x; e < e1 && db3; e += blockDim.x) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += dz3[b * E + e];
     db3[e] = s;
   }
-  for (int i = threadIdx.x; i < B * H; i += blockDim.x) {
-    const int b = i / H, j = i % H;
+  for (int i = threadIdx.x; i < B * jn; i += blockDim.x) {
+    const int b = i / jn, j = j0 + i % jn;
     float s = 0.f;
     for (int e = 0; e < E; ++e) s = fmaf(dz3[b * E + e], __ldg(w3 + e * H + j), s);
-    const float y = hid[i];
-    dz0[i] = s * (1.f - y * y);
+    const float y = hid[b * H + j];
+    dz0[b * jn + (j - j0)] = s * (1.f - y * y);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < H * bdim && dw0; i += blockDim.x) {
+  for (int i = threadIdx.x; i < jn * bdim && dw0; i += blockDim.x) {
     const int j = i / bdim, k = i % bdim;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s = fmaf(dz0[b * H + j], beh[b * bdim + k], s);
-    dw0[i] = s;
+    for (int b = 0; b < B; ++b) s = fmaf(dz0[b * jn + j], beh[b * bdim + k], s);
+    dw0[(j0 + j) * bdim + k] = s;
   }
-  for (int j = threadIdx.x; j < H && db0; j += blockDim.x) {
+  for (int j = threadIdx.x; j < jn && db0; j += blockDim.x) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dz0[b * H + j];
-    db0[j] = s;
+    for (int b = 0; b < B; ++b) s += dz0[b * jn + j];
+    db0[j0 + j] = s;
   }
 }
 
@@ -641,7 +646,7 @@ int bmlp_backward(const float* dlat, const float* lat, const float* hid, const f
     V1T_CUDA(cudaFuncSetAttribute(bmlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  bmlp_backward_kernel<<<1, 1024, smem, st>>>(dlat, lat, hid, beh, w3, dw0, db0, dw3, db3, B, bdim, H, E);
+  bmlp_backward_kernel<<<16, 256, smem, st>>>(dlat, lat, hid, beh, w3, dw0, db0, dw3, db3, B, bdim, H, E);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

@@ -140,25 +140,34 @@ __device__ __forceinline__ int64_t ungroup(int64_t i, int gin, int gout) {
   if (gout <= 0) return i;
   return (i % gout < gin) ? (i / gout) * gin + i % gout : -1;
 }
-__global__ void reduce_partials_ld_kernel(const float* __restrict__ partials, float* __restrict__ out, int parts,
-                                          int64_t rows, int64_t cols, int64_t in_ld, int64_t out_ld,
-                                          int accumulate, GroupMap gm) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cols) return;
-  const int64_t r = i / cols, c = i % cols;
+// block (64, 4): threadIdx.x = consecutive outputs (coalesced rows of every partial), the 4 y-lanes take every 4th
+// partial so that 4x as many loads are in flight; fixed-order smem reduction over y (deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_ld_kernel(const float* __restrict__ partials, float* __restrict__ out,
+                                                                 int parts, int64_t rows, int64_t cols, int64_t in_ld,
+                                                                 int64_t out_ld, int accumulate, GroupMap gm) {
+  __shared__ float red[4][64];
+  const int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  const bool in = i < rows * cols;
+  const int64_t r = in ? i / cols : 0, c = in ? i % cols : 0;
+  float s = 0.f;
+  if (in) {
+    const float* pp = partials + r * in_ld + c;
+    const int64_t ps = rows * in_ld;
+    int p = threadIdx.y;
+    for (; p + 12 < parts; p += 16) {  // four loads in flight per thread
+      const float v0 = pp[p * ps], v1 = pp[(p + 4) * ps], v2 = pp[(p + 8) * ps], v3 = pp[(p + 12) * ps];
+      s += (v0 + v1) + (v2 + v3);
+    }
+    for (; p < parts; p += 4) s += pp[p * ps];
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || !in) return;
   const int64_t ro = ungroup(r, gm.row_gin, gm.row_gout), co = ungroup(c, gm.col_gin, gm.col_gout);
   if (ro < 0 || co < 0) return;  // padded row / column of a head-padded product
-  float s = 0.f;
-  const float* pp = partials + r * in_ld + c;
-  const int64_t ps = rows * in_ld;
-  int p = 0;
-  for (; p + 3 < parts; p += 4) {  // four loads in flight; fixed order
-    const float v0 = pp[p * ps], v1 = pp[(p + 1) * ps], v2 = pp[(p + 2) * ps], v3 = pp[(p + 3) * ps];
-    s += (v0 + v1) + (v2 + v3);
-  }
-  for (; p < parts; ++p) s += pp[p * ps];
+  const float t = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
   float* o = out + ro * out_ld + co;
-  *o = accumulate ? *o + s : s;
+  *o = accumulate ? *o + t : t;
 }
 
 }  // namespace
@@ -166,8 +175,8 @@ __global__ void reduce_partials_ld_kernel(const float* __restrict__ partials, fl
 int reduce_partials_ld(const float* partials, float* out, int parts, int64_t rows, int64_t cols, int64_t in_ld,
                        int64_t out_ld, int accumulate, cudaStream_t st, GroupMap gm) {
   if (rows * cols == 0) return V1T_OK;
-  reduce_partials_ld_kernel<<<cdiv(rows * cols, 256), 256, 0, st>>>(partials, out, parts, rows, cols, in_ld, out_ld,
-                                                                    accumulate, gm);
+  reduce_partials_ld_kernel<<<cdiv(rows * cols, 64), dim3(64, 4), 0, st>>>(partials, out, parts, rows, cols, in_ld,
+                                                                           out_ld, accumulate, gm);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
