@@ -182,6 +182,84 @@ int v1t_poisson_forward(const float* y_pred, const float* y_true, int64_t n, flo
 int v1t_poisson_backward(const float* y_pred, const float* y_true, int64_t n, float eps, float loss_scale,
                          const float* dloss, float* dy, void* stream);
 
+/* ---- callers either side of the path (SURVEY.md section 8f "next" rows) ------------------------------- */
+
+/* n1: fused L1 regulariser + AdamW over every parameter tensor in one launch.  Replaces the regulariser graph
+ * (vit.py:419-421, gaussian2d.py:83-100, core_shifter.py:35-36, model.py:141-149, train.py:71-73) and
+ * torch.optim.AdamW(weight_decay=0).step() (train.py:217-223,77-80).  Per element:
+ *   g = grad_scale * grad + l1 * sign(p);  p *= 1 - lr * weight_decay;  m += (g - m)(1 - beta1);
+ *   v = beta2 v + (1 - beta2) g g;  p -= lr / bias_corr1 * m / (sqrt(v) / bias_corr2_sqrt + eps)
+ * tensors_dev: DEVICE array of n_tensors records; chunk_prefix_dev: DEVICE int32 [n_tensors + 1], prefix sums of
+ * ceil(numel / v1t_opt_chunk_elems()); n_chunks = chunk_prefix[n_tensors].  bias_corr1 = 1 - beta1^t,
+ * bias_corr2_sqrt = sqrt(1 - beta2^t) for the step count t the caller keeps.  zero_grad != 0 clears the gradients in
+ * the same pass.  l1_sums_dev (optional, [n_groups]) receives sum |p| per group BEFORE the update (what the
+ * reference logs as reg_loss / reg_scale); needs scratch of v1t_adamw_l1_scratch_bytes(n_chunks). */
+typedef struct v1t_opt_tensor {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  float lr;            /* learning rate of the tensor's param group */
+  float l1;            /* reg_scale * (times the regulariser entered the loss this step); 0 = not regularised */
+  float weight_decay;  /* decoupled decay (the reference passes 0) */
+  int32_t group;       /* index into l1_sums_dev */
+} v1t_opt_tensor;
+int v1t_opt_chunk_elems(void);
+size_t v1t_adamw_l1_scratch_bytes(int n_chunks);
+int v1t_adamw_l1_step(const v1t_opt_tensor* tensors_dev, const int32_t* chunk_prefix_dev, int n_tensors, int n_chunks,
+                      float beta1, float beta2, float eps, float bias_corr1, float bias_corr2_sqrt, float grad_scale,
+                      int zero_grad, float* l1_sums_dev, int n_groups, void* scratch, void* stream);
+
+/* a11 / n3: the small MLPs either side of the readout as one kernel per direction: the readout's grid predictor
+ * Linear-ELU-Linear-Tanh over the neurons (gaussian2d.py:102-136,188-193) and the core / image shifters'
+ * Linear-Tanh stacks over the batch (core_shifter.py:24-40, image_cropper.py:27-48).  Weights in nn.Linear layout
+ * ([out, in], bias [out] or NULL).  The backward recomputes the activations from x (nothing saved) and OVERWRITES
+ * every non-NULL gradient pointer; no gradient with respect to x (both inputs are data). */
+#define V1T_MLP_MAX_LAYERS 3
+#define V1T_MLP_MAX_WIDTH 32
+#define V1T_ACT_NONE 0
+#define V1T_ACT_TANH 1
+#define V1T_ACT_ELU 2
+typedef struct v1t_mlp_spec {
+  int32_t rows;                          /* neurons (grid predictor) or samples (shifters) */
+  int32_t layers;                        /* 1..V1T_MLP_MAX_LAYERS Linear layers, layer l followed by act[l] */
+  int32_t width[V1T_MLP_MAX_LAYERS + 1]; /* width[0] = input features, width[l+1] = outputs of layer l; <= 32 */
+  int32_t act[V1T_MLP_MAX_LAYERS];       /* V1T_ACT_* */
+  int64_t x_ld;                          /* row stride of x in floats (>= width[0]) */
+} v1t_mlp_spec;
+typedef struct v1t_mlp_ptrs {
+  float* w[V1T_MLP_MAX_LAYERS];
+  float* b[V1T_MLP_MAX_LAYERS];
+} v1t_mlp_ptrs;
+size_t v1t_small_mlp_scratch_bytes(const v1t_mlp_spec* s);
+int v1t_small_mlp_forward(const v1t_mlp_spec* s, const v1t_mlp_ptrs* params, const float* x, float* y, void* stream);
+int v1t_small_mlp_backward(const v1t_mlp_spec* s, const v1t_mlp_ptrs* params, const float* x, const float* dy,
+                           const v1t_mlp_ptrs* grads, void* scratch, void* stream);
+
+/* n3: ImageCropper.forward (image_cropper.py:120-140) as one gather: images [B,C,in_h,in_w]; grid [crop_h,crop_w,2]
+ * is the module's (x,y) crop-grid buffer (image_cropper.py:104-112); shifts [B,2] or NULL (ImageShifter output);
+ * nearest sampling with align_corners and zero padding, then bilinear resize (antialias off) to (out_h,out_w) when
+ * it differs from the crop, then `behavior_planes` constant planes from behaviors [B,behavior_planes]
+ * (behavior_mode 1).  out [B, C + behavior_planes, out_h, out_w].  No gradient: nearest sampling has none. */
+typedef struct v1t_crop_shape {
+  int32_t batch, channels, in_h, in_w;
+  int32_t crop_h, crop_w;
+  int32_t out_h, out_w;
+  int32_t behavior_planes;
+} v1t_crop_shape;
+int v1t_crop_resize(const v1t_crop_shape* s, const float* images, const float* grid, const float* shifts,
+                    const float* behaviors, float* out, void* stream);
+
+/* n2: attention rollout of recorded attention maps (attention_rollout.py:92-133, attention_rollouts): attn
+ * [B,L,H,T,T] (what Recorder stacks, attention_rollout.py:72-75) -> heatmaps [B,out_h,out_w]: head max, + identity,
+ * row-normalise, product over the blocks, row 0 without the CLS column as a (gh,gw) map, min-max normalised and
+ * bilinear-resized.  Only row 0 of the product is needed, so each block is one vector-matrix pass over its
+ * attention matrices (each read once; the last block contributes only its first row). */
+size_t v1t_rollout_scratch_bytes(int B, int T);
+int v1t_attention_rollout(const float* attn, int B, int L, int H, int T, int gh, int gw, int out_h, int out_w,
+                          float* heatmaps, void* scratch, void* stream);
+
 /* ---- building blocks, exported for unit tests -------------------------------------------------------- */
 /* C[b][m,n] = alpha * sum_k A[b][m,k] * B[b][k,n] (+ bias[n]) (+ R[b][m,n]); arbitrary element strides */
 typedef struct v1t_gemm_desc {

@@ -57,6 +57,30 @@ class GemmDesc(C.Structure):
                 ("alpha", C.c_float), ("accumulate", C.c_int32)]
 
 
+class OptTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("lr", C.c_float), ("l1", C.c_float), ("weight_decay", C.c_float),
+                ("group", C.c_int32)]
+
+
+MLP_MAX_LAYERS, MLP_MAX_WIDTH = 3, 32
+ACT_NONE, ACT_TANH, ACT_ELU = 0, 1, 2
+
+
+class MlpSpec(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("layers", C.c_int32), ("width", C.c_int32 * (MLP_MAX_LAYERS + 1)),
+                ("act", C.c_int32 * MLP_MAX_LAYERS), ("x_ld", C.c_int64)]
+
+
+class MlpPtrs(C.Structure):
+    _fields_ = [("w", C.c_void_p * MLP_MAX_LAYERS), ("b", C.c_void_p * MLP_MAX_LAYERS)]
+
+
+class CropShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("batch", "channels", "in_h", "in_w", "crop_h", "crop_w", "out_h", "out_w",
+                                         "behavior_planes")]
+
+
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libv1t_b200.so")
 
 # every symbol include/v1t_b200.h declares: (restype, argtypes)
@@ -101,6 +125,18 @@ SYMBOLS = {
     "v1t_bulk_microbench": (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "v1t_ts_selftest": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "v1t_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint32, _f, _vp]),
+    "v1t_opt_chunk_elems": (C.c_int, []),
+    "v1t_adamw_l1_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "v1t_adamw_l1_step": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f, _f, _f, _f, _f, _f, C.c_int, _vp, C.c_int, _vp,
+                                    _vp]),
+    "v1t_small_mlp_scratch_bytes": (C.c_size_t, [C.POINTER(MlpSpec)]),
+    "v1t_small_mlp_forward": (C.c_int, [C.POINTER(MlpSpec), C.POINTER(MlpPtrs), _vp, _vp, _vp]),
+    "v1t_small_mlp_backward": (C.c_int, [C.POINTER(MlpSpec), C.POINTER(MlpPtrs), _vp, _vp, C.POINTER(MlpPtrs), _vp,
+                                         _vp]),
+    "v1t_crop_resize": (C.c_int, [C.POINTER(CropShape), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "v1t_rollout_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "v1t_attention_rollout": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -344,3 +344,142 @@ def dropout_mask(n: int, seed: int, site: int, p: float, device) -> torch.Tensor
 
 def loss_scale(ds_size: float, batch_size: int, ds_scale: bool = True) -> float:
     return math.sqrt(ds_size / batch_size) if ds_scale else 1.0
+
+
+# ------------------------------------------------------------------------------------------------------
+# callers either side of the path: small MLPs, image cropper, attention rollout
+# ------------------------------------------------------------------------------------------------------
+_ACTS = {None: _lib.ACT_NONE, "none": _lib.ACT_NONE, "tanh": _lib.ACT_TANH, "elu": _lib.ACT_ELU}
+
+
+def _mlp_spec(x: torch.Tensor, weights: Sequence[torch.Tensor], acts: Sequence[Optional[str]]) -> _lib.MlpSpec:
+    if not 1 <= len(weights) <= _lib.MLP_MAX_LAYERS or len(acts) != len(weights):
+        raise RuntimeError(f"small_mlp: {len(weights)} layers / {len(acts)} activations unsupported")
+    spec = _lib.MlpSpec(rows=x.shape[0], layers=len(weights), x_ld=x.stride(0))
+    spec.width[0] = weights[0].shape[1]
+    for i, w in enumerate(weights):
+        if w.shape[1] != spec.width[i]:
+            raise RuntimeError(f"small_mlp: layer {i} expects {w.shape[1]} inputs, got {spec.width[i]}")
+        spec.width[i + 1] = w.shape[0]
+        spec.act[i] = _ACTS[acts[i]]
+    if max(spec.width[: len(weights) + 1]) > _lib.MLP_MAX_WIDTH:
+        raise NotImplementedError(f"small_mlp: widths {list(spec.width)} exceed {_lib.MLP_MAX_WIDTH}")
+    if x.shape[1] < spec.width[0] or x.stride(1) != 1:
+        raise RuntimeError("small_mlp: x must be [rows, >= in_features] with unit column stride")
+    return spec
+
+
+def _mlp_ptrs(weights, biases) -> _lib.MlpPtrs:
+    p = _lib.MlpPtrs()
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        p.w[i] = _ptr(w)
+        p.b[i] = _ptr(b)
+    return p
+
+
+class _SmallMlpFunction(torch.autograd.Function):
+    """y = act_L(Linear_L(... act_1(Linear_1(x)))) for the grid predictor (gaussian2d.py:102-136) and the shifters
+    (core_shifter.py:24-40): one kernel forward, one backward that recomputes the activations."""
+
+    @staticmethod
+    def forward(ctx, x, acts, *params):
+        lib = _lib.load()
+        weights, biases = list(params[0::2]), list(params[1::2])
+        _need_cuda(x, *weights, *biases)
+        if x.dtype != torch.float32:
+            x = x.float()
+        if x.dim() != 2 or x.stride(1) != 1:
+            x = x.reshape(x.shape[0], -1).contiguous()
+        weights = [_f32c(w) for w in weights]
+        biases = [_f32c(b) for b in biases]
+        spec = _mlp_spec(x, weights, acts)
+        dev = x.device
+        y = torch.empty((x.shape[0], weights[-1].shape[0]), dtype=torch.float32, device=dev)
+        ptrs = _mlp_ptrs(weights, biases)
+        with torch.cuda.device(dev):
+            _lib.check(lib.v1t_small_mlp_forward(C.byref(spec), C.byref(ptrs), x.data_ptr(), y.data_ptr(),
+                                                 _stream_ptr(dev)), "small_mlp_forward")
+        ctx.acts = tuple(acts)
+        ctx.n_layers = len(weights)
+        ctx.save_for_backward(x, *weights, *[b for b in biases if b is not None])
+        ctx.has_bias = [b is not None for b in biases]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        sv = list(ctx.saved_tensors)
+        x = sv.pop(0)
+        weights = [sv.pop(0) for _ in range(ctx.n_layers)]
+        biases = [sv.pop(0) if h else None for h in ctx.has_bias]
+        spec = _mlp_spec(x, weights, ctx.acts)
+        dev = x.device
+        dy = _f32c(dy)
+        gw = [torch.empty_like(w) for w in weights]
+        gb = [torch.empty_like(b) if b is not None else None for b in biases]
+        if x.shape[0] == 0:
+            for g in gw + [g for g in gb if g is not None]:
+                g.zero_()
+        else:
+            scratch = _scratch(dev, lib.v1t_small_mlp_scratch_bytes(C.byref(spec)))
+            pp, gp = _mlp_ptrs(weights, biases), _mlp_ptrs(gw, gb)
+            with torch.cuda.device(dev):
+                _lib.check(lib.v1t_small_mlp_backward(C.byref(spec), C.byref(pp), x.data_ptr(), dy.data_ptr(),
+                                                      C.byref(gp), scratch.data_ptr(), _stream_ptr(dev)),
+                           "small_mlp_backward")
+        out = [None, None]
+        for w, b in zip(gw, gb):
+            out += [w, b]
+        return tuple(out)
+
+
+def small_mlp(x: torch.Tensor, layers: Sequence, acts: Sequence[Optional[str]]) -> torch.Tensor:
+    """``layers``: nn.Linear modules (or (weight, bias) pairs); ``acts``: "tanh" | "elu" | None after each layer.
+    x [rows, in] is data (no gradient flows into it)."""
+    if x.requires_grad:
+        raise NotImplementedError("small_mlp: gradients with respect to the input are not computed")
+    params = []
+    for l in layers:
+        w, b = (l.weight, l.bias) if hasattr(l, "weight") else l
+        params += [w, b]
+    return _SmallMlpFunction.apply(x, tuple(acts), *params)
+
+
+def crop_resize(images: torch.Tensor, grid: torch.Tensor, shifts: Optional[torch.Tensor], out_hw,
+                behaviors: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ImageCropper.forward's tensor work (image_cropper.py:120-140): nearest crop on ``grid`` [1|-,crop_h,crop_w,2]
+    (+ per-sample ``shifts`` [B,2]), bilinear resize to ``out_hw``, behaviour planes appended when given."""
+    lib = _lib.load()
+    _need_cuda(images, grid, shifts, behaviors)
+    images, grid, shifts, behaviors = _f32c(images), _f32c(grid), _f32c(shifts), _f32c(behaviors)
+    b, c, in_h, in_w = images.shape
+    crop_h, crop_w = grid.shape[-3], grid.shape[-2]
+    planes = 0 if behaviors is None else behaviors.shape[1]
+    cs = _lib.CropShape(batch=b, channels=c, in_h=in_h, in_w=in_w, crop_h=crop_h, crop_w=crop_w, out_h=out_hw[0],
+                        out_w=out_hw[1], behavior_planes=planes)
+    out = torch.empty((b, c + planes, out_hw[0], out_hw[1]), dtype=torch.float32, device=images.device)
+    with torch.cuda.device(images.device):
+        _lib.check(lib.v1t_crop_resize(C.byref(cs), images.data_ptr(), grid.data_ptr(), _ptr(shifts), _ptr(behaviors),
+                                       out.data_ptr(), _stream_ptr(images.device)), "crop_resize")
+    return out
+
+
+def attention_rollouts(attentions: torch.Tensor, image_shape, grid_hw) -> torch.Tensor:
+    """attentions [B,L,H,T,T] -> heatmaps [B,*image_shape] (attention_rollout.py:92-133); grid_hw = (gh, gw) with
+    gh*gw = T-1 (the reference's find_shape)."""
+    lib = _lib.load()
+    _need_cuda(attentions)
+    if attentions.dim() != 5 or attentions.shape[-1] != attentions.shape[-2]:
+        raise RuntimeError(f"attention_rollouts: expected [B,L,H,T,T], got {tuple(attentions.shape)}")
+    a = _f32c(attentions)
+    b, l, h, t, _ = a.shape
+    dev = a.device
+    out = torch.empty((b, int(image_shape[0]), int(image_shape[1])), dtype=torch.float32, device=dev)
+    if b == 0:
+        return out
+    scratch = _scratch(dev, lib.v1t_rollout_scratch_bytes(b, t))
+    with torch.cuda.device(dev):
+        _lib.check(lib.v1t_attention_rollout(a.data_ptr(), b, l, h, t, int(grid_hw[0]), int(grid_hw[1]),
+                                             out.shape[1], out.shape[2], out.data_ptr(), scratch.data_ptr(),
+                                             _stream_ptr(dev)), "attention_rollout")
+    return out

@@ -370,8 +370,9 @@ class Gaussian2DReadout(Readout):
 
     @property
     def mu(self):
-        if self._predicted_grid:
-            return self.mu_transform(self.source_grid.squeeze()).view(*self.grid_shape)
+        if self._predicted_grid:  # Linear-ELU-Linear-Tanh over the neurons: one kernel each way (gaussian2d.py:188-193)
+            mt = self.mu_transform
+            return VF.small_mlp(self.source_grid, (mt[0], mt[2]), ("elu", "tanh")).view(*self.grid_shape)
         return self._mu
 
     def forward(self, inputs: torch.Tensor, sample: bool = None, shifts: torch.Tensor = None,
@@ -453,7 +454,7 @@ def get_criterion(args, ds):
 
 
 # ------------------------------------------------------------------------------------------------------
-# callers either side of the path (kept in torch: tiny, SURVEY §2 "next" rows n3)
+# callers either side of the path: shifters and cropper, native through functional.small_mlp / crop_resize
 # ------------------------------------------------------------------------------------------------------
 class CoreShifter(nn.Module):
     def __init__(self, args, in_features: int, hidden_features: int, num_layers: int, name: str = "CoreShifter"):
@@ -470,8 +471,9 @@ class CoreShifter(nn.Module):
     def regularizer(self):
         return self.reg_scale * sum(p.abs().sum() for p in self.parameters())
 
-    def forward(self, pupil_center):
-        return self.mlp(pupil_center)
+    def forward(self, pupil_center):  # Linear-Tanh stack (core_shifter.py:38-39): one kernel each way
+        linears = [m for m in self.mlp if isinstance(m, nn.Linear)]
+        return VF.small_mlp(pupil_center, linears, ("tanh",) * len(linears))
 
 
 class CoreShifters(nn.ModuleDict):
@@ -487,24 +489,63 @@ class CoreShifters(nn.ModuleDict):
         return self[mouse_id](pupil_centers)
 
 
+class ImageShifter(nn.Module):
+    """image_cropper.py:10-48: Linear-Tanh stack on the pupil centre (+ behaviours for shift_mode 4), scaled by
+    max_shift."""
+
+    def __init__(self, args, max_shift: float, hidden_features: int = 10, num_layers: int = 1,
+                 name: str = "ImageShifter"):
+        super().__init__()
+        assert 0 <= max_shift <= 1
+        self.name = name
+        self.shift_mode = args.shift_mode
+        self.register_buffer("max_shift", torch.tensor(max_shift))
+        self.register_buffer("reg_scale", torch.tensor(args.cropper_reg_scale))
+        layers, width = [], 5 if self.shift_mode == 4 else 2
+        for _ in range(num_layers - 1):
+            layers += [nn.Linear(width, hidden_features), nn.Tanh()]
+            width = hidden_features
+        layers += [nn.Linear(width, 2), nn.Tanh()]
+        self.mlp = nn.Sequential(*layers)
+
+    def regularizer(self):
+        return self.reg_scale * sum(p.abs().sum() for p in self.parameters())
+
+    def forward(self, behaviors, pupil_centers):
+        inputs = pupil_centers
+        if self.shift_mode == 4:
+            inputs = torch.cat((behaviors, pupil_centers), dim=-1)
+        linears = [m for m in self.mlp if isinstance(m, nn.Linear)]
+        return VF.small_mlp(inputs, linears, ("tanh",) * len(linears)) * self.max_shift
+
+
 class ImageCropper(nn.Module):
-    """Identity crop (+ optional 36x64 bilinear resize) — the step before the hot path (image_cropper.py:51-140).
-    Only ``center_crop == 1`` and shift_mode in (0, 2) are supported here; it keeps the ``grid`` buffer so that
-    reference checkpoints load strictly."""
+    """The step before the hot path (image_cropper.py:51-140), all shift modes and crop scales: the crop (nearest
+    sampling on the shifted grid), the 36x64 bilinear resize and the behaviour planes are one gather kernel
+    (csrc/cropper.cu).  Same buffers / sub-module names as the reference so checkpoints load strictly."""
 
     def __init__(self, args, ds):
         super().__init__()
-        if args.center_crop != 1 or args.shift_mode not in (0, 2):
-            raise NotImplementedError("v1t_b200.ImageCropper: only center_crop=1 and shift_mode in (0,2)")
         self.shift_mode, self.input_shape, self.behavior_mode = args.shift_mode, args.input_shape, args.behavior_mode
         c, in_h, in_w = args.input_shape
+        out_h, out_w = in_h, in_w
         if self.behavior_mode == 1:
             c += 3
-        ys, xs = torch.linspace(-1, 1, in_h), torch.linspace(-1, 1, in_w)
+        self.crop_scale = args.center_crop
+        self.crop_h, self.crop_w = in_h, in_w
+        if self.crop_scale < 1:
+            out_h = self.crop_h = int(in_h * self.crop_scale)
+            out_w = self.crop_w = int(in_w * self.crop_scale)
+        ys = torch.linspace(-self.crop_scale, self.crop_scale, self.crop_h)
+        xs = torch.linspace(-self.crop_scale, self.crop_scale, self.crop_w)
         my, mx = torch.meshgrid(ys, xs, indexing="ij")
-        self.register_buffer("grid", torch.stack((mx, my), dim=2).unsqueeze(0))
-        self.image_shifter = None
-        out_h, out_w = in_h, in_w
+        self.register_buffer("grid", torch.stack((mx, my), dim=2).unsqueeze(0))  # (x, y), image_cropper.py:104-112
+        if self.shift_mode in (1, 3, 4):
+            self.add_module("image_shifter", nn.ModuleDict({
+                m: ImageShifter(args, max_shift=1 - self.crop_scale, num_layers=3, name=f"Mouse{m}ImageShifter")
+                for m in list(ds.keys())}))
+        else:
+            self.image_shifter = None
         self.resize = None
         if getattr(args, "resize_image", 0) == 1 and getattr(args, "ds_name", "") != "franke2022":
             out_h, out_w = 36, 64
@@ -512,16 +553,18 @@ class ImageCropper(nn.Module):
         self.output_shape = (c, out_h, out_w)
 
     def regularizer(self, mouse_id: str):
-        return 0
+        return 0 if self.image_shifter is None else self.image_shifter[mouse_id].regularizer()
 
     def forward(self, inputs, mouse_id, behaviors, pupil_centers):
         grid = self.grid.expand(inputs.size(0), -1, -1, -1)
-        outputs = inputs  # nearest sampling on the identity grid
-        if self.resize is not None:
-            outputs = torch.nn.functional.interpolate(outputs, size=self.resize, mode="bilinear", align_corners=False)
-        if self.behavior_mode == 1:
-            h, w = outputs.shape[2:]
-            outputs = torch.cat((outputs, behaviors[:, :, None, None].expand(-1, -1, h, w)), dim=1)
+        shifts = None
+        if self.image_shifter is not None:
+            shifts = self.image_shifter[mouse_id](behaviors=behaviors, pupil_centers=pupil_centers)
+            grid = grid + shifts[:, None, None, :]
+        if shifts is None and self.resize is None and self.behavior_mode != 1 and self.crop_scale == 1:
+            return inputs, grid  # nearest sampling on the identity grid returns the image itself
+        outputs = VF.crop_resize(inputs, self.grid, None if shifts is None else shifts.detach(),
+                                 self.output_shape[1:], behaviors if self.behavior_mode == 1 else None)
         return outputs, grid
 
 
@@ -552,6 +595,8 @@ class Model(nn.Module):
         if not self.core.frozen:
             params.append({"params": self.core.parameters(), "lr": core_lr, "name": "core"})
         params.append({"params": self.readouts.parameters(), "name": "readouts"})
+        if self.image_cropper.image_shifter is not None:
+            params.append({"params": self.image_cropper.parameters(), "name": "image_cropper"})
         if self.core_shifter is not None:
             params.append({"params": self.core_shifter.parameters(), "name": "core_shifter"})
         return params
@@ -561,6 +606,7 @@ class Model(nn.Module):
         if not self.core.frozen:
             reg = reg + self.core.regularizer()
         reg = reg + self.readouts.regularizer(mouse_id=mouse_id)
+        reg = reg + self.image_cropper.regularizer(mouse_id=mouse_id)
         if self.core_shifter is not None:
             reg = reg + self.core_shifter.regularizer(mouse_id=mouse_id)
         return reg
