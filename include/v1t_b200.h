@@ -260,6 +260,21 @@ size_t v1t_rollout_scratch_bytes(int B, int T);
 int v1t_attention_rollout(const float* attn, int B, int L, int H, int T, int gh, int gw, int out_h, int out_w,
                           float* heatmaps, void* scratch, void* stream);
 
+/* n4: ensemble output module (ensemble.py:30-80 OutputModule, :131-151 EnsembleModel.forward): the K members'
+ * pre-activation responses x_k [n = B*N each] -> y = elu(sum_k weight[k] x_k + bias) + 1, or with weight == NULL
+ * the mean over members (ensemble_mode 0); the [B,N,K] stack the reference concatenates is never built.  Backward
+ * (modes 1/2, the only trained parameters of fit_ensemble): d_weight [K], d_bias [1] from dy. */
+#define V1T_ENSEMBLE_MAX 16
+typedef struct v1t_ensemble_members {
+  const float* x[V1T_ENSEMBLE_MAX];
+  int32_t count;
+} v1t_ensemble_members;
+size_t v1t_ensemble_scratch_bytes(int64_t n, int count);
+int v1t_ensemble_forward(const v1t_ensemble_members* members, const float* weight, const float* bias, int64_t n,
+                         float* y, void* stream);
+int v1t_ensemble_backward(const v1t_ensemble_members* members, const float* weight, const float* bias,
+                          const float* dy, int64_t n, float* d_weight, float* d_bias, void* scratch, void* stream);
+
 /* ---- building blocks, exported for unit tests -------------------------------------------------------- */
 /* C[b][m,n] = alpha * sum_k A[b][m,k] * B[b][k,n] (+ bias[n]) (+ R[b][m,n]); arbitrary element strides */
 typedef struct v1t_gemm_desc {

@@ -176,3 +176,26 @@ def attention_rollout(attention, image_shape):
 def attention_rollouts(attentions, image_shape):
     """attention_rollout.py:124-133."""
     return np.stack([attention_rollout(a, image_shape) for a in attentions])
+
+
+# ---------------------------------------------------------------------------------------------------
+# n4: ensemble output module (ensemble.py:30-80 OutputModule, :131-151 EnsembleModel.forward)
+# ---------------------------------------------------------------------------------------------------
+def ensemble_combine(members, weight=None, bias=None):
+    """members [K,B,N] pre-activation responses; weight [1,K] / bias [1] of nn.Linear(K,1), or None = mean
+    (ensemble_mode 0).  Returns (y = elu(z) + 1, z)."""
+    x = np.asarray(members, dtype=np.float64)
+    if weight is None:
+        z = x.mean(axis=0)
+    else:
+        z = np.tensordot(np.asarray(weight, dtype=np.float64).reshape(-1), x, axes=(0, 0))
+        if bias is not None:
+            z = z + float(np.asarray(bias).reshape(-1)[0])
+    return np.where(z > 0, z, np.expm1(np.minimum(z, 0))) + 1.0, z
+
+
+def ensemble_backward(members, z, dy):
+    """Gradients of the Linear output module: (d_weight [1,K], d_bias [1])."""
+    x = np.asarray(members, dtype=np.float64)
+    dz = np.asarray(dy, dtype=np.float64) * np.where(z > 0, 1.0, np.exp(np.minimum(z, 0)))
+    return np.tensordot(x, dz, axes=([1, 2], [0, 1]))[None, :], np.array([dz.sum()])

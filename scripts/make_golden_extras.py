@@ -9,6 +9,7 @@ Holds, for the callers either side of the hot path:
               output images and grids, for crop scales / shift modes / resize / behaviour planes
   opt/*       torch.optim.AdamW(weight_decay=0) driven the way the reference drives it (train.py:71-80,217-223):
               data gradients + autograd of reg_scale * |p|.sum(), three steps, parameters and moments after each
+  ens<k>/*    the ensemble OutputModule's arithmetic (ensemble.py:68-80): mean / Linear over the member stack + ELU1
   mlp<k>/*    nn.Sequential Linear/ELU/Tanh stacks (gaussian2d.py:102-136, core_shifter.py:24-40): output and
               autograd weight gradients
 """
@@ -148,6 +149,34 @@ def mlp_cases(out):
             out[f"mlp{k}/gb{i}"] = m.bias.grad.numpy()
 
 
+def ensemble_cases(out):
+    """OutputModule arithmetic (ensemble.py:68-80) restated with the same torch ops: mean(dim=-1) | nn.Linear(K, 1)
+    on the [B,N,K] stack, then ELU + 1; gradients of the Linear by autograd."""
+    g = torch.Generator().manual_seed(23)
+    for k, (B, N, K, linear) in {"0": (3, 41, 5, False), "1": (2, 1000, 5, True), "2": (4, 17, 1, True)}.items():
+        xs = [torch.randn((B, N), generator=g) * 1.5 for _ in range(K)]
+        stack = torch.cat([x[..., None] for x in xs], dim=-1)
+        if linear:
+            lin = nn.Linear(K, 1)
+            with torch.no_grad():
+                lin.weight.copy_(torch.randn(lin.weight.shape, generator=g) * 0.5)
+                lin.bias.copy_(torch.randn(lin.bias.shape, generator=g) * 0.2)
+            z = lin(stack)[..., 0]
+        else:
+            z = torch.mean(stack, dim=-1)
+        y = torch.nn.functional.elu(z) + 1
+        out[f"ens{k}/x"] = torch.stack(xs).numpy()
+        out[f"ens{k}/y"] = y.detach().numpy()
+        if linear:
+            dy = torch.randn(y.shape, generator=g)
+            (y * dy).sum().backward()
+            out[f"ens{k}/dy"] = dy.numpy()
+            out[f"ens{k}/w"] = lin.weight.detach().numpy()
+            out[f"ens{k}/b"] = lin.bias.detach().numpy()
+            out[f"ens{k}/gw"] = lin.weight.grad.numpy()
+            out[f"ens{k}/gb"] = lin.bias.grad.numpy()
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     out = {}
@@ -155,5 +184,6 @@ if __name__ == "__main__":
     cropper_cases(out)
     optimizer_case(out)
     mlp_cases(out)
+    ensemble_cases(out)
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT} ({os.path.getsize(OUT) / 1e6:.2f} MB, {len(out)} arrays)")

@@ -127,3 +127,31 @@ def test_dropin_install_overwrites_reference_registries():
     finally:
         (ref_core._CORES["vit"], ref_readout._READOUTS["gaussian2d"], ref_losses._CRITERION["poisson"],
          ref_model.ELU1, ref_model.get_model_info) = keep
+
+
+def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):
+    """sizeof / field offsets of every struct in include/v1t_b200.h, from a C program, against the ctypes mirrors."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"v1t_core_shape": _lib.CoreShape, "v1t_core_dims": _lib.CoreDims, "v1t_block_ptrs": _lib.BlockPtrs,
+             "v1t_core_ptrs": _lib.CorePtrs, "v1t_readout_shape": _lib.ReadoutShape, "v1t_gemm_desc": _lib.GemmDesc,
+             "v1t_opt_tensor": _lib.OptTensor, "v1t_mlp_spec": _lib.MlpSpec, "v1t_mlp_ptrs": _lib.MlpPtrs,
+             "v1t_crop_shape": _lib.CropShape, "v1t_ensemble_members": _lib.EnsembleMembers}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/v1t_b200.h"', "int main(void){"]
+    for cname, ct in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0;}")
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"

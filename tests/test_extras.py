@@ -16,6 +16,7 @@ Z = np.load(os.path.join(GOLDEN_DIR, "extras.npz"))
 ROLLOUT_CASES = sorted({k.split("/")[1] for k in Z.files if k.startswith("rollout/")})
 CROP_CASES = sorted({k.split("/")[0][4:] for k in Z.files if k.startswith("crop")})
 MLP_CASES = sorted({k.split("/")[0][3:] for k in Z.files if k.startswith("mlp")})
+ENS_CASES = sorted({k.split("/")[0][3:] for k in Z.files if k.startswith("ens")})
 N_OPT = len([k for k in Z.files if k.startswith("opt/p0/")])
 
 TOL_F32 = 2e-6   # fp32 kernels against fp64 oracle / fp32 torch, max|d| / max|ref|
@@ -102,6 +103,17 @@ def test_oracle_small_mlp_matches_torch(k):
     for i in range(len(w)):
         assert rel_err(gw[i], Z[f"mlp{k}/gw{i}"]) < 1e-5
         assert rel_err(gb[i], Z[f"mlp{k}/gb{i}"]) < 1e-5
+
+
+@pytest.mark.parametrize("k", ENS_CASES)
+def test_oracle_ensemble_matches_torch(k):
+    x = Z[f"ens{k}/x"]
+    linear = f"ens{k}/w" in Z.files
+    y, z = XO.ensemble_combine(x, Z[f"ens{k}/w"] if linear else None, Z[f"ens{k}/b"] if linear else None)
+    assert rel_err(y, Z[f"ens{k}/y"]) < 1e-6
+    if linear:
+        gw, gb = XO.ensemble_backward(x, z, Z[f"ens{k}/dy"])
+        assert rel_err(gw, Z[f"ens{k}/gw"]) < 1e-5 and rel_err(gb, Z[f"ens{k}/gb"]) < 1e-5
 
 
 def test_optimizer_refuses_cpu_parameters():
@@ -301,3 +313,21 @@ def test_fused_adamw_steps_regularised_parameter_without_gradient():
                                  0.999, 1e-8, l1=0.3)
     assert rel_err(p.detach().cpu().numpy(), ref) < TOL_F32
     assert torch.equal(q.detach(), torch.ones(3, device="cuda")) and len(opt.state[q]) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", ENS_CASES)
+def test_ensemble_output_module_matches_torch(k):
+    from v1t_b200 import functional as VF
+
+    x = [cu(a) for a in Z[f"ens{k}/x"]]
+    if f"ens{k}/w" not in Z.files:
+        y = VF.ensemble_combine(x)
+        assert rel_err(y.cpu().numpy(), Z[f"ens{k}/y"]) < TOL_F32
+        return
+    w, b = cu(Z[f"ens{k}/w"]).requires_grad_(True), cu(Z[f"ens{k}/b"]).requires_grad_(True)
+    y = VF.ensemble_combine(x, w, b)
+    assert rel_err(y.detach().cpu().numpy(), Z[f"ens{k}/y"]) < TOL_F32
+    (y * cu(Z[f"ens{k}/dy"])).sum().backward()
+    assert rel_err(w.grad.cpu().numpy(), Z[f"ens{k}/gw"]) < 1e-5
+    assert rel_err(b.grad.cpu().numpy(), Z[f"ens{k}/gb"]) < 1e-5

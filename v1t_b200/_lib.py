@@ -81,6 +81,13 @@ class CropShape(C.Structure):
                                          "behavior_planes")]
 
 
+ENSEMBLE_MAX = 16
+
+
+class EnsembleMembers(C.Structure):
+    _fields_ = [("x", C.c_void_p * ENSEMBLE_MAX), ("count", C.c_int32)]
+
+
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libv1t_b200.so")
 
 # every symbol include/v1t_b200.h declares: (restype, argtypes)
@@ -134,6 +141,9 @@ SYMBOLS = {
     "v1t_small_mlp_backward": (C.c_int, [C.POINTER(MlpSpec), C.POINTER(MlpPtrs), _vp, _vp, C.POINTER(MlpPtrs), _vp,
                                          _vp]),
     "v1t_crop_resize": (C.c_int, [C.POINTER(CropShape), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "v1t_ensemble_scratch_bytes": (C.c_size_t, [_i64, C.c_int]),
+    "v1t_ensemble_forward": (C.c_int, [C.POINTER(EnsembleMembers), _vp, _vp, _i64, _vp, _vp]),
+    "v1t_ensemble_backward": (C.c_int, [C.POINTER(EnsembleMembers), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "v1t_rollout_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "v1t_attention_rollout": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         _vp, _vp, _vp]),

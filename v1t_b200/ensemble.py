@@ -1,0 +1,67 @@
+"""Ensemble inference — mirror of ensemble.py:30-151 (OutputModule, EnsembleModel).
+
+The members are ordinary ``v1t_b200.Model`` instances (frozen, ensemble.py:106) run back to back through the native
+path on the same inputs with ``activate=False``; the output module (mean / shared Linear / per-mouse Linear, then
+ELU+1) is one fused kernel over the K response tensors (csrc/ensemble.cu) instead of rearrange + cat + mean/Linear +
+ELU1 over a materialised [B,N,K] stack.  State-dict keys match the reference (``ensemble.<name>.…``,
+``output_module.linear.…``)."""
+from __future__ import annotations
+
+import typing as t
+
+import torch
+from torch import nn
+
+from . import functional as VF
+from .modules import ELU1, Model
+
+
+class OutputModule(nn.Module):
+    """ensemble.py:30-80.  ensemble_mode 0: mean; 1: one Linear(K,1); 2: one Linear(K,1) per mouse."""
+
+    def __init__(self, args, in_features: int):
+        super().__init__()
+        self.in_features = in_features
+        self.output_shapes = args.output_shapes
+        self.ensemble_mode = args.ensemble_mode
+        assert self.ensemble_mode in (0, 1, 2)
+        if self.ensemble_mode == 1:
+            self.linear = nn.Linear(in_features, 1)
+        elif self.ensemble_mode == 2:
+            self.linear = nn.ModuleDict({m: nn.Linear(in_features, 1) for m in self.output_shapes.keys()})
+        self.activation = ELU1()
+        for m in self.modules():
+            if isinstance(m, nn.Linear):  # ensemble.py:57-66
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, members: t.Sequence[torch.Tensor], mouse_id: str):
+        """members: the K pre-activation responses [B,N] (the reference passes them concatenated as [B,N,K])."""
+        if self.ensemble_mode == 0:
+            return VF.ensemble_combine(members)
+        lin = self.linear if self.ensemble_mode == 1 else self.linear[mouse_id]
+        return VF.ensemble_combine(members, lin.weight, lin.bias)
+
+
+class EnsembleModel(nn.Module):
+    """ensemble.py:83-151 with the members passed in (checkpoint discovery / args.yaml parsing stay with the
+    caller: ``members`` maps the reference's model names to constructed-and-loaded Models)."""
+
+    def __init__(self, args, members: t.Dict[str, Model]):
+        super().__init__()
+        self.input_shape = args.input_shape
+        self.output_shapes = args.output_shapes
+        self.ensemble = nn.ModuleDict(members)
+        self.ensemble.requires_grad_(False)
+        self.output_module = OutputModule(args, in_features=len(members))
+
+    def regularizer(self, mouse_id: str):
+        return torch.tensor(0.0)
+
+    def forward(self, inputs, mouse_id: str, behaviors, pupil_centers):
+        outs = []
+        for name in self.ensemble.keys():
+            y, _, _ = self.ensemble[name](inputs, mouse_id=mouse_id, behaviors=behaviors,
+                                          pupil_centers=pupil_centers, activate=False)
+            outs.append(y)
+        return self.output_module(outs, mouse_id=mouse_id), None, None

@@ -483,3 +483,63 @@ def attention_rollouts(attentions: torch.Tensor, image_shape, grid_hw) -> torch.
                                              out.shape[1], out.shape[2], out.data_ptr(), scratch.data_ptr(),
                                              _stream_ptr(dev)), "attention_rollout")
     return out
+
+
+class _EnsembleFunction(torch.autograd.Function):
+    """y = elu(sum_k w[k] x_k + b) + 1, or elu(mean_k x_k) + 1 when w is None (ensemble.py:30-80,131-151)."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, *members):
+        lib = _lib.load()
+        _need_cuda(weight, bias, *members)
+        if not 1 <= len(members) <= _lib.ENSEMBLE_MAX:
+            raise NotImplementedError(f"ensemble: {len(members)} members outside 1..{_lib.ENSEMBLE_MAX}")
+        members = [_f32c(m) for m in members]
+        if any(m.shape != members[0].shape for m in members):
+            raise RuntimeError("ensemble: members disagree on the output shape")
+        weight, bias = _f32c(weight), _f32c(bias)
+        if weight is not None and weight.numel() != len(members):
+            raise RuntimeError(f"ensemble: weight has {weight.numel()} entries for {len(members)} members")
+        tab = _lib.EnsembleMembers(count=len(members))
+        for k, m in enumerate(members):
+            tab.x[k] = m.data_ptr()
+        y = torch.empty_like(members[0])
+        dev = y.device
+        with torch.cuda.device(dev):
+            _lib.check(lib.v1t_ensemble_forward(C.byref(tab), _ptr(weight), _ptr(bias), y.numel(), y.data_ptr(),
+                                                _stream_ptr(dev)), "ensemble_forward")
+        ctx.has = (weight is not None, bias is not None)
+        ctx.save_for_backward(*[t for t in (weight, bias) if t is not None], *members)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        sv = list(ctx.saved_tensors)
+        weight = sv.pop(0) if ctx.has[0] else None
+        bias = sv.pop(0) if ctx.has[1] else None
+        members = sv
+        if any(ctx.needs_input_grad[2:]):
+            raise NotImplementedError("ensemble: the members are frozen (ensemble.py:106); no gradient flows into them")
+        if weight is None:
+            return (None, None) + (None,) * len(members)
+        tab = _lib.EnsembleMembers(count=len(members))
+        for k, m in enumerate(members):
+            tab.x[k] = m.data_ptr()
+        dev = dy.device
+        dy = _f32c(dy)
+        dw = torch.empty_like(weight)
+        db = torch.empty_like(bias) if bias is not None else None
+        scratch = _scratch(dev, lib.v1t_ensemble_scratch_bytes(dy.numel(), len(members)))
+        with torch.cuda.device(dev):
+            _lib.check(lib.v1t_ensemble_backward(C.byref(tab), weight.data_ptr(), _ptr(bias), dy.data_ptr(), dy.numel(),
+                                                 dw.data_ptr(), _ptr(db), scratch.data_ptr(), _stream_ptr(dev)),
+                       "ensemble_backward")
+        return (dw, db) + (None,) * len(members)
+
+
+def ensemble_combine(members: Sequence[torch.Tensor], weight: Optional[torch.Tensor] = None,
+                     bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """members: K pre-activation responses [B,N]; weight [1,K] / bias [1] of the nn.Linear(K,1) output module, or
+    None for the mean (ensemble_mode 0).  Returns the activated ensemble response [B,N]."""
+    return _EnsembleFunction.apply(weight, bias, *members)
