@@ -331,3 +331,26 @@ def test_ensemble_output_module_matches_torch(k):
     (y * cu(Z[f"ens{k}/dy"])).sum().backward()
     assert rel_err(w.grad.cpu().numpy(), Z[f"ens{k}/gw"]) < 1e-5
     assert rel_err(b.grad.cpu().numpy(), Z[f"ens{k}/gb"]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_fused_adamw_unaligned_parameter_takes_the_scalar_path():
+    """A parameter that is a 4-byte-aligned view of a flat buffer (not 16-byte aligned) must give the same update."""
+    from v1t_b200.optim import FusedAdamWL1
+
+    rng = np.random.default_rng(0)
+    n = 4099 + 37
+    p0, g0 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    flat, gflat = torch.zeros(n + 1, device="cuda"), torch.zeros(n + 3, device="cuda")
+    p = torch.nn.Parameter(flat[1:])
+    with torch.no_grad():
+        p.copy_(cu(p0))
+    p.grad = gflat[3:]
+    p.grad.copy_(cu(g0))
+    assert p.data_ptr() % 16 != 0
+    opt = FusedAdamWL1([p], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, l1={p: 0.05})
+    opt.step(grad_scale=0.5)
+    want, m, v = XO.adamw_l1_step(p0, g0, np.zeros(n), np.zeros(n), 1, 1e-2, 0.9, 0.999, 1e-8, l1=0.05,
+                                  weight_decay=0.1, grad_scale=0.5)
+    assert rel_err(p.detach().cpu().numpy(), want) < TOL_F32
+    assert rel_err(opt.state[p]["exp_avg"].cpu().numpy(), m) < TOL_F32
