@@ -191,7 +191,8 @@ int v1t_poisson_backward(const float* y_pred, const float* y_true, int64_t n, fl
  *   v = beta2 v + (1 - beta2) g g;  p -= lr / bias_corr1 * m / (sqrt(v) / bias_corr2_sqrt + eps)
  * tensors_dev: DEVICE array of n_tensors records; chunk_prefix_dev: DEVICE int32 [n_tensors + 1], prefix sums of
  * ceil(numel / v1t_opt_chunk_elems()); n_chunks = chunk_prefix[n_tensors].  bias_corr1 = 1 - beta1^t,
- * bias_corr2_sqrt = sqrt(1 - beta2^t) for the step count t the caller keeps.  zero_grad != 0 clears the gradients in
+ * bias_corr2_sqrt = sqrt(1 - beta2^t) for the step count t the caller keeps; the hyper-parameters are doubles so that
+ * 1 - beta is formed in double precision as torch does (1 - float(0.9999) is off by 1.7e-4 relative).  zero_grad != 0 clears the gradients in
  * the same pass.  l1_sums_dev (optional, [n_groups]) receives sum |p| per group BEFORE the update (what the
  * reference logs as reg_loss / reg_scale); needs scratch of v1t_adamw_l1_scratch_bytes(n_chunks). */
 typedef struct v1t_opt_tensor {
@@ -208,8 +209,9 @@ typedef struct v1t_opt_tensor {
 int v1t_opt_chunk_elems(void);
 size_t v1t_adamw_l1_scratch_bytes(int n_chunks);
 int v1t_adamw_l1_step(const v1t_opt_tensor* tensors_dev, const int32_t* chunk_prefix_dev, int n_tensors, int n_chunks,
-                      float beta1, float beta2, float eps, float bias_corr1, float bias_corr2_sqrt, float grad_scale,
-                      int zero_grad, float* l1_sums_dev, int n_groups, void* scratch, void* stream);
+                      double beta1, double beta2, double eps, double bias_corr1, double bias_corr2_sqrt,
+                      double grad_scale, int zero_grad, float* l1_sums_dev, int n_groups, void* scratch,
+                      void* stream);
 
 /* a11 / n3: the small MLPs either side of the readout as one kernel per direction: the readout's grid predictor
  * Linear-ELU-Linear-Tanh over the neurons (gaussian2d.py:102-136,188-193) and the core / image shifters'

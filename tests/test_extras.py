@@ -185,7 +185,7 @@ def test_cropper_module_matches_reference(k):
     assert tuple(crop.output_shape) == tuple(meta["output_shape"])
     out, grid = crop(cu(Z[f"crop{k}/images"]), mouse_id="A", behaviors=cu(Z[f"crop{k}/behaviors"]),
                      pupil_centers=cu(Z[f"crop{k}/pupil_centers"]))
-    assert rel_err(grid.cpu().numpy(), Z[f"crop{k}/grid"]) < TOL_F32
+    assert rel_err(grid.detach().cpu().numpy(), Z[f"crop{k}/grid"]) < TOL_F32
     ref = Z[f"crop{k}/out"]
     assert out.shape == ref.shape
     got = out.cpu().numpy()
@@ -260,7 +260,7 @@ def test_fused_adamw_l1_matches_torch_adamw():
         for i, p in enumerate(params):
             assert rel_err(p.detach().cpu().numpy(), Z[f"opt/p{step}/{i}"]) < TOL_F32, (step, i)
             assert rel_err(opt.state[p]["exp_avg"].cpu().numpy(), Z[f"opt/m{step}/{i}"]) < TOL_F32
-            assert rel_err(opt.state[p]["exp_avg_sq"].cpu().numpy(), Z[f"opt/v{step}/{i}"]) < 1e-5
+            assert rel_err(opt.state[p]["exp_avg_sq"].cpu().numpy(), Z[f"opt/v{step}/{i}"]) < TOL_F32
             assert float(opt.state[p]["step"]) == step
             if step == 2:
                 assert float(p.grad.abs().max()) == 0.0

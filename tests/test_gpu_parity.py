@@ -603,3 +603,58 @@ def test_ts_mma_tensor_memory_operand(N, K):
     torch.cuda.synchronize()
     ref = A.bfloat16().double() @ Bm.bfloat16().double().T
     assert rel_err(Cm.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+def test_fused_gradient_accumulation_equals_autograd_accumulation():
+    """Two mice through the shared core (per-mouse behaviour MLPs, behavior_mode 4): gradients accumulated by the
+    flat sink (one add per backward) equal autograd's per-parameter accumulation, and the summed golden gradients."""
+    from v1t_b200 import parallel
+
+    g = Golden("color_mode4")
+    model, crit = build(g, b200_impl="fp32")
+    model.train(True)
+    batches = {m: {"image": cu(d["images"]), "behavior": cu(d["behaviors"]), "pupil_center": cu(d["pupil_centers"]),
+                   "response": cu(d["y_true"])} for m, d in g.mice.items()}
+    noises = {m: cu(d["noise"]) for m, d in g.mice.items()}
+    gb = {m: d["images"].shape[0] for m, d in g.mice.items()}
+
+    def run(fused):
+        model.zero_grad(set_to_none=True)
+        if fused:
+            model.core.fused_grad_accumulation(True)
+        for m, b in batches.items():
+            y, _, _ = model(b["image"], mouse_id=m, behaviors=b["behavior"], pupil_centers=b["pupil_center"],
+                            noise=noises[m])
+            crit(y_true=b["response"], y_pred=y, mouse_id=m, batch_size=gb[m]).backward()
+        if fused:
+            model.core.fused_grad_accumulation(False)
+        return {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    plain = run(False)
+    fused = run(True)
+    assert set(plain) == set(fused)
+    for k in plain:
+        assert rel_err(fused[k].cpu().numpy(), plain[k].cpu().numpy()) < 1e-6, k
+    want = {}
+    for d in g.mice.values():
+        for k, v in d["grads"].items():
+            want[k] = want.get(k, 0) + v
+    for k, ref in want.items():
+        if np.abs(ref).max() > 0:
+            assert rel_err(fused[k].cpu().numpy(), ref) < TOL_GRAD, k
+    # a second armed sweep starting from existing gradients accumulates on top of them
+    model.core.fused_grad_accumulation(True)
+    core_p = next(model.core.parameters())
+    assert core_p.grad.data_ptr() == model.core.grad_sink.view_of(core_p, model.core.grad_sink.flat).data_ptr()
+    before = core_p.grad.clone()
+    m0 = next(iter(batches))
+    y, _, _ = model(batches[m0]["image"], mouse_id=m0, behaviors=batches[m0]["behavior"],
+                    pupil_centers=batches[m0]["pupil_center"], noise=noises[m0])
+    crit(y_true=batches[m0]["response"], y_pred=y, mouse_id=m0, batch_size=gb[m0]).backward()
+    model.core.fused_grad_accumulation(False)
+    assert not torch.equal(core_p.grad, before)
+    # sweep() with the flag is the same thing
+    model.zero_grad(set_to_none=True)
+    torch.manual_seed(0)
+    parallel.sweep(model, crit, batches, gb, None, fused_accumulate=True)
+    assert all(p.grad is not None for p in model.core.parameters())

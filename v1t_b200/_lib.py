@@ -134,8 +134,8 @@ SYMBOLS = {
     "v1t_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint32, _f, _vp]),
     "v1t_opt_chunk_elems": (C.c_int, []),
     "v1t_adamw_l1_scratch_bytes": (C.c_size_t, [C.c_int]),
-    "v1t_adamw_l1_step": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f, _f, _f, _f, _f, _f, C.c_int, _vp, C.c_int, _vp,
-                                    _vp]),
+    "v1t_adamw_l1_step": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, C.c_double, C.c_int, _vp, C.c_int, _vp, _vp]),
     "v1t_small_mlp_scratch_bytes": (C.c_size_t, [C.POINTER(MlpSpec)]),
     "v1t_small_mlp_forward": (C.c_int, [C.POINTER(MlpSpec), C.POINTER(MlpPtrs), _vp, _vp, _vp]),
     "v1t_small_mlp_backward": (C.c_int, [C.POINTER(MlpSpec), C.POINTER(MlpPtrs), _vp, _vp, C.POINTER(MlpPtrs), _vp,

@@ -395,23 +395,28 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
 }
 
 // dgamma[c] = sum_p partials[p][0][c], dbeta[c] = sum_p partials[p][1][c].  lane = column (coalesced rows of the
-// partials), the 8 warps of a block take every 8th partial, fixed-order smem reduction (deterministic).
+// partials), the 32 warps of a block take every 32nd partial (888 partials: 28 independent loads per lane instead of
+// 111 -- the kernel is pure load latency), fixed-order smem reduction (deterministic).
 // grid (ceil(E/32), 2): blockIdx.y = 0 -> dgamma, 1 -> dbeta
-__global__ void __launch_bounds__(256) ln_finish_kernel(const float* __restrict__ partials, float* __restrict__ dgamma,
-                                                        float* __restrict__ dbeta, int parts, int E) {
-  __shared__ float red[8][33];
+constexpr int kLnFinishWarps = 32;
+__global__ void __launch_bounds__(kLnFinishWarps * 32) ln_finish_kernel(const float* __restrict__ partials,
+                                                                        float* __restrict__ dgamma,
+                                                                        float* __restrict__ dbeta, int parts, int E) {
+  __shared__ float red[kLnFinishWarps][33];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const int which = blockIdx.y;
   float s = 0.f;
-  if (c < E)
-    for (int p = wid; p < parts; p += 8) s += partials[((int64_t)p * 2 + which) * E + c];
+  if (c < E) {
+#pragma unroll 4
+    for (int p = wid; p < parts; p += kLnFinishWarps) s += partials[((int64_t)p * 2 + which) * E + c];
+  }
   red[wid][lane] = s;
   __syncthreads();
   if (wid == 0 && c < E) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    for (int w = 0; w < kLnFinishWarps; ++w) t += red[w][lane];
     float* out = which == 0 ? dgamma : dbeta;
     if (out) out[c] = t;
   }
@@ -691,7 +696,7 @@ int ln_backward(const float* dh, const float* x, const float* stats, const float
   V1T_LN_DISPATCH(8, ln_backward_kernel, dh, x, stats, gamma, dx_accum, partials, rows, E, ld)
   { ln_backward_kernel<16><<<grid, 256, 0, st>>>(dh, x, stats, gamma, dx_accum, partials, rows, E, ld); }
   V1T_LAUNCH_CHECK();
-  ln_finish_kernel<<<dim3(cdiv(E, 32), 2), 256, 0, st>>>(partials, dgamma, dbeta, grid, E);
+  ln_finish_kernel<<<dim3(cdiv(E, 32), 2), kLnFinishWarps * 32, 0, st>>>(partials, dgamma, dbeta, grid, E);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

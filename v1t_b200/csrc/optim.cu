@@ -22,8 +22,8 @@ namespace {
 constexpr int kChunk = 4096;  // elements per CTA
 constexpr int kThreads = 256;
 
-struct AdamConsts {
-  float beta1, beta2, eps, inv_bc1, inv_bc2_sqrt, grad_scale;
+struct AdamConsts {  // derived on the host in double precision, like torch derives 1 - beta from Python floats
+  float one_minus_beta1, beta2, one_minus_beta2, eps, inv_bc1, inv_bc2_sqrt, grad_scale;
   int zero_grad;
 };
 
@@ -34,15 +34,16 @@ __device__ __forceinline__ void adam_one(float& p, float g_raw, float& m, float&
   abs_sum += fabsf(p);
   const float g = fmaf(g_raw, k.grad_scale, t.l1 * signf(p));
   float pw = p * (1.f - t.lr * t.weight_decay);
-  m = fmaf(g - m, 1.f - k.beta1, m);
-  v = fmaf(v, k.beta2, (1.f - k.beta2) * g * g);
+  m = fmaf(g - m, k.one_minus_beta1, m);
+  v = fmaf(v, k.beta2, k.one_minus_beta2 * g * g);
   const float denom = sqrtf(v) * k.inv_bc2_sqrt + k.eps;
   p = pw - (t.lr * k.inv_bc1) * (m / denom);
 }
 
 __global__ void __launch_bounds__(kThreads) adamw_l1_kernel(const v1t_opt_tensor* __restrict__ tensors,
                                                             const int32_t* __restrict__ chunk_prefix, int n_tensors,
-                                                            AdamConsts k, float* __restrict__ abs_partials) {
+                                                            AdamConsts k, float* __restrict__ abs_partials,
+                                                            int32_t* __restrict__ chunk_group) {
   __shared__ v1t_opt_tensor t;
   __shared__ int64_t s_off;
   __shared__ float red[kThreads / 32];
@@ -98,26 +99,28 @@ __global__ void __launch_bounds__(kThreads) adamw_l1_kernel(const v1t_opt_tensor
 #pragma unroll
       for (int w = 0; w < kThreads / 32; ++w) s += red[w];
       abs_partials[blockIdx.x] = s;
+      chunk_group[blockIdx.x] = t.group;
     }
   }
 }
 
-// l1_sums[group] = sum over the group's tensors (table order) of their chunk partials (chunk order): deterministic
-__global__ void l1_finish_kernel(const v1t_opt_tensor* __restrict__ tensors, const int32_t* __restrict__ chunk_prefix,
-                                 int n_tensors, const float* __restrict__ abs_partials, float* __restrict__ l1_sums) {
-  __shared__ float red[32];
+// l1_sums[group] = sum of the chunk partials tagged with that group; fixed assignment of chunks to threads and a
+// fixed-order block reduction -> deterministic
+__global__ void __launch_bounds__(256) l1_finish_kernel(const float* __restrict__ abs_partials,
+                                                        const int32_t* __restrict__ chunk_group, int n_chunks,
+                                                        float* __restrict__ l1_sums) {
+  __shared__ float red[8];
   const int group = blockIdx.x;
   float s = 0.f;
-  for (int ti = 0; ti < n_tensors; ++ti) {
-    if (tensors[ti].group != group) continue;  // block-uniform
-    for (int c = chunk_prefix[ti] + threadIdx.x; c < chunk_prefix[ti + 1]; c += blockDim.x) s += abs_partials[c];
-  }
+  for (int c = threadIdx.x; c < n_chunks; c += blockDim.x)
+    if (chunk_group[c] == group) s += abs_partials[c];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tsum = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tsum += red[w];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tsum += red[w];
     l1_sums[group] = tsum;
   }
 }
@@ -129,27 +132,30 @@ using namespace v1t;
 
 extern "C" int v1t_opt_chunk_elems(void) { return kChunk; }
 
-extern "C" size_t v1t_adamw_l1_scratch_bytes(int n_chunks) { return sizeof(float) * (size_t)(n_chunks > 0 ? n_chunks : 0); }
+extern "C" size_t v1t_adamw_l1_scratch_bytes(int n_chunks) {  // per chunk: |p| partial (float) + group tag (int32)
+  return (sizeof(float) + sizeof(int32_t)) * (size_t)(n_chunks > 0 ? n_chunks : 0);
+}
 
 extern "C" int v1t_adamw_l1_step(const v1t_opt_tensor* tensors_dev, const int32_t* chunk_prefix_dev, int n_tensors,
-                                 int n_chunks, float beta1, float beta2, float eps, float bias_corr1,
-                                 float bias_corr2_sqrt, float grad_scale, int zero_grad, float* l1_sums_dev,
+                                 int n_chunks, double beta1, double beta2, double eps, double bias_corr1,
+                                 double bias_corr2_sqrt, double grad_scale, int zero_grad, float* l1_sums_dev,
                                  int n_groups, void* scratch, void* stream) {
   V1T_CHECK_ARG(n_tensors >= 0 && n_chunks >= 0, "adamw_l1_step: negative count");
   if (n_tensors == 0 || n_chunks == 0) return V1T_OK;
   V1T_CHECK_ARG(tensors_dev && chunk_prefix_dev, "adamw_l1_step: null table");
-  V1T_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
+  V1T_CHECK_ARG(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0.,
                 "adamw_l1_step: bad hyper-parameters (beta1 %g beta2 %g eps %g)", beta1, beta2, eps);
-  V1T_CHECK_ARG(bias_corr1 > 0.f && bias_corr2_sqrt > 0.f, "adamw_l1_step: bias corrections must be positive");
+  V1T_CHECK_ARG(bias_corr1 > 0. && bias_corr2_sqrt > 0., "adamw_l1_step: bias corrections must be positive");
   V1T_CHECK_ARG(!l1_sums_dev || (n_groups > 0 && scratch), "adamw_l1_step: l1 sums need n_groups and scratch");
   cudaStream_t st = (cudaStream_t)stream;
-  AdamConsts k{beta1, beta2, eps, 1.f / bias_corr1, 1.f / bias_corr2_sqrt, grad_scale, zero_grad};
-  adamw_l1_kernel<<<n_chunks, kThreads, 0, st>>>(tensors_dev, chunk_prefix_dev, n_tensors, k,
-                                                 l1_sums_dev ? (float*)scratch : nullptr);
+  AdamConsts k{(float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)(1.0 / bias_corr1),
+               (float)(1.0 / bias_corr2_sqrt), (float)grad_scale, zero_grad};
+  float* partials = l1_sums_dev ? (float*)scratch : nullptr;
+  int32_t* groups = l1_sums_dev ? (int32_t*)((float*)scratch + n_chunks) : nullptr;
+  adamw_l1_kernel<<<n_chunks, kThreads, 0, st>>>(tensors_dev, chunk_prefix_dev, n_tensors, k, partials, groups);
   V1T_LAUNCH_CHECK();
   if (l1_sums_dev) {
-    l1_finish_kernel<<<n_groups, 256, 0, st>>>(tensors_dev, chunk_prefix_dev, n_tensors, (const float*)scratch,
-                                               l1_sums_dev);
+    l1_finish_kernel<<<n_groups, 256, 0, st>>>(partials, groups, n_chunks, l1_sums_dev);
     V1T_LAUNCH_CHECK();
   }
   return V1T_OK;

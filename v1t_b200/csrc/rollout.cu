@@ -12,8 +12,8 @@
 //
 // Work decomposition: a warp owns a row i of one sample: 2*NQ columns per lane in registers (128-bit-friendly float2
 // loads of the H head rows in flight together), warp-shuffle row sum, accumulation of c_i M[i,:] in registers over
-// the warp's rows; the CTA's warps combine through shared memory, CTAs through per-CTA partials summed in a fixed
-// order (deterministic, no atomics).
+// the warp's rows; the CTA's warps combine through shared memory, CTAs through per-CTA partials that the NEXT launch
+// sums in a fixed order when it reads the row vector (deterministic, no atomics, no combine launch).
 #include "common.cuh"
 
 namespace v1t {
@@ -77,16 +77,31 @@ __global__ void __launch_bounds__(32) rollout_init_kernel(const float* __restric
     }
 }
 
+// The row vector entering a step: either stored directly (from the init kernel) or still split into the previous
+// step's per-CTA partials + identity term, summed here by the warp that needs the element (lanes stride over the
+// partials, then a shuffle tree: fixed order) -- no combine launch between the blocks.
+struct RowVec {
+  const float* direct;   // [B][T] or null
+  const float* partial;  // [B][G][T]
+  const float* cvec;     // [B][T]
+  int G;
+};
+__device__ __forceinline__ float row_value(const RowVec& r, int T, int b, int row, int lane) {
+  if (r.direct) return r.direct[(int64_t)b * T + row];
+  float t = 0.f;
+  for (int g = lane; g < r.G; g += 32) t += r.partial[((int64_t)b * r.G + g) * T + row];
+  return warp_sum(t) + r.cvec[(int64_t)b * T + row];
+}
+
 // grid (G, B).  partial [B][G][T]: this CTA's sum over its rows of c_i M[i,:];  cvec [B][T]: c_i (the identity term)
 template <int NQ, bool VEC>
 __global__ void __launch_bounds__(kThreads, 1) rollout_step_kernel(const float* __restrict__ attn, int L, int H,
-                                                                   int T, int n, const float* __restrict__ r_in,
+                                                                   int T, int n, RowVec r_in,
                                                                    float* __restrict__ partial,
                                                                    float* __restrict__ cvec) {
   extern __shared__ float slab[];  // [kWarps][T]
   const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* blk = attn + ((int64_t)b * L + n) * H * (int64_t)T * T;
-  const float* r = r_in + (int64_t)b * T;
   float acc[NQ][2];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) acc[q][0] = acc[q][1] = 0.f;
@@ -97,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_step_kernel(const float* 
 #pragma unroll
     for (int q = 0; q < NQ; ++q) s += m[q][0] + m[q][1];
     s = warp_sum(s) + 1.f;
-    const float c = r[row] / s;
+    const float c = row_value(r_in, T, b, row, lane) / s;
     if (lane == 0) cvec[(int64_t)b * T + row] = c;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -122,27 +137,27 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_step_kernel(const float* 
   }
 }
 
-// r_out[b][j] = sum_g partial[b][g][j] + cvec[b][j]
-__global__ void rollout_combine_kernel(const float* __restrict__ partial, const float* __restrict__ cvec, int G, int T,
-                                       float* __restrict__ r_out) {
-  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= T) return;
-  float t = 0.f;
-  for (int g = 0; g < G; ++g) t += partial[((int64_t)b * G + g) * T + j];
-  r_out[(int64_t)b * T + j] = t + cvec[(int64_t)b * T + j];
-}
-
-// heat = normalize(r[1:]) as (gh, gw), bilinear-resized (align_corners = false, no antialias) to (oh, ow); CTA per sample
-__global__ void __launch_bounds__(256) rollout_heatmap_kernel(const float* __restrict__ r, int T, int gh, int gw,
-                                                              int oh, int ow, float* __restrict__ out) {
+// heat = normalize(r[1:]) as (gh, gw), bilinear-resized (align_corners = false, no antialias) to (oh, ow); CTA per
+// sample; the final row vector is assembled from the last step's partials into shared memory ([T - 1] floats)
+__global__ void __launch_bounds__(256) rollout_heatmap_kernel(RowVec r, int T, int gh, int gw, int oh, int ow,
+                                                              float* __restrict__ out) {
+  extern __shared__ float h[];  // [gh * gw]
   __shared__ float rmin[8], rmax[8];
   const int b = blockIdx.x;
-  const float* h = r + (int64_t)b * T + 1;
   const int n = gh * gw;
   float lo = INFINITY, hi = -INFINITY;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    lo = fminf(lo, h[i]);
-    hi = fmaxf(hi, h[i]);
+    float v;
+    if (r.direct) {
+      v = r.direct[(int64_t)b * T + 1 + i];
+    } else {
+      v = 0.f;
+      for (int g = 0; g < r.G; ++g) v += r.partial[((int64_t)b * r.G + g) * T + 1 + i];
+      v += r.cvec[(int64_t)b * T + 1 + i];
+    }
+    h[i] = v;
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
   }
   hi = warp_max(hi);
   lo = -warp_max(-lo);
@@ -150,7 +165,7 @@ __global__ void __launch_bounds__(256) rollout_heatmap_kernel(const float* __res
     rmin[threadIdx.x >> 5] = lo;
     rmax[threadIdx.x >> 5] = hi;
   }
-  __syncthreads();
+  __syncthreads();  // also publishes h[]
   lo = rmin[0];
   hi = rmax[0];
   for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
@@ -175,7 +190,7 @@ __global__ void __launch_bounds__(256) rollout_heatmap_kernel(const float* __res
 int rows_groups(int B) { return B >= kNumSMs ? 1 : (kNumSMs / B > 0 ? kNumSMs / B : 1); }
 
 struct RolloutScratch {
-  float *r0, *r1, *cvec, *partial;
+  float *r0, *cvec[2], *partial[2];
   size_t total;
 };
 RolloutScratch carve(int B, int T, void* base) {
@@ -188,9 +203,10 @@ RolloutScratch carve(int B, int T, void* base) {
     return (float*)q;
   };
   s.r0 = take(sizeof(float) * (size_t)B * T);
-  s.r1 = take(sizeof(float) * (size_t)B * T);
-  s.cvec = take(sizeof(float) * (size_t)B * T);
-  s.partial = take(sizeof(float) * (size_t)B * rows_groups(B) * T);
+  for (int i = 0; i < 2; ++i) {  // double-buffered: step n reads step n+1's partials while writing its own
+    s.cvec[i] = take(sizeof(float) * (size_t)B * T);
+    s.partial[i] = take(sizeof(float) * (size_t)B * rows_groups(B) * T);
+  }
   s.total = off;
   return s;
 }
@@ -202,21 +218,19 @@ int run(const float* attn, int B, int L, int H, int T, int gh, int gw, int oh, i
   const int G = rows_groups(B);
   rollout_init_kernel<NQ, VEC><<<B, 32, 0, st>>>(attn, L, H, T, ws.r0);
   V1T_LAUNCH_CHECK();
-  float *cur = ws.r0, *nxt = ws.r1;
+  RowVec cur{ws.r0, nullptr, nullptr, 0};
   const size_t smem = sizeof(float) * (size_t)kWarps * T;
   if (L > 1 && smem > 48 * 1024)
     V1T_CUDA(cudaFuncSetAttribute(rollout_step_kernel<NQ, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-  for (int n = L - 2; n >= 0; --n) {
-    rollout_step_kernel<NQ, VEC><<<dim3(G, B), kThreads, smem, st>>>(attn, L, H, T, n, cur, ws.partial, ws.cvec);
+  int buf = 0;
+  for (int n = L - 2; n >= 0; --n, buf ^= 1) {
+    rollout_step_kernel<NQ, VEC><<<dim3(G, B), kThreads, smem, st>>>(attn, L, H, T, n, cur, ws.partial[buf],
+                                                                    ws.cvec[buf]);
     V1T_LAUNCH_CHECK();
-    rollout_combine_kernel<<<dim3(cdiv(T, 256), B), 256, 0, st>>>(ws.partial, ws.cvec, G, T, nxt);
-    V1T_LAUNCH_CHECK();
-    float* t = cur;
-    cur = nxt;
-    nxt = t;
+    cur = RowVec{nullptr, ws.partial[buf], ws.cvec[buf], G};
   }
-  rollout_heatmap_kernel<<<B, 256, 0, st>>>(cur, T, gh, gw, oh, ow, heat);
+  rollout_heatmap_kernel<<<B, 256, sizeof(float) * (size_t)(T - 1), st>>>(cur, T, gh, gw, oh, ow, heat);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

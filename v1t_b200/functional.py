@@ -101,11 +101,68 @@ def _fill_ptrs(tensors: Sequence[Optional[torch.Tensor]], blocks: int) -> CorePt
     return p
 
 
+class GradSink:
+    """One flat fp32 buffer holding the gradients of a set of parameters, whose ``.grad`` are views into it.
+
+    Autograd accumulates a parameter used by several backward passes with one small ``add`` kernel per parameter per
+    pass (the shared core: 52 tensors x 7 mice per optimizer step, train.py:97-111).  With a sink armed, the core's
+    backward writes all its parameter gradients into one temporary flat buffer, adds it to the sink with ONE kernel
+    and reports no gradient to autograd; ``p.grad`` (a view of the sink) sees the sum.  Used by the repo's own step
+    function (parallel.sweep(fused_accumulate=True)); plain ``loss.backward()`` on a model is unchanged."""
+
+    ALIGN = 4  # floats: keeps every view 16-byte aligned for the fused optimizer's 128-bit accesses
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        self.offsets = {}
+        off = 0
+        for p in self.params:
+            self.offsets[id(p)] = (off, p.numel())
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.flat: Optional[torch.Tensor] = None
+        self.armed = False
+
+    def view_of(self, p: torch.Tensor, flat: torch.Tensor) -> torch.Tensor:
+        off, n = self.offsets[id(p)]
+        return flat[off:off + n].view(p.shape)
+
+    def arm(self):
+        """Make every parameter's .grad the sink's view (existing gradients are carried over, None becomes 0)."""
+        if not self.params:
+            return
+        dev = self.params[0].device
+        if self.flat is None or self.flat.device != dev:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+            fresh = True
+        else:
+            fresh = False
+        if not fresh and all(p.grad is None for p in self.params):
+            self.flat.zero_()
+            fresh = True
+        for p in self.params:
+            view = self.view_of(p, self.flat)
+            if p.grad is None:
+                if not fresh:
+                    view.zero_()
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
+        self.armed = True
+
+    def disarm(self):
+        self.armed = False
+
+    def slots(self, tensors: Sequence[Optional[torch.Tensor]]):
+        """(offset, numel) of each tensor of a call's parameter list (None where absent / not in the sink)."""
+        return [self.offsets.get(id(t)) if t is not None else None for t in tensors]
+
+
 class _CoreFunction(torch.autograd.Function):
     """tokens[B,T,emb_ld] = ViTCore(images, behaviors; params)   (vit.py:423-436 without the final view)."""
 
     @staticmethod
-    def forward(ctx, spec: CoreSpec, p_tokens: float, p_block: float, seed: int, keep_saved, images, behaviors,
+    def forward(ctx, spec: CoreSpec, p_tokens: float, p_block: float, seed: int, keep_saved, sink, images, behaviors,
                 *params):
         lib = _lib.load()
         _need_cuda(images, behaviors, *params)
@@ -135,6 +192,7 @@ class _CoreFunction(torch.autograd.Function):
         ctx.save_for_backward(images, *([behaviors] if behaviors is not None else []),
                               *[p for p in params if p is not None])
         ctx.param_present = [p is not None for p in params]
+        ctx.sink = sink  # (GradSink, slots) or None
         if isinstance(keep_saved, dict):
             keep_saved["saved"], keep_saved["shape"] = saved, shape
         return tokens
@@ -150,9 +208,18 @@ class _CoreFunction(torch.autograd.Function):
         shape = spec.shape(*ctx.shape_args)
         dev = images.device
         d_tokens = d_tokens.contiguous().clone()  # clobbered by the library
-        needs = ctx.needs_input_grad[7:]
-        grads = [torch.empty_like(p) if (p is not None and need) else None for p, need in zip(params, needs)]
-        d_images = torch.empty_like(images) if ctx.needs_input_grad[5] else None
+        needs = ctx.needs_input_grad[8:]
+        flat_tmp = None
+        if ctx.sink is not None and ctx.sink[0].armed:
+            sink, slots = ctx.sink
+            if any(p is not None and need and slot is None for p, need, slot in zip(params, needs, slots)):
+                raise RuntimeError("core backward: a parameter that needs a gradient is not in the armed GradSink")
+            flat_tmp = torch.zeros_like(sink.flat)  # absent parameters (other mice's b-mlp) contribute zero
+            grads = [flat_tmp[slot[0]:slot[0] + slot[1]].view(p.shape) if (p is not None and need) else None
+                     for p, need, slot in zip(params, needs, slots)]
+        else:
+            grads = [torch.empty_like(p) if (p is not None and need) else None for p, need in zip(params, needs)]
+        d_images = torch.empty_like(images) if ctx.needs_input_grad[6] else None
         scratch = _scratch(dev, lib.v1t_core_scratch_bytes(C.byref(shape)))
         pptr, gptr = _fill_ptrs(params, spec.blocks), _fill_ptrs(grads, spec.blocks)
         with torch.cuda.device(dev):
@@ -160,12 +227,19 @@ class _CoreFunction(torch.autograd.Function):
                                        d_tokens.data_ptr(), ctx.saved_buf.data_ptr(), scratch.data_ptr(),
                                        C.byref(gptr), _ptr(d_images), _stream_ptr(dev))
         _lib.check(rc, "core_backward")
-        return (None, None, None, None, None, d_images, None, *grads)
+        if flat_tmp is not None:
+            ctx.sink[0].flat.add_(flat_tmp)  # one kernel for every core parameter; autograd sees no gradient
+            grads = [None] * len(grads)
+        return (None, None, None, None, None, None, d_images, None, *grads)
 
 
-def core_forward(spec: CoreSpec, images, behaviors, params, p_tokens=0.0, p_block=0.0, seed=0, keep_saved=None):
-    """Returns tokens [B, T, emb_ld] (fp32).  `params`: list in the order cls,pos,wpe,bpe + BLOCK_FIELDS per block."""
-    return _CoreFunction.apply(spec, float(p_tokens), float(p_block), int(seed), keep_saved, images, behaviors, *params)
+def core_forward(spec: CoreSpec, images, behaviors, params, p_tokens=0.0, p_block=0.0, seed=0, keep_saved=None,
+                 sink: Optional[GradSink] = None):
+    """Returns tokens [B, T, emb_ld] (fp32).  `params`: list in the order cls,pos,wpe,bpe + BLOCK_FIELDS per block.
+    ``sink``: an armed GradSink receives the parameter gradients in one add instead of autograd's per-tensor adds."""
+    sink_arg = (sink, sink.slots(params)) if (sink is not None and sink.armed) else None
+    return _CoreFunction.apply(spec, float(p_tokens), float(p_block), int(seed), keep_saved, sink_arg, images,
+                               behaviors, *params)
 
 
 def attention_probs(spec: CoreSpec, keep: dict, block: int) -> torch.Tensor:

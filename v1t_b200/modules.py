@@ -224,6 +224,7 @@ class ViTCore(Core):
                                 emb=args.emb_dim, heads=args.num_heads, mlp=args.mlp_dim, blocks=args.num_blocks,
                                 bdim=bdim, impl=_lib.IMPL_NAMES[impl] if isinstance(impl, str) else int(impl))
         self.dropout_seed: t.Optional[int] = None  # set to pin the dropout masks (tests)
+        self.grad_sink: t.Optional[VF.GradSink] = None  # see fused_grad_accumulation()
         self.last_dropout_seed = 0
 
     @staticmethod
@@ -253,6 +254,19 @@ class ViTCore(Core):
                 out += [None, None, None, None]
         return out
 
+    def fused_grad_accumulation(self, on: bool = True):
+        """Arm (or disarm) the flat gradient sink of the core parameters: while armed, every backward through the
+        core adds all its parameter gradients into ``p.grad`` with one kernel instead of one per tensor."""
+        if not on or self.frozen:
+            if self.grad_sink is not None:
+                self.grad_sink.disarm()
+            return None
+        if self.grad_sink is None or [id(p) for p in self.grad_sink.params] != [id(p) for p in self.parameters()
+                                                                                   if p.requires_grad]:
+            self.grad_sink = VF.GradSink(list(self.parameters()))
+        self.grad_sink.arm()
+        return self.grad_sink
+
     def _hooked_attends(self):
         return [(i, blk["mha"].attend) for i, blk in enumerate(self.transformer.blocks)
                 if len(blk["mha"].attend._forward_hooks) > 0]
@@ -274,7 +288,8 @@ class ViTCore(Core):
         self.last_dropout_seed = seed
         hooked = self._hooked_attends()
         keep = {} if hooked else None
-        tokens = VF.core_forward(self.spec, inputs, beh, self.flat_params(mouse_id), p_tok, p_blk, seed, keep)
+        tokens = VF.core_forward(self.spec, inputs, beh, self.flat_params(mouse_id), p_tok, p_blk, seed, keep,
+                                 sink=self.grad_sink)
         for i, attend in hooked:  # emit softmax probabilities for hooks (attention rollout)
             attend(VF.attention_probs(self.spec, keep, i))
         e, h, w = self.output_shape

@@ -96,16 +96,20 @@ class GradSync:
 
 
 def sweep(model, criterion, batches: t.Dict[str, t.Dict[str, torch.Tensor]], global_batch: t.Dict[str, int],
-          sync: t.Optional[GradSync] = None):
+          sync: t.Optional[GradSync] = None, fused_accumulate: bool = False):
     """One optimizer step's worth of forward/backward: every mouse batch once, gradients accumulated
     (train.py:84-111 without the optimizer), then the gradient exchange.  Returns the summed loss (device scalar)."""
     total = None
+    if fused_accumulate:  # one add per backward for all shared-core gradients instead of one per parameter
+        model.core.fused_grad_accumulation(True)
     for mouse_id, b in batches.items():
         y, _, _ = model(inputs=b["image"], mouse_id=mouse_id, behaviors=b["behavior"],
                         pupil_centers=b["pupil_center"])
         loss = criterion(y_true=b["response"], y_pred=y, mouse_id=mouse_id, batch_size=global_batch[mouse_id])
         loss.backward()
         total = loss.detach() if total is None else total + loss.detach()
+    if fused_accumulate:
+        model.core.fused_grad_accumulation(False)
     if sync is not None:
         sync.all_reduce()
     return total
