@@ -171,12 +171,15 @@ def test_dropout_masks_replay_exactly_against_oracle():
         assert rel_err(p.grad.cpu().numpy(), ref["grads"][k]) < TOL_GRAD, k
 
 
-def test_readout_edge_cases_against_oracle():
+@pytest.mark.parametrize("ld,C", [(32, 19), (21, 19), (160, 155), (157, 155), (8, 5)])
+def test_readout_edge_cases_against_oracle(ld, C):
     """Clamped positions, shifts pushing corners out of the map (zero padding), ragged N (not a multiple of the
-    32-neuron CTA tile), batch larger than one batch tile, strided channel-last input with padded rows."""
+    32-neuron CTA tile), batch larger than one batch tile, strided channel-last input with padded rows.  Row strides
+    that are multiples of 4 floats take the 128-bit kernels (a 4-channel chunk straddling C handled element-wise),
+    the others the scalar kernels."""
     rng = np.random.default_rng(3)
-    B, gh, gw, C, N = 37, 5, 7, 19, 45
-    base = torch.zeros(B, gh * gw + 1, 32, device=DEV)
+    B, gh, gw, N = 37, 5, 7, 45
+    base = torch.zeros(B, gh * gw + 1, ld, device=DEV)
     fm = rng.standard_normal((B, gh, gw, C)).astype(np.float32)
     base[:, 1:, :C] = cu(fm).reshape(B, gh * gw, C)
     fmap = base[:, 1:, :C].unflatten(1, (gh, gw)).permute(0, 3, 1, 2).requires_grad_(True)

@@ -12,6 +12,8 @@
 // uses fp32 reductions (red.global.add), 128 B coalesced per request.
 #include "common.cuh"
 #include "kernels.cuh"
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace v1t {
@@ -141,6 +143,115 @@ __global__ void __launch_bounds__(kWarps * 32) readout_forward_kernel(
   __syncthreads();
 
   // coalesced epilogue over the [batch tile][32 neurons] tile: z, y = elu(z)+1, Poisson partial
+  float lsum = 0.f;
+  const int n = n0 + lane;
+  for (int bl = wid; bl < b_end - b_begin; bl += kWarps) {
+    if (n < N) {
+      const int64_t o = (int64_t)(b_begin + bl) * N + n;
+      const float z = zt[bl * 33 + lane];
+      z_out[o] = z;
+      const float y = elu1(z);
+      if (y_out) y_out[o] = y;
+      if (loss_partials) {
+        const float yp = y + kEpsF32, yt = __ldg(y_true + o) + kEpsF32;
+        lsum += yp - yt * logf(yp);
+      }
+    }
+  }
+  if (loss_partials) {
+    lsum = warp_sum(lsum);
+    if (lane == 0) red[wid] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += red[w];
+      loss_partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
+// ---- 128-bit variants ---------------------------------------------------------------------------------
+// When the map's strides and base are 16-byte aligned (the core emits rows of emb_ld = 160 floats) a lane owns the
+// 4-channel chunks lane, lane + 32, ...: one LDG.128 per chunk instead of four scalar loads, and in the backward one
+// red.global.add.v4.f32 instead of four scalar reductions (the backward is bound by the rate at which an SM can
+// issue reductions: 79 M scalar ones per pass at B=16, N=8000).  A chunk that straddles C (155 = 38 chunks + 3) is
+// handled element-wise.  NC = ceil(C / 128) chunk rounds per lane.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int NC>
+__device__ __forceinline__ void load_feature_chunks(const float* fs, int C, int j, int lane, float (&f)[NC][4]) {
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * (lane + 32 * i) + e;
+      f[i][e] = c < C ? fs[c * 33 + j] : 0.f;
+    }
+}
+
+// grid / smem as readout_forward_kernel
+template <int NC>
+__global__ void __launch_bounds__(kWarps * 32) readout_forward_v4_kernel(
+    v1t_readout_shape s, const float* __restrict__ fmap, const float* __restrict__ mu,
+    const float* __restrict__ sigma, const float* __restrict__ noise, const float* __restrict__ shifts,
+    const float* __restrict__ features, const float* __restrict__ bias, const float* __restrict__ y_true,
+    float* __restrict__ z_out, float* __restrict__ y_out, float* __restrict__ loss_partials) {
+  extern __shared__ float smem[];
+  float* fs = smem;                                  // [C][33]
+  float* zt = smem + (size_t)s.channels * 33;        // [kBatchTile][33]
+  __shared__ float red[kWarps];
+  const int C = s.channels, N = s.neurons, B = s.batch;
+  const int n0 = blockIdx.x * kNeuronsPerCta;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b_begin = blockIdx.y * kBatchTile, b_end = min(B, b_begin + kBatchTile);
+
+  stage_features(features, fs, C, N, n0);
+  __syncthreads();
+
+  for (int j = wid; j < kNeuronsPerCta; j += kWarps) {
+    const int n = n0 + j;
+    if (n >= N) break;  // warp-uniform
+    float f[NC][4];
+    load_feature_chunks<NC>(fs, C, j, lane, f);
+    const float bn = bias ? __ldg(bias + n) : 0.f;
+    for (int b = b_begin; b < b_end; ++b) {
+      const GridPos g = grid_position(mu, sigma, noise, shifts, b, n, N, s.gh, s.gw);
+      Corner cr;
+      make_corners(g, s.gh, s.gw, s.fs_y, s.fs_x, cr);
+      const float* base = fmap + (int64_t)b * s.fs_b;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (cr.w[k] != 0.f) {  // warp-uniform
+          const float* px = base + cr.off[k];
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < NC; ++i) {
+            const int c = 4 * (lane + 32 * i);
+            if (c + 3 < C) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(px + c));
+              t = fmaf(v.x, f[i][0], t);
+              t = fmaf(v.y, f[i][1], t);
+              t = fmaf(v.z, f[i][2], t);
+              t = fmaf(v.w, f[i][3], t);
+            } else if (c < C) {
+#pragma unroll
+              for (int e = 0; e < 3; ++e)
+                if (c + e < C) t = fmaf(__ldg(px + c + e), f[i][e], t);
+            }
+          }
+          acc = fmaf(cr.w[k], t, acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) zt[(b - b_begin) * 33 + j] = acc + bn;
+    }
+  }
+  __syncthreads();
+
   float lsum = 0.f;
   const int n = n0 + lane;
   for (int bl = wid; bl < b_end - b_begin; bl += kWarps) {
@@ -325,6 +436,164 @@ __global__ void __launch_bounds__(kWarps * 32) readout_backward_kernel(
   }
 }
 
+// 128-bit variant of readout_backward_kernel (same grid, smem and outputs)
+template <int NC>
+__global__ void __launch_bounds__(kWarps * 32) readout_backward_v4_kernel(
+    v1t_readout_shape s, const float* __restrict__ fmap, const float* __restrict__ mu,
+    const float* __restrict__ sigma, const float* __restrict__ noise, const float* __restrict__ shifts,
+    const float* __restrict__ features, const float* __restrict__ z_in, const float* __restrict__ dz_in,
+    const float* __restrict__ y_true, float gscale, float* __restrict__ d_fmap, float* __restrict__ d_feat_part,
+    float* __restrict__ d_small_part, float* __restrict__ d_shift_part) {
+  extern __shared__ float smem[];
+  float* fs = smem;                                         // [C][33] features, later d_features
+  float* sh = smem + (size_t)s.channels * 33;               // [kBatchTile][32][2] d_grid per (b, neuron)
+  const int C = s.channels, N = s.neurons, B = s.batch;
+  const int n0 = blockIdx.x * kNeuronsPerCta;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int b_begin = blockIdx.y * kBatchTile, b_end = min(B, b_begin + kBatchTile);
+  const float half_w = 0.5f * (float)(s.gw - 1), half_h = 0.5f * (float)(s.gh - 1);
+
+  stage_features(features, fs, C, N, n0);
+  for (int i = threadIdx.x; i < kBatchTile * 64; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+
+  float df_keep[(kNeuronsPerCta / kWarps)][NC][4];  // d_features of this warp's neurons
+#pragma unroll
+  for (int q = 0; q < kNeuronsPerCta / kWarps; ++q) {
+    const int j = wid + q * kWarps;
+    const int n = n0 + j;
+    float f[NC][4], df[NC][4];
+    load_feature_chunks<NC>(fs, C, j, lane, f);
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) df[i][e] = 0.f;
+    float dbias = 0.f, dmx = 0.f, dmy = 0.f, ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
+    if (n < N) {
+      for (int b = b_begin; b < b_end; ++b) {
+        const int64_t o = (int64_t)b * N + n;
+        float g;
+        if (dz_in) {
+          g = __ldg(dz_in + o);
+        } else {  // fused ELU1 + Poisson gradient
+          const float z = __ldg(z_in + o);
+          const float y = elu1(z);
+          g = gscale * (1.f - (__ldg(y_true + o) + kEpsF32) / (y + kEpsF32)) * (z > 0.f ? 1.f : expf(z));
+        }
+        const GridPos gp = grid_position(mu, sigma, noise, shifts, b, n, N, s.gh, s.gw);
+        Corner cr;
+        make_corners(gp, s.gh, s.gw, s.fs_y, s.fs_x, cr);
+        const float* base = fmap + (int64_t)b * s.fs_b;
+        float* dbase = d_fmap ? d_fmap + (int64_t)b * s.fs_b : nullptr;
+        float dotk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float t = 0.f;
+          if (cr.valid[k] != 0.f) {  // warp-uniform
+            const float* px = base + cr.off[k];
+            const float gw_k = g * cr.w[k];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+              const int c = 4 * (lane + 32 * i);
+              if (c + 3 < C) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(px + c));
+                t = fmaf(v.x, f[i][0], t);
+                t = fmaf(v.y, f[i][1], t);
+                t = fmaf(v.z, f[i][2], t);
+                t = fmaf(v.w, f[i][3], t);
+                df[i][0] = fmaf(gw_k, v.x, df[i][0]);
+                df[i][1] = fmaf(gw_k, v.y, df[i][1]);
+                df[i][2] = fmaf(gw_k, v.z, df[i][2]);
+                df[i][3] = fmaf(gw_k, v.w, df[i][3]);
+                if (dbase)
+                  red_add_v4(dbase + cr.off[k] + c, gw_k * f[i][0], gw_k * f[i][1], gw_k * f[i][2], gw_k * f[i][3]);
+              } else if (c < C) {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                  if (c + e < C) {
+                    const float v = __ldg(px + c + e);
+                    t = fmaf(v, f[i][e], t);
+                    df[i][e] = fmaf(gw_k, v, df[i][e]);
+                    if (dbase) atomicAdd(dbase + cr.off[k] + c + e, gw_k * f[i][e]);
+                  }
+                }
+              }
+            }
+          }
+          dotk[k] = t;
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dotk[k] += __shfl_xor_sync(0xffffffffu, dotk[k], o2);
+        }
+        float gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float sx = (k & 1) ? 1.f : -1.f, sy = (k >> 1) ? 1.f : -1.f;
+          gx += cr.valid[k] * sx * cr.wy[k] * dotk[k];
+          gy += cr.valid[k] * sy * cr.wx[k] * dotk[k];
+        }
+        gx *= g * half_w;
+        gy *= g * half_h;
+        if (lane == 0) {
+          sh[((b - b_begin) * 32 + j) * 2] = gx;
+          sh[((b - b_begin) * 32 + j) * 2 + 1] = gy;
+        }
+        const float mx = (gp.pre_x >= -1.f && gp.pre_x <= 1.f) ? gx : 0.f;  // clamp backward
+        const float my = (gp.pre_y >= -1.f && gp.pre_y <= 1.f) ? gy : 0.f;
+        dbias += g;
+        dmx += mx;
+        dmy += my;
+        if (noise) {
+          const float q0 = noise[o * 2], q1 = noise[o * 2 + 1];
+          ds0 = fmaf(mx, q0, ds0);
+          ds1 = fmaf(mx, q1, ds1);
+          ds2 = fmaf(my, q0, ds2);
+          ds3 = fmaf(my, q1, ds3);
+        }
+      }
+      if (lane == 0 && d_small_part) {
+        float* dst = d_small_part + ((int64_t)blockIdx.y * N + n) * 7;
+        dst[0] = dbias; dst[1] = dmx; dst[2] = dmy; dst[3] = ds0; dst[4] = ds1; dst[5] = ds2; dst[6] = ds3;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) df_keep[q][i][e] = df[i][e];
+  }
+  __syncthreads();  // all warps done reading fs as features
+  if (d_feat_part) {
+#pragma unroll
+    for (int q = 0; q < kNeuronsPerCta / kWarps; ++q) {
+      const int j = wid + q * kWarps;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * (lane + 32 * i) + e;
+          if (c < C) fs[c * 33 + j] = df_keep[q][i][e];
+        }
+    }
+    __syncthreads();
+    float* dst = d_feat_part + (int64_t)blockIdx.y * C * N;
+    for (int i = threadIdx.x; i < C * kNeuronsPerCta; i += blockDim.x) {
+      const int c = i / kNeuronsPerCta, j = i % kNeuronsPerCta;
+      if (n0 + j < N) dst[(int64_t)c * N + n0 + j] = fs[c * 33 + j];
+    }
+  }
+  if (d_shift_part) {
+    for (int i = threadIdx.x; i < (b_end - b_begin) * 2; i += blockDim.x) {
+      const int bl = i >> 1, xy = i & 1;
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t += sh[(bl * 32 + j) * 2 + xy];
+      d_shift_part[((int64_t)blockIdx.x * B + b_begin + bl) * 2 + xy] = t;
+    }
+  }
+}
+
 // out[i] = sum_p part[p*n + i]
 __global__ void sum_parts_kernel(const float* __restrict__ part, int parts, int64_t n, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,6 +685,16 @@ int check_shape(const v1t_readout_shape* s) {
   return V1T_OK;
 }
 
+// 128-bit path: base pointers 16-byte aligned and every stride a multiple of 4 floats
+bool vec4_ok(const v1t_readout_shape& s, const float* fmap, const float* d_fmap) {
+  static const bool enabled = [] {  // measurement knob: V1T_READOUT_V4=0 forces the scalar kernels
+    const char* e = getenv("V1T_READOUT_V4");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && (((uintptr_t)fmap | (uintptr_t)d_fmap) & 15u) == 0 && s.fs_b % 4 == 0 && s.fs_y % 4 == 0 && s.fs_x % 4 == 0 &&
+         s.channels >= 4;
+}
+
 size_t fwd_smem(const v1t_readout_shape& s) { return sizeof(float) * ((size_t)s.channels * 33 + kBatchTile * 33); }
 size_t bwd_smem(const v1t_readout_shape& s) { return sizeof(float) * ((size_t)s.channels * 33 + kBatchTile * 64); }
 
@@ -428,6 +707,11 @@ extern "C" size_t v1t_readout_scratch_bytes(const v1t_readout_shape* s) {
   if (!s) return 0;
   return carve(*s, nullptr).total;
 }
+
+#define V1T_NC_DISPATCH(channels, CALL) \
+  if (channels <= 128) { CALL(1); }     \
+  else if (channels <= 256) { CALL(2); } \
+  else { CALL(4); }
 
 #define V1T_NV_DISPATCH(nv, CALL)             \
   if (nv <= 1) { CALL(1); }                   \
@@ -459,7 +743,21 @@ extern "C" int v1t_readout_forward(const v1t_readout_shape* s, const float* fmap
                                                                  bias, y_true, z, y_out,                       \
                                                                  loss_out ? ws.loss_partials : nullptr);       \
   } while (0)
-  V1T_NV_DISPATCH(nv, CALL)
+#define CALL4(NCC)                                                                                               \
+  do {                                                                                                           \
+    if (smem > 48 * 1024)                                                                                        \
+      V1T_CUDA(cudaFuncSetAttribute(readout_forward_v4_kernel<NCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                 \
+    readout_forward_v4_kernel<NCC><<<grid, kWarps * 32, smem, st>>>(*s, fmap, mu, sigma, noise, shifts, features, \
+                                                                    bias, y_true, z, y_out,                       \
+                                                                    loss_out ? ws.loss_partials : nullptr);       \
+  } while (0)
+  if (vec4_ok(*s, fmap, nullptr)) {
+    V1T_NC_DISPATCH(s->channels, CALL4)
+  } else {
+    V1T_NV_DISPATCH(nv, CALL)
+  }
+#undef CALL4
 #undef CALL
   V1T_LAUNCH_CHECK();
   if (loss_out) {
@@ -498,7 +796,21 @@ extern "C" int v1t_readout_backward(const v1t_readout_shape* s, const float* fma
         *s, fmap, mu, sigma, noise, shifts, features, z, dz, y_true, loss_scale * dloss, d_fmap, feat_dst,      \
         want_small ? ws.small_part : nullptr, d_shifts ? ws.shift_part : nullptr);                              \
   } while (0)
-  V1T_NV_DISPATCH(nv, CALL)
+#define CALL4(NCC)                                                                                                \
+  do {                                                                                                            \
+    if (smem > 48 * 1024)                                                                                         \
+      V1T_CUDA(cudaFuncSetAttribute(readout_backward_v4_kernel<NCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)smem));                                                                  \
+    readout_backward_v4_kernel<NCC><<<grid, kWarps * 32, smem, st>>>(                                             \
+        *s, fmap, mu, sigma, noise, shifts, features, z, dz, y_true, loss_scale * dloss, d_fmap, feat_dst,        \
+        want_small ? ws.small_part : nullptr, d_shifts ? ws.shift_part : nullptr);                                \
+  } while (0)
+  if (vec4_ok(*s, fmap, d_fmap)) {
+    V1T_NC_DISPATCH(s->channels, CALL4)
+  } else {
+    V1T_NV_DISPATCH(nv, CALL)
+  }
+#undef CALL4
 #undef CALL
   V1T_LAUNCH_CHECK();
   if (d_features && tiles > 1) {
