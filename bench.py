@@ -388,7 +388,7 @@ def extras_rooflines(model, neurons, dev, peaks):
         ms = timed_ms(kernel_only, 50)
         gbs = 28.0 * numel / (ms / 1e3) / 1e9
         out["adamw_l1"] = {"ms_per_step": ms, "ms_per_step_api": ms_api, "params": numel, "bound": "hbm",
-                           "achieved": gbs,
+                           "traffic": extras_traffic("adamw_l1_kernel"), "achieved": gbs,
                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                            "bytes_per_element": 28}
     except Exception as e:  # keep the headline line; report the failure
@@ -402,12 +402,23 @@ def extras_rooflines(model, neurons, dev, peaks):
         gbs = nbytes / (ms / 1e3) / 1e9
         out["attention_rollout"] = {"ms": ms, "shape": [B, L, H, T, T], "bound": "hbm", "achieved": gbs,
                                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                    "launches_per_call": L + 1,
+                                    "launches_per_call": L + 1, "traffic_per_step_launch_b4": extras_traffic("rollout_step_kernel"),
                                     "note": "2.8 GB stack, 2.1 GB read per call (blocks 0..L-2 once, block L-1 row 0)"}
         del attn
     except Exception as e:
         out["attention_rollout"] = {"error": repr(e)}
     return out
+
+
+def extras_traffic(kernel):
+    """dram read + write bytes per launch of an extras kernel from the committed ncu capture (profiles/)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_extras_traffic.json")
+    try:
+        with open(path) as fh:
+            k = json.load(fh)["kernels"][kernel]
+        return k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def attention_traffic():

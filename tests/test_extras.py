@@ -265,7 +265,7 @@ def test_fused_adamw_l1_matches_torch_adamw():
             if step == 2:
                 assert float(p.grad.abs().max()) == 0.0
         sums = opt.last_l1_sums.cpu().numpy()
-        want = np.zeros(3)
+        want = np.zeros(opt.n_l1_groups)
         for i, s in enumerate(before):
             want[i % 3] += s
         assert rel_err(sums, want) < 1e-5

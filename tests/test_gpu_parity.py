@@ -661,3 +661,105 @@ def test_fused_gradient_accumulation_equals_autograd_accumulation():
     torch.manual_seed(0)
     parallel.sweep(model, crit, batches, gb, None, fused_accumulate=True)
     assert all(p.grad is not None for p in model.core.parameters())
+
+
+def test_recorder_and_rollout_module_against_oracle():
+    """Recorder (hook contract of attention_rollout.py:15-75) + attention_rollouts on the recorded stack."""
+    from oracle import extras_oracle as XO
+    from v1t_b200.rollout import Recorder, attention_rollouts, find_shape
+
+    g = Golden("tiny_eval")
+    model, _ = build(g)
+    model.train(False)
+    d = g.mice["A"]
+    rec = Recorder(model.core)
+    with torch.no_grad():
+        out, attn = rec(images=cu(d["images"]), behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]),
+                        mouse_id="A")
+    B, T = d["images"].shape[0], model.core.patch_embedding.num_patches
+    assert tuple(attn.shape) == (B, g.args["num_blocks"], g.args["num_heads"], T, T)
+    assert rel_err(attn.sum(-1).cpu().numpy(), np.ones((B, g.args["num_blocks"], g.args["num_heads"], T))) < 1e-5
+    assert rel_err(out.permute(0, 2, 3, 1).cpu().numpy(), d["fmap"]) < TOL_FWD
+    assert find_shape(T - 1) == model.core.find_shape(T - 1)
+    shape = d["images"].shape[2:]
+    heat = attention_rollouts(attn, shape)
+    assert rel_err(heat.cpu().numpy(), XO.attention_rollouts(attn.cpu().numpy(), shape)) < 2e-5
+    core = rec.eject()
+    assert core is model.core and all(len(b["mha"].attend._forward_hooks) == 0 for b in core.transformer.blocks)
+
+
+def test_ensemble_model_matches_member_average():
+    """EnsembleModel (ensemble.py:83-151): members run with activate=False, output module fused (mean and Linear)."""
+    from types import SimpleNamespace
+    from v1t_b200.ensemble import EnsembleModel
+
+    g = Golden("tiny_eval")
+    members = {}
+    for i in range(3):
+        m, _ = build(g)
+        with torch.no_grad():
+            for p in m.readouts.parameters():
+                p.add_(0.05 * i)
+        members[f"m{i}"] = m.train(False)
+    d = g.mice["A"]
+    x = dict(mouse_id="A", behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]))
+    with torch.no_grad():
+        zs = [m(cu(d["images"]), activate=False, **x)[0] for m in members.values()]
+    for mode in (0, 1, 2):
+        args = SimpleNamespace(input_shape=tuple(g.meta["in_shape"]), ensemble_mode=mode,
+                               output_shapes={k: (n,) for k, n in g.meta["neurons"].items()})
+        ens = EnsembleModel(args, members).to(DEV)
+        assert not any(p.requires_grad for p in ens.ensemble.parameters())
+        y, _, _ = ens(cu(d["images"]), **x)
+        stack = torch.stack(zs, dim=-1)
+        if mode == 0:
+            want = torch.nn.functional.elu(stack.mean(-1)) + 1
+        else:
+            lin = ens.output_module.linear if mode == 1 else ens.output_module.linear["A"]
+            want = torch.nn.functional.elu(torch.nn.functional.linear(stack, lin.weight, lin.bias)[..., 0]) + 1
+        assert rel_err(y.detach().cpu().numpy(), want.detach().cpu().numpy()) < 2e-6
+        if mode > 0:  # the output module is trainable
+            gw_ref = torch.autograd.grad(want.sum(), lin.weight)[0]
+            y.sum().backward()
+            assert rel_err(lin.weight.grad.cpu().numpy(), gw_ref.cpu().numpy()) < 1e-5
+
+
+def test_train_step_with_fused_optimizer_matches_oracle_update():
+    """optim.train_step + build_optimizer: one update over a mouse batch equals the oracle AdamW + L1 step applied to
+    the gradients of the same forward/backward (same torch seed -> same sampled readout positions)."""
+    from types import SimpleNamespace
+    from oracle import extras_oracle as XO
+    from v1t_b200 import optim
+
+    g = Golden("tiny_train")
+    model, crit = build(g, b200_impl="fp32")
+    model.train(True)
+    d = g.mice["A"]
+    batch = {"image": cu(d["images"]), "behavior": cu(d["behaviors"]), "pupil_center": cu(d["pupil_centers"]),
+             "response": cu(d["y_true"])}
+    torch.manual_seed(5)
+    y, _, _ = model(batch["image"], mouse_id="A", behaviors=batch["behavior"], pupil_centers=batch["pupil_center"])
+    crit(y_true=batch["response"], y_pred=y, mouse_id="A", batch_size=y.shape[0]).backward()
+    p0 = {k: p.detach().cpu().numpy().copy() for k, p in model.named_parameters()}
+    g0 = {k: p.grad.cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    hp = SimpleNamespace(lr=2e-3, core_lr=5e-4, adam_beta1=0.9, adam_beta2=0.9999, adam_eps=1e-8)
+    opt = optim.build_optimizer(model, hp, ["A"])
+    assert [grp["name"] for grp in opt.param_groups] == ["core", "readouts", "core_shifter"]
+    torch.manual_seed(5)
+    res = optim.train_step("A", batch, model, opt, crit, update=True, micro_batch_size=batch["image"].shape[0],
+                           device=DEV)
+    assert np.isfinite(float(res["loss/loss"]))
+    coef = optim.l1_coefficients(model, ["A"])
+    named = dict(model.named_parameters())
+    for k, grad in g0.items():
+        lr = hp.core_lr if k.startswith("core.") else hp.lr
+        want, _, _ = XO.adamw_l1_step(p0[k], grad, np.zeros_like(grad), np.zeros_like(grad), 1, lr, 0.9, 0.9999, 1e-8,
+                                      l1=coef.get(named[k], (0.0, 0))[0])
+        assert rel_err(named[k].detach().cpu().numpy(), want) < 1e-5, k
+        assert float(named[k].grad.abs().max()) == 0.0  # zeroed in the same pass
+    # reg_loss by-product = what the reference's model.regularizer("A") evaluates to on the pre-update parameters
+    reg_ref = g.args["core_reg_scale"] * sum(np.abs(v).sum() for k, v in p0.items() if k.startswith("core.")) \
+        + g.args["readout_reg_scale"] * np.abs(p0["readouts.A.features"]).sum()
+    got = opt.reg_loss([g.args["core_reg_scale"], g.args["readout_reg_scale"], g.args["shifter_reg_scale"]])
+    assert abs(float(got) - reg_ref) / reg_ref < 1e-5

@@ -29,7 +29,7 @@ from .functional import _stream_ptr
 def l1_coefficients(model, mouse_ids: t.Sequence[str]) -> t.Dict[torch.nn.Parameter, t.Tuple[float, int]]:
     """(coefficient, group) of the L1 term each parameter receives over ONE optimizer step that visits every mouse
     in ``mouse_ids`` once (train.py:97-111).  Groups: 0 = core (regularised once per mouse step, model.py:143-144),
-    1 = readout features, 2 = shifters."""
+    1 = readout features, 2 = shifters (parameters without a regulariser land in the optimizer's last group)."""
     coef: t.Dict[torch.nn.Parameter, t.Tuple[float, int]] = {}
     if not model.core.frozen:
         scale = float(model.core.reg_scale) * len(mouse_ids)
@@ -49,7 +49,7 @@ def l1_coefficients(model, mouse_ids: t.Sequence[str]) -> t.Dict[torch.nn.Parame
     return coef
 
 
-L1_GROUP_NAMES = ("core", "readout_features", "shifters")
+L1_GROUP_NAMES = ("core", "readout_features", "shifters", "unregularised")  # the last one: every other parameter
 
 
 class FusedAdamWL1(torch.optim.Optimizer):
@@ -76,7 +76,7 @@ class FusedAdamWL1(torch.optim.Optimizer):
     def set_l1(self, l1: dict):
         self._l1 = {}
         for p, v in l1.items():
-            c, g = (v if isinstance(v, tuple) else (v, 0))
+            c, g = (v if isinstance(v, tuple) else (v, 0))  # a bare coefficient goes to group 0
             if not 0 <= g < self.n_l1_groups:
                 raise ValueError(f"FusedAdamWL1: l1 group {g} outside 0..{self.n_l1_groups - 1}")
             self._l1[p] = (float(c), int(g))
@@ -89,7 +89,7 @@ class FusedAdamWL1(torch.optim.Optimizer):
             if group["amsgrad"] or group["maximize"]:
                 raise NotImplementedError("FusedAdamWL1: amsgrad / maximize are not implemented")
             for p in group["params"]:
-                c, g = self._l1.get(p, (0.0, 0))
+                c, g = self._l1.get(p, (0.0, self.n_l1_groups - 1))
                 if p.grad is None:
                     if c == 0.0:
                         continue
@@ -174,7 +174,9 @@ class FusedAdamWL1(torch.optim.Optimizer):
         over groups of reg_scale[group] * sum|p|."""
         if self.last_l1_sums is None:
             raise RuntimeError("FusedAdamWL1.reg_loss: no step taken yet")
-        w = torch.tensor(list(reg_scales), dtype=torch.float32, device=self.last_l1_sums.device)
+        scales = list(reg_scales)[: self.n_l1_groups]
+        w = torch.tensor(scales + [0.0] * (self.n_l1_groups - len(scales)), dtype=torch.float32,
+                         device=self.last_l1_sums.device)
         return (self.last_l1_sums * w).sum()
 
 
