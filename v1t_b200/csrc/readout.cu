@@ -20,7 +20,8 @@ namespace v1t {
 namespace {
 
 constexpr int kNeuronsPerCta = 32;
-constexpr int kWarps = 16;  // 2 neurons per warp: 27 warps/SM at N=8000 (one warp walks a neuron over the batch: latency-bound)
+constexpr int kWarps = 16;     // backward: 2 neurons per warp (96-107 registers per thread: one 512-thread CTA per SM)
+constexpr int kFwdWarps = 32;  // forward: 1 neuron per warp, 54 warps/SM at N=8000 (58 registers per thread)
 constexpr int kBatchTile = 32;  // samples staged per output tile
 constexpr float kEpsF32 = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (losses.py:22)
 
@@ -88,9 +89,10 @@ __device__ __forceinline__ void stage_features(const float* __restrict__ feature
   }
 }
 
-// grid (ceil(N/32), batch tiles); block 256.  smem: fs [C][33] + zt [kBatchTile][33]
+// grid (ceil(N/32), batch tiles); block 1024: one warp per neuron (the walk over the batch is a chain of dependent
+// L2 latencies, so the forward wants as many warps in flight as the SM holds: 2 CTAs x 32 warps).  smem: fs [C][33] + zt [kBatchTile][33]
 template <int NV>
-__global__ void __launch_bounds__(kWarps * 32) readout_forward_kernel(
+__global__ void __launch_bounds__(kFwdWarps * 32) readout_forward_kernel(
     v1t_readout_shape s, const float* __restrict__ fmap, const float* __restrict__ mu,
     const float* __restrict__ sigma, const float* __restrict__ noise, const float* __restrict__ shifts,
     const float* __restrict__ features, const float* __restrict__ bias, const float* __restrict__ y_true,
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kWarps * 32) readout_forward_kernel(
   extern __shared__ float smem[];
   float* fs = smem;                                  // [C][33]
   float* zt = smem + (size_t)s.channels * 33;        // [kBatchTile][33]
-  __shared__ float red[kWarps];
+  __shared__ float red[kFwdWarps];
   const int C = s.channels, N = s.neurons, B = s.batch;
   const int n0 = blockIdx.x * kNeuronsPerCta;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kWarps * 32) readout_forward_kernel(
   stage_features(features, fs, C, N, n0);
   __syncthreads();
 
-  for (int j = wid; j < kNeuronsPerCta; j += kWarps) {
+  for (int j = wid; j < kNeuronsPerCta; j += kFwdWarps) {
     const int n = n0 + j;
     if (n >= N) break;  // warp-uniform
     float f[NV];
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kWarps * 32) readout_forward_kernel(
   // coalesced epilogue over the [batch tile][32 neurons] tile: z, y = elu(z)+1, Poisson partial
   float lsum = 0.f;
   const int n = n0 + lane;
-  for (int bl = wid; bl < b_end - b_begin; bl += kWarps) {
+  for (int bl = wid; bl < b_end - b_begin; bl += kFwdWarps) {
     if (n < N) {
       const int64_t o = (int64_t)(b_begin + bl) * N + n;
       const float z = zt[bl * 33 + lane];
@@ -165,18 +167,19 @@ __global__ void __launch_bounds__(kWarps * 32) readout_forward_kernel(
     if (threadIdx.x == 0) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) t += red[w];
+      for (int w = 0; w < kFwdWarps; ++w) t += red[w];
       loss_partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
     }
   }
 }
 
-// ---- 128-bit variants ---------------------------------------------------------------------------------
-// When the map's strides and base are 16-byte aligned (the core emits rows of emb_ld = 160 floats) a lane owns the
-// 4-channel chunks lane, lane + 32, ...: one LDG.128 per chunk instead of four scalar loads, and in the backward one
-// red.global.add.v4.f32 instead of four scalar reductions (the backward is bound by the rate at which an SM can
-// issue reductions: 79 M scalar ones per pass at B=16, N=8000).  A chunk that straddles C (155 = 38 chunks + 3) is
-// handled element-wise.  NC = ceil(C / 128) chunk rounds per lane.
+// ---- 128-bit backward ---------------------------------------------------------------------------------
+// When the map's strides and base are 16-byte aligned (the core emits rows of emb_ld = 160 floats) a lane of the
+// backward owns the 4-channel chunks lane, lane + 32, ...: one LDG.128 per chunk and one red.global.add.v4.f32
+// instead of four scalar reductions (79 M scalar ones per pass at B=16, N=8000).  A chunk that straddles C
+// (155 = 38 chunks + 3) is handled element-wise.  NC = ceil(C / 128) chunk rounds per lane.  Measured on the bench
+// workload: backward 1.89 -> 1.69 ms per step; the same layout in the FORWARD was slower (0.48 -> 0.78 ms: 25 of 32
+// lanes idle in the second round against 155/160 in the scalar layout) and is not used.
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -190,94 +193,6 @@ __device__ __forceinline__ void load_feature_chunks(const float* fs, int C, int 
       const int c = 4 * (lane + 32 * i) + e;
       f[i][e] = c < C ? fs[c * 33 + j] : 0.f;
     }
-}
-
-// grid / smem as readout_forward_kernel
-template <int NC>
-__global__ void __launch_bounds__(kWarps * 32) readout_forward_v4_kernel(
-    v1t_readout_shape s, const float* __restrict__ fmap, const float* __restrict__ mu,
-    const float* __restrict__ sigma, const float* __restrict__ noise, const float* __restrict__ shifts,
-    const float* __restrict__ features, const float* __restrict__ bias, const float* __restrict__ y_true,
-    float* __restrict__ z_out, float* __restrict__ y_out, float* __restrict__ loss_partials) {
-  extern __shared__ float smem[];
-  float* fs = smem;                                  // [C][33]
-  float* zt = smem + (size_t)s.channels * 33;        // [kBatchTile][33]
-  __shared__ float red[kWarps];
-  const int C = s.channels, N = s.neurons, B = s.batch;
-  const int n0 = blockIdx.x * kNeuronsPerCta;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int b_begin = blockIdx.y * kBatchTile, b_end = min(B, b_begin + kBatchTile);
-
-  stage_features(features, fs, C, N, n0);
-  __syncthreads();
-
-  for (int j = wid; j < kNeuronsPerCta; j += kWarps) {
-    const int n = n0 + j;
-    if (n >= N) break;  // warp-uniform
-    float f[NC][4];
-    load_feature_chunks<NC>(fs, C, j, lane, f);
-    const float bn = bias ? __ldg(bias + n) : 0.f;
-    for (int b = b_begin; b < b_end; ++b) {
-      const GridPos g = grid_position(mu, sigma, noise, shifts, b, n, N, s.gh, s.gw);
-      Corner cr;
-      make_corners(g, s.gh, s.gw, s.fs_y, s.fs_x, cr);
-      const float* base = fmap + (int64_t)b * s.fs_b;
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (cr.w[k] != 0.f) {  // warp-uniform
-          const float* px = base + cr.off[k];
-          float t = 0.f;
-#pragma unroll
-          for (int i = 0; i < NC; ++i) {
-            const int c = 4 * (lane + 32 * i);
-            if (c + 3 < C) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(px + c));
-              t = fmaf(v.x, f[i][0], t);
-              t = fmaf(v.y, f[i][1], t);
-              t = fmaf(v.z, f[i][2], t);
-              t = fmaf(v.w, f[i][3], t);
-            } else if (c < C) {
-#pragma unroll
-              for (int e = 0; e < 3; ++e)
-                if (c + e < C) t = fmaf(__ldg(px + c + e), f[i][e], t);
-            }
-          }
-          acc = fmaf(cr.w[k], t, acc);
-        }
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) zt[(b - b_begin) * 33 + j] = acc + bn;
-    }
-  }
-  __syncthreads();
-
-  float lsum = 0.f;
-  const int n = n0 + lane;
-  for (int bl = wid; bl < b_end - b_begin; bl += kWarps) {
-    if (n < N) {
-      const int64_t o = (int64_t)(b_begin + bl) * N + n;
-      const float z = zt[bl * 33 + lane];
-      z_out[o] = z;
-      const float y = elu1(z);
-      if (y_out) y_out[o] = y;
-      if (loss_partials) {
-        const float yp = y + kEpsF32, yt = __ldg(y_true + o) + kEpsF32;
-        lsum += yp - yt * logf(yp);
-      }
-    }
-  }
-  if (loss_partials) {
-    lsum = warp_sum(lsum);
-    if (lane == 0) red[wid] = lsum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) t += red[w];
-      loss_partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
-    }
-  }
 }
 
 __global__ void sum_scale_kernel(const float* __restrict__ partials, int n, float scale, float* __restrict__ out) {
@@ -739,25 +654,11 @@ extern "C" int v1t_readout_forward(const v1t_readout_shape* s, const float* fmap
     if (smem > 48 * 1024)                                                                                      \
       V1T_CUDA(cudaFuncSetAttribute(readout_forward_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                     (int)smem));                                                               \
-    readout_forward_kernel<NVV><<<grid, kWarps * 32, smem, st>>>(*s, fmap, mu, sigma, noise, shifts, features, \
+    readout_forward_kernel<NVV><<<grid, kFwdWarps * 32, smem, st>>>(*s, fmap, mu, sigma, noise, shifts, features, \
                                                                  bias, y_true, z, y_out,                       \
                                                                  loss_out ? ws.loss_partials : nullptr);       \
   } while (0)
-#define CALL4(NCC)                                                                                               \
-  do {                                                                                                           \
-    if (smem > 48 * 1024)                                                                                        \
-      V1T_CUDA(cudaFuncSetAttribute(readout_forward_v4_kernel<NCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)smem));                                                                 \
-    readout_forward_v4_kernel<NCC><<<grid, kWarps * 32, smem, st>>>(*s, fmap, mu, sigma, noise, shifts, features, \
-                                                                    bias, y_true, z, y_out,                       \
-                                                                    loss_out ? ws.loss_partials : nullptr);       \
-  } while (0)
-  if (vec4_ok(*s, fmap, nullptr)) {
-    V1T_NC_DISPATCH(s->channels, CALL4)
-  } else {
-    V1T_NV_DISPATCH(nv, CALL)
-  }
-#undef CALL4
+  V1T_NV_DISPATCH(nv, CALL)
 #undef CALL
   V1T_LAUNCH_CHECK();
   if (loss_out) {
