@@ -33,8 +33,23 @@ def _worker(rank, world, port, out):
     sync = parallel.GradSync(params + [frozen], bucket_mb=0.002)  # force several buckets
     assert len(list(sync.buckets())) > 1
     sync.all_reduce()
+    # second exchange: the first two parameters live in a flat gradient sink (shared-core case): reduced in place
+    from v1t_b200.functional import GradSink
+
+    shared = [torch.nn.Parameter(torch.randn(s)) for s in ((5, 3), (130,))]
+    own = [torch.nn.Parameter(torch.randn(s)) for s in ((9,), (4, 4))]
+    sink = GradSink(shared)
+    sink.arm()
+    g2 = torch.Generator().manual_seed(200 + rank)
+    for p in shared:
+        p.grad.copy_(torch.randn(p.shape, generator=g2))  # written through the view, like the core backward's add
+    for p in own:
+        p.grad = torch.randn(p.shape, generator=g2)
+    sync2 = parallel.GradSync(shared + own, bucket_mb=0.0002)
+    sync2.all_reduce(sinks=[sink])
+    views_ok = all(p.grad.data_ptr() == sink.view_of(p, sink.flat).data_ptr() for p in shared)
     if rank == 0:
-        out.put([p.grad.clone() for p in params])
+        out.put(([p.grad.clone() for p in params], [p.grad.clone() for p in shared + own], views_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,7 +61,7 @@ def test_gradsync_two_ranks_gloo():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = q.get()
+    got, got2, views_ok = q.get()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
@@ -61,6 +76,15 @@ def test_gradsync_two_ranks_gloo():
         want.append(tot)
     for a, b in zip(got, want):
         assert torch.allclose(a, b, atol=1e-6)
+    # sink exchange: same sums, and the shared parameters' .grad still view the sink's flat buffer
+    assert views_ok
+    shapes2 = ((5, 3), (130,), (9,), (4, 4))
+    gens2 = [torch.Generator().manual_seed(200 + r) for r in range(world)]
+    for i, s in enumerate(shapes2):
+        tot = torch.zeros(s)
+        for r in range(world):
+            tot += torch.randn(s, generator=gens2[r])
+        assert torch.allclose(got2[i], tot, atol=1e-6), i
 
 
 def test_mouse_assignment():

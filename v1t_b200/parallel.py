@@ -65,11 +65,30 @@ class GradSync:
         if cur:
             yield cur
 
+    @staticmethod
+    def _sink_is_live(sink) -> bool:
+        """True when every parameter of the sink has its .grad viewing the sink's flat buffer (GradSink.arm)."""
+        if sink is None or sink.flat is None or not sink.params:
+            return False
+        return all(p.grad is not None and p.grad.data_ptr() == sink.view_of(p, sink.flat).data_ptr()
+                   for p in sink.params)
+
     @torch.no_grad()
-    def all_reduce(self):
+    def all_reduce(self, sinks: t.Sequence = ()):
+        """``sinks``: GradSinks (functional.GradSink) whose flat buffers already hold their parameters' gradients
+        contiguously: those are reduced in place with one call each and their parameters skip the bucket copies.
+        Every rank must pass the same sinks (the collectives are issued in the same order on all ranks)."""
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
+        skip = set()
+        for sink in sinks:
+            if self._sink_is_live(sink):
+                dist.all_reduce(sink.flat, op=dist.ReduceOp.SUM)
+                skip.update(id(p) for p in sink.params)
         for i, bucket in enumerate(self.buckets()):
+            bucket = [p for p in bucket if id(p) not in skip]
+            if not bucket:
+                continue
             n = sum(p.numel() for p in bucket)
             flat = self._flat.get(i)
             dev = bucket[0].device
@@ -108,8 +127,10 @@ def sweep(model, criterion, batches: t.Dict[str, t.Dict[str, torch.Tensor]], glo
         loss = criterion(y_true=b["response"], y_pred=y, mouse_id=mouse_id, batch_size=global_batch[mouse_id])
         loss.backward()
         total = loss.detach() if total is None else total + loss.detach()
+    sinks = ()
     if fused_accumulate:
         model.core.fused_grad_accumulation(False)
+        sinks = (model.core.grad_sink,)  # its flat buffer IS the core gradients: reduced in place, no bucket copies
     if sync is not None:
-        sync.all_reduce()
+        sync.all_reduce(sinks=sinks)
     return total
