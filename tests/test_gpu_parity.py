@@ -763,3 +763,33 @@ def test_train_step_with_fused_optimizer_matches_oracle_update():
         + g.args["readout_reg_scale"] * np.abs(p0["readouts.A.features"]).sum()
     got = opt.reg_loss([g.args["core_reg_scale"], g.args["readout_reg_scale"], g.args["shifter_reg_scale"]])
     assert abs(float(got) - reg_ref) / reg_ref < 1e-5
+
+
+def test_extract_attention_maps_over_a_loader():
+    """rollout.extract_attention_maps (attention_rollout.py:136-203) on a two-batch loader, truncated to num_samples."""
+    from types import SimpleNamespace
+    from v1t_b200.rollout import Recorder, attention_rollouts, extract_attention_maps
+
+    g = Golden("tiny_eval")
+    model, _ = build(g)
+    d = g.mice["A"]
+    batch = {"image": torch.from_numpy(d["images"]), "behavior": torch.from_numpy(d["behaviors"]),
+             "pupil_center": torch.from_numpy(d["pupil_centers"])}
+
+    class Loader(list):
+        dataset = SimpleNamespace(mouse_id="A", i_transform_image=lambda x: x * 2.0)
+
+    B = d["images"].shape[0]
+    res = extract_attention_maps(Loader([batch, batch]), model, num_samples=B + 1, device=DEV)
+    assert set(res) == {"images", "heatmaps", "behaviors", "pupil_centers"}
+    assert res["heatmaps"].shape == (B + 1,) + d["images"].shape[2:]
+    assert res["images"].shape == (B + 1,) + d["images"].shape[1:]
+    assert np.allclose(res["images"][:B], 2.0 * d["images"]) and np.allclose(res["behaviors"][:B], d["behaviors"])
+    rec = Recorder(model.core)
+    with torch.no_grad():
+        _, attn = rec(images=cu(d["images"]), behaviors=cu(d["behaviors"]), pupil_centers=cu(d["pupil_centers"]),
+                      mouse_id="A")
+    want = attention_rollouts(attn, d["images"].shape[2:]).cpu().numpy()
+    rec.eject()
+    assert rel_err(res["heatmaps"][:B], want) < 1e-6 and rel_err(res["heatmaps"][B], want[0]) < 1e-6
+    assert all(len(b["mha"].attend._forward_hooks) == 0 for b in model.core.transformer.blocks)

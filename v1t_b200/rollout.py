@@ -25,44 +25,44 @@ def find_shape(num_patches: int):
 
 
 class Recorder(nn.Module):
-    """attention_rollout.py:15-75."""
+    """Collects the attention probabilities of every block during a core forward (the contract of
+    attention_rollout.py:15-75: hooks on ``mha.attend``; ``forward`` returns (core output, [B, blocks, heads, T, T]);
+    ``eject`` gives the core back without hooks)."""
 
     def __init__(self, core: ViTCore):
         super().__init__()
         self.core = core
         self.cache: t.List[torch.Tensor] = []
-        self.hooks = []
-        self.hook_registered = False
+        self._handles: t.List = []
         self.ejected = False
 
-    def _hook(self, _, inputs, outputs):
-        self.cache.append(outputs.detach())  # the probabilities are a fresh tensor per call: no clone needed
+    @property
+    def hook_registered(self) -> bool:
+        return bool(self._handles)
 
-    def _register_hook(self):
-        for module in self.core.transformer.modules():
-            if isinstance(module, Attention):
-                self.hooks.append(module.attend.register_forward_hook(self._hook))
-        self.hook_registered = True
-
-    def eject(self):
-        self.ejected = True
-        for hook in self.hooks:
-            hook.remove()
-        self.hooks.clear()
-        return self.core
+    def _attach(self):
+        attends = [m.attend for m in self.core.transformer.modules() if isinstance(m, Attention)]
+        # the probabilities handed to the hook are a fresh tensor per call: keep them without cloning
+        self._handles = [a.register_forward_hook(lambda _m, _i, probs: self.cache.append(probs.detach()))
+                         for a in attends]
 
     def clear(self):
-        self.cache.clear()
+        self.cache = []
+
+    def eject(self) -> ViTCore:
+        while self._handles:
+            self._handles.pop().remove()
+        self.ejected = True
+        return self.core
 
     def forward(self, images, behaviors, pupil_centers, mouse_id: str):
-        """Returns (core output, attentions [B, blocks, heads, T, T])."""
-        assert not self.ejected, "recorder has been ejected, cannot be used anymore"
+        if self.ejected:
+            raise AssertionError("recorder has been ejected, cannot be used anymore")
         self.clear()
-        if not self.hook_registered:
-            self._register_hook()
+        if not self._handles:
+            self._attach()
         outputs = self.core(inputs=images, behaviors=behaviors, pupil_centers=pupil_centers, mouse_id=mouse_id)
-        attentions = torch.stack(self.cache, dim=1) if self.cache else None
-        return outputs, attentions
+        return outputs, (torch.stack(self.cache, dim=1) if self.cache else None)
 
 
 def attention_rollouts(attentions: torch.Tensor, image_shape: t.Sequence[int]) -> torch.Tensor:
@@ -79,35 +79,33 @@ def attention_rollout(attention: torch.Tensor, image_shape: t.Sequence[int]) -> 
 
 @torch.no_grad()
 def extract_attention_maps(ds, model, num_samples: int = None, device="cuda") -> t.Dict[str, "torch.Tensor"]:
-    """attention_rollout.py:136-203 without the dataset's inverse transforms being optional: they are applied when
-    the dataset provides them."""
-    model.to(device)
-    model.train(False)
+    """Rollout heat maps for the samples of one mouse's DataLoader (attention_rollout.py:136-203): returns numpy arrays
+    ``images``, ``heatmaps``, ``behaviors``, ``pupil_centers`` (inverse-transformed when the dataset provides the
+    ``i_transform_*`` callables), truncated to ``num_samples``."""
     dataset = ds.dataset
     mouse_id = dataset.mouse_id
-    ident = lambda x: x  # noqa: E731
-    inv_image = getattr(dataset, "i_transform_image", ident)
-    inv_behavior = getattr(dataset, "i_transform_behavior", ident)
-    inv_pupil = getattr(dataset, "i_transform_pupil_center", ident)
+    undo = {name: getattr(dataset, attr, None) or (lambda x: x)
+            for name, attr in (("images", "i_transform_image"), ("behaviors", "i_transform_behavior"),
+                               ("pupil_centers", "i_transform_pupil_center"))}
+    model.to(device).train(False)
     recorder = Recorder(model.core)
-    results = {"images": [], "heatmaps": [], "pupil_centers": [], "behaviors": []}
-    count = num_samples
-    for batch in ds:
-        images, behaviors = batch["image"].to(device), batch["behavior"].to(device)
-        pupil_centers = batch["pupil_center"].to(device)
-        images, _ = model.image_cropper(inputs=images, mouse_id=mouse_id, behaviors=behaviors,
-                                        pupil_centers=pupil_centers)
-        _, attentions = recorder(images=images, behaviors=behaviors, pupil_centers=pupil_centers, mouse_id=mouse_id)
-        recorder.clear()
-        heatmaps = attention_rollouts(attentions, image_shape=images.shape[2:])
-        results["images"].append(inv_image(images.cpu()))
-        results["heatmaps"].append(heatmaps.cpu())
-        results["behaviors"].append(inv_behavior(behaviors.cpu()))
-        results["pupil_centers"].append(inv_pupil(pupil_centers.cpu()))
-        if num_samples is not None and (count := count - len(images)) <= 0:
-            break
-    recorder.eject()
-    results = {k: torch.vstack(v).numpy() for k, v in results.items()}
-    if num_samples is not None:
-        results = {k: v[:num_samples] for k, v in results.items()}
-    return results
+    chunks: t.Dict[str, list] = {"images": [], "heatmaps": [], "behaviors": [], "pupil_centers": []}
+    seen = 0
+    try:
+        for batch in ds:
+            if num_samples is not None and seen >= num_samples:
+                break
+            x = {k: batch[k].to(device) for k in ("image", "behavior", "pupil_center")}
+            images, _ = model.image_cropper(inputs=x["image"], mouse_id=mouse_id, behaviors=x["behavior"],
+                                            pupil_centers=x["pupil_center"])
+            _, attentions = recorder(images=images, behaviors=x["behavior"], pupil_centers=x["pupil_center"],
+                                     mouse_id=mouse_id)
+            recorder.clear()  # one batch of [B, L, H, T, T] at a time
+            chunks["heatmaps"].append(attention_rollouts(attentions, image_shape=images.shape[2:]).cpu())
+            chunks["images"].append(undo["images"](images.cpu()))
+            chunks["behaviors"].append(undo["behaviors"](x["behavior"].cpu()))
+            chunks["pupil_centers"].append(undo["pupil_centers"](x["pupil_center"].cpu()))
+            seen += len(images)
+    finally:
+        recorder.eject()
+    return {k: torch.vstack(v).numpy()[:num_samples] for k, v in chunks.items()}
