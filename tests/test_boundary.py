@@ -155,3 +155,63 @@ def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(ct), cname
         for fname, _ in ct._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+
+
+def test_grad_sink_views_accumulate_and_rearm_on_cpu():
+    """GradSink host logic (pure torch): .grad become views of one flat buffer, existing gradients are carried over,
+    a flat add shows up in every view, re-arming after zero_grad(set_to_none) starts from zero."""
+    from v1t_b200.functional import GradSink
+
+    ps = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7)),
+          torch.nn.Parameter(torch.randn(2), requires_grad=False)]
+    sink = GradSink(ps)
+    assert sink.numel == 16 + 8 and len(sink.params) == 2  # 16-byte aligned slots, frozen parameter left out
+    ps[1].grad = torch.ones(7)
+    sink.arm()
+    assert sink.armed and float(ps[0].grad.abs().sum()) == 0.0 and float(ps[1].grad.sum()) == 7.0
+    assert ps[0].grad.data_ptr() == sink.flat.data_ptr() and ps[1].grad.data_ptr() == sink.flat[16:].data_ptr()
+    slots = sink.slots([ps[0], None, ps[1], ps[2]])
+    assert slots == [(0, 15), None, (16, 7), None]
+    tmp = torch.zeros_like(sink.flat)
+    tmp[slots[0][0]:slots[0][0] + slots[0][1]].view(3, 5).fill_(2.0)
+    sink.flat.add_(tmp)
+    assert float(ps[0].grad.sum()) == 30.0 and float(ps[1].grad.sum()) == 7.0
+    for p in ps[:2]:
+        p.grad = None
+    sink.arm()
+    assert float(ps[0].grad.abs().sum()) == 0.0 and float(ps[1].grad.abs().sum()) == 0.0
+    sink.disarm()
+    assert not sink.armed and ps[0].grad.data_ptr() == sink.flat.data_ptr()  # views stay valid after disarming
+
+
+def test_fused_optimizer_device_table_packing_on_cpu():
+    """The optimizer's device table (v1t_opt_tensor records + chunk prefix) built on the host: pointers, sizes, group
+    learning rates, L1 coefficients and chunk counts land in the bytes the kernel will read."""
+    from v1t_b200.optim import FusedAdamWL1
+
+    lib = _lib.load()
+    chunk = lib.v1t_opt_chunk_elems()
+    a, b, c = (torch.nn.Parameter(torch.randn(n)) for n in (5, chunk + 1, 3 * chunk))
+    for p in (a, b, c):
+        p.grad = torch.zeros_like(p)
+    opt = FusedAdamWL1([{"params": [a, b], "lr": 0.5}, {"params": [c]}], lr=0.25, weight_decay=0.125,
+                       l1={a: (0.75, 1), c: 2.0})
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        opt._entries()  # the real path refuses CPU parameters; build the same records by hand for the packing check
+    entries = []
+    for group in opt.param_groups:
+        for p in group["params"]:
+            opt.state[p].update(step=torch.tensor(0.0), exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
+            coef, grp = opt._l1.get(p, (0.0, opt.n_l1_groups - 1))
+            entries.append((p, group, opt.state[p], coef, grp))
+    table, prefix, n_tensors, n_chunks, scratch, sums = opt._build_table(entries, torch.device("cpu"))
+    assert n_tensors == 3 and n_chunks == 1 + 2 + 3 and prefix.tolist() == [0, 1, 3, 6]
+    assert scratch.numel() >= lib.v1t_adamw_l1_scratch_bytes(n_chunks) == 8 * n_chunks and sums.numel() == opt.n_l1_groups
+    recs = (_lib.OptTensor * 3).from_buffer_copy(table.numpy().tobytes())
+    for rec, p, lr, l1, grp in zip(recs, (a, b, c), (0.5, 0.5, 0.25), (0.75, 0.0, 2.0), (1, opt.n_l1_groups - 1, 0)):
+        assert rec.param == p.data_ptr() and rec.grad == p.grad.data_ptr() and rec.numel == p.numel()
+        assert rec.exp_avg == opt.state[p]["exp_avg"].data_ptr() and rec.exp_avg_sq == opt.state[p]["exp_avg_sq"].data_ptr()
+        assert (rec.lr, rec.l1, rec.weight_decay, rec.group) == (lr, l1, 0.125, grp)
+    assert opt._build_table(entries, torch.device("cpu")) is opt._table  # unchanged pointers: table reused
+    sd = opt.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and len(sd["param_groups"]) == 2
