@@ -215,3 +215,43 @@ def test_fused_optimizer_device_table_packing_on_cpu():
     assert opt._build_table(entries, torch.device("cpu")) is opt._table  # unchanged pointers: table reused
     sd = opt.state_dict()
     assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and len(sd["param_groups"]) == 2
+
+
+def test_c_program_links_and_calls_the_library_without_python(tmp_path):
+    """The boundary is a plain C ABI: a C translation unit that only includes include/v1t_b200.h links against
+    libv1t_b200.so and calls the host-side entry points (sizes, error plumbing) with no GPU and no Python."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    _lib.load()  # builds the library if it is missing
+    src = tmp_path / "client.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "v1t_b200.h"
+int main(void) {
+  v1t_core_shape s;
+  memset(&s, 0, sizeof s);
+  s.batch = 16; s.in_ch = 1; s.in_h = 36; s.in_w = 64; s.patch = 8; s.stride = 1; s.emb = 155; s.heads = 4;
+  s.mlp = 488; s.blocks = 4; s.bdim = 5; s.impl = V1T_IMPL_BF16X3;
+  v1t_core_dims d;
+  if (v1t_core_dims_of(&s, &d) != V1T_OK) { printf("dims failed: %s\n", v1t_last_error()); return 1; }
+  printf("version %d tokens %d grid %dx%d emb_ld %d saved %zu scratch %zu\n", v1t_version(), d.tokens, d.gh, d.gw,
+         d.emb_ld, v1t_core_saved_bytes(&s), v1t_core_scratch_bytes(&s));
+  v1t_readout_shape r = {16, 8000, 155, 29, 57, 1654 * 160, 57 * 160, 160};
+  printf("readout scratch %zu rollout scratch %zu opt chunk %d\n", v1t_readout_scratch_bytes(&r),
+         v1t_rollout_scratch_bytes(16, 1654), v1t_opt_chunk_elems());
+  /* error path: a null member table must be refused before anything touches a device */
+  int rc = v1t_ensemble_forward(NULL, NULL, NULL, 10, NULL, NULL);
+  printf("rc %d err %s\n", rc, v1t_last_error());
+  return rc == V1T_ERR_INVALID ? 0 : 2;
+}
+''')
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", f"-I{ROOT}/include", "-o", str(exe), str(src),
+                    f"-L{libdir}", "-lv1t_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "tokens 1654 grid 29x57 emb_ld 160" in out and "rc -1 err ensemble: null member table" in out
