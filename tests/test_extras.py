@@ -354,3 +354,78 @@ def test_fused_adamw_unaligned_parameter_takes_the_scalar_path():
                                   weight_decay=0.1, grad_scale=0.5)
     assert rel_err(p.detach().cpu().numpy(), want) < TOL_F32
     assert rel_err(opt.state[p]["exp_avg"].cpu().numpy(), m) < TOL_F32
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU: size-independent properties of the oracle restatements (beyond the pinned fixtures)
+# ---------------------------------------------------------------------------------------------------
+def test_oracle_small_mlp_gradients_agree_with_finite_differences():
+    rng = np.random.default_rng(4)
+    w = [rng.standard_normal((6, 3)), rng.standard_normal((4, 6)), rng.standard_normal((2, 4))]
+    b = [rng.standard_normal(6), None, rng.standard_normal(2)]
+    acts = ["elu", "tanh", None]
+    x, dy = rng.standard_normal((9, 3)), rng.standard_normal((9, 2))
+    y, cache = XO.small_mlp_forward(x, w, b, acts)
+    gw, gb = XO.small_mlp_backward(dy, w, b, acts, cache)
+    assert gb[1] is None
+    eps = 1e-6
+    for l, idx in ((0, (2, 1)), (1, (3, 5)), (2, (1, 0))):
+        wp = [a.copy() for a in w]
+        wp[l][idx] += eps
+        wm = [a.copy() for a in w]
+        wm[l][idx] -= eps
+        num = ((XO.small_mlp_forward(x, wp, b, acts)[0] - XO.small_mlp_forward(x, wm, b, acts)[0]) * dy).sum() / (2 * eps)
+        assert abs(num - gw[l][idx]) < 1e-6 * max(1.0, abs(num))
+    bp, bm = [None if a is None else a.copy() for a in b], [None if a is None else a.copy() for a in b]
+    bp[0][3] += eps
+    bm[0][3] -= eps
+    num = ((XO.small_mlp_forward(x, w, bp, acts)[0] - XO.small_mlp_forward(x, w, bm, acts)[0]) * dy).sum() / (2 * eps)
+    assert abs(num - gb[0][3]) < 1e-6 * max(1.0, abs(num))
+
+
+def test_oracle_rollout_invariants():
+    """Head order does not matter (max over heads); a stack whose blocks all attend uniformly gives a map that is
+    constant before normalisation (0/0 -> NaN in the reference too), so use a one-hot perturbation instead: the
+    perturbed patch is the arg-max of the map."""
+    rng = np.random.default_rng(8)
+    L, H, T = 3, 4, 21
+    gh, gw = XO.find_shape(T - 1)  # (5, 4): the reference's own factorisation of the 20 patches
+    a = rng.random((L, H, T, T)) + 0.1
+    a /= a.sum(-1, keepdims=True)
+    base = XO.attention_rollout(a, (gh, gw))
+    assert np.allclose(XO.attention_rollout(a[:, ::-1], (gh, gw)), base)
+    assert base.min() == 0.0 and base.max() == 1.0
+    hot = np.full((L, H, T, T), 1.0 / T)
+    hot[:, :, :, 7] += 0.5  # every token of every block looks harder at token 7 = patch 6
+    hot /= hot.sum(-1, keepdims=True)
+    heat = XO.attention_rollout(hot, (gh, gw))  # same size as the patch grid: the resize is the identity
+    assert np.unravel_index(np.argmax(heat), heat.shape) == divmod(6, gw)
+    # row-vector formulation used by the CUDA kernel == matrix chain of the reference
+    m = a.max(1) + np.eye(T)
+    m /= m.sum(-1, keepdims=True)
+    r = m[-1][0]
+    for n in range(L - 2, -1, -1):
+        r = r @ m[n]
+    chain = m[0]
+    for n in range(1, L):
+        chain = m[n] @ chain
+    assert np.allclose(r, chain[0])
+
+
+def test_oracle_cropper_identity_and_adamw_closed_form():
+    rng = np.random.default_rng(2)
+    img = rng.standard_normal((2, 3, 6, 9))
+    ys, xs = np.linspace(-1, 1, 6, dtype=np.float32), np.linspace(-1, 1, 9, dtype=np.float32)
+    grid = np.stack(np.meshgrid(xs, ys), axis=-1)  # (x, y) at [row, col]
+    assert np.array_equal(XO.crop_resize(img, grid), img)
+    far = XO.crop_resize(img, grid, shifts=np.array([[3.0, 0.0], [0.0, -3.0]]))
+    assert np.all(far == 0.0)  # shifted fully outside: zero padding
+    # first AdamW step without regulariser or decay moves every coordinate by lr * sign(g) (up to eps)
+    p, g = rng.standard_normal(50), rng.standard_normal(50)
+    p1, m1, v1 = XO.adamw_l1_step(p, g, np.zeros(50), np.zeros(50), 1, 0.01, 0.9, 0.999, 1e-12)
+    assert np.allclose(p1, p - 0.01 * np.sign(g), atol=1e-9)
+    assert np.allclose(m1, 0.1 * g) and np.allclose(v1, 0.001 * g * g)
+    # the L1 term alone (zero data gradient) pulls towards zero and leaves exact zeros in place
+    q = np.array([0.5, -0.25, 0.0])
+    q1, _, _ = XO.adamw_l1_step(q, np.zeros(3), np.zeros(3), np.zeros(3), 1, 0.01, 0.9, 0.999, 1e-12, l1=0.3)
+    assert np.allclose(q1, [0.49, -0.24, 0.0])
