@@ -93,3 +93,121 @@ def test_mouse_assignment():
     owned = [parallel.mice_of_rank(mice, r, 8, "mouse") for r in range(8)]
     assert sorted(sum(owned, [])) == mice and owned[7] == []
     assert parallel.mice_of_rank(mice, 1, 2, "mouse") == ["B", "D", "F"]
+
+
+# ---- sweep() end to end on two ranks with a CPU stand-in for the model ------------------------------------------
+class _SinkLinear(torch.autograd.Function):
+    """y = x @ W^T with the core's sink protocol (functional._CoreFunction.backward): when the sink is armed the
+    weight gradient is added into the sink's flat buffer and autograd is told there is none."""
+
+    @staticmethod
+    def forward(ctx, x, w, sink_arg):
+        ctx.save_for_backward(x, w)
+        ctx.sink = sink_arg
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        gw = dy.t() @ x
+        if ctx.sink is not None and ctx.sink[0].armed:
+            sink, slots = ctx.sink
+            tmp = torch.zeros_like(sink.flat)
+            tmp[slots[0][0]:slots[0][0] + slots[0][1]].view(w.shape).copy_(gw)
+            sink.flat.add_(tmp)
+            gw = None
+        return None, gw, None
+
+
+class _FakeCore(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.randn(6, 4))
+        self.unused = torch.nn.Parameter(torch.randn(3))  # e.g. another mouse's behaviour MLP: zero gradient
+        self.frozen = False
+        self.grad_sink = None
+
+    def fused_grad_accumulation(self, on=True):
+        from v1t_b200.functional import GradSink
+
+        if not on:
+            if self.grad_sink is not None:
+                self.grad_sink.disarm()
+            return None
+        if self.grad_sink is None:
+            self.grad_sink = GradSink(list(self.parameters()))
+        self.grad_sink.arm()
+        return self.grad_sink
+
+    def forward(self, x):
+        arg = (self.grad_sink, self.grad_sink.slots([self.w])) if (self.grad_sink and self.grad_sink.armed) else None
+        return _SinkLinear.apply(x, self.w, arg)
+
+
+class _FakeModel(torch.nn.Module):
+    def __init__(self, mice):
+        super().__init__()
+        self.core = _FakeCore()
+        self.readouts = torch.nn.ModuleDict({m: torch.nn.Linear(6, 5) for m in mice})
+
+    def forward(self, inputs, mouse_id, behaviors, pupil_centers):
+        return self.readouts[mouse_id](self.core(inputs)), None, None
+
+
+def _sweep_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend="gloo")
+    mice = ["A", "B", "C"]
+    torch.manual_seed(3)
+    model = _FakeModel(mice)
+    g = torch.Generator().manual_seed(50 + rank)
+    batches = {m: {"image": torch.randn(4, 4, generator=g), "behavior": None, "pupil_center": None,
+                   "response": torch.randn(4, 5, generator=g)} for m in mice}
+    crit = lambda y_true, y_pred, mouse_id, batch_size: ((y_pred - y_true) ** 2).sum() / batch_size  # noqa: E731
+    gb = {m: 4 * world for m in mice}
+    sync = parallel.GradSync(model.parameters(), bucket_mb=0.0001)
+    results = []
+    for fused in (False, True, True):  # the second fused sweep starts from set_to_none gradients again
+        model.zero_grad(set_to_none=True)
+        total = parallel.sweep(model, crit, batches, gb, sync, fused_accumulate=fused)
+        results.append(({k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_parameters()},
+                        float(total)))
+    if rank == 0:
+        out.put((results, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sweep_two_ranks_fused_accumulation_matches_plain_and_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results, sd = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    (plain, loss0), (fused, loss1), (fused2, loss2) = results
+    assert loss0 == loss1 == loss2
+    for k in plain:
+        if plain[k] is None:  # never touched without the sink; the sink reports an explicit zero gradient
+            assert fused[k] is None or float(fused[k].abs().max()) == 0.0
+            continue
+        assert torch.allclose(fused[k], plain[k], atol=1e-6), k
+        assert torch.allclose(fused2[k], plain[k], atol=1e-6), k
+    # single-process reference: both ranks' batches through plain autograd on one copy of the model
+    mice = ["A", "B", "C"]
+    model = _FakeModel(mice)
+    model.load_state_dict(sd)
+    for rank in range(world):
+        g = torch.Generator().manual_seed(50 + rank)
+        for m in mice:
+            x, y = torch.randn(4, 4, generator=g), torch.randn(4, 5, generator=g)
+            pred, _, _ = model(x, m, None, None)
+            (((pred - y) ** 2).sum() / (4 * world)).backward()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(plain[k], p.grad, atol=1e-5), k
