@@ -100,7 +100,9 @@ int v1t_version(void);
 #define V1T_PHASE_LINEAR_BWD 6  /* dgrad/wgrad GEMMs, LN/GELU backward, reductions (K10) */
 #define V1T_PHASE_READOUT_FWD 7 /* readout + ELU1 + Poisson forward (K8) */
 #define V1T_PHASE_READOUT_BWD 8 /* readout backward (K9) */
-#define V1T_NUM_PHASES 9
+#define V1T_PHASE_ATTN_FWD_KERNEL 9  /* the fused attention forward launch alone (inside V1T_PHASE_ATTN_FWD) */
+#define V1T_PHASE_ATTN_BWD_KERNEL 10 /* the fused attention backward launch alone (inside V1T_PHASE_ATTN_BWD) */
+#define V1T_NUM_PHASES 11
 uint64_t v1t_launch_count(void);
 int v1t_prof_enable(int on);
 int v1t_prof_reset(void);

@@ -1,10 +1,11 @@
-"""Import the LIVE reference (bryanlimy/V1T) in the build container — TEST INFRASTRUCTURE.
+"""Import the LIVE reference (bryanlimy/V1T) — TEST / BASELINE INFRASTRUCTURE.
 
-Used only by scripts/make_golden.py and by the optional ``reference present`` checks in
-tests/ (skipped when /root/reference is absent, e.g. on the GPU box).  Recipe from
-SURVEY.md Appendix C: stub ``torchinfo`` (model.py:4) and ``v1t.utils.tensorboard``
-(model.py:13, needs matplotlib/seaborn) so ``from v1t.models import Model`` works
-without touching the reference tree.
+Looks for the reference at $V1T_REFERENCE_SRC, then /root/reference/src (build container), then oracle/_ref/src
+(the byte-identical copy staged by oracle/make_ref.py, which is what exists on the GPU box).  Used by
+scripts/make_golden*.py, tests/, __graft_entry__.smoke() and bench.py's reference / eager-baseline legs only.
+Recipe from SURVEY.md Appendix C: stub ``torchinfo`` (model.py:4) and ``v1t.utils.tensorboard`` (model.py:13, needs
+matplotlib/seaborn) so ``from v1t.models import Model`` works without touching the reference tree; ``import_train``
+additionally stubs ruamel.yaml / h5py (utils/yaml.py:7, data.py) so the reference's own train.py imports.
 """
 from __future__ import annotations
 
@@ -16,7 +17,19 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-REF_SRC = os.environ.get("V1T_REFERENCE_SRC", "/root/reference/src")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_ref_src() -> str:
+    cands = [os.environ.get("V1T_REFERENCE_SRC"), "/root/reference/src", os.path.join(_HERE, "_ref", "src")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "v1t")):
+            return c
+    return cands[1]
+
+
+REF_SRC = _find_ref_src()
+REF_ROOT = os.path.dirname(REF_SRC)  # train.py / ensemble.py live next to src/
 
 
 def reference_available() -> bool:
@@ -43,6 +56,38 @@ def import_reference():
     from v1t.utils import attention_rollout  # type: ignore
 
     return Model, losses, attention_rollout
+
+
+class _Stub:
+    """Attribute/call sink for optional third-party modules the hot path never touches."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __getattr__(self, name):
+        return _Stub()
+
+    def __call__(self, *a, **k):
+        return _Stub()
+
+
+def import_train():
+    """The reference's own top-level ``train`` module (train_step: train.py:42-81) with plotting / yaml / hdf5
+    dependencies stubbed.  Returns the module."""
+    import_reference()
+    for name in ("ruamel", "ruamel.yaml", "matplotlib", "seaborn", "h5py"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["ruamel.yaml"], "YAML"):
+        sys.modules["ruamel.yaml"].YAML = _Stub
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import train  # type: ignore
+
+    return train
 
 
 class FakeDataset:

@@ -113,8 +113,8 @@ def test_dropin_install_overwrites_reference_registries():
     import v1t.models.model as ref_model
     keep = (ref_core._CORES["vit"], ref_readout._READOUTS["gaussian2d"], ref_losses._CRITERION["poisson"],
             ref_model.ELU1, ref_model.get_model_info)
+    from v1t_b200 import dropin
     try:
-        from v1t_b200 import dropin
         dropin.install()
         g = Golden("tiny_train")
         model = ref_model.Model(_args(g), ds=make_ds(g.meta["neurons"]))  # the REFERENCE's Model class
@@ -125,8 +125,9 @@ def test_dropin_install_overwrites_reference_registries():
         crit = ref_losses.get_criterion(_args(g), ds=make_ds(g.meta["neurons"]))
         assert isinstance(crit, v1t_b200.PoissonLoss)
     finally:
-        (ref_core._CORES["vit"], ref_readout._READOUTS["gaussian2d"], ref_losses._CRITERION["poisson"],
-         ref_model.ELU1, ref_model.get_model_info) = keep
+        dropin.uninstall()
+    assert keep == (ref_core._CORES["vit"], ref_readout._READOUTS["gaussian2d"], ref_losses._CRITERION["poisson"],
+                    ref_model.ELU1, ref_model.get_model_info)  # uninstall() put the reference's own classes back
 
 
 def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):

@@ -747,9 +747,11 @@ def test_train_step_with_fused_optimizer_matches_oracle_update():
     opt = optim.build_optimizer(model, hp, ["A"])
     assert [grp["name"] for grp in opt.param_groups] == ["core", "readouts", "core_shifter"]
     torch.manual_seed(5)
-    res = optim.train_step("A", batch, model, opt, crit, update=True, micro_batch_size=batch["image"].shape[0],
-                           device=DEV)
+    # called exactly like train.py:97-108 does (keywords, a GradScaler argument)
+    res = optim.train_step(mouse_id="A", batch=batch, model=model, optimizer=opt, criterion=crit, scaler=None,
+                           update=True, micro_batch_size=batch["image"].shape[0], device=DEV)
     assert np.isfinite(float(res["loss/loss"]))
+    assert set(res) == {"loss/loss", "loss/reg_loss", "loss/total_loss"}  # the keys train.py:50 logs
     coef = optim.l1_coefficients(model, ["A"])
     named = dict(model.named_parameters())
     for k, grad in g0.items():
@@ -763,6 +765,9 @@ def test_train_step_with_fused_optimizer_matches_oracle_update():
         + g.args["readout_reg_scale"] * np.abs(p0["readouts.A.features"]).sum()
     got = opt.reg_loss([g.args["core_reg_scale"], g.args["readout_reg_scale"], g.args["shifter_reg_scale"]])
     assert abs(float(got) - reg_ref) / reg_ref < 1e-5
+    assert abs(float(res["loss/reg_loss"]) - reg_ref) / reg_ref < 1e-5  # model.regularizer("A") before any update
+    assert abs(float(res["loss/total_loss"]) - float(res["loss/loss"]) - reg_ref) / reg_ref < 1e-4
+    assert abs(float(optim.reg_loss_of(opt, model, "A")) - reg_ref) / reg_ref < 1e-5  # from the |p| by-product
 
 
 def test_extract_attention_maps_over_a_loader():

@@ -211,3 +211,92 @@ def test_sweep_two_ranks_fused_accumulation_matches_plain_and_single_process():
     for k, p in model.named_parameters():
         if p.grad is not None:
             assert torch.allclose(plain[k], p.grad, atol=1e-5), k
+
+
+# ---- rank plans (2-D mouse layout) and the group-wise exchange ----------------------------------------------------
+def test_plan_mouse2d_partitions_every_mouse_exactly_once_and_balances_ranks():
+    mice = list("ABCDEFG")
+    for world in (1, 2, 3, 4, 8):
+        batch = 16
+        plans = [parallel.make_plan(mice, r, world, "mouse2d", batch) for r in range(world)]
+        gb = batch * world
+        assert all(p.global_batch == {m: gb if world > 1 else batch for m in mice} for p in plans)
+        for p in plans:  # equal work, no idle rank, at most two mice at 7 mice / 8 ranks
+            rows = sum(hi - lo for lo, hi in p.my_slices.values())
+            assert rows == len(mice) * batch
+        if world == 8:
+            assert all(1 <= len(p.my_slices) <= 2 for p in plans)
+        for m in mice:  # the slices of one mouse tile [0, global batch) without gaps or overlap
+            cover = sorted(p.my_slices[m] for p in plans if m in p.my_slices)
+            assert cover[0][0] == 0 and cover[-1][1] == plans[0].global_batch[m]
+            assert all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+            assert plans[0].group_of(m) == tuple(r for r, p in enumerate(plans) if m in p.my_slices)
+    assert parallel.make_plan(mice, 0, 8, "mouse2d", 16).scaling == "weak"
+    assert parallel.make_plan(mice, 0, 8, "mouse", 16).scaling == "strong"
+    assert parallel.make_plan(mice, 7, 8, "mouse", 16).my_slices == {}
+
+
+def _plan_worker(rank, world, port, mode, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend="gloo")
+    mice = ["A", "B", "C", "D"]
+    batch = 3
+    torch.manual_seed(3)
+    model = _FakeModel(mice)
+    plan = parallel.make_plan(mice, rank, world, mode, batch)
+    sync = parallel.GradSync(model, plan)
+    g = torch.Generator().manual_seed(77)  # the GLOBAL batch of every mouse, identical on all ranks
+    full = {m: {"image": torch.randn(plan.global_batch[m], 4, generator=g), "behavior": None, "pupil_center": None,
+                "response": torch.randn(plan.global_batch[m], 5, generator=g)} for m in mice}
+    mine = {m: {k: (v[lo:hi] if v is not None else None) for k, v in full[m].items()}
+            for m, (lo, hi) in plan.my_slices.items()}
+    crit = lambda y_true, y_pred, mouse_id, batch_size: ((y_pred - y_true) ** 2).sum() / batch_size  # noqa: E731
+    for _ in range(2):  # the second sweep re-arms the flat buffers after set_to_none
+        model.zero_grad(set_to_none=True)
+        parallel.sweep(model, crit, mine, plan.global_batch, sync, fused_accumulate=True, micro_batch=2)
+    grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_parameters()}
+    out.put((rank, grads, dict(plan.my_slices), {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_plan_case(world, mode):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_plan_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get() for _ in range(world)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got.sort(key=lambda t: t[0])
+    mice = ["A", "B", "C", "D"]
+    gbatch = parallel.make_plan(mice, 0, world, mode, 3).global_batch
+    model = _FakeModel(mice)
+    model.load_state_dict(got[0][3])
+    g = torch.Generator().manual_seed(77)
+    for m in mice:  # single process: the whole global batch of every mouse through plain autograd
+        x, y = torch.randn(gbatch[m], 4, generator=g), torch.randn(gbatch[m], 5, generator=g)
+        pred, _, _ = model(x, m, None, None)
+        (((pred - y) ** 2).sum() / gbatch[m]).backward()
+    want = {k: p.grad for k, p in model.named_parameters()}
+    for rank, grads, slices, _ in got:
+        assert torch.allclose(grads["core.w"], want["core.w"], atol=1e-5), (rank, "core")  # shared core: every rank
+        for m in mice:
+            for suffix in ("weight", "bias"):
+                k = f"readouts.{m}.{suffix}"
+                if m in slices:  # a readout is complete on every rank of its mouse's group ...
+                    assert torch.allclose(grads[k], want[k], atol=1e-5), (rank, k)
+                else:            # ... and never reaches the others
+                    assert grads[k] is None, (rank, k)
+
+
+def test_sweep_mouse2d_three_ranks_gloo_matches_single_process():
+    _run_plan_case(3, "mouse2d")
+
+
+def test_sweep_batch_mode_two_ranks_gloo_matches_single_process():
+    _run_plan_case(2, "batch")

@@ -26,18 +26,38 @@ def _digest():
     files = _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files.append(os.path.join(os.path.dirname(PKG), "include", "v1t_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())  # names, not absolute paths: the tree moves (gpurun snapshot)
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
+def is_current() -> bool:
+    """True when the in-tree library was built from exactly the sources (and flags) that are in the tree now."""
+    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == _digest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ and link the shared library.  Returns its path."""
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+    """Compile every .cu under csrc/ and link the shared library.  Returns its path.  Serialised across processes
+    (torchrun ranks) by a file lock; the ranks that waited find the library current and return."""
+    import fcntl
+
+    if not force and is_current():
         return LIB
+    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    with open(os.path.join(PKG, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    digest = _digest()
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libv1t_b200.so")

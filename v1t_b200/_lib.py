@@ -11,7 +11,9 @@ import os
 
 V1T_MAX_BLOCKS = 16
 IMPL_FP32, IMPL_BF16X3, IMPL_BF16 = 0, 1, 2
-PHASES = ["patch", "ln_qkv", "attn_fwd", "proj", "mlp", "attn_bwd", "linear_bwd", "readout_fwd", "readout_bwd"]
+PHASES = ["patch", "ln_qkv", "attn_fwd", "proj", "mlp", "attn_bwd", "linear_bwd", "readout_fwd", "readout_bwd",
+          "attn_fwd_kernel", "attn_bwd_kernel"]  # the last two are nested inside attn_fwd / attn_bwd
+NESTED_PHASES = ("attn_fwd_kernel", "attn_bwd_kernel")
 IMPL_NAMES = {"fp32": IMPL_FP32, "bf16x3": IMPL_BF16X3, "exact": IMPL_BF16X3, "bf16": IMPL_BF16, "fast": IMPL_BF16}
 
 _f32p = C.POINTER(C.c_float)
@@ -157,11 +159,17 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise RuntimeError(f"{LIB_PATH} is missing; run `python -m v1t_b200._build`")
-        from . import _build
+    from . import _build
 
+    if not _build.is_current():
+        # absent, or stale relative to csrc/ + include/v1t_b200.h (a struct-layout change behind ctypes would corrupt
+        # memory silently): rebuild when nvcc is here, otherwise refuse to load
+        import shutil
+
+        have_nvcc = shutil.which("nvcc") is not None or os.path.exists("/usr/local/cuda/bin/nvcc")
+        if not build_if_missing or not have_nvcc:
+            state = "stale (sources changed since it was built)" if os.path.exists(LIB_PATH) else "missing"
+            raise RuntimeError(f"{LIB_PATH} is {state}; run `python -m v1t_b200._build`")
         _build.build()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():

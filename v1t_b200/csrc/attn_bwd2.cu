@@ -89,7 +89,11 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * 128, bh = blockIdx.y;
+  const int r0 = blockIdx.x * 128, bh = blockIdx.z;
+  // precision-budget experiment (kernels.cuh: attn_prec_env); 0 = all three bf16x3 terms everywhere
+  const bool out_lo = a.x3 && !(a.prec & 1);   // A_lo * B_hi term of the accumulating contraction
+  const bool dp_ylo = a.x3 && !(a.prec & 6);   // Y_lo * y_hi term of dP' (resident lo plane in shared memory, SS form)
+  const bool dp_ysl = a.x3 && !(a.prec & 4);   // Y_hi * y_lo term of dP'
   const int nt = (a.T + N - 1) / N;
   constexpr bool kv_roles = MODE == MODE_V ? true : KV;  // rows = keys, streamed = queries
   const uint8_t* X_hi = kv_roles ? a.k_hi : a.q_hi;   const uint8_t* X_lo = kv_roles ? a.k_lo : a.q_lo;
@@ -135,7 +139,7 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
     if (lane == 0) {
       const bool is_x = warp == kLoadWarpX;
       if (is_x) {  // also fetches the resident Y lo plane
-        if (MODE == MODE_S && a.x3) {
+        if (MODE == MODE_S && dp_ylo) {
           mbar_expect_tx(res_full, L::kYlo);
 #pragma unroll
           for (int at_i = 0; at_i < AD; ++at_i) {  // resident layout [atom][128 rows][64 B] from two 64-row plane tiles
@@ -214,10 +218,8 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
           const uint32_t bo = (ks >> 1) * (tb / 16) + (ks & 1) * 2, ao = (ks >> 1) * (8192 / 16) + (ks & 1) * 2;
           if (leader) {
             umma_bf16_ts(dDP, tY_hi + ks * 8, yh + bo, idesc_s, ks > 0 ? 1u : 0u);
-            if (a.x3) {
-              umma_bf16(dDP, dYlo + ao, yh + bo, idesc_s, 1u);
-              umma_bf16_ts(dDP, tY_hi + ks * 8, yl + bo, idesc_s, 1u);
-            }
+            if (dp_ylo) umma_bf16(dDP, dYlo + ao, yh + bo, idesc_s, 1u);
+            if (dp_ysl) umma_bf16_ts(dDP, tY_hi + ks * 8, yl + bo, idesc_s, 1u);
           }
         }
       }
@@ -240,10 +242,8 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
       for (int ks = 0; ks < N / 16; ++ks) {
         if (leader) {
           umma_bf16_ts(tOut, tPS_hi + ks * 8, bh_ + ks * 64, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-          if (a.x3) {
-            umma_bf16_ts(tOut, tPS_lo + ks * 8, bh_ + ks * 64, idesc_o, 1u);
-            umma_bf16_ts(tOut, tPS_hi + ks * 8, bl_ + ks * 64, idesc_o, 1u);
-          }
+          if (out_lo) umma_bf16_ts(tOut, tPS_lo + ks * 8, bh_ + ks * 64, idesc_o, 1u);
+          if (a.x3) umma_bf16_ts(tOut, tPS_hi + ks * 8, bl_ + ks * 64, idesc_o, 1u);
         }
       }
       if (leader) {
@@ -409,7 +409,7 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
         split8_words(x, hw, lw);
         const uint32_t col = (slot * NH + ch * 8) / 2;
         tmem_st4(tmem_base + lane_off + cPS_hi + col, hw[0], hw[1], hw[2], hw[3]);
-        if (a.x3) tmem_st4(tmem_base + lane_off + cPS_lo + col, lw[0], lw[1], lw[2], lw[3]);
+        if (out_lo) tmem_st4(tmem_base + lane_off + cPS_lo + col, lw[0], lw[1], lw[2], lw[3]);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -476,13 +476,16 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
-// The three launches (dV, dK, dQ) are independent: ONE grid runs them back to back (blockIdx.z = which) so that the
-// 5.6-wave tails of three separate launches (832 CTAs on 148 SMs each) become one 16.9-wave launch.
+// The three passes (dK, dQ, dV) are independent: ONE grid runs them (blockIdx.y = which) so that the 5.6-wave tails of
+// three separate launches (832 CTAs on 148 SMs each) become one 16.9-wave launch.  (b, h) is the OUTERMOST grid
+// index: the 39 CTAs of one head are dispatched together and share its Q / K / V / dO planes (4.3 MB) through L2
+// instead of every pass re-streaming all heads from HBM (753 MB read per launch with the pass outermost).  The dV
+// CTAs (half as long as the other two) come last within a head, so the launch also ends on short CTAs.
 template <int AD>
 __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a) {
-  if (blockIdx.z == 0) attn_bwd2_body<MODE_V, true, 64, AD>(a);        // dV
-  else if (blockIdx.z == 1) attn_bwd2_body<MODE_S, true, 32, AD>(a);   // dK
-  else attn_bwd2_body<MODE_S, false, 32, AD>(a);                       // dQ
+  if (blockIdx.y == 0) attn_bwd2_body<MODE_S, true, 32, AD>(a);        // dK
+  else if (blockIdx.y == 1) attn_bwd2_body<MODE_S, false, 32, AD>(a);  // dQ
+  else attn_bwd2_body<MODE_V, true, 64, AD>(a);                        // dV
 }
 
 template <int AD>
@@ -490,7 +493,7 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
   constexpr uint32_t smem = std::max({Smem2<MODE_V, 64, AD>::total, Smem2<MODE_S, 32, AD>::total});
   static_assert(smem <= 232448, "shared memory budget exceeded");
   V1T_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(a.T, 128), a.B * a.H, 3);
+  dim3 grid(cdiv(a.T, 128), 3, a.B * a.H);
   attn_bwd2_kernel<AD><<<grid, kThreadsAttn, smem, st>>>(a);
   V1T_LAUNCH_CHECK();
   return V1T_OK;

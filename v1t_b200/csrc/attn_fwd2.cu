@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
   const int q0 = qt * BQ;
   const int at = a.Tp / 32;
   const int nk = (a.T + BKEY - 1) / BKEY;
+  const bool p_lo = a.x3 && !(a.prec & 1);  // P_lo * V_hi term of P V (precision-budget experiment, kernels.cuh)
 
   if (threadIdx.x == 0) {
     mbar_init(q_ready, kSmThreads);
@@ -203,10 +204,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
         const uint32_t vo = ks * (16 * 64 / 16);
         if (leader) {
           umma_bf16_ts(tO, tP_hi + ks * 8, vh + vo, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-          if (a.x3) {
-            umma_bf16_ts(tO, tP_lo + ks * 8, vh + vo, idesc_o, 1u);
-            umma_bf16_ts(tO, tP_hi + ks * 8, vl + vo, idesc_o, 1u);
-          }
+          if (p_lo) umma_bf16_ts(tO, tP_lo + ks * 8, vh + vo, idesc_o, 1u);
+          if (a.x3) umma_bf16_ts(tO, tP_hi + ks * 8, vl + vo, idesc_o, 1u);
         }
       }
       if (leader) {
@@ -346,7 +345,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
         split8_words(x, hw, lw);
         const uint32_t col = (slot * NW + ch * 8) / 2;
         tmem_st4(tmem_base + lane_off + cP_hi + col, hw[0], hw[1], hw[2], hw[3]);
-        if (a.x3) tmem_st4(tmem_base + lane_off + cP_lo + col, lw[0], lw[1], lw[2], lw[3]);
+        if (p_lo) tmem_st4(tmem_base + lane_off + cP_lo + col, lw[0], lw[1], lw[2], lw[3]);
       }
       tmem_st_wait();
       tc_fence_before();

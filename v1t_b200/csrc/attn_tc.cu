@@ -42,6 +42,10 @@ AttnPlanes carve_attn_planes(void* base, int B, int H, int Tp, int Dp, bool with
 }  // namespace v1t
 
 namespace v1t {
+int attn_prec_env() {
+  const char* e = getenv("V1T_ATTN_PREC");  // read on every call: tests switch it between launches
+  return e ? atoi(e) & 7 : 0;
+}
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
   return attn_fwd2_tc(a, st);
 }
@@ -75,6 +79,7 @@ extern "C" int v1t_attn_forward(const float* qkv, int B, int H, int T, int E, in
   a.B = B; a.H = H; a.T = T; a.Tp = Tp; a.E = E; a.Dp = Dp;
   a.scale_log2 = (1.0f / sqrtf((float)E)) * 1.4426950408889634f;
   a.x3 = x3;
+  a.prec = attn_prec_env();
   a.drop = DropSpec{seed, site, p_drop};
   return attn_fwd_dispatch(a, st);
 }
@@ -105,6 +110,7 @@ extern "C" int v1t_attn_backward(const float* qkv, const float* out, const float
   a.scale = 1.0f / sqrtf((float)E);
   a.scale_log2 = a.scale * 1.4426950408889634f;
   a.x3 = x3;
+  a.prec = attn_prec_env();
   a.drop = DropSpec{seed, site, p_drop};
   return attn_bwd_dispatch(a, st);
 }

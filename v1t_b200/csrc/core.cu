@@ -365,8 +365,12 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       fa.B = d.B; fa.H = d.heads; fa.T = d.T; fa.Tp = d.Tq; fa.E = d.E; fa.Dp = d.Ep;
       fa.scale_log2 = (1.0f / sqrtf((float)d.E)) * 1.4426950408889634f;
       fa.x3 = x3;
+      fa.prec = attn_prec_env();
       fa.drop = site_drop(*shape, i, kSiteAttn);
-      V1T_TRY(attn_fwd_dispatch(fa, st));
+      {
+        ProfScope kprof(V1T_PHASE_ATTN_FWD_KERNEL, st);
+        V1T_TRY(attn_fwd_dispatch(fa, st));
+      }
     }
     for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);
@@ -565,8 +569,12 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       ba.B = d.B; ba.H = d.heads; ba.T = d.T; ba.Tp = d.Tq; ba.E = d.E; ba.Dp = d.Ep;
       ba.scale = scale; ba.scale_log2 = scale * 1.4426950408889634f;
       ba.x3 = x3;
+      ba.prec = attn_prec_env();
       ba.drop = site_drop(*shape, i, kSiteAttn);
-      V1T_TRY(attn_bwd_dispatch(ba, st));
+      {
+        ProfScope kprof(V1T_PHASE_ATTN_BWD_KERNEL, st);
+        V1T_TRY(attn_bwd_dispatch(ba, st));
+      }
     }
     for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_BWD, st);

@@ -154,8 +154,13 @@ struct AttnFwdArgs {
   int B, H, T, Tp, E, Dp;
   float scale_log2;  // E^-0.5 * log2(e)
   int x3;
+  int prec;          // precision-budget experiment (attn_prec_env): bit 0 = P enters P V as its bf16 hi plane only
   DropSpec drop;
 };
+// V1T_ATTN_PREC (default 0 = every contraction with all three bf16x3 terms).  Bits drop ONE cross term of a
+// contraction: 1 = the Pd'/dS'/P operand of the accumulating MMAs is hi-only, 2 = dP' without the resident-lo term
+// (the only SS-form MMAs of the backward), 4 = dP' from the hi planes alone.  Measured in DESIGN.md 4.2.
+int attn_prec_env();
 int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // Q and P in tensor memory (attn_fwd2.cu)
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st);
 struct AttnBwdArgs {
@@ -167,6 +172,7 @@ struct AttnBwdArgs {
   int B, H, T, Tp, E, Dp;
   float scale_log2, scale;
   int x3;
+  int prec;            // see attn_prec_env()
   DropSpec drop;
 };
 int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st);  // resident operands in tensor memory (attn_bwd2.cu)

@@ -162,8 +162,8 @@ class _CoreFunction(torch.autograd.Function):
     """tokens[B,T,emb_ld] = ViTCore(images, behaviors; params)   (vit.py:423-436 without the final view)."""
 
     @staticmethod
-    def forward(ctx, spec: CoreSpec, p_tokens: float, p_block: float, seed: int, keep_saved, sink, images, behaviors,
-                *params):
+    def forward(ctx, spec: CoreSpec, p_tokens: float, p_block: float, seed: int, keep_saved, sink, want_grad: bool,
+                images, behaviors, *params):
         lib = _lib.load()
         _need_cuda(images, behaviors, *params)
         images = _f32c(images)
@@ -173,8 +173,10 @@ class _CoreFunction(torch.autograd.Function):
         shape = spec.shape(B, p_tokens, p_block, seed)
         dims = spec.dims()
         dev = images.device
-        need_grad = any(ctx.needs_input_grad)
-        keep = bool(need_grad or keep_saved)
+        # `want_grad` is evaluated by core_forward() OUTSIDE this Function: ctx.needs_input_grad ignores
+        # torch.no_grad() and grad mode always reads as disabled in here.  `keep_saved` (a dict, possibly empty) asks
+        # for the saved activations regardless (attention-map hooks on a frozen / no_grad model).
+        keep = bool(want_grad) or keep_saved is not None
         saved = None
         if keep:
             saved = torch.empty(lib.v1t_core_saved_bytes(C.byref(shape)), dtype=torch.uint8, device=dev)
@@ -208,7 +210,7 @@ class _CoreFunction(torch.autograd.Function):
         shape = spec.shape(*ctx.shape_args)
         dev = images.device
         d_tokens = d_tokens.contiguous().clone()  # clobbered by the library
-        needs = ctx.needs_input_grad[8:]
+        needs = ctx.needs_input_grad[9:]
         flat_tmp = None
         if ctx.sink is not None and ctx.sink[0].armed:
             sink, slots = ctx.sink
@@ -219,7 +221,7 @@ class _CoreFunction(torch.autograd.Function):
                      for p, need, slot in zip(params, needs, slots)]
         else:
             grads = [torch.empty_like(p) if (p is not None and need) else None for p, need in zip(params, needs)]
-        d_images = torch.empty_like(images) if ctx.needs_input_grad[6] else None
+        d_images = torch.empty_like(images) if ctx.needs_input_grad[7] else None
         scratch = _scratch(dev, lib.v1t_core_scratch_bytes(C.byref(shape)))
         pptr, gptr = _fill_ptrs(params, spec.blocks), _fill_ptrs(grads, spec.blocks)
         with torch.cuda.device(dev):
@@ -230,7 +232,7 @@ class _CoreFunction(torch.autograd.Function):
         if flat_tmp is not None:
             ctx.sink[0].flat.add_(flat_tmp)  # one kernel for every core parameter; autograd sees no gradient
             grads = [None] * len(grads)
-        return (None, None, None, None, None, None, d_images, None, *grads)
+        return (None, None, None, None, None, None, None, d_images, None, *grads)
 
 
 def core_forward(spec: CoreSpec, images, behaviors, params, p_tokens=0.0, p_block=0.0, seed=0, keep_saved=None,
@@ -238,8 +240,10 @@ def core_forward(spec: CoreSpec, images, behaviors, params, p_tokens=0.0, p_bloc
     """Returns tokens [B, T, emb_ld] (fp32).  `params`: list in the order cls,pos,wpe,bpe + BLOCK_FIELDS per block.
     ``sink``: an armed GradSink receives the parameter gradients in one add instead of autograd's per-tensor adds."""
     sink_arg = (sink, sink.slots(params)) if (sink is not None and sink.armed) else None
-    return _CoreFunction.apply(spec, float(p_tokens), float(p_block), int(seed), keep_saved, sink_arg, images,
-                               behaviors, *params)
+    want_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (images, behaviors, *params))
+    return _CoreFunction.apply(spec, float(p_tokens), float(p_block), int(seed), keep_saved, sink_arg, want_grad,
+                               images, behaviors, *params)
 
 
 def attention_probs(spec: CoreSpec, keep: dict, block: int) -> torch.Tensor:

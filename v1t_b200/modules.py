@@ -402,6 +402,11 @@ class Gaussian2DReadout(Readout):
             noise = torch.empty((b, n, 1, 2), dtype=torch.float32, device=inputs.device).normal_()
         if noise is not None:
             noise = noise.reshape(b, n, 2)
+        if not self._predicted_grid:
+            # the reference clamps the `_mu` PARAMETER in place on every forward (gaussian2d.py:212-215; with the grid
+            # predictor the same line acts on a temporary and is a no-op)
+            with torch.no_grad():
+                self._mu.clamp_(min=-1, max=1)
         return VF.readout_forward(inputs, self.mu.view(n, 2), self.sigma.view(n, 2, 2), noise, shifts,
                                   self.features.view(c, n), self.bias)
 

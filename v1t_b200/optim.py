@@ -26,27 +26,36 @@ from . import _lib
 from .functional import _stream_ptr
 
 
-def l1_coefficients(model, mouse_ids: t.Sequence[str]) -> t.Dict[torch.nn.Parameter, t.Tuple[float, int]]:
+def l1_coefficients(model, mouse_ids: t.Sequence[str], per_mouse_groups: bool = False
+                    ) -> t.Dict[torch.nn.Parameter, t.Tuple[float, int]]:
     """(coefficient, group) of the L1 term each parameter receives over ONE optimizer step that visits every mouse
     in ``mouse_ids`` once (train.py:97-111).  Groups: 0 = core (regularised once per mouse step, model.py:143-144),
-    1 = readout features, 2 = shifters (parameters without a regulariser land in the optimizer's last group)."""
+    1 = readout features, 2 = shifters (parameters without a regulariser land in the optimizer's last group).
+    ``per_mouse_groups``: mouse i gets its own groups 1+3i (readout features), 2+3i (core shifter), 3+3i (image
+    shifter), so that the per-mouse ``loss/reg_loss`` of train.py:71 can be read back (see ``l1_group_count``)."""
     coef: t.Dict[torch.nn.Parameter, t.Tuple[float, int]] = {}
     if not model.core.frozen:
         scale = float(model.core.reg_scale) * len(mouse_ids)
         for p in model.core.parameters():
             coef[p] = (scale, 0)
-    for m in mouse_ids:
+    for i, m in enumerate(mouse_ids):
+        g_feat, g_cs, g_is = (1 + 3 * i, 2 + 3 * i, 3 + 3 * i) if per_mouse_groups else (1, 2, 2)
         readout = model.readouts[m]
-        coef[readout.features] = (float(readout.reg_scale), 1)
+        coef[readout.features] = (float(readout.reg_scale), g_feat)
         if getattr(model, "core_shifter", None) is not None:
             shifter = model.core_shifter[m]
             for p in shifter.parameters():
-                coef[p] = (float(shifter.reg_scale), 2)
+                coef[p] = (float(shifter.reg_scale), g_cs)
         image_shifter = getattr(model.image_cropper, "image_shifter", None)
         if image_shifter is not None:
             for p in image_shifter[m].parameters():
-                coef[p] = (float(image_shifter[m].reg_scale), 2)
+                coef[p] = (float(image_shifter[m].reg_scale), g_is)
     return coef
+
+
+def l1_group_count(n_mice: int) -> int:
+    """Number of L1 groups of the per-mouse layout: core + 3 per mouse + the trailing unregularised group."""
+    return 1 + 3 * n_mice + 1
 
 
 L1_GROUP_NAMES = ("core", "readout_features", "shifters", "unregularised")  # the last one: every other parameter
@@ -181,19 +190,45 @@ class FusedAdamWL1(torch.optim.Optimizer):
 
 
 def build_optimizer(model, args, mouse_ids: t.Sequence[str]) -> FusedAdamWL1:
-    """The reference's optimizer construction (train.py:216-223) with the regulariser folded in."""
+    """The reference's optimizer construction (train.py:216-223) with the regulariser folded in; per-mouse L1 groups
+    so that ``train_step`` can report the reference's per-mouse ``loss/reg_loss``."""
     core_lr = args.lr if getattr(args, "core_lr", None) is None else args.core_lr
-    return FusedAdamWL1(model.get_parameters(core_lr=core_lr), lr=args.lr,
-                        betas=(args.adam_beta1, args.adam_beta2), eps=args.adam_eps, weight_decay=0,
-                        l1=l1_coefficients(model, mouse_ids))
+    mouse_ids = list(mouse_ids)
+    opt = FusedAdamWL1(model.get_parameters(core_lr=core_lr), lr=args.lr,
+                       betas=(args.adam_beta1, args.adam_beta2), eps=args.adam_eps, weight_decay=0,
+                       l1=l1_coefficients(model, mouse_ids, per_mouse_groups=True),
+                       n_l1_groups=l1_group_count(len(mouse_ids)))
+    image_shifter = getattr(model.image_cropper, "image_shifter", None)
+    opt.l1_layout = {
+        "core": 0.0 if model.core.frozen else float(model.core.reg_scale),
+        "mice": {m: (i, float(model.readouts[m].reg_scale),
+                     float(model.core_shifter[m].reg_scale) if getattr(model, "core_shifter", None) is not None else 0.0,
+                     float(image_shifter[m].reg_scale) if image_shifter is not None else 0.0)
+                 for i, m in enumerate(mouse_ids)}}
+    return opt
+
+
+def reg_loss_of(optimizer: FusedAdamWL1, model, mouse_id: str) -> torch.Tensor:
+    """model.regularizer(mouse_id) (model.py:141-149) from the |p| sums of the optimizer's last pass (the parameters
+    as they were before that update); computed directly while no step has been taken yet."""
+    layout = getattr(optimizer, "l1_layout", None)
+    if layout is None or optimizer.last_l1_sums is None or mouse_id not in layout["mice"]:
+        with torch.no_grad():
+            return torch.as_tensor(model.regularizer(mouse_id), dtype=torch.float32)
+    i, r_feat, r_cs, r_is = layout["mice"][mouse_id]
+    s = optimizer.last_l1_sums
+    return layout["core"] * s[0] + r_feat * s[1 + 3 * i] + r_cs * s[2 + 3 * i] + r_is * s[3 + 3 * i]
 
 
 def train_step(mouse_id: str, batch: t.Dict[str, torch.Tensor], model, optimizer: FusedAdamWL1, criterion,
-               update: bool, micro_batch_size: int, device: torch.device = "cuda") -> t.Dict[str, torch.Tensor]:
-    """Mirror of the reference's train_step (train.py:40-81; no GradScaler: fp16 AMP is replaced by the declared
-    bf16x3 / bf16 modes).  The regulariser is not part of the graph: its gradient is applied by
-    ``optimizer.step`` and its value is reported after an update from the optimizer's by-product."""
+               scaler=None, update: bool = True, micro_batch_size: int = 0, device: torch.device = "cuda"
+               ) -> t.Dict[str, torch.Tensor]:
+    """Same signature and result keys as the reference's train_step (train.py:42-81), so the call at train.py:97-108
+    works unchanged.  ``scaler`` is accepted and ignored (fp16 AMP is replaced by the declared bf16x3 / bf16 modes,
+    SURVEY F7).  The regulariser is not part of the graph: its gradient is applied by ``optimizer.step``; its value
+    (``loss/reg_loss``, per mouse) comes from the optimizer's by-product, i.e. one update behind the parameters."""
     model.to(device)
+    micro_batch_size = micro_batch_size or batch["image"].size(0)
     batch_size = batch["image"].size(0)
     losses = []
     for lo in range(0, batch_size, micro_batch_size):
@@ -205,7 +240,9 @@ def train_step(mouse_id: str, batch: t.Dict[str, torch.Tensor], model, optimizer
         loss = criterion(y_true=y_true, y_pred=y_pred, mouse_id=mouse_id, batch_size=batch_size)
         loss.backward()
         losses.append(loss.detach())
-    result = {"loss/loss": torch.stack(losses).sum()}
+    loss = torch.stack(losses).sum()
+    reg = reg_loss_of(optimizer, model, mouse_id).to(loss.device)  # the micro-batch fractions of train.py:71 sum to 1
+    result = {"loss/loss": loss.cpu(), "loss/reg_loss": reg.cpu(), "loss/total_loss": (loss + reg).cpu()}
     if update:
         optimizer.step(zero_grad=True)
     return result
