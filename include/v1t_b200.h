@@ -64,7 +64,15 @@ typedef struct v1t_core_dims { /* derived sizes, see v1t_core_dims_of() */
   int32_t mlp_ld;   /* row stride of the MLP hidden buffer (M rounded up to 32) */
   int32_t patch_dim;/* C*patch*patch */
   int32_t hid;      /* BehaviorMLP hidden = E/2 */
+  int32_t attn_path;/* V1T_ATTN_FUSED or V1T_ATTN_MATERIALISED: which attention kernels this shape/impl runs */
 } v1t_core_dims;
+/* Attention dispatch (decided by shape and impl, reported here so that no caller is switched silently):
+ * FUSED: tcgen05 flash-style kernels, operands resident in tensor memory; needs head dim (= emb) <= 160, because the
+ * 128 x Dp fp32 accumulators plus the resident bf16 operands must fit the 512 TMEM columns.
+ * MATERIALISED: softmax(QK^T) of a batch chunk is written out ([chunk,H,T,T] fp32) between batched GEMMs -- CUDA-core
+ * GEMMs for V1T_IMPL_FP32, tcgen05 GEMMs otherwise (the scaled core, emb 512 = head dim 512). */
+#define V1T_ATTN_MATERIALISED 0
+#define V1T_ATTN_FUSED 1
 
 /* per-block parameter pointers, reference state-dict layouts; NULL = absent bias */
 typedef struct v1t_block_ptrs {

@@ -29,7 +29,11 @@ class CoreShape(C.Structure):
 
 
 class CoreDims(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("gh", "gw", "tokens", "emb_ld", "inner", "mlp_ld", "patch_dim", "hid")]
+    _fields_ = [(n, C.c_int32) for n in ("gh", "gw", "tokens", "emb_ld", "inner", "mlp_ld", "patch_dim", "hid",
+                                         "attn_path")]
+
+
+ATTN_MATERIALISED, ATTN_FUSED = 0, 1
 
 
 BLOCK_FIELDS = ("ln1_w", "ln1_b", "wqkv", "wproj", "bproj", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2",

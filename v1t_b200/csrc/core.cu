@@ -242,6 +242,7 @@ extern "C" int v1t_core_dims_of(const v1t_core_shape* shape, v1t_core_dims* out)
   V1T_CHECK_ARG(out, "core_dims_of: null out");
   out->gh = d.gh; out->gw = d.gw; out->tokens = d.T; out->emb_ld = d.Ep; out->inner = d.I; out->mlp_ld = d.Mp;
   out->patch_dim = d.pd; out->hid = d.hid;
+  out->attn_path = d.fused ? V1T_ATTN_FUSED : V1T_ATTN_MATERIALISED;
   return V1T_OK;
 }
 

@@ -234,6 +234,13 @@ class ViTCore(Core):
             d1 -= 1
         return d1, num_patches // d1
 
+    @property
+    def attention_path(self) -> str:
+        """"fused" (tcgen05 flash-style kernels, head dim <= 160) or "materialised" (batched GEMMs around a [chunk,H,T,T]
+        probability buffer: the fp32 impl, and head dims the 512 TMEM columns cannot hold) — decided by the library
+        from shape and impl, reported so that nothing is switched silently."""
+        return "fused" if self.spec.dims().attn_path == _lib.ATTN_FUSED else "materialised"
+
     def regularizer(self):
         """L1 over all core parameters (vit.py:419-421)."""
         return self.reg_scale * sum(p.abs().sum() for p in self.parameters())
