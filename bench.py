@@ -354,8 +354,9 @@ def run_b200(args, cfg):
     plan = parallel.make_plan(list(neurons), rank, world, args.dp_mode, args.batch)
     sync = parallel.GradSync(model, plan) if world > 1 else None
     host = {}
-    for m, (lo, hi) in plan.my_slices.items():  # this rank's rows of each mouse's GLOBAL batch
-        full = host_batches({m: neurons[m]}, plan.global_batch[m], 0, pin=False, in_shape=cfg["in_shape"])[m]
+    for m, (lo, hi) in plan.my_slices.items():  # this rank's rows of each mouse's GLOBAL batch (same on every rank)
+        full = host_batches({m: neurons[m]}, plan.global_batch[m], list(neurons).index(m), pin=False,
+                            in_shape=cfg["in_shape"])[m]
         host[m] = {k: v[lo:hi].contiguous().pin_memory() for k, v in full.items()}
     resident = {m: {k: v.to(dev) for k, v in b.items()} for m, b in host.items()}
     samples_per_step_rank = sum(hi - lo for lo, hi in plan.my_slices.values())
