@@ -277,11 +277,13 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
-def gpu_eager_baseline(cfg, dev, steps=3, warmup=2):
+def gpu_eager_baseline(cfg, dev, steps=3, warmup=2, micro=0, max_mice=None):
     """The reference's own modules on this GPU in PyTorch eager, TF32 as utils/utils.py:42-43 enables it, the same
     sweep as the timed workload (every mouse batch once, fwd + loss + bwd, train mode), both with the reference's
     CUDA default (gradient checkpointing of the attention, vit.py:377-380) and without."""
     neurons = neuron_counts(cfg["mice"], cfg["neurons"])
+    if max_mice:  # bounded sample for the big configs: the first mice only (the per-sample rate is what is reported)
+        neurons = dict(list(neurons.items())[:max_mice])
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -299,7 +301,10 @@ def gpu_eager_baseline(cfg, dev, steps=3, warmup=2):
             def sweep():
                 model.zero_grad(set_to_none=True)
                 for m, b in resident.items():
-                    reference_step(model, crit, m, b, cfg["batch"])
+                    rows = b["image"].shape[0]
+                    step = micro or rows
+                    for lo in range(0, rows, step):  # data.micro_batching (train.py:55)
+                        reference_step(model, crit, m, {k: v[lo:lo + step] for k, v in b.items()}, cfg["batch"])
 
             for _ in range(warmup):
                 sweep()
@@ -319,7 +324,8 @@ def gpu_eager_baseline(cfg, dev, steps=3, warmup=2):
     best = max(out.values(), key=lambda r: r["value"])
     return {"value": best["value"], "unit": "samples/s", "ms_per_step": best["ms_per_step"], "steps": steps,
             "warmup": warmup, "kind": "reference modules (oracle/_ref), PyTorch eager on this GPU, TF32 matmul",
-            "variants": out, "note": "value = the faster variant"}
+            "mice": len(neurons), "micro_batch": micro or cfg["batch"], "variants": out,
+            "note": "value = the faster variant"}
 
 
 def workload_config(args, cfg, world):
@@ -483,7 +489,9 @@ def run_b200(args, cfg):
         VF.release_scratch()
         torch.cuda.empty_cache()
         try:
-            eg = gpu_eager_baseline(cfg, dev)
+            big = bool(args.micro)
+            eg = gpu_eager_baseline(cfg, dev, steps=1 if big else 3, warmup=1 if big else 2, micro=args.micro,
+                                    max_mice=1 if big else None)
         except Exception as e:  # keep the headline line; report the failure
             eg = {"error": repr(e)[:300]}
         line["gpu_eager_baseline"] = eg
