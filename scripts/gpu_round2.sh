@@ -9,7 +9,7 @@ import os
 print("cores", os.cpu_count())
 PY
 if [[ $what == *tests* ]]; then
-  ( time timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -x ) > gpurun_out/pytest_gpu.log 2>&1
+  ( time timeout 1500 python -m pytest tests -m gpu -q --timeout 600 ) > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit $?"; tail -8 gpurun_out/pytest_gpu.log
   ( time timeout 300 python __graft_entry__.py --smoke ) > gpurun_out/smoke.log 2>&1
   echo "smoke exit $?"; tail -4 gpurun_out/smoke.log
