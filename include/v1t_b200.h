@@ -319,19 +319,6 @@ int v1t_gemm_tc_planes(const v1t_gemm_desc* d, const float* A, const float* B, f
                        const float* R, int impl, const void* a_hi, const void* a_lo, int64_t a_rows, int64_t a_cols,
                        const void* b_hi, const void* b_lo, int64_t b_rows, int64_t b_cols, void* stream);
 
-/* measurement helper: cycles for iters*8 tcgen05.mma (M=128, K=16, bf16) of width N on all SMs; ts=1: A operand
- * from tensor memory, mn_b=1: MN-major B.  out_dev: 148 int64 cycle counts (device memory). */
-int v1t_mma_microbench(int N, int ts, int iters, int mn_b, long long* out_dev, void* stream);
-
-/* measurement helper: every SM streams iters rounds of `copies` cp.async.bulk copies of `bytes` bytes from a global
- * buffer (span bytes, wrapped) into a ring of `slots` shared-memory slots; out_dev: 148 int64 cycle counts.  Measures
- * the per-SM global->shared fill ceiling that bounds the bf16x3 main loops. */
-int v1t_bulk_microbench(const void* src, long long span, int bytes, int copies, int slots, int iters,
-                        long long* out_dev, void* stream);
-
-/* self-test of the tensor-memory A operand (tcgen05.st + TS-form tcgen05.mma): C[128,N] = bf16(A[128,K]) bf16(B[N,K])^T */
-int v1t_ts_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
-
 /* the inverted-dropout multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` =
  * block*8 + {0 tokens, 1 attention probs, 2 proj out, 3 MLP hidden, 4 MLP out}; element index = row-major
  * index in the logical tensor ([B,T,E], [B,T,M], [B,H,T,T]) with the LAST dimension's stride rounded up to 4

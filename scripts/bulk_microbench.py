@@ -2,7 +2,7 @@
 import sys, torch
 sys.path.insert(0, ".")
 from v1t_b200 import _lib
-lib = _lib.load(); DEV = "cuda:0"
+lib = _lib.load_diag(); DEV = "cuda:0"
 st = torch.cuda.current_stream().cuda_stream
 out = torch.zeros(148, dtype=torch.int64, device=DEV)
 clk = 1.965e9
@@ -13,7 +13,7 @@ for span_mb, label in ((64, "L2-resident 64 MB"), (2048, "HBM 2 GB")):
                                   (40960, 1, 2), (40960, 1, 4), (2048, 18, 3), (2048, 18, 5), (16384, 2, 6)):
         iters = 400
         for _ in range(2):
-            assert lib.v1t_bulk_microbench(src.data_ptr(), src.numel(), nbytes, copies, slots, iters, out.data_ptr(), st) == 0, _lib.last_error()
+            assert lib.v1t_bulk_microbench(src.data_ptr(), src.numel(), nbytes, copies, slots, iters, out.data_ptr(), st) == 0, lib.v1t_diag_last_error()
         torch.cuda.synchronize()
         cyc = out.max().item()
         total = nbytes * copies * iters

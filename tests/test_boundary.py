@@ -25,6 +25,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/v1t_b200.h but not exported"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     assert lib.v1t_version() >= 1
+    # diagnostics live in their own header / library and are not exported by the product library
+    diag_header = open(os.path.join(ROOT, "include", "v1t_b200_diag.h")).read()
+    diag_declared = set(re.findall(r"\b(v1t_[a-z0-9_]+)\s*\(", diag_header))
+    assert diag_declared == set(_lib.DIAG_SYMBOLS)
+    diag = _lib.load_diag()
+    for name in diag_declared:
+        assert hasattr(diag, name) and not hasattr(lib, name), name
 
 
 def test_struct_layouts_match_header_sizes():

@@ -627,13 +627,13 @@ def test_fused_attention_backward(B, H, T, E, p, impl, tol):
 def test_ts_mma_tensor_memory_operand(N, K):
     """tcgen05.st + TS-form tcgen05.mma (A operand in tensor memory) against a bf16-rounded fp64 product."""
     from v1t_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_diag()  # diagnostics library (include/v1t_b200_diag.h), not the product ABI
     g = torch.Generator(device=DEV).manual_seed(N + K)
     A = torch.randn(128, K, device=DEV, generator=g)
     Bm = torch.randn(N, K, device=DEV, generator=g)
     Cm = torch.full((128, N), float("nan"), device=DEV)
     rc = lib.v1t_ts_selftest(A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), N, K, torch.cuda.current_stream().cuda_stream)
-    assert rc == 0, _lib.last_error()
+    assert rc == 0, lib.v1t_diag_last_error()
     torch.cuda.synchronize()
     ref = A.bfloat16().double() @ Bm.bfloat16().double().T
     assert rel_err(Cm.cpu().numpy(), ref.cpu().numpy()) < 1e-5

@@ -10,6 +10,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libv1t_b200.so")
+DIAG_LIB = os.path.join(PKG, "libv1t_b200_diag.so")  # micro-benchmarks / self-tests (csrc/diag), not the product ABI
 STAMP = os.path.join(PKG, ".libv1t_b200.stamp")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -21,10 +22,17 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _diag_sources():
+    d = os.path.join(CSRC, "diag")
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cu")) if os.path.isdir(d) else []
+
+
 def _digest():
     h = hashlib.sha256()
-    files = _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    files = _sources() + _diag_sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                                                    if f.endswith((".cuh", ".h")))
     files.append(os.path.join(os.path.dirname(PKG), "include", "v1t_b200.h"))
+    files.append(os.path.join(os.path.dirname(PKG), "include", "v1t_b200_diag.h"))
     for f in files:
         h.update(os.path.basename(f).encode())  # names, not absolute paths: the tree moves (gpurun snapshot)
         with open(f, "rb") as fh:
@@ -35,7 +43,8 @@ def _digest():
 
 def is_current() -> bool:
     """True when the in-tree library was built from exactly the sources (and flags) that are in the tree now."""
-    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == _digest()
+    return (os.path.exists(LIB) and os.path.exists(DIAG_LIB) and os.path.exists(STAMP)
+            and open(STAMP).read().strip() == _digest())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -64,22 +73,23 @@ def _build_locked(verbose: bool) -> str:
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
-    for src in _sources():
+    for src in _sources() + _diag_sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    objs = []
+    objs, diag_objs = [], []
     log = []
     for src, obj, p in procs:
         out, _ = p.communicate()
         log.append(f"== {os.path.basename(src)}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
-        objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}")
+        (diag_objs if os.path.dirname(src).endswith("diag") else objs).append(obj)
+    for lib, group in ((LIB, objs), (DIAG_LIB, diag_objs)):
+        cmd = [nvcc, "-shared", "-o", lib, *group, "-lcudart"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}")
     with open(os.path.join(objdir, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
     with open(STAMP, "w") as fh:

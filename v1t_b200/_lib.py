@@ -134,9 +134,6 @@ SYMBOLS = {
                                    _vp, _vp, _vp, _vp]),
     "v1t_attn_backward": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f, C.c_uint64,
                                     C.c_uint32, _vp, _vp, _vp]),
-    "v1t_mma_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
-    "v1t_bulk_microbench": (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
-    "v1t_ts_selftest": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "v1t_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, C.c_uint32, _f, _vp]),
     "v1t_opt_chunk_elems": (C.c_int, []),
     "v1t_adamw_l1_scratch_bytes": (C.c_size_t, [C.c_int]),
@@ -155,7 +152,31 @@ SYMBOLS = {
                                         _vp, _vp, _vp]),
 }
 
+# include/v1t_b200_diag.h: micro-benchmarks / self-test, in their own library (not the product ABI)
+DIAG_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libv1t_b200_diag.so")
+DIAG_SYMBOLS = {
+    "v1t_diag_last_error": (C.c_char_p, []),
+    "v1t_mma_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "v1t_bulk_microbench": (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "v1t_ts_selftest": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+}
+
 _lib = None
+_diag = None
+
+
+def load_diag():
+    """The diagnostics library (scripts/*_microbench.py, one GPU self-test)."""
+    global _diag
+    if _diag is None:
+        load()  # builds both libraries when needed
+        lib = C.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in DIAG_SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = lib
+    return _diag
 
 
 def load(build_if_missing: bool = True):

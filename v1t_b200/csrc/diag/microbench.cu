@@ -1,8 +1,24 @@
 // Measurement helper (not on the product path): cycles per tcgen05.mma (M=128, K=16, bf16) as a function of N and
 // of the operand source (A from shared memory "SS" vs A from tensor memory "TS").  Used to size the attention /
 // GEMM tiles ("MMA cost model").
-#include "common.cuh"
-#include "tc_common.cuh"
+#include <stdarg.h>
+
+#include "../common.cuh"
+#include "../tc_common.cuh"
+#include "../../../include/v1t_b200_diag.h"
+
+// libv1t_b200_diag.so is self-contained (it is NOT part of the product library): local error plumbing
+namespace v1t {
+static thread_local char g_diag_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_diag_err, sizeof(g_diag_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() {}
+}  // namespace v1t
+extern "C" const char* v1t_diag_last_error(void) { return v1t::g_diag_err; }
 
 namespace v1t {
 namespace {
