@@ -590,10 +590,13 @@ def test_fused_attention_forward_dropout_replay():
 @pytest.mark.parametrize("B,H,T,E,p", [(1, 1, 64, 32, 0.0), (2, 2, 200, 24, 0.0), (1, 2, 1654, 155, 0.0),
                                        (2, 3, 333, 155, 0.25)])
 @pytest.mark.parametrize("impl,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
-def test_fused_attention_backward(B, H, T, E, p, impl, tol):
-    """dQ, dK, dV of the fused tcgen05 attention vs fp64 autograd of softmax(QK^T)V (same dropout mask)."""
+@pytest.mark.parametrize("variant", ["three-pass", "pair"])
+def test_fused_attention_backward(B, H, T, E, p, impl, tol, variant, monkeypatch):
+    """dQ, dK, dV of the fused tcgen05 attention vs fp64 autograd of softmax(QK^T)V (same dropout mask).  Both
+    backward organisations: three atomic-free passes, and dV + dK by two-CTA clusters sharing P' (V1T_ATTN_BWD=pair)."""
     from v1t_b200 import _lib
     lib = _lib.load()
+    monkeypatch.setenv("V1T_ATTN_BWD", variant)
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + T + 1)
     qkv = torch.randn(B, T, 3 * H * E, device=DEV, generator=g)
     d_out = torch.randn(B, T, H * E, device=DEV, generator=g)

@@ -476,16 +476,446 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
+// =====================================================================================================================
+// dV + dK from ONE recomputation of the scores: a CLUSTER OF TWO CTAs per 128-key tile (V1T_ATTN_BWD=pair).
+//
+// dV and dK of a key tile both need P' of every (key, query) pair, but the tensor memory of one SM cannot hold both
+// accumulators (2 x 160 columns) next to the resident operands, the scores and the A operand of the accumulating MMA.
+// Two CTAs of a cluster split the work instead and exchange P' through distributed shared memory:
+//
+//   rank 0 ("P side")   K in TMEM; per 64-query tile j:  S'^T = K Q_j^T,  P' = exp2(S' c - lse)  --P' (32 KB)-->  rank 1
+//                       Pd' = P' * dropout  ->  dV += Pd'^T dO_j
+//   rank 1 ("dS side")  V in TMEM; per tile j:  dP'^T = V dO_j^T,  dS' = P' (dP' * dropout - delta)  ->  dK += dS'^T Q_j
+//
+// Both ranks stream the same (Q_j, dO_j) tiles with 64-column MMAs (the fused dK pass of the three-pass kernel only has
+// TMEM for 32-column tiles) and run the same MMA / bulk-copy code: ring 0 feeds the score MMA (rank 0: Q_j, rank 1:
+// dO_j), ring 1 the accumulating MMA (rank 0: dO_j, rank 1: Q_j).  P' crosses as fp32 with the dropout decision in the
+// SIGN bit (P' >= 0), so rank 1 neither draws nor transposes the mask.  MMA units per (key tile, query tile):
+// 3 + 3 (rank 0) and 3 + 3 (rank 1) instead of 6 (dV pass) + 9 (dK pass); dQ stays the query-stationary pass above.
+// TMEM columns (both ranks): R_hi | R_lo | scores[2][64] | A_hi[32] | A_lo[32] | out[Dp] = 2 HC + 192 + Dp (512 @ Dp = 160).
+// =====================================================================================================================
+template <int AD>
+struct SmemPair {
+  static constexpr int N = 64;
+  static constexpr uint32_t kTile = AD * N * 64;   // one bf16 plane of a streamed 64-row tile
+  static constexpr uint32_t kSlot = 2 * kTile;     // hi + lo
+  static constexpr uint32_t ring0 = 0;             // 2 slots: operand of the score MMA
+  static constexpr uint32_t ring1 = 2 * kSlot;     // 2 slots: operand of the accumulating MMA
+  static constexpr uint32_t xch = 4 * kSlot;       // rank 1: P' from rank 0, [2 buffers][4 slots][4 chunks][128 rows][16 B]
+                                                   // rank 0: dropout-mask transpose tiles ([warp][16][kMaskLd] floats)
+  static constexpr uint32_t kXch = 2 * 4 * 4 * 128 * 16;
+  static constexpr int kMaskLd = 36;
+  static_assert(kSmWarps * 16 * kMaskLd * 4 <= (int)kXch, "mask tiles must fit the exchange region");
+  static constexpr uint32_t bars = xch + kXch;
+  static constexpr uint32_t total = bars + 512 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {  // releases this thread's prior writes
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // bounded like mbar_wait
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+template <int AD>
+__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const AttnBwdArgs a) {
+  constexpr int N = 64, Dp = AD * 32, HC = AD * 16, NH = N / kSlots, OPC = N / 2;
+  using L = SmemPair<AD>;
+  extern __shared__ uint8_t smem_raw[];
+  // the dynamic shared window starts at the same offset in both CTAs of the cluster, so this rounding agrees too
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint64_t* res_full = bars + 0;   // resident operand rows stored to TMEM by the softmax threads
+  uint64_t* ps_full = bars + 1;    // A operand of the accumulating MMA written
+  uint64_t* ps_empty = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint64_t* r0_full = bars + 4;    // [2] ring 0
+  uint64_t* r0_empty = bars + 6;
+  uint64_t* r1_full = bars + 8;    // [2] ring 1
+  uint64_t* r1_empty = bars + 10;
+  uint64_t* sp_full = bars + 12;   // [2] score buffers
+  uint64_t* sp_empty = bars + 14;
+  uint64_t* pe_full = bars + 16;   // [2] rank 1: P' of a tile has arrived (512 remote arrivals)
+  uint64_t* pe_empty = bars + 18;  // [2] rank 0: rank 1 has read the buffer (512 remote arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0: P side (dV), 1: dS side (dK)
+  const int r0 = (blockIdx.x >> 1) * 128, bh = blockIdx.z;
+  const int nt = (a.T + N - 1) / N;
+  const uint8_t* R_hi = rank == 0 ? a.k_hi : a.v_hi;  const uint8_t* R_lo = rank == 0 ? a.k_lo : a.v_lo;   // resident
+  const uint8_t* s0_hi = rank == 0 ? a.q_hi : a.do_hi; const uint8_t* s0_lo = rank == 0 ? a.q_lo : a.do_lo; // ring 0
+  const uint8_t* s1_hi = rank == 0 ? a.do_hi : a.q_hi; const uint8_t* s1_lo = rank == 0 ? a.do_lo : a.q_lo; // ring 1
+
+  if (threadIdx.x == 0) {
+    mbar_init(res_full, kSmThreads);
+    mbar_init(ps_full, kSmThreads);
+    mbar_init(ps_empty, 1);
+    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&r0_full[i], 1);
+      mbar_init(&r0_empty[i], 1);
+      mbar_init(&r1_full[i], 1);
+      mbar_init(&r1_empty[i], 1);
+      mbar_init(&sp_full[i], 1);
+      mbar_init(&sp_empty[i], kSmThreads);
+      mbar_init(&pe_full[i], kSmThreads);
+      mbar_init(&pe_empty[i], kSmThreads);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t cR_hi = 0, cR_lo = HC, cS = 2 * HC, cPS_hi = cS + 2 * N, cPS_lo = cPS_hi + OPC, cOut = cPS_lo + OPC;
+  static_assert(cOut + Dp <= 512, "TMEM budget exceeded");
+
+  if (warp == kLoadWarpX || warp == kLoadWarpY) {
+    // ============================== BULK-COPY PRODUCERS (one warp per ring) ==============================
+    if (lane == 0) {
+      const bool is0 = warp == kLoadWarpX;
+      uint64_t* fullb = is0 ? r0_full : r1_full;
+      uint64_t* emptyb = is0 ? r0_empty : r1_empty;
+      const uint8_t* src_hi = is0 ? s0_hi : s1_hi;
+      const uint8_t* src_lo = is0 ? s0_lo : s1_lo;
+      uint8_t* ring = smem + (is0 ? L::ring0 : L::ring1);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        mbar_wait(&emptyb[s], ((j >> 1) & 1) ^ 1);
+        uint8_t* base = ring + s * L::kSlot;
+        mbar_expect_tx(&fullb[s], (a.x3 ? 2 : 1) * L::kTile);
+        const int64_t src = attn_plane_off(bh, 0, j * N, a.Tp, AD);  // a 64-row plane tile is contiguous: one copy per plane
+        bulk_g2s(base, src_hi + src, L::kTile, &fullb[s]);
+        if (a.x3) bulk_g2s(base + L::kTile, src_lo + src, L::kTile, &fullb[s]);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ============================== MMA ISSUER (identical for both ranks) ==============================
+    const bool leader = elect_one();
+    const uint32_t idesc_s = idesc_bf16(128, N, 0, 0);
+    const uint32_t idesc_o = idesc_bf16(128, Dp, 0, 1);  // B = streamed tile viewed MN-major (head dim contiguous)
+    constexpr uint32_t tb = N * 64;
+    const uint32_t g0 = smem_u32(smem + L::ring0) >> 4, g1 = smem_u32(smem + L::ring1) >> 4;
+    const uint64_t mn_base = desc_mn_sw64_base(tb);
+    const uint32_t tR_hi = tmem_base + cR_hi, tR_lo = tmem_base + cR_lo;
+    const uint32_t tPS_hi = tmem_base + cPS_hi, tPS_lo = tmem_base + cPS_lo, tOut = tmem_base + cOut;
+
+    auto issue_scores = [&](int j) {
+      const int s = j & 1;
+      const uint32_t xb = g0 + s * (L::kSlot >> 4);
+      mbar_wait(&r0_full[s], (j >> 1) & 1);
+      mbar_wait(&sp_empty[s], ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint64_t xh = kDescK64 | (uint64_t)xb, xl = kDescK64 | (uint64_t)(xb + (L::kTile >> 4));
+      const uint32_t dS = tmem_base + cS + s * N;
+#pragma unroll
+      for (int ks = 0; ks < 2 * AD; ++ks) {
+        const uint32_t bo = (ks >> 1) * (tb / 16) + (ks & 1) * 2;
+        if (leader) {
+          umma_bf16_ts(dS, tR_hi + ks * 8, xh + bo, idesc_s, ks > 0 ? 1u : 0u);
+          if (a.x3) {
+            umma_bf16_ts(dS, tR_lo + ks * 8, xh + bo, idesc_s, 1u);
+            umma_bf16_ts(dS, tR_hi + ks * 8, xl + bo, idesc_s, 1u);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(&r0_empty[s]);
+        umma_commit(&sp_full[s]);
+      }
+      __syncwarp();
+    };
+    auto issue_out = [&](int j, bool last) {
+      const int s = j & 1;
+      mbar_wait(&r1_full[s], (j >> 1) & 1);
+      mbar_wait(ps_full, j & 1);
+      tc_fence_after();
+      const uint32_t sb = g1 + s * (L::kSlot >> 4);
+      const uint64_t bh_ = mn_base | (uint64_t)sb, bl_ = mn_base | (uint64_t)(sb + (L::kTile >> 4));
+#pragma unroll
+      for (int ks = 0; ks < N / 16; ++ks) {
+        if (leader) {
+          umma_bf16_ts(tOut, tPS_hi + ks * 8, bh_ + ks * 64, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          if (a.x3) {
+            umma_bf16_ts(tOut, tPS_lo + ks * 8, bh_ + ks * 64, idesc_o, 1u);
+            umma_bf16_ts(tOut, tPS_hi + ks * 8, bl_ + ks * 64, idesc_o, 1u);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(ps_empty);
+        umma_commit(&r1_empty[s]);
+        if (last) umma_commit(o_full);
+      }
+      __syncwarp();
+    };
+
+    mbar_wait(res_full, 0);
+    tc_fence_after();
+    issue_scores(0);
+    for (int j = 0; j + 1 < nt; ++j) {
+      issue_scores(j + 1);
+      issue_out(j, false);
+    }
+    issue_out(nt - 1, true);
+  } else {
+    // ============================== SOFTMAX-BACKWARD / EPILOGUE ==============================
+    const int quarter = warp & 3, slot = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int ri = r0 + row;  // key index
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int b = bh / a.H, h = bh % a.H;
+
+    {  // resident operand: plane rows -> TMEM (slot 0: hi plane, slot 1: lo plane)
+      const int sw = (ri >> 1) & 3;
+      if (slot == 0 || (slot == 1 && a.x3)) {
+        const uint8_t* plane = slot == 0 ? R_hi : R_lo;
+        const uint32_t tcol = slot == 0 ? cR_hi : cR_lo;
+#pragma unroll
+        for (int at_i = 0; at_i < AD; ++at_i) {
+          const uint4* src = reinterpret_cast<const uint4*>(plane + attn_plane_off(bh, at_i, ri, a.Tp, AD));
+          uint4 ph[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 v = ph[c ^ sw];
+            tmem_st4(tmem_base + lane_off + tcol + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(res_full);
+    }
+
+    const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
+    const int Tc = (int)drop_stride(a.T);
+    const float* lse = a.lse + (int64_t)bh * a.Tp;
+    const float* delta = a.delta + (int64_t)bh * a.Tp;
+    // exchange buffer addressing: chunk c (4 floats) of this thread's 16 columns sits at
+    //   xch + ((buf * 4 + slot) * 4 + c) * 2048 + row * 16      (8 adjacent lanes = 128 contiguous bytes)
+    const uint32_t xch_local = smem_u32(smem + L::xch) + (uint32_t)slot * 8192u + (uint32_t)row * 16u;
+    const uint32_t xch_peer = mapa_u32(xch_local, 1u);                          // used by rank 0
+    const uint32_t pe_full_peer = mapa_u32(smem_u32(pe_full), 1u);              // rank 0 -> rank 1
+    const uint32_t pe_empty_peer = mapa_u32(smem_u32(pe_empty), 0u);            // rank 1 -> rank 0
+
+    for (int j = 0; j < nt; ++j) {
+      const int buf = j & 1;
+      const int c0 = j * N + slot * NH;
+      float stat[NH];  // rank 0: lse of this warp's query columns; rank 1: their delta
+      {
+        const float4* s4 = reinterpret_cast<const float4*>((rank == 0 ? lse : delta) + c0);
+#pragma unroll
+        for (int g = 0; g < NH / 4; ++g) {
+          const float4 v = __ldg(s4 + g);
+          stat[4 * g] = v.x; stat[4 * g + 1] = v.y; stat[4 * g + 2] = v.z; stat[4 * g + 3] = v.w;
+        }
+      }
+      float sv[NH];
+      if (rank == 0) {
+        // dropout multipliers (thread = key row, columns = queries): one Philox call covers 8 adjacent KEYS of one
+        // query = 8 adjacent lanes; generated per key group and transposed through a private smem tile
+        float mult[NH];
+#pragma unroll
+        for (int c = 0; c < NH; ++c) mult[c] = 1.f;
+        if (a.drop.p > 0.f) {
+          float* mt = reinterpret_cast<float*>(smem + L::xch) + warp * (NH * L::kMaskLd);
+          const int kg = lane >> 3, cq = lane & 7;
+          const int key0 = r0 + quarter * 32 + kg * 8;
+#pragma unroll
+          for (int i = 0; i < NH / 8; ++i) {
+            const int c = 8 * i + cq;
+            float mk[8];
+            const uint64_t idx = ((uint64_t)bh * a.T + (uint64_t)min(c0 + c, a.T - 1)) * (uint64_t)Tc + key0;
+            dropout_mult8(a.drop.seed, a.drop.site, idx >> 3, a.drop.p, inv_keep, mk);
+            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8) = make_float4(mk[0], mk[1], mk[2], mk[3]);
+            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8 + 4) = make_float4(mk[4], mk[5], mk[6], mk[7]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < NH; ++c) mult[c] = mt[c * L::kMaskLd + lane];
+          __syncwarp();
+        }
+        mbar_wait(&sp_full[buf], (j >> 1) & 1);
+        tc_fence_after();
+        {
+          uint32_t v1[NH];
+          tmem_ld16(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NH; ++c) sv[c] = __uint_as_float(v1[c]);
+        }
+        tc_fence_before();
+        mbar_arrive(&sp_empty[buf]);
+#pragma unroll
+        for (int c = 0; c < NH; ++c) sv[c] = fast_exp2(fmaf(sv[c], a.scale_log2, -stat[c]));  // P' (0 for padded queries)
+        // ---- ship P' to rank 1: fp32, dropped elements carry the sign bit
+        mbar_wait_cluster(&pe_empty[buf], ((j >> 1) & 1) ^ 1);
+#pragma unroll
+        for (int c = 0; c < NH / 4; ++c) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = mult[4 * c + e] == 0.f ? __uint_as_float(__float_as_uint(sv[4 * c + e]) | 0x80000000u) : sv[4 * c + e];
+          st_cluster_v4(xch_peer + (uint32_t)buf * 32768u + (uint32_t)c * 2048u, o[0], o[1], o[2], o[3]);
+        }
+        mbar_arrive_remote(pe_full_peer + (uint32_t)buf * 8u);
+#pragma unroll
+        for (int c = 0; c < NH; ++c) sv[c] *= mult[c];  // Pd'
+      } else {
+        mbar_wait(&sp_full[buf], (j >> 1) & 1);
+        tc_fence_after();
+        float dv[NH];
+        {
+          uint32_t v1[NH];
+          tmem_ld16(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NH; ++c) dv[c] = __uint_as_float(v1[c]);
+        }
+        tc_fence_before();
+        mbar_arrive(&sp_empty[buf]);
+        // ---- P' from rank 0
+        mbar_wait_cluster(&pe_full[buf], (j >> 1) & 1);
+#pragma unroll
+        for (int c = 0; c < NH / 4; ++c) {
+          const uint4 v = lds128(xch_local + (uint32_t)buf * 32768u + (uint32_t)c * 2048u);
+          sv[4 * c] = __uint_as_float(v.x); sv[4 * c + 1] = __uint_as_float(v.y);
+          sv[4 * c + 2] = __uint_as_float(v.z); sv[4 * c + 3] = __uint_as_float(v.w);
+        }
+        mbar_arrive_remote(pe_empty_peer + (uint32_t)buf * 8u);
+#pragma unroll
+        for (int c = 0; c < NH; ++c) {
+          const uint32_t u = __float_as_uint(sv[c]);
+          const float p = __uint_as_float(u & 0x7fffffffu);
+          const float m = (u & 0x80000000u) ? 0.f : inv_keep;
+          sv[c] = p * (dv[c] * m - stat[c]);  // dS'
+        }
+      }
+      // A operand of the accumulating MMA -> TMEM (two bf16 per column), hi and lo planes
+      mbar_wait(ps_empty, (j & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < NH / 8; ++ch) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = sv[ch * 8 + e];
+        uint32_t hw[4], lw[4];
+        split8_words(x, hw, lw);
+        const uint32_t col = (slot * NH + ch * 8) / 2;
+        tmem_st4(tmem_base + lane_off + cPS_hi + col, hw[0], hw[1], hw[2], hw[3]);
+        if (a.x3) tmem_st4(tmem_base + lane_off + cPS_lo + col, lw[0], lw[1], lw[2], lw[3]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ps_full);
+    }
+    // ---- epilogue: rank 0 -> dV (column block 2I), rank 1 -> dK (column block I, scaled); see attn_bwd2_body
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int I = a.H * a.E;
+    const int kSec = rank == 0 ? 2 : 1;
+    float* dst = a.dqkv ? a.dqkv + ((int64_t)b * a.T + ri) * (3 * I) + h * a.E + kSec * I : nullptr;
+    const float sc = rank == 0 ? 1.f : a.scale;
+    const int64_t prow = (int64_t)b * a.T + ri;
+    const int atom0 = (kSec * a.H + h) * AD;
+    const uint32_t stage = smem_u32(smem + L::ring0);  // both rings are idle now: 4 x 40 KB >= 2 x AD x 8 KB
+#pragma unroll
+    for (int cc = 0; cc < AD; ++cc) {
+      const int d0 = slot * (AD * 8) + cc * 8;
+      uint32_t v[8];
+      tmem_ld8(tmem_base + lane_off + cOut + d0, v);
+      tmem_ld_wait();
+      if (ri < a.T && dst) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
+      }
+      if (a.dq_pl.hi) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[e]) * sc;
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t so = (uint32_t)(d0 >> 5) * (128 * 64) + row * 64 + ((((d0 & 31) >> 3) ^ (int)((prow >> 1) & 3)) << 4);
+        sts128(stage + so, hi);
+        if (a.dq_pl.lo) sts128(stage + AD * 128 * 64 + so, lo);
+      }
+    }
+    if (a.dq_pl.hi) {
+      fence_proxy_async();
+      named_bar_sync(1, kSmThreads);
+      const int rows_valid = min(128, a.T - r0);
+      if (threadIdx.x < AD * 2 && rows_valid > 0) {
+        const int at_i = threadIdx.x >> 1, pln = threadIdx.x & 1;
+        uint8_t* dstp = pln ? a.dq_pl.lo : a.dq_pl.hi;
+        if (dstp) {
+          const int64_t off = ((int64_t)(atom0 + at_i) * a.dq_pl.rows_p + ((int64_t)b * a.T + r0)) * 64;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp + off),
+                       "r"(stage + (uint32_t)(pln * AD + at_i) * (128 * 64)), "r"(rows_valid * 64)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves while its peer may still store into its shared memory or barriers
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
 // The three passes (dK, dQ, dV) are independent: ONE grid runs them (blockIdx.y = which) so that the 5.6-wave tails of
 // three separate launches (832 CTAs on 148 SMs each) become one 16.9-wave launch.  (b, h) is the OUTERMOST grid
 // index: the 39 CTAs of one head are dispatched together and share its Q / K / V / dO planes (4.3 MB) through L2
 // instead of every pass re-streaming all heads from HBM (753 MB read per launch with the pass outermost).  The dV
 // CTAs (half as long as the other two) come last within a head, so the launch also ends on short CTAs.
 template <int AD>
-__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a) {
-  if (blockIdx.y == 0) attn_bwd2_body<MODE_S, true, 32, AD>(a);        // dK
-  else if (blockIdx.y == 1) attn_bwd2_body<MODE_S, false, 32, AD>(a);  // dQ
-  else attn_bwd2_body<MODE_V, true, 64, AD>(a);                        // dV
+__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a, const int only_dq) {
+  if (only_dq || blockIdx.y == 1) attn_bwd2_body<MODE_S, false, 32, AD>(a);  // dQ
+  else if (blockIdx.y == 0) attn_bwd2_body<MODE_S, true, 32, AD>(a);         // dK
+  else attn_bwd2_body<MODE_V, true, 64, AD>(a);                              // dV
 }
 
 template <int AD>
@@ -493,8 +923,32 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
   constexpr uint32_t smem = std::max({Smem2<MODE_V, 64, AD>::total, Smem2<MODE_S, 32, AD>::total});
   static_assert(smem <= 232448, "shared memory budget exceeded");
   V1T_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (attn_bwd_pair_env()) {
+    // dV + dK by clusters of two CTAs that share one recomputation of P' (see attn_bwd_pair_kernel), then dQ alone
+    using LP = SmemPair<AD>;
+    static_assert(LP::total <= 232448, "shared memory budget exceeded");
+    V1T_CUDA(cudaFuncSetAttribute(attn_bwd_pair_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP::total));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * cdiv(a.T, 128), 1, a.B * a.H);
+    cfg.blockDim = dim3(kThreadsAttn, 1, 1);
+    cfg.dynamicSmemBytes = LP::total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    V1T_CUDA(cudaLaunchKernelEx(&cfg, attn_bwd_pair_kernel<AD>, a));
+    V1T_LAUNCH_CHECK();
+    dim3 gq(cdiv(a.T, 128), 1, a.B * a.H);
+    attn_bwd2_kernel<AD><<<gq, kThreadsAttn, smem, st>>>(a, 1);
+    V1T_LAUNCH_CHECK();
+    return V1T_OK;
+  }
   dim3 grid(cdiv(a.T, 128), 3, a.B * a.H);
-  attn_bwd2_kernel<AD><<<grid, kThreadsAttn, smem, st>>>(a);
+  attn_bwd2_kernel<AD><<<grid, kThreadsAttn, smem, st>>>(a, 0);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

@@ -46,6 +46,10 @@ int attn_prec_env() {
   const char* e = getenv("V1T_ATTN_PREC");  // read on every call: tests switch it between launches
   return e ? atoi(e) & 7 : 0;
 }
+int attn_bwd_pair_env() {
+  const char* e = getenv("V1T_ATTN_BWD");
+  return e && e[0] == 'p';
+}
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
   return attn_fwd2_tc(a, st);
 }

@@ -161,6 +161,8 @@ struct AttnFwdArgs {
 // contraction: 1 = the Pd'/dS'/P operand of the accumulating MMAs is hi-only, 2 = dP' without the resident-lo term
 // (the only SS-form MMAs of the backward), 4 = dP' from the hi planes alone.  Measured in DESIGN.md 4.2.
 int attn_prec_env();
+// V1T_ATTN_BWD=pair: dV + dK from one recomputation of P' by two-CTA clusters (attn_bwd2.cu); default: three passes
+int attn_bwd_pair_env();
 int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // Q and P in tensor memory (attn_fwd2.cu)
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st);
 struct AttnBwdArgs {
