@@ -67,7 +67,7 @@ struct Smem2 {
 };
 
 template <int MODE, bool KV, int N, int AD>
-__device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
+__device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a, const int tile, const int bh) {
   constexpr int Dp = AD * 32, HC = AD * 16;
   constexpr int NH = N / kSlots;  // tile columns per softmax warp
   constexpr int OPC = N / 2;      // TMEM columns of one bf16 plane of the Pd' / dS' operand
@@ -89,7 +89,7 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * 128, bh = blockIdx.z;
+  const int r0 = tile * 128;
   // precision-budget experiment (kernels.cuh: attn_prec_env); 0 = all three bf16x3 terms everywhere
   const bool out_lo = a.x3 && !(a.prec & 1);   // A_lo * B_hi term of the accumulating contraction
   const bool dp_ylo = a.x3 && !(a.prec & 6);   // Y_lo * y_hi term of dP' (resident lo plane in shared memory, SS form)
@@ -906,16 +906,33 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
-// The three passes (dK, dQ, dV) are independent: ONE grid runs them (blockIdx.y = which) so that the 5.6-wave tails of
-// three separate launches (832 CTAs on 148 SMs each) become one 16.9-wave launch.  (b, h) is the OUTERMOST grid
-// index: the 39 CTAs of one head are dispatched together and share its Q / K / V / dO planes (4.3 MB) through L2
-// instead of every pass re-streaming all heads from HBM (753 MB read per launch with the pass outermost).  The dV
-// CTAs (half as long as the other two) come last within a head, so the launch also ends on short CTAs.
+// The three passes (dK, dQ, dV) are independent: ONE 1-D grid runs them, so that the 5.6-wave tails of three separate
+// launches (832 CTAs on 148 SMs each) become one 16.9-wave launch.  Block order: heads are taken in GROUPS of `group`
+// (b, h) pairs; within a group all dK CTAs come first, then all dQ, then all dV.
+//   * group = B*H (pass outermost) re-streams every head's Q / K / V / dO planes from HBM once per pass: 753 MB of
+//     DRAM reads per launch at B = 16 against 271 MB algorithmic;
+//   * group = 1 ((b, h) outermost) reads 275 MB but measured 3.6 % SLOWER (1209 vs 1167 us under ncu): the SMs then run
+//     a mix of the three template bodies (8.2 k SASS instructions together) instead of one at a time;
+//   * a group of 16 heads keeps the group's planes (69 MB) in the 126 MB L2 while ~all resident CTAs run the same body.
+// The dV CTAs (half as long as the others) come last within a group, so the launch also ends on short CTAs.
 template <int AD>
-__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a, const int only_dq) {
-  if (only_dq || blockIdx.y == 1) attn_bwd2_body<MODE_S, false, 32, AD>(a);  // dQ
-  else if (blockIdx.y == 0) attn_bwd2_body<MODE_S, true, 32, AD>(a);         // dK
-  else attn_bwd2_body<MODE_V, true, 64, AD>(a);                              // dV
+__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBwdArgs a, const int only_dq, const int tiles,
+                                                                    const int group) {
+  if (only_dq) {  // grid (tiles, 1, B*H): the query-stationary pass alone (the pair kernel has done dV and dK)
+    attn_bwd2_body<MODE_S, false, 32, AD>(a, blockIdx.x, blockIdx.z);
+    return;
+  }
+  const int BH = a.B * a.H;
+  const int per_full = 3 * tiles * group;
+  const int g = blockIdx.x / per_full;
+  const int gsz = min(group, BH - g * group);
+  int rem = blockIdx.x - g * per_full;
+  const int pass = rem / (tiles * gsz);
+  rem -= pass * tiles * gsz;
+  const int bh = g * group + rem / tiles, tile = rem % tiles;
+  if (pass == 0) attn_bwd2_body<MODE_S, true, 32, AD>(a, tile, bh);        // dK
+  else if (pass == 1) attn_bwd2_body<MODE_S, false, 32, AD>(a, tile, bh);  // dQ
+  else attn_bwd2_body<MODE_V, true, 64, AD>(a, tile, bh);                  // dV
 }
 
 template <int AD>
@@ -943,12 +960,14 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
     V1T_CUDA(cudaLaunchKernelEx(&cfg, attn_bwd_pair_kernel<AD>, a));
     V1T_LAUNCH_CHECK();
     dim3 gq(cdiv(a.T, 128), 1, a.B * a.H);
-    attn_bwd2_kernel<AD><<<gq, kThreadsAttn, smem, st>>>(a, 1);
+    attn_bwd2_kernel<AD><<<gq, kThreadsAttn, smem, st>>>(a, 1, cdiv(a.T, 128), 1);
     V1T_LAUNCH_CHECK();
     return V1T_OK;
   }
-  dim3 grid(cdiv(a.T, 128), 3, a.B * a.H);
-  attn_bwd2_kernel<AD><<<grid, kThreadsAttn, smem, st>>>(a, 0);
+  const int tiles = cdiv(a.T, 128), BH = a.B * a.H;
+  const int group = std::max(1, std::min(attn_bwd_group_env(), BH));
+  V1T_CHECK_ARG((int64_t)3 * tiles * BH <= 2147483647ll, "attn_bwd2_tc: grid too large");
+  attn_bwd2_kernel<AD><<<dim3(3 * tiles * BH), kThreadsAttn, smem, st>>>(a, 0, tiles, group);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

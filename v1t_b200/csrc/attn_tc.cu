@@ -50,6 +50,11 @@ int attn_bwd_pair_env() {
   const char* e = getenv("V1T_ATTN_BWD");
   return e && e[0] == 'p';
 }
+int attn_bwd_group_env() {
+  const char* e = getenv("V1T_ATTN_BWD_GROUP");
+  const int g = e ? atoi(e) : 16;
+  return g > 0 ? g : 16;
+}
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st) {
   return attn_fwd2_tc(a, st);
 }

@@ -163,6 +163,8 @@ struct AttnFwdArgs {
 int attn_prec_env();
 // V1T_ATTN_BWD=pair: dV + dK from one recomputation of P' by two-CTA clusters (attn_bwd2.cu); default: three passes
 int attn_bwd_pair_env();
+// V1T_ATTN_BWD_GROUP: (b, h) pairs per block-order group of the three-pass backward (default 16; see attn_bwd2.cu)
+int attn_bwd_group_env();
 int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // Q and P in tensor memory (attn_fwd2.cu)
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st);
 struct AttnBwdArgs {
