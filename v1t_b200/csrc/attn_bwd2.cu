@@ -525,33 +525,18 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// asynchronous 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on an mbarrier of
+// THAT CTA (STAS): the receiver's wait on the barrier's phase orders the data, no fence on the sender
+__device__ __forceinline__ void st_async_v4(uint32_t addr, float a, float b, float c, float d, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(mbar)
+               : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {  // releases this thread's prior writes
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// "buffer consumed" signal to the peer: no data travels with it, so no release fence (a release.cluster arrive by
+// every thread cost a MEMBAR each: stall_membar was the top stall reason of the first version, 870 us)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-      "selp.b32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // bounded like mbar_wait
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-
 template <int AD>
 __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const AttnBwdArgs a) {
   constexpr int N = 64, Dp = AD * 32, HC = AD * 16, NH = N / kSlots, OPC = N / 2;
@@ -570,8 +555,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
   uint64_t* r1_empty = bars + 10;
   uint64_t* sp_full = bars + 12;   // [2] score buffers
   uint64_t* sp_empty = bars + 14;
-  uint64_t* pe_full = bars + 16;   // [2] rank 1: P' of a tile has arrived (512 remote arrivals)
-  uint64_t* pe_empty = bars + 18;  // [2] rank 0: rank 1 has read the buffer (512 remote arrivals)
+  uint64_t* pe_full = bars + 16;   // [2] rank 1: P' of a tile has landed (arming arrive + 32 KB of st.async bytes)
+  uint64_t* pe_empty = bars + 18;  // [2] rank 0: rank 1 has consumed the buffer (one remote arrive per warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -594,8 +579,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       mbar_init(&r1_empty[i], 1);
       mbar_init(&sp_full[i], 1);
       mbar_init(&sp_empty[i], kSmThreads);
-      mbar_init(&pe_full[i], kSmThreads);
-      mbar_init(&pe_empty[i], kSmThreads);
+      mbar_init(&pe_full[i], 1);          // one arming arrive (expect_tx) + 32 KB of st.async transaction bytes
+      mbar_init(&pe_empty[i], kSmWarps);  // one remote arrive per softmax warp of rank 1
     }
     fence_barrier_init();
   }
@@ -633,7 +618,10 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     const uint32_t idesc_s = idesc_bf16(128, N, 0, 0);
     const uint32_t idesc_o = idesc_bf16(128, Dp, 0, 1);  // B = streamed tile viewed MN-major (head dim contiguous)
     constexpr uint32_t tb = N * 64;
-    const uint32_t g0 = smem_u32(smem + L::ring0) >> 4, g1 = smem_u32(smem + L::ring1) >> 4;
+    // descriptor start addresses are 14-bit fields: in a cluster launch the shared-window address of a CTA with a
+    // non-zero rank carries the rank in its upper bits, which would otherwise spill into the LBO field of the MN-major
+    // descriptors below (rank 1 then read every head-dim atom but the first from the wrong place)
+    const uint32_t g0 = (smem_u32(smem + L::ring0) >> 4) & 0x3FFFu, g1 = (smem_u32(smem + L::ring1) >> 4) & 0x3FFFu;
     const uint64_t mn_base = desc_mn_sw64_base(tb);
     const uint32_t tR_hi = tmem_base + cR_hi, tR_lo = tmem_base + cR_lo;
     const uint32_t tPS_hi = tmem_base + cPS_hi, tPS_lo = tmem_base + cPS_lo, tOut = tmem_base + cOut;
@@ -737,6 +725,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     const uint32_t xch_peer = mapa_u32(xch_local, 1u);                          // used by rank 0
     const uint32_t pe_full_peer = mapa_u32(smem_u32(pe_full), 1u);              // rank 0 -> rank 1
     const uint32_t pe_empty_peer = mapa_u32(smem_u32(pe_empty), 0u);            // rank 1 -> rank 0
+    constexpr uint32_t kTileBytes = 128 * N * 4;                                // P' of one tile
+    if (rank == 1 && threadIdx.x == 0) {  // arm the two exchange buffers for tiles 0 and 1
+      mbar_expect_tx(&pe_full[0], kTileBytes);
+      if (nt > 1) mbar_expect_tx(&pe_full[1], kTileBytes);
+    }
 
     for (int j = 0; j < nt; ++j) {
       const int buf = j & 1;
@@ -789,16 +782,16 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
 #pragma unroll
         for (int c = 0; c < NH; ++c) sv[c] = fast_exp2(fmaf(sv[c], a.scale_log2, -stat[c]));  // P' (0 for padded queries)
         // ---- ship P' to rank 1: fp32, dropped elements carry the sign bit
-        mbar_wait_cluster(&pe_empty[buf], ((j >> 1) & 1) ^ 1);
+        mbar_wait(&pe_empty[buf], ((j >> 1) & 1) ^ 1);  // rank 1 has consumed tile j - 2 (two tiles of slack)
 #pragma unroll
         for (int c = 0; c < NH / 4; ++c) {
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             o[e] = mult[4 * c + e] == 0.f ? __uint_as_float(__float_as_uint(sv[4 * c + e]) | 0x80000000u) : sv[4 * c + e];
-          st_cluster_v4(xch_peer + (uint32_t)buf * 32768u + (uint32_t)c * 2048u, o[0], o[1], o[2], o[3]);
+          st_async_v4(xch_peer + (uint32_t)buf * 32768u + (uint32_t)c * 2048u, o[0], o[1], o[2], o[3],
+                      pe_full_peer + (uint32_t)buf * 8u);
         }
-        mbar_arrive_remote(pe_full_peer + (uint32_t)buf * 8u);
 #pragma unroll
         for (int c = 0; c < NH; ++c) sv[c] *= mult[c];  // Pd'
       } else {
@@ -815,14 +808,16 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         tc_fence_before();
         mbar_arrive(&sp_empty[buf]);
         // ---- P' from rank 0
-        mbar_wait_cluster(&pe_full[buf], (j >> 1) & 1);
+        mbar_wait(&pe_full[buf], (j >> 1) & 1);  // all 32 KB of tile j have landed (st.async transaction bytes)
 #pragma unroll
         for (int c = 0; c < NH / 4; ++c) {
           const uint4 v = lds128(xch_local + (uint32_t)buf * 32768u + (uint32_t)c * 2048u);
           sv[4 * c] = __uint_as_float(v.x); sv[4 * c + 1] = __uint_as_float(v.y);
           sv[4 * c + 2] = __uint_as_float(v.z); sv[4 * c + 3] = __uint_as_float(v.w);
         }
-        mbar_arrive_remote(pe_empty_peer + (uint32_t)buf * 8u);
+        // re-arm this buffer for tile j + 2: its bytes cannot start to arrive before every warp of this CTA has signalled
+        // pe_empty below, i.e. not before all of them have passed the wait above
+        if (threadIdx.x == 0 && j + 2 < nt) mbar_expect_tx(&pe_full[buf], kTileBytes);
 #pragma unroll
         for (int c = 0; c < NH; ++c) {
           const uint32_t u = __float_as_uint(sv[c]);
@@ -848,6 +843,10 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ps_full);
+      if (rank == 1) {  // P' of tile j is consumed (its values went through the dS' -> TMEM chain above): one signal per warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(pe_empty_peer + (uint32_t)buf * 8u);
+      }
     }
     // ---- epilogue: rank 0 -> dV (column block 2I), rank 1 -> dK (column block I, scaled); see attn_bwd2_body
     mbar_wait(o_full, 0);
