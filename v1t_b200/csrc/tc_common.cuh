@@ -19,8 +19,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait is a potentially BLOCKING test: the hardware may suspend the thread until the phase completes or a
+// system-dependent time limit passes.  A suspendTimeHint operand (compile with -DV1T_MBAR_HINT_NS=<ns>) stretches that
+// limit -- SASS: `@!P0 NANOSLEEP.SYNCS <ns>` after the first failed check.  Measured with 20 us on the bench step: the
+// polling instructions (SYNCS / ISETP / BRA / CS2R / IADD3: ~40 % of the executed warp instructions of the attention
+// backward in the ncu source view) disappear, but every kernel got 3-5 % SLOWER (attention forward 320 -> 330 us,
+// backward 1251 -> 1317 us): the wake-up adds latency on the MMA-issue and softmax critical paths.  Default: no hint.
+#ifndef V1T_MBAR_HINT_NS
+#define V1T_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if V1T_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)V1T_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -30,14 +50,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> CUDA error surfaced to Python) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> CUDA error surfaced to Python) instead of hanging the GPU.  The clock is read
+// once per 256 failed polls only.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if ((++polls & 255u) == 0u && clock64() - t0 > 4000000000ll) __trap();
   }
 }
 // explicit shared-space 128-bit accesses (pointers derived through integer casts otherwise compile to generic LD/ST)
