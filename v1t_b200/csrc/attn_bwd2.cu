@@ -61,9 +61,7 @@ struct Smem2 {
   static constexpr uint32_t x_ring = MODE == MODE_S ? kYlo : 0;
   static constexpr uint32_t y_ring = x_ring + kXS * kSlot;
   static constexpr uint32_t bars = y_ring + kYS * kSlot;
-  static constexpr int kMaskLd = 36;                  // floats per column of the mask tile (32 keys + 4: conflict-free)
-  static constexpr uint32_t mask = bars + 256;        // dropout multipliers, [warp][N/kSlots][kMaskLd] floats
-  static constexpr uint32_t total = mask + kSmWarps * (N / kSlots) * kMaskLd * 4 + 1024;
+  static constexpr uint32_t total = bars + 256 + 1024;
 };
 
 template <int MODE, bool KV, int N, int AD>
@@ -297,7 +295,6 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a, const int t
     }
 
     const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
-    const int Tc = (int)drop_stride(a.T);
     const float* lse = a.lse + (int64_t)bh * a.Tp;
     const float* delta = a.delta + (int64_t)bh * a.Tp;
     float lse_r = 0.f, delta_r = 0.f;
@@ -320,41 +317,29 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a, const int t
           }
         }
       }
-      // dropout multipliers of this tile: independent of the scores, so they are drawn before the wait below and
-      // stay off the S' -> dS' critical path that the output MMA waits for
+      // dropout multipliers of this tile from the keep bits the forward wrote (bit k of row q of the [Tp, Tp/8]-byte mask
+      // of this head): independent of the scores, so they are fetched before the wait below.  Re-drawing the Philox
+      // decisions here cost ~14 instructions per element in the key-major passes (a call covers 8 adjacent KEYS of one
+      // query = 8 adjacent lanes, so the calls went through a shared-memory transpose) on warps that are instruction-bound.
       const int c0 = j * N + slot * NH;
       float mult[NH];
 #pragma unroll
       for (int c = 0; c < NH; ++c) mult[c] = 1.f;
       if (a.drop.p > 0.f) {
+        const uint8_t* bits = a.drop_bits + (int64_t)bh * a.Tp * (a.Tp >> 3);
         if constexpr (kv_roles) {
-          // thread = key row, columns = queries.  One Philox call covers 8 adjacent KEYS of one query, i.e. 8
-          // adjacent lanes: lane (kg = lane/8, cq = lane%8) generates the calls of key-group kg for the columns
-          // c = 8i + cq and the warp transposes them through a private smem tile [column][lane].
-          float* mt = reinterpret_cast<float*>(smem + L::mask) + warp * (NH * L::kMaskLd);
-          const int kg = lane >> 3, cq = lane & 7;
-          const int key0 = r0 + quarter * 32 + kg * 8;
+          // thread = key row, columns = queries: the 32 keys of this warp are one aligned 32-bit word of a query's mask row;
+          // lane c fetches the word of query c0 + c, a shuffle hands it to everybody, lane l tests bit l
+          const int kw = (r0 + quarter * 32) >> 5;
+          const uint32_t mine = lane < NH ? __ldg(reinterpret_cast<const uint32_t*>(bits + (int64_t)(c0 + lane) * (a.Tp >> 3)) + kw) : 0u;
 #pragma unroll
-          for (int i = 0; i < NH / 8; ++i) {
-            const int c = 8 * i + cq;
-            float mk[8];
-            const uint64_t idx = ((uint64_t)bh * a.T + (uint64_t)min(c0 + c, a.T - 1)) * (uint64_t)Tc + key0;
-            dropout_mult8(a.drop.seed, a.drop.site, idx >> 3, a.drop.p, inv_keep, mk);
-            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8) = make_float4(mk[0], mk[1], mk[2], mk[3]);
-            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8 + 4) = make_float4(mk[4], mk[5], mk[6], mk[7]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < NH; ++c) mult[c] = mt[c * L::kMaskLd + lane];
-          __syncwarp();
-        } else {                   // thread = query row, columns = keys: 8 adjacent keys share one Philox call
-          const uint64_t rowb = ((uint64_t)bh * a.T + (uint64_t)min(ri, a.T - 1)) * (uint64_t)Tc;
+          for (int c = 0; c < NH; ++c) mult[c] = (__shfl_sync(0xffffffffu, mine, c) >> lane) & 1u ? inv_keep : 0.f;
+        } else {  // thread = query row, columns = keys c0 .. c0 + NH - 1: NH / 8 bytes of this row's mask
 #pragma unroll
           for (int g = 0; g < NH / 8; ++g) {
-            float mk[8];
-            dropout_mult8(a.drop.seed, a.drop.site, (rowb + (uint64_t)(c0 + 8 * g)) >> 3, a.drop.p, inv_keep, mk);
+            const uint32_t kb = __ldg(bits + (int64_t)ri * (a.Tp >> 3) + ((c0 + 8 * g) >> 3));
 #pragma unroll
-            for (int e = 0; e < 8; ++e) mult[8 * g + e] = mk[e];
+            for (int e = 0; e < 8; ++e) mult[8 * g + e] = (kb >> e) & 1u ? inv_keep : 0.f;
           }
         }
       }
@@ -502,10 +487,7 @@ struct SmemPair {
   static constexpr uint32_t ring0 = 0;             // 2 slots: operand of the score MMA
   static constexpr uint32_t ring1 = 2 * kSlot;     // 2 slots: operand of the accumulating MMA
   static constexpr uint32_t xch = 4 * kSlot;       // rank 1: P' from rank 0, [2 buffers][4 slots][4 chunks][128 rows][16 B]
-                                                   // rank 0: dropout-mask transpose tiles ([warp][16][kMaskLd] floats)
   static constexpr uint32_t kXch = 2 * 4 * 4 * 128 * 16;
-  static constexpr int kMaskLd = 36;
-  static_assert(kSmWarps * 16 * kMaskLd * 4 <= (int)kXch, "mask tiles must fit the exchange region");
   static constexpr uint32_t bars = xch + kXch;
   static constexpr uint32_t total = bars + 512 + 1024;
 };
@@ -716,7 +698,6 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     }
 
     const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
-    const int Tc = (int)drop_stride(a.T);
     const float* lse = a.lse + (int64_t)bh * a.Tp;
     const float* delta = a.delta + (int64_t)bh * a.Tp;
     // exchange buffer addressing: chunk c (4 floats) of this thread's 16 columns sits at
@@ -745,28 +726,17 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       }
       float sv[NH];
       if (rank == 0) {
-        // dropout multipliers (thread = key row, columns = queries): one Philox call covers 8 adjacent KEYS of one
-        // query = 8 adjacent lanes; generated per key group and transposed through a private smem tile
+        // dropout multipliers from the forward's keep bits (see attn_bwd2_body): lane c fetches the 32-key word of query
+        // c0 + c, lane l tests bit l
         float mult[NH];
 #pragma unroll
         for (int c = 0; c < NH; ++c) mult[c] = 1.f;
         if (a.drop.p > 0.f) {
-          float* mt = reinterpret_cast<float*>(smem + L::xch) + warp * (NH * L::kMaskLd);
-          const int kg = lane >> 3, cq = lane & 7;
-          const int key0 = r0 + quarter * 32 + kg * 8;
+          const uint8_t* bits = a.drop_bits + (int64_t)bh * a.Tp * (a.Tp >> 3);
+          const int kw = (r0 + quarter * 32) >> 5;
+          const uint32_t mine = lane < NH ? __ldg(reinterpret_cast<const uint32_t*>(bits + (int64_t)(c0 + lane) * (a.Tp >> 3)) + kw) : 0u;
 #pragma unroll
-          for (int i = 0; i < NH / 8; ++i) {
-            const int c = 8 * i + cq;
-            float mk[8];
-            const uint64_t idx = ((uint64_t)bh * a.T + (uint64_t)min(c0 + c, a.T - 1)) * (uint64_t)Tc + key0;
-            dropout_mult8(a.drop.seed, a.drop.site, idx >> 3, a.drop.p, inv_keep, mk);
-            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8) = make_float4(mk[0], mk[1], mk[2], mk[3]);
-            *reinterpret_cast<float4*>(mt + c * L::kMaskLd + kg * 8 + 4) = make_float4(mk[4], mk[5], mk[6], mk[7]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < NH; ++c) mult[c] = mt[c * L::kMaskLd + lane];
-          __syncwarp();
+          for (int c = 0; c < NH; ++c) mult[c] = (__shfl_sync(0xffffffffu, mine, c) >> lane) & 1u ? inv_keep : 0.f;
         }
         mbar_wait(&sp_full[buf], (j >> 1) & 1);
         tc_fence_after();
@@ -977,6 +947,7 @@ int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st) {
   V1T_CHECK_ARG(a.Dp % 32 == 0 && a.Dp >= 32 && a.Dp <= 160 && a.Tp % 128 == 0 && a.Tp >= a.T && a.E <= a.Dp,
                 "attn_bwd2_tc: unsupported dims (Dp %d, Tp %d)", a.Dp, a.Tp);
   V1T_CHECK_ARG(a.B * a.H <= 65535, "attn_bwd2_tc: too many (batch, head) pairs");
+  V1T_CHECK_ARG(a.drop.p <= 0.f || a.drop_bits, "attn_bwd2_tc: dropout needs the keep bits written by the forward");
   switch (a.Dp / 32) {
     case 1: return bwd2_all<1>(a, st);
     case 2: return bwd2_all<2>(a, st);

@@ -295,15 +295,16 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       const int jb = j * BKEY + slot * NW;
       // the dropout multipliers do not depend on S: draw them BEFORE waiting for the scores, so that the chain from
       // "S(j) complete" to "P(j) in TMEM" (which the P V MMA waits for) holds no Philox latency
-      float mk[NW];
+      uint32_t keep = 0xffffu;  // bit c: key jb + c is kept
       if (a.drop.p > 0.f) {
+        keep = 0;
 #pragma unroll
-        for (int g = 0; g < NW / 8; ++g) {  // one Philox call per 8 adjacent keys
-          float m8[8];
-          dropout_mult8(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 8 * g)) >> 3, a.drop.p, inv_keep, m8);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) mk[8 * g + e] = m8[e];
-        }
+        for (int g = 0; g < NW / 8; ++g)  // one Philox call per 8 adjacent keys
+          keep |= dropout_keep8(a.drop.seed, a.drop.site, (drop_row + (uint64_t)(jb + 8 * g)) >> 3, a.drop.p) << (8 * g);
+        // the backward reads the decisions instead of re-drawing them (its softmax warps are instruction-bound and the
+        // key-major passes would also have to transpose the calls): 16 bits per thread per tile, 22 MB per layer at B = 16
+        if (a.drop_bits)
+          *reinterpret_cast<uint16_t*>(a.drop_bits + ((int64_t)bh * a.Tp + qi) * (a.Tp >> 3) + (jb >> 3)) = (uint16_t)keep;
       }
       mbar_wait(&s_full[buf], (its >> 1) & 1);
       tc_fence_after();
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       }
       if (a.drop.p > 0.f) {
 #pragma unroll
-        for (int c = 0; c < NW; ++c) p[c] *= mk[c];
+        for (int c = 0; c < NW; ++c) p[c] = (keep >> c) & 1u ? p[c] * inv_keep : 0.f;
       }
       mbar_wait(p_empty, (j & 1) ^ 1);  // P V of the previous tile has consumed the operand
       tc_fence_after();

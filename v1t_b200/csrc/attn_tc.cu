@@ -36,6 +36,8 @@ AttnPlanes carve_attn_planes(void* base, int B, int H, int Tp, int Dp, bool with
   off += (size_t)round_up((int64_t)B * H * Tp * 4, 1024);
   p.delta = (float*)(c ? c + off : nullptr);
   off += (size_t)round_up((int64_t)B * H * Tp * 4, 1024);
+  p.drop_bits = (uint8_t*)(c ? c + off : nullptr);  // standalone entry points: forward writes, backward reads
+  off += (size_t)round_up((int64_t)attn_drop_bits_bytes(B, H, Tp), 1024);
   p.total = off;
   return p;
 }
@@ -85,6 +87,7 @@ extern "C" int v1t_attn_forward(const float* qkv, int B, int H, int T, int E, in
   AttnFwdArgs a{};
   a.q_hi = p.q[0]; a.q_lo = p.q[1]; a.k_hi = p.k[0]; a.k_lo = p.k[1]; a.v_hi = p.v[0]; a.v_lo = p.v[1];
   a.O = out; a.o_ld = I; a.lse = lse_out ? lse_out : p.lse;
+  a.drop_bits = p_drop > 0.f ? p.drop_bits : nullptr;
   a.B = B; a.H = H; a.T = T; a.Tp = Tp; a.E = E; a.Dp = Dp;
   a.scale_log2 = (1.0f / sqrtf((float)E)) * 1.4426950408889634f;
   a.x3 = x3;
@@ -115,6 +118,7 @@ extern "C" int v1t_attn_backward(const float* qkv, const float* out, const float
   a.q_hi = p.q[0]; a.q_lo = p.q[1]; a.k_hi = p.k[0]; a.k_lo = p.k[1]; a.v_hi = p.v[0]; a.v_lo = p.v[1];
   a.do_hi = p.dO[0]; a.do_lo = p.dO[1];
   a.lse = lse; a.delta = p.delta; a.dqkv = d_qkv;
+  a.drop_bits = p_drop > 0.f ? p.drop_bits : nullptr;  // written by v1t_attn_forward into the same scratch
   a.B = B; a.H = H; a.T = T; a.Tp = Tp; a.E = E; a.Dp = Dp;
   a.scale = 1.0f / sqrtf((float)E);
   a.scale_log2 = a.scale * 1.4426950408889634f;

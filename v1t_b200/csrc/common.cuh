@@ -105,6 +105,19 @@ __device__ __forceinline__ void dropout_mult8(uint64_t seed, uint32_t site, uint
     m[2 * i + 1] = (w[i] >> 16) >= thr ? inv_keep : 0.0f;
   }
 }
+// the same eight keep decisions as a bit mask (bit e = element 8*group + e is KEPT)
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, uint64_t group, float p) {
+  const uint4 r = philox4x32(seed, group, site, 0x5eedu);
+  const uint32_t thr = dropout_thr16(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bits |= ((w[i] & 0xffffu) >= thr ? 1u : 0u) << (2 * i);
+    bits |= ((w[i] >> 16) >= thr ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;
+}
 // keep-multiplier of element `idx` of dropout site `site`: call idx >> 3, 16-bit lane idx & 7
 __device__ __forceinline__ float dropout_mult(uint64_t seed, uint32_t site, uint64_t idx, float p, float inv_keep) {
   const uint4 r = philox4x32(seed, idx >> 3, site, 0x5eedu);

@@ -21,6 +21,7 @@ inline DropSpec site_drop(const v1t_core_shape& s, int block, Site site) {
 struct Dims {
   int B, C, H, W, p, s, gh, gw, L, T, Tp, Tq, E, Ep, heads, I, M, Mp, pd, hid, bdim, blocks, impl;
   bool fused;  // fused tcgen05 attention (tensor-core impls, head dim <= 160)
+  bool drop;   // block dropout active (the fused attention then keeps its keep-bit mask for the backward)
   int64_t R;  // B*T rows
 };
 
@@ -56,6 +57,7 @@ int make_dims(const v1t_core_shape* sh, Dims& d) {
   d.R = (int64_t)d.B * d.T;
   d.Tq = (int)round_up(d.T, 128);  // token padding of the attention operand planes
   d.fused = d.impl != V1T_IMPL_FP32 && d.Ep <= 160 && (int64_t)d.B * d.heads <= 65535;
+  d.drop = sh->p_drop_block > 0.f;
   return V1T_OK;
 }
 
@@ -79,6 +81,7 @@ struct BlockSaved {
   uint8_t* wqp[2];                 // Wqkv planes with every head's rows padded to Ep (head-aligned QKV GEMM output)
   uint8_t* wpp[2];                 // Wproj planes with every head's columns padded to Ep
   uint8_t* opl[2];                 // operand planes of the head-padded attention output [R, H*Ep]
+  uint8_t* dbits;                  // keep bits of the attention dropout [B*H, Tq, Tq/8] (fused attention, p > 0)
 };
 struct Saved {
   BlockSaved blk[V1T_MAX_BLOCKS];
@@ -96,6 +99,7 @@ void carve_block(Carver& c, const Dims& d, BlockSaved& b) {
   b.bhid = c.take((int64_t)d.B * d.hid + 1);
   b.blat = c.take((int64_t)d.B * d.E);
   b.lse = c.take(d.fused ? (int64_t)d.B * d.heads * d.Tq : 1);
+  b.dbits = (uint8_t*)c.take(d.fused && d.drop ? (int64_t)(attn_drop_bits_bytes(d.B, d.heads, d.Tq) / sizeof(float)) : 1);
   const int64_t pf = d.fused ? (int64_t)(plane_bytes(d.B, d.heads, d.Tq, d.Ep) / sizeof(float)) : 1;
   for (int i = 0; i < 2; ++i) {
     b.qp[i] = (uint8_t*)c.take(pf);
@@ -357,6 +361,7 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       AttnFwdArgs fa{};
       fa.q_hi = S.qp[0]; fa.q_lo = S.qp[1]; fa.k_hi = S.kp[0]; fa.k_lo = S.kp[1]; fa.v_hi = S.vp[0]; fa.v_lo = S.vp[1];
       fa.O = S.o; fa.o_ld = d.I; fa.lse = S.lse;
+      fa.drop_bits = d.drop ? S.dbits : nullptr;
       if (qkv_to_planes(d)) {  // O leaves the kernel only as operand planes of the head-padded [R, H*Ep] matrix
         fa.O = nullptr;
         fa.o_pl = act_plane_out(d, S.opl);
@@ -559,6 +564,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       ba.q_hi = S.qp[0]; ba.q_lo = S.qp[1]; ba.k_hi = S.kp[0]; ba.k_lo = S.kp[1]; ba.v_hi = S.vp[0]; ba.v_lo = S.vp[1];
       ba.do_hi = pl.dO[0]; ba.do_lo = pl.dO[1];
       ba.lse = S.lse; ba.delta = pl.delta;
+      ba.drop_bits = d.drop ? S.dbits : nullptr;
       if (qkv_to_planes(d)) {  // dQ | dK | dV leave the kernels as operand planes of the head-padded gradient only
         ba.dqkv = nullptr;
         ba.dq_pl = act_plane_out(d, sc.dqpl);

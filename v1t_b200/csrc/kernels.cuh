@@ -151,6 +151,8 @@ struct AttnFwdArgs {
   PlaneOut o_pl;     // optional: GEMM-operand planes of the head-padded [B*T, H*Dp] output
   int64_t o_ld;
   float* lse;        // [B*H, Tp] log2-domain log-sum-exp (may be null)
+  uint8_t* drop_bits;  // [B*H, Tp, Tp/8] keep bits of the attention dropout (bit k of row q: P[q,k] kept), written
+                       // when drop.p > 0 and non-null; the backward reads them instead of re-drawing (attn_drop_bits_bytes)
   int B, H, T, Tp, E, Dp;
   float scale_log2;  // E^-0.5 * log2(e)
   int x3;
@@ -165,12 +167,15 @@ int attn_prec_env();
 int attn_bwd_pair_env();
 // V1T_ATTN_BWD_GROUP: (b, h) pairs per block-order group of the three-pass backward (default 16; see attn_bwd2.cu)
 int attn_bwd_group_env();
+// bytes of the keep-bit mask of one attention call (0 rows are never read for padded queries)
+static inline size_t attn_drop_bits_bytes(int B, int H, int Tp) { return (size_t)B * H * Tp * (size_t)(Tp / 8); }
 int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // Q and P in tensor memory (attn_fwd2.cu)
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st);
 struct AttnBwdArgs {
   const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo, *do_hi, *do_lo;  // RM planes (rows = tokens, K = head dim)
   const float* lse;    // [B*H, Tp] base-2 log-sum-exp saved by the forward
   const float* delta;  // [B*H, Tp] rowsum(dO * O)
+  const uint8_t* drop_bits;  // keep bits written by the forward (required when drop.p > 0)
   float* dqkv;         // [B, T, 3*H*E] packed like to_qkv's output: dQ | dK | dV (may be null when dq_pl is given)
   PlaneOut dq_pl;      // optional: GEMM-operand planes of the head-padded [B*T, 3*H*Dp] gradient (dQ | dK | dV)
   int B, H, T, Tp, E, Dp;
@@ -185,6 +190,7 @@ struct AttnPlanes {  // [0] = hi, [1] = lo
   uint8_t *q[2], *k[2], *v[2];    // RM planes (rows = tokens, K = head dim)
   uint8_t *dO[2];                 // backward
   float *lse, *delta;                                 // [B*H, Tp]
+  uint8_t* drop_bits;                                 // [B*H, Tp, Tp/8] (standalone entry points)
   size_t total;
 };
 AttnPlanes carve_attn_planes(void* base, int B, int H, int Tp, int Dp, bool with_backward);
