@@ -25,6 +25,13 @@ int v1t_bulk_microbench(const void* src, long long span, int bytes, int copies, 
 /* self-test of the tensor-memory A operand (tcgen05.st + TS-form tcgen05.mma): C[128,N] = bf16(A[128,K]) bf16(B[N,K])^T */
 int v1t_ts_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
 
+/* hook exported by the PRODUCT library (libv1t_b200.so), not by the diagnostics library: device buffer of
+ * 2 ranks x 24 tiles x 8 events (int64 cycles since the cluster's start barrier) that CTAs 0/1 of head 0 of the
+ * pair attention-backward kernel fill (events: MMA warp 0 = scores wait begins, 1 = scores issue, 2 = accumulate wait
+ * begins, 3 = accumulate issue; softmax warp 0: 4 = scores arrived, 5 = exchange wait passed, 6 = operand slot free,
+ * 7 = operand written); NULL switches the trace off.  scripts/pair_trace.py prints the timeline. */
+int v1t_diag_attn_pair_trace(long long* buf);
+
 #ifdef __cplusplus
 }
 #endif

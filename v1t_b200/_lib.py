@@ -159,7 +159,9 @@ DIAG_SYMBOLS = {
     "v1t_mma_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "v1t_bulk_microbench": (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "v1t_ts_selftest": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "v1t_diag_attn_pair_trace": (C.c_int, [_vp]),
 }
+PRODUCT_HOSTED_DIAG = ("v1t_diag_attn_pair_trace",)  # diagnostics hooks that live inside libv1t_b200.so itself
 
 _lib = None
 _diag = None
@@ -172,9 +174,11 @@ def load_diag():
         load()  # builds both libraries when needed
         lib = C.CDLL(DIAG_LIB_PATH)
         for name, (res, args) in DIAG_SYMBOLS.items():
-            fn = getattr(lib, name)
+            fn = getattr(_lib if name in PRODUCT_HOSTED_DIAG else lib, name)
             fn.restype = res
             fn.argtypes = args
+            if name in PRODUCT_HOSTED_DIAG:
+                setattr(lib, name, fn)
         _diag = lib
     return _diag
 

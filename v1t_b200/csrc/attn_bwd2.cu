@@ -269,26 +269,17 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a, const int t
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int b = bh / a.H, h = bh % a.H;
 
-    // ---- resident operands: plane rows -> TMEM (thread = row; slot 0: X hi, slot 1: X lo, slot 2: Y hi)
+    // ---- resident operands: plane rows -> TMEM (thread = row)
     {
-      const int sw = (ri >> 1) & 3;
-      auto load_plane_row = [&](const uint8_t* plane, uint32_t tcol) {
-#pragma unroll
-        for (int at_i = 0; at_i < AD; ++at_i) {
-          const uint4* src = reinterpret_cast<const uint4*>(plane + attn_plane_off(bh, at_i, ri, a.Tp, AD));
-          uint4 ph[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {  // logical chunk c sits at physical position c ^ sw
-            const uint4 v = ph[c ^ sw];
-            tmem_st4(tmem_base + lane_off + tcol + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
-          }
-        }
-      };
-      if (slot == 0) load_plane_row(X_hi, cX_hi);
-      if (slot == 1 && a.x3) load_plane_row(X_lo, cX_lo);
-      if (slot == 2 && MODE == MODE_S) load_plane_row(Y_hi, cY_hi);
+      if constexpr (MODE == MODE_S) {  // three planes: slot 0: X hi, slot 1: X lo, slot 2: Y hi (all atoms each)
+        if (slot == 0) plane_row_to_tmem<AD>(X_hi, bh, ri, a.Tp, tmem_base + lane_off + cX_hi, 0, 1);
+        if (slot == 1 && a.x3) plane_row_to_tmem<AD>(X_lo, bh, ri, a.Tp, tmem_base + lane_off + cX_lo, 0, 1);
+        if (slot == 2) plane_row_to_tmem<AD>(Y_hi, bh, ri, a.Tp, tmem_base + lane_off + cY_hi, 0, 1);
+      } else {  // two planes: slot s takes plane (s & 1) and the head-dim atoms of parity (s >> 1)
+        const bool lo = (slot & 1) != 0;
+        if (!lo || a.x3)
+          plane_row_to_tmem<AD>(lo ? X_lo : X_hi, bh, ri, a.Tp, tmem_base + lane_off + (lo ? cX_lo : cX_hi), slot >> 1, 2);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(res_full);
@@ -479,6 +470,14 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a, const int t
 // 3 + 3 (rank 0) and 3 + 3 (rank 1) instead of 6 (dV pass) + 9 (dK pass); dQ stays the query-stationary pass above.
 // TMEM columns (both ranks): R_hi | R_lo | scores[2][64] | A_hi[32] | A_lo[32] | out[Dp] = 2 HC + 192 + Dp (512 @ Dp = 160).
 // =====================================================================================================================
+// optional per-tile timeline of one cluster (diagnostics: include/v1t_b200_diag.h, scripts/pair_trace.py); null = off
+__device__ long long* g_pair_trace = nullptr;
+constexpr int kTraceTiles = 24, kTraceEvents = 8;  // [rank 2][tile][event] cycles since the cluster's start barrier
+#define PAIR_TRACE(ev, j)                                                                                       \
+  do {                                                                                                          \
+    if (trace && (j) < kTraceTiles) trace[((int)rank * kTraceTiles + (j)) * kTraceEvents + (ev)] = clock64() - t_start; \
+  } while (0)
+
 template <int AD>
 struct SmemPair {
   static constexpr int N = 64;
@@ -571,6 +570,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
   __syncthreads();
   tc_fence_after();
   cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  const long long t_start = clock64();
+  long long* trace = (g_pair_trace && blockIdx.x < 2 && blockIdx.z == 0 && (threadIdx.x & 31) == 0) ? g_pair_trace : nullptr;
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t cR_hi = 0, cR_lo = HC, cS = 2 * HC, cPS_hi = cS + 2 * N, cPS_lo = cPS_hi + OPC, cOut = cPS_lo + OPC;
   static_assert(cOut + Dp <= 512, "TMEM budget exceeded");
@@ -611,9 +612,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     auto issue_scores = [&](int j) {
       const int s = j & 1;
       const uint32_t xb = g0 + s * (L::kSlot >> 4);
+      PAIR_TRACE(0, j);
       mbar_wait(&r0_full[s], (j >> 1) & 1);
       mbar_wait(&sp_empty[s], ((j >> 1) & 1) ^ 1);
       tc_fence_after();
+      PAIR_TRACE(1, j);
       const uint64_t xh = kDescK64 | (uint64_t)xb, xl = kDescK64 | (uint64_t)(xb + (L::kTile >> 4));
       const uint32_t dS = tmem_base + cS + s * N;
 #pragma unroll
@@ -635,9 +638,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     };
     auto issue_out = [&](int j, bool last) {
       const int s = j & 1;
+      PAIR_TRACE(2, j);
       mbar_wait(&r1_full[s], (j >> 1) & 1);
       mbar_wait(ps_full, j & 1);
       tc_fence_after();
+      PAIR_TRACE(3, j);
       const uint32_t sb = g1 + s * (L::kSlot >> 4);
       const uint64_t bh_ = mn_base | (uint64_t)sb, bl_ = mn_base | (uint64_t)(sb + (L::kTile >> 4));
 #pragma unroll
@@ -674,24 +679,10 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int b = bh / a.H, h = bh % a.H;
 
-    {  // resident operand: plane rows -> TMEM (slot 0: hi plane, slot 1: lo plane)
-      const int sw = (ri >> 1) & 3;
-      if (slot == 0 || (slot == 1 && a.x3)) {
-        const uint8_t* plane = slot == 0 ? R_hi : R_lo;
-        const uint32_t tcol = slot == 0 ? cR_hi : cR_lo;
-#pragma unroll
-        for (int at_i = 0; at_i < AD; ++at_i) {
-          const uint4* src = reinterpret_cast<const uint4*>(plane + attn_plane_off(bh, at_i, ri, a.Tp, AD));
-          uint4 ph[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 v = ph[c ^ sw];
-            tmem_st4(tmem_base + lane_off + tcol + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
-          }
-        }
-      }
+    {  // resident operand: plane rows -> TMEM; slot s takes plane (s & 1) and the head-dim atoms of parity (s >> 1)
+      const bool lo = (slot & 1) != 0;
+      if (!lo || a.x3)
+        plane_row_to_tmem<AD>(lo ? R_lo : R_hi, bh, ri, a.Tp, tmem_base + lane_off + (lo ? cR_lo : cR_hi), slot >> 1, 2);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(res_full);
@@ -740,6 +731,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         }
         mbar_wait(&sp_full[buf], (j >> 1) & 1);
         tc_fence_after();
+        if (warp == 0) PAIR_TRACE(4, j);
         {
           uint32_t v1[NH];
           tmem_ld16(tmem_base + lane_off + cS + buf * N + slot * NH, v1);
@@ -753,6 +745,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         for (int c = 0; c < NH; ++c) sv[c] = fast_exp2(fmaf(sv[c], a.scale_log2, -stat[c]));  // P' (0 for padded queries)
         // ---- ship P' to rank 1: fp32, dropped elements carry the sign bit
         mbar_wait(&pe_empty[buf], ((j >> 1) & 1) ^ 1);  // rank 1 has consumed tile j - 2 (two tiles of slack)
+        if (warp == 0) PAIR_TRACE(5, j);
 #pragma unroll
         for (int c = 0; c < NH / 4; ++c) {
           float o[4];
@@ -767,6 +760,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       } else {
         mbar_wait(&sp_full[buf], (j >> 1) & 1);
         tc_fence_after();
+        if (warp == 0) PAIR_TRACE(4, j);
         float dv[NH];
         {
           uint32_t v1[NH];
@@ -779,6 +773,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         mbar_arrive(&sp_empty[buf]);
         // ---- P' from rank 0
         mbar_wait(&pe_full[buf], (j >> 1) & 1);  // all 32 KB of tile j have landed (st.async transaction bytes)
+        if (warp == 0) PAIR_TRACE(5, j);
 #pragma unroll
         for (int c = 0; c < NH / 4; ++c) {
           const uint4 v = lds128(xch_local + (uint32_t)buf * 32768u + (uint32_t)c * 2048u);
@@ -799,6 +794,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       // A operand of the accumulating MMA -> TMEM (two bf16 per column), hi and lo planes
       mbar_wait(ps_empty, (j & 1) ^ 1);
       tc_fence_after();
+      if (warp == 0) PAIR_TRACE(6, j);
 #pragma unroll
       for (int ch = 0; ch < NH / 8; ++ch) {
         float x[8];
@@ -813,6 +809,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ps_full);
+      if (warp == 0) PAIR_TRACE(7, j);
       if (rank == 1) {  // P' of tile j is consumed (its values went through the dS' -> TMEM chain above): one signal per warp
         __syncwarp();
         if (lane == 0) mbar_arrive_remote_relaxed(pe_empty_peer + (uint32_t)buf * 8u);
@@ -943,6 +940,12 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+// diagnostics hook (include/v1t_b200_diag.h): per-tile timeline buffer of the pair kernel, 2 * 24 * 8 int64, or null
+int attn_pair_trace_set(long long* buf) {
+  V1T_CUDA(cudaMemcpyToSymbol(g_pair_trace, &buf, sizeof(buf)));
+  return V1T_OK;
+}
+
 int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st) {
   V1T_CHECK_ARG(a.Dp % 32 == 0 && a.Dp >= 32 && a.Dp <= 160 && a.Tp % 128 == 0 && a.Tp >= a.T && a.E <= a.Dp,
                 "attn_bwd2_tc: unsupported dims (Dp %d, Tp %d)", a.Dp, a.Tp);
@@ -958,3 +961,5 @@ int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st) {
 }
 
 }  // namespace v1t
+
+extern "C" int v1t_diag_attn_pair_trace(long long* buf) { return v1t::attn_pair_trace_set(buf); }

@@ -235,24 +235,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     const int qi = q0 + row;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int b = bh / a.H, h = bh % a.H;
-    // ---- Q rows -> TMEM (slot 0: hi plane, slot 1: lo plane)
+    // ---- Q rows -> TMEM: slot s takes plane (s & 1) and the head-dim atoms of parity (s >> 1)
     {
-      const int sw = (qi >> 1) & 3;
-      const uint8_t* plane = slot == 0 ? a.q_hi : a.q_lo;
-      if (slot == 0 || (slot == 1 && a.x3)) {
-#pragma unroll
-        for (int at_i = 0; at_i < AD; ++at_i) {
-          const uint4* src = reinterpret_cast<const uint4*>(plane + attn_plane_off(bh, at_i, qi, a.Tp, AD));
-          uint4 ph[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) ph[p] = __ldg(src + p);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 v = ph[c ^ sw];
-            tmem_st4(tmem_base + lane_off + (slot == 0 ? cQ_hi : cQ_lo) + at_i * 16 + c * 4, v.x, v.y, v.z, v.w);
-          }
-        }
-      }
+      const bool lo = (slot & 1) != 0;
+      if (!lo || a.x3)
+        plane_row_to_tmem<AD>(lo ? a.q_lo : a.q_hi, bh, qi, a.Tp, tmem_base + lane_off + (lo ? cQ_lo : cQ_hi), slot >> 1, 2);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(q_ready);

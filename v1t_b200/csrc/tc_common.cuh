@@ -249,6 +249,34 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 __host__ __device__ __forceinline__ int64_t attn_plane_off(int64_t bh, int atom, int t, int Tq, int AD) {
   return ((((bh * (Tq >> 6) + (t >> 6)) * AD + atom) << 6) + (t & 63)) << 6;
 }
+// Row `t` of a 128-row RESIDENT operand (attention plane of head `bh`) -> tensor memory columns [tcol, tcol + AD*16) of
+// this thread's lane, for the head-dim atoms at0, at0 + astep, ...  All global loads are issued before the first
+// tcgen05.st: the stores are asm volatile, so a load-store-load-store sequence serialised one global round trip per
+// atom (the prologue of the attention kernels measured ~12 k cycles per CTA, scripts/pair_trace.py).
+template <int AD>
+__device__ __forceinline__ void plane_row_to_tmem(const uint8_t* plane, int64_t bh, int t, int Tp, uint32_t taddr,
+                                                  int at0, int astep) {
+  uint4 ph[AD][4];
+#pragma unroll
+  for (int at_i = 0; at_i < AD; ++at_i) {
+    if (at_i >= at0 && (at_i - at0) % astep == 0) {
+      const uint4* src = reinterpret_cast<const uint4*>(plane + attn_plane_off(bh, at_i, t, Tp, AD));
+#pragma unroll
+      for (int p = 0; p < 4; ++p) ph[at_i][p] = __ldg(src + p);
+    }
+  }
+  const int sw = (t >> 1) & 3;  // the 16-byte chunk at physical position p holds logical chunk p ^ sw
+#pragma unroll
+  for (int at_i = 0; at_i < AD; ++at_i) {
+    if (at_i >= at0 && (at_i - at0) % astep == 0) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {  // runtime COLUMN offset instead of a runtime register index (no local-memory array)
+        const uint4 v = ph[at_i][p];
+        tmem_st4(taddr + at_i * 16 + ((p ^ sw) << 2), v.x, v.y, v.z, v.w);
+      }
+    }
+  }
+}
 // byte offset of 16-byte chunk `chunk` of row `row` in column atom `atom` of a matrix plane ([atoms][rows_p][64 B])
 __device__ __forceinline__ int64_t plane_chunk_off(int64_t atom, int64_t rows_p, int64_t row, int chunk) {
   return (atom * rows_p + row) * 64 + ((chunk ^ (int)((row >> 1) & 3)) << 4);
