@@ -590,7 +590,7 @@ def test_fused_attention_forward_dropout_replay():
 @pytest.mark.parametrize("B,H,T,E,p", [(1, 1, 64, 32, 0.0), (2, 2, 200, 24, 0.0), (1, 2, 1654, 155, 0.0),
                                        (2, 3, 333, 155, 0.25)])
 @pytest.mark.parametrize("impl,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
-@pytest.mark.parametrize("variant", ["three-pass", "pair"])
+@pytest.mark.parametrize("variant", ["three", "pair"])
 def test_fused_attention_backward(B, H, T, E, p, impl, tol, variant, monkeypatch):
     """dQ, dK, dV of the fused tcgen05 attention vs fp64 autograd of softmax(QK^T)V (same dropout mask).  Both
     backward organisations: three atomic-free passes, and dV + dK by two-CTA clusters sharing P' (V1T_ATTN_BWD=pair)."""

@@ -48,9 +48,9 @@ int attn_prec_env() {
   const char* e = getenv("V1T_ATTN_PREC");  // read on every call: tests switch it between launches
   return e ? atoi(e) & 7 : 0;
 }
-int attn_bwd_pair_env() {
+int attn_bwd_pair_env() {  // default: pair; V1T_ATTN_BWD=three selects the three-pass organisation
   const char* e = getenv("V1T_ATTN_BWD");
-  return e && e[0] == 'p';
+  return !(e && e[0] == 't');
 }
 int attn_bwd_group_env() {
   const char* e = getenv("V1T_ATTN_BWD_GROUP");

@@ -163,7 +163,8 @@ struct AttnFwdArgs {
 // contraction: 1 = the Pd'/dS'/P operand of the accumulating MMAs is hi-only, 2 = dP' without the resident-lo term
 // (the only SS-form MMAs of the backward), 4 = dP' from the hi planes alone.  Measured in DESIGN.md 4.2.
 int attn_prec_env();
-// V1T_ATTN_BWD=pair: dV + dK from one recomputation of P' by two-CTA clusters (attn_bwd2.cu); default: three passes
+// dV + dK from one recomputation of P' by two-CTA clusters (attn_bwd2.cu) -- the default; V1T_ATTN_BWD=three selects
+// the three atomic-free passes (dK | dQ | dV) instead
 int attn_bwd_pair_env();
 // V1T_ATTN_BWD_GROUP: (b, h) pairs per block-order group of the three-pass backward (default 16; see attn_bwd2.cu)
 int attn_bwd_group_env();

@@ -265,15 +265,24 @@ __device__ __forceinline__ void plane_row_to_tmem(const uint8_t* plane, int64_t 
       for (int p = 0; p < 4; ++p) ph[at_i][p] = __ldg(src + p);
     }
   }
-  const int sw = (t >> 1) & 3;  // the 16-byte chunk at physical position p holds logical chunk p ^ sw
+  // logical chunk c sits at physical position c ^ sw.  tcgen05.st takes ONE address per warp (lane i writes TMEM lane
+  // base + i at the same columns), so the per-row swizzle must permute the DATA, not the column: an XOR network of
+  // conditional swaps (no runtime register index, i.e. no local-memory array)
+  const int sw = (t >> 1) & 3;
+  auto cswap = [](bool on, uint4& x, uint4& y) {
+    const uint4 a = x, b = y;
+    x = on ? b : a;
+    y = on ? a : b;
+  };
 #pragma unroll
   for (int at_i = 0; at_i < AD; ++at_i) {
     if (at_i >= at0 && (at_i - at0) % astep == 0) {
+      cswap(sw & 1, ph[at_i][0], ph[at_i][1]);
+      cswap(sw & 1, ph[at_i][2], ph[at_i][3]);
+      cswap(sw & 2, ph[at_i][0], ph[at_i][2]);
+      cswap(sw & 2, ph[at_i][1], ph[at_i][3]);
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {  // runtime COLUMN offset instead of a runtime register index (no local-memory array)
-        const uint4 v = ph[at_i][p];
-        tmem_st4(taddr + at_i * 16 + ((p ^ sw) << 2), v.x, v.y, v.z, v.w);
-      }
+      for (int c = 0; c < 4; ++c) tmem_st4(taddr + at_i * 16 + c * 4, ph[at_i][c].x, ph[at_i][c].y, ph[at_i][c].z, ph[at_i][c].w);
     }
   }
 }
