@@ -333,6 +333,8 @@ def workload_config(args, cfg, world):
             "batch_per_mouse_per_gpu": args.batch, "global_batch": args.mice * args.batch * world,
             "neurons_per_mouse": args.neurons, "parallelism": f"dp{world} ({args.dp_mode})", "impl": args.b200_impl,
             "micro_batch": args.micro or args.batch,
+            "core_passes": "one per mouse" if (getattr(args, "no_fuse_core", False) or args.micro) else
+                           "one over all mice of the step (shared core, per-mouse readouts on row slices)",
             "l2": "per-step working set (saved activations ~1.4 GB per mouse batch) >> 126 MB L2; no explicit flush"}
 
 
@@ -368,15 +370,18 @@ def run_b200(args, cfg):
     samples_per_step_rank = sum(hi - lo for lo, hi in plan.my_slices.values())
     h2d = sum(v.numel() * 4 for b in host.values() for v in b.values())
     micro = args.micro
+    fuse = not args.no_fuse_core
 
     def step_resident():
         model.zero_grad(set_to_none=True)
-        return parallel.sweep(model, crit, resident, plan.global_batch, sync, fused_accumulate=True, micro_batch=micro)
+        return parallel.sweep(model, crit, resident, plan.global_batch, sync, fused_accumulate=True, micro_batch=micro,
+                              fuse_core=fuse)
 
     def step_e2e():
         model.zero_grad(set_to_none=True)
         dev_b = {m: {k: v.to(dev, non_blocking=True) for k, v in b.items()} for m, b in host.items()}
-        loss = parallel.sweep(model, crit, dev_b, plan.global_batch, sync, fused_accumulate=True, micro_batch=micro)
+        loss = parallel.sweep(model, crit, dev_b, plan.global_batch, sync, fused_accumulate=True, micro_batch=micro,
+                              fuse_core=fuse)
         return float(loss.item()) if loss is not None else 0.0  # device->host read of the step's loss
 
     def barrier():
@@ -742,7 +747,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--neurons", type=int, default=None)
     ap.add_argument("--micro", type=int, default=None, help="micro-batch size (0 = whole mouse batch at once)")
-    ap.add_argument("--dp-mode", dest="dp_mode", default="batch", choices=["batch", "mouse", "mouse2d"])
+    ap.add_argument("--dp-mode", dest="dp_mode", default="mouse2d", choices=["batch", "mouse", "mouse2d"])
+    ap.add_argument("--no-fuse-core", action="store_true",
+                    help="one core pass per mouse (as the reference loops) instead of one over all mice of the step")
     ap.add_argument("--ref-batch", dest="ref_batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true")

@@ -107,3 +107,35 @@ def test_two_gpu_step_equals_one_gpu_step_with_twice_the_batch(mode):
             # split-batch sums differ from the one-pass sums only by fp32 / bf16x3 summation order
             assert e < 2e-4, (mode, rank, k, e)
         print(f"[{mode}] rank {rank}: worst relative gradient difference {worst:.2e}")
+
+
+def test_fused_core_pass_equals_per_mouse_passes():
+    """sweep(fuse_core=True): ONE core pass over the concatenated batches of all mice gives the gradients of the
+    reference's mouse-by-mouse accumulation (train.py:84-111), and is refused for per-mouse behaviour MLPs."""
+    from v1t_b200 import parallel
+
+    dev = torch.device("cuda", 0)
+    model, crit = _model(dev)
+    plan = parallel.make_plan(list(MICE), 0, 1, "mouse2d", BATCH)
+    g = torch.Generator().manual_seed(11)
+    batches = {}
+    for i, (m, n) in enumerate(MICE.items()):
+        rows = BATCH + i  # unequal batch sizes per mouse
+        batches[m] = {"image": torch.randn((rows, 1, 36, 64), generator=g).to(dev), "behavior": torch.rand((rows, 3), generator=g).to(dev),
+                      "pupil_center": torch.rand((rows, 2), generator=g).to(dev),
+                      "response": (torch.rand((rows, n), generator=g) * 2).to(dev)}
+    gb = {m: BATCH for m in MICE}
+    out = []
+    for fuse in (False, True):
+        model.zero_grad(set_to_none=True)
+        loss = parallel.sweep(model, crit, batches, gb, None, fused_accumulate=True, fuse_core=fuse)
+        out.append((float(loss), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}))
+    assert abs(out[0][0] - out[1][0]) / abs(out[0][0]) < 1e-5
+    assert set(out[0][1]) == set(out[1][1])
+    for k, gref in out[0][1].items():
+        denom = max(float(gref.abs().max()), 1e-30)
+        assert float((out[1][1][k] - gref).abs().max()) / denom < 1e-4, k
+    model.core.behavior_mode = 4
+    assert not parallel._can_fuse_core(model, batches, 0)
+    model.core.behavior_mode = 3
+    assert parallel._can_fuse_core(model, batches, 0) and not parallel._can_fuse_core(model, batches, 8)

@@ -277,16 +277,56 @@ class GradSync:
                 o += k
 
 
+def _can_fuse_core(model, batches, micro_batch: int) -> bool:
+    """One core pass over all mice of the step is possible when the core's parameters do not depend on the mouse
+    (behavior_mode 4 has per-mouse behaviour MLPs), the step is not micro-batched and the model has the repo's wiring."""
+    core = getattr(model, "core", None)
+    return (len(batches) > 1 and not (micro_batch and micro_batch > 0) and getattr(core, "behavior_mode", 4) != 4
+            and all(hasattr(model, a) for a in ("image_cropper", "readouts", "elu1", "core_shifter")))
+
+
+def _fused_core_pass(model, criterion, batches, global_batch):
+    """The shared core runs ONCE on the concatenated batches of all mice (same samples, same math: the reference feeds
+    the mice one after the other only because Model.forward takes one mouse_id, model.py:151-177); readout, ELU1 and
+    the loss stay per mouse on row slices of the core's output view, and one backward through the summed loss gives the
+    gradients train.py:84-111 accumulates step by step."""
+    mice = list(batches)
+    images, behaviors, pupils, sizes = [], [], [], []
+    for m in mice:
+        b = batches[m]
+        im, _ = model.image_cropper(b["image"], mouse_id=m, behaviors=b["behavior"], pupil_centers=b["pupil_center"])
+        images.append(im)
+        behaviors.append(b["behavior"])
+        pupils.append(b["pupil_center"])
+        sizes.append(im.shape[0])
+    fmap = model.core(torch.cat(images), mouse_id=mice[0], behaviors=torch.cat(behaviors),
+                      pupil_centers=torch.cat(pupils))
+    total = None
+    for m, f in zip(mice, fmap.split(sizes)):  # row slices of the channel-last view (strides preserved)
+        b = batches[m]
+        shifts = model.core_shifter(b["pupil_center"], mouse_id=m) if model.core_shifter is not None else None
+        y = model.elu1(model.readouts(f, mouse_id=m, shifts=shifts))
+        loss = criterion(y_true=b["response"], y_pred=y, mouse_id=m, batch_size=global_batch[m])
+        total = loss if total is None else total + loss
+    total.backward()
+    return total.detach()
+
+
 def sweep(model, criterion, batches: t.Dict[str, t.Dict[str, torch.Tensor]], global_batch: t.Dict[str, int],
-          sync: t.Optional[GradSync] = None, fused_accumulate: bool = False, micro_batch: int = 0):
+          sync: t.Optional[GradSync] = None, fused_accumulate: bool = False, micro_batch: int = 0,
+          fuse_core: bool = False):
     """One optimizer step's worth of forward/backward: every mouse batch of this rank once (in micro-batches of
     ``micro_batch`` rows when > 0, like data.micro_batching / train.py:55), gradients accumulated (train.py:84-111
-    without the optimizer), then the gradient exchange.  Returns the summed loss (device scalar)."""
+    without the optimizer), then the gradient exchange.  ``fuse_core``: run the shared core once over all mice of the
+    step (see _fused_core_pass) when the model allows it.  Returns the summed loss (device scalar)."""
     total = None
     if fused_accumulate:  # one add per backward for all shared-core gradients instead of one per parameter
         model.core.fused_grad_accumulation(True)
     if sync is not None:
         sync.arm()
+    if fuse_core and _can_fuse_core(model, batches, micro_batch):
+        total = _fused_core_pass(model, criterion, batches, global_batch)
+        batches = {}
     for mouse_id, b in batches.items():
         rows = b["image"].shape[0]
         step = micro_batch if micro_batch and micro_batch > 0 else rows
