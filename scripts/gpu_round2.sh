@@ -1,40 +1,46 @@
 #!/bin/bash
-# One gpurun call of round 2: GPU tests, smoke, bench lines, precision experiment, ncu evidence.  Outputs: gpurun_out/.
-# usage: scripts/gpu_round2.sh [tests] [bench] [prec] [ncu] [configs]   (no argument = everything)
+# One gpurun call of round 2: GPU tests, smoke, bench lines, sanitizers, ncu evidence.  Outputs: gpurun_out/.
+# usage: scripts/gpu_round2.sh [tests] [bench] [prec] [ncu] [configs] [sanitize]   (no argument = everything but prec)
 mkdir -p gpurun_out
-what="${*:-tests bench prec ncu configs}"
+what="${*:-tests bench ncu configs sanitize}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv,noheader
-python - <<'PY'
-import os
-print("cores", os.cpu_count())
-PY
+python -c "import os; print('cores', os.cpu_count())"
 if [[ $what == *tests* ]]; then
-  ( time timeout 1500 python -m pytest tests -m gpu -q --timeout 600 ) > gpurun_out/pytest_gpu.log 2>&1
+  ( time timeout 1500 python -m pytest tests -m gpu -q -rs --timeout 600 ) > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit $?"; tail -8 gpurun_out/pytest_gpu.log
   ( time timeout 300 python __graft_entry__.py --smoke ) > gpurun_out/smoke.log 2>&1
   echo "smoke exit $?"; tail -4 gpurun_out/smoke.log
 fi
 if [[ $what == *bench* ]]; then
   ( time timeout 900 python bench.py --steps 10 --warmup 3 ) > gpurun_out/bench.json 2> gpurun_out/bench.err
-  echo "bench exit $?"; tail -c 2500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+  echo "bench exit $?"; tail -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
   ( time timeout 600 python bench.py --impl reference --steps 5 --warmup 1 ) > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err
-  echo "reference arm exit $?"; tail -c 1200 gpurun_out/bench_reference.json
+  echo "reference arm exit $?"; tail -c 600 gpurun_out/bench_reference.json
+  timeout 300 python bench.py --steps 8 --warmup 3 --no-fuse-core --no-cpu-baseline --no-eager-baseline --no-extras > gpurun_out/bench_per_mouse_core.json 2>> gpurun_out/bench.err
+  V1T_ATTN_BWD=three timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-extras > gpurun_out/bench_three_pass.json 2>> gpurun_out/bench.err
 fi
 if [[ $what == *prec* ]]; then
   ( time timeout 1200 python scripts/attn_prec_experiment.py ) > gpurun_out/attn_prec.json 2> gpurun_out/attn_prec.err
-  echo "prec exit $?"; tail -c 3000 gpurun_out/attn_prec.json; tail -3 gpurun_out/attn_prec.err
+  echo "prec exit $?"; tail -3 gpurun_out/attn_prec.err
 fi
 if [[ $what == *configs* ]]; then
   for c in franke ensemble scaled; do
     ( time timeout 900 python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline --no-extras ) > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
-    echo "bench $c exit $?"; tail -c 1500 gpurun_out/bench_$c.json; tail -3 gpurun_out/bench_$c.err
+    echo "bench $c exit $?"; tail -c 400 gpurun_out/bench_$c.json; tail -3 gpurun_out/bench_$c.err
+  done
+fi
+if [[ $what == *sanitize* ]]; then
+  for tool in racecheck memcheck; do
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 800 \
+      -k "fused_attention or (gemm and tc) or (golden and tiny_train and bf16x3) or ts_mma" > gpurun_out/sanitizer_$tool.log 2>&1
+    echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/sanitizer_$tool.log | head -4
   done
 fi
 if [[ $what == *ncu* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4000 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline --no-extras > gpurun_out/ncu_bench.log 2>&1
   echo "ncu launches exit $?"; wc -l gpurun_out/launches.csv
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:'attn_bwd2_kernel|attn_fwd2_kernel' -s 8 -c 4 \
+  timeout 900 ncu --set full --import-source on --clock-control none -k regex:'attn_bwd_pair_kernel|attn_bwd2_kernel|attn_fwd2_kernel' -s 12 -c 6 \
     -f -o gpurun_out/attn python bench.py --steps 1 --warmup 3 --mice 1 --no-cpu-baseline --no-eager-baseline --no-extras > gpurun_out/ncu_attn.log 2>&1
   echo "ncu attn exit $?"; tail -2 gpurun_out/ncu_attn.log; ls -la gpurun_out/*.ncu-rep
 fi
