@@ -756,6 +756,12 @@ def test_ensemble_model_matches_member_average():
             gw_ref = torch.autograd.grad(want.sum(), lin.weight)[0]
             y.sum().backward()
             assert rel_err(lin.weight.grad.cpu().numpy(), gw_ref.cpu().numpy()) < 1e-5
+        # inference: the members run concurrently on their own CUDA streams (own scratch arenas) -- same numbers, repeatedly
+        with torch.no_grad():
+            for _ in range(3):
+                y2, _, _ = ens(cu(d["images"]), **x)
+                assert torch.equal(y2, y.detach())
+        assert len(ens._streams) == 3
 
 
 def test_train_step_with_fused_optimizer_matches_oracle_update():

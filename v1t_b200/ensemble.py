@@ -47,21 +47,46 @@ class EnsembleModel(nn.Module):
     """ensemble.py:83-151 with the members passed in (checkpoint discovery / args.yaml parsing stay with the
     caller: ``members`` maps the reference's model names to constructed-and-loaded Models)."""
 
-    def __init__(self, args, members: t.Dict[str, Model]):
+    def __init__(self, args, members: t.Dict[str, Model], concurrent: bool = True):
         super().__init__()
         self.input_shape = args.input_shape
         self.output_shapes = args.output_shapes
         self.ensemble = nn.ModuleDict(members)
         self.ensemble.requires_grad_(False)
         self.output_module = OutputModule(args, in_features=len(members))
+        # The K members share inputs but not weights: each runs its native launch sequence on its OWN CUDA stream (own
+        # scratch arena), so their kernels interleave on the device instead of running back to back; the output module
+        # joins the streams.  (One grouped launch sequence with a model index per row block is the design that would
+        # remove the remaining per-member launches; see DESIGN.md.)
+        self.concurrent = concurrent
+        self._streams: t.List[torch.cuda.Stream] = []
 
     def regularizer(self, mouse_id: str):
         return torch.tensor(0.0)
 
     def forward(self, inputs, mouse_id: str, behaviors, pupil_centers):
+        names = list(self.ensemble.keys())
         outs = []
-        for name in self.ensemble.keys():
-            y, _, _ = self.ensemble[name](inputs, mouse_id=mouse_id, behaviors=behaviors,
-                                          pupil_centers=pupil_centers, activate=False)
-            outs.append(y)
+        side = self.concurrent and inputs.is_cuda and len(names) > 1 and not torch.is_grad_enabled()
+        if side:
+            cur = torch.cuda.current_stream(inputs.device)
+            while len(self._streams) < len(names):
+                self._streams.append(torch.cuda.Stream(device=inputs.device))
+            for name, st in zip(names, self._streams):
+                st.wait_stream(cur)  # inputs (and the members' weights) are ready on the caller's stream
+                with torch.cuda.stream(st):
+                    y, _, _ = self.ensemble[name](inputs, mouse_id=mouse_id, behaviors=behaviors,
+                                                  pupil_centers=pupil_centers, activate=False)
+                    y.record_stream(cur)
+                outs.append(y)
+            for st in self._streams[: len(names)]:
+                cur.wait_stream(st)
+            for x in (inputs, behaviors, pupil_centers):
+                for st in self._streams[: len(names)]:
+                    x.record_stream(st)
+        else:
+            for name in names:
+                y, _, _ = self.ensemble[name](inputs, mouse_id=mouse_id, behaviors=behaviors,
+                                              pupil_centers=pupil_centers, activate=False)
+                outs.append(y)
         return self.output_module(outs, mouse_id=mouse_id), None, None

@@ -17,12 +17,13 @@ from ._lib import BLOCK_FIELDS, CoreDims, CorePtrs, CoreShape, ReadoutShape
 
 EPS_F32 = float(torch.finfo(torch.float32).eps)
 
-# one reusable scratch arena per device (single-stream use; the library never allocates)
+# one reusable scratch arena per (device, stream): kernels of one stream run in order, so a stream can reuse its arena
+# from call to call; members of an ensemble running on side streams each get their own (the library never allocates)
 _SCRATCH = {}
 
 
 def _scratch(device: torch.device, nbytes: int) -> torch.Tensor:
-    key = (device.type, device.index)
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
     buf = _SCRATCH.get(key)
     if buf is None or buf.numel() < nbytes:
         _SCRATCH.pop(key, None)

@@ -314,7 +314,7 @@ def _fused_core_pass(model, criterion, batches, global_batch):
 
 def sweep(model, criterion, batches: t.Dict[str, t.Dict[str, torch.Tensor]], global_batch: t.Dict[str, int],
           sync: t.Optional[GradSync] = None, fused_accumulate: bool = False, micro_batch: int = 0,
-          fuse_core: bool = False):
+          fuse_core: bool = False, fuse_rows: int = 128):
     """One optimizer step's worth of forward/backward: every mouse batch of this rank once (in micro-batches of
     ``micro_batch`` rows when > 0, like data.micro_batching / train.py:55), gradients accumulated (train.py:84-111
     without the optimizer), then the gradient exchange.  ``fuse_core``: run the shared core once over all mice of the
@@ -325,7 +325,19 @@ def sweep(model, criterion, batches: t.Dict[str, t.Dict[str, torch.Tensor]], glo
     if sync is not None:
         sync.arm()
     if fuse_core and _can_fuse_core(model, batches, micro_batch):
-        total = _fused_core_pass(model, criterion, batches, global_batch)
+        # consecutive mice are grouped while a core pass stays within ``fuse_rows`` samples (saved activations: ~150 MB
+        # per sample of the default core); a group of one mouse is the ordinary per-mouse pass
+        group, rows = {}, 0
+        for mouse_id, b in list(batches.items()) + [(None, None)]:
+            n = b["image"].shape[0] if b is not None else 0
+            if group and (b is None or rows + n > fuse_rows):
+                part = (_fused_core_pass(model, criterion, group, global_batch) if len(group) > 1
+                        else sweep(model, criterion, group, global_batch, None, False, 0, False))
+                total = part if total is None else total + part
+                group, rows = {}, 0
+            if b is not None:
+                group[mouse_id] = b
+                rows += n
         batches = {}
     for mouse_id, b in batches.items():
         rows = b["image"].shape[0]
