@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
   uint64_t* pe_full = bars + 16;   // [2] rank 1: P' of a tile has landed (arming arrive + 32 KB of st.async bytes)
   uint64_t* pe_empty = bars + 18;  // [2] rank 0: rank 1 has consumed the buffer (one remote arrive per warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* stage_full = bars + 22;  // the resident operand's 128-row tile has landed in ring 1 (bulk copy)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0: P side (dV), 1: dS side (dK)
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
 
   if (threadIdx.x == 0) {
     mbar_init(res_full, kSmThreads);
+    mbar_init(stage_full, 1);
     mbar_init(ps_full, kSmThreads);
     mbar_init(ps_empty, 1);
     mbar_init(o_full, 1);
@@ -585,6 +587,15 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       const uint8_t* src_hi = is0 ? s0_hi : s1_hi;
       const uint8_t* src_lo = is0 ? s0_lo : s1_lo;
       uint8_t* ring = smem + (is0 ? L::ring0 : L::ring1);
+      if (!is0) {
+        // ring 1 is idle until the first accumulating MMA: it first carries the resident operand's 128 rows (two
+        // consecutive 64-row plane tiles = ONE contiguous copy per plane) to the softmax warps, which move them to TMEM
+        const int64_t roff = attn_plane_off(bh, 0, r0, a.Tp, AD);
+        mbar_expect_tx(stage_full, (a.x3 ? 2 : 1) * 2 * L::kTile);
+        bulk_g2s(ring, R_hi + roff, 2 * L::kTile, stage_full);
+        if (a.x3) bulk_g2s(ring + 2 * L::kTile, R_lo + roff, 2 * L::kTile, stage_full);
+        mbar_wait(res_full, 0);  // every row has been read out of the ring
+      }
       for (int j = 0; j < nt; ++j) {
         const int s = j & 1;
         mbar_wait(&emptyb[s], ((j >> 1) & 1) ^ 1);
@@ -679,10 +690,12 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const int b = bh / a.H, h = bh % a.H;
 
-    {  // resident operand: plane rows -> TMEM; slot s takes plane (s & 1) and the head-dim atoms of parity (s >> 1)
+    {  // resident operand: staged rows (ring 1) -> TMEM; slot s takes plane (s & 1) and the head-dim atoms of parity (s >> 1)
       const bool lo = (slot & 1) != 0;
+      mbar_wait(stage_full, 0);
       if (!lo || a.x3)
-        plane_row_to_tmem<AD>(lo ? R_lo : R_hi, bh, ri, a.Tp, tmem_base + lane_off + (lo ? cR_lo : cR_hi), slot >> 1, 2);
+        smem_row_to_tmem<AD>(smem_u32(smem + L::ring1) + (lo ? 2 * L::kTile : 0), row, tmem_base + lane_off + (lo ? cR_lo : cR_hi),
+                             slot >> 1, 2);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(res_full);

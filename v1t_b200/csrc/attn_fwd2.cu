@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
   uint64_t* r_full = bars + 20;   // [4] pass-1 ring
   uint64_t* r_empty = bars + 24;  // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* stage_full = bars + 30;  // the 128 Q rows have landed in the V ring (bulk copy)
   constexpr int kKS = L::kKS;
   float* xch = reinterpret_cast<float*>(smem + L::xch);
 
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
 
   if (threadIdx.x == 0) {
     mbar_init(q_ready, kSmThreads);
+    mbar_init(stage_full, 1);
     mbar_init(p_full, kSmThreads);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
@@ -141,6 +143,14 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
   } else if (warp == kLoadWarpV) {
     // ============================== V^T PRODUCER ==============================
     if (lane == 0) {
+      {  // the V ring is idle during pass 1: it first carries the 128 Q rows (two consecutive 64-row plane tiles = one
+         // contiguous copy per plane) to the softmax warps, which move them into tensor memory
+        const int64_t qoff = attn_plane_off(bh, 0, q0, a.Tp, AD);
+        mbar_expect_tx(stage_full, (a.x3 ? 2 : 1) * 2 * L::kVTile);
+        bulk_g2s(smem + L::v_ring, a.q_hi + qoff, 2 * L::kVTile, stage_full);
+        if (a.x3) bulk_g2s(smem + L::v_ring + 2 * L::kVTile, a.q_lo + qoff, 2 * L::kVTile, stage_full);
+        mbar_wait(q_ready, 0);  // every row has been read out of the ring
+      }
       for (int j = 0; j < nk; ++j) {
         const int s = j & 1;
         mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
@@ -238,8 +248,10 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     // ---- Q rows -> TMEM: slot s takes plane (s & 1) and the head-dim atoms of parity (s >> 1)
     {
       const bool lo = (slot & 1) != 0;
+      mbar_wait(stage_full, 0);
       if (!lo || a.x3)
-        plane_row_to_tmem<AD>(lo ? a.q_lo : a.q_hi, bh, qi, a.Tp, tmem_base + lane_off + (lo ? cQ_lo : cQ_hi), slot >> 1, 2);
+        smem_row_to_tmem<AD>(smem_u32(smem + L::v_ring) + (lo ? 2 * L::kVTile : 0), row, tmem_base + lane_off + (lo ? cQ_lo : cQ_hi),
+                             slot >> 1, 2);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(q_ready);

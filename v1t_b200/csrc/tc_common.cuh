@@ -286,6 +286,28 @@ __device__ __forceinline__ void plane_row_to_tmem(const uint8_t* plane, int64_t 
     }
   }
 }
+// The same from a copy of the 128-row tile that a bulk copy staged in shared memory ([2 tiles of 64 rows][AD atoms][64 rows]
+// [64 B], exactly as it lies in the plane): the per-row swizzle is resolved by the (per-lane) shared-memory ADDRESS, so the
+// tensor-memory address stays warp-uniform.  One TMA fetch of 40 KB per plane replaces 128 x AD scattered 64-byte row
+// pieces per plane (the register-path prologue measured 7.9 k cycles per CTA).
+template <int AD>
+__device__ __forceinline__ void smem_row_to_tmem(uint32_t smem_plane, int row, uint32_t taddr, int at0, int astep) {
+  const uint32_t base = smem_plane + (uint32_t)(row >> 6) * (AD * 4096u) + (uint32_t)(row & 63) * 64u;
+  const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+  uint4 v[AD][4];
+#pragma unroll
+  for (int at_i = 0; at_i < AD; ++at_i)
+    if (at_i >= at0 && (at_i - at0) % astep == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[at_i][c] = lds128(base + at_i * 4096u + ((c ^ sw) << 4));
+    }
+#pragma unroll
+  for (int at_i = 0; at_i < AD; ++at_i)
+    if (at_i >= at0 && (at_i - at0) % astep == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st4(taddr + at_i * 16 + c * 4, v[at_i][c].x, v[at_i][c].y, v[at_i][c].z, v[at_i][c].w);
+    }
+}
 // byte offset of 16-byte chunk `chunk` of row `row` in column atom `atom` of a matrix plane ([atoms][rows_p][64 B])
 __device__ __forceinline__ int64_t plane_chunk_off(int64_t atom, int64_t rows_p, int64_t row, int chunk) {
   return (atom * rows_p + row) * 64 + ((chunk ^ (int)((row >> 1) & 3)) << 4);
