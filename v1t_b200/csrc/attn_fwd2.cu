@@ -51,7 +51,7 @@ struct FSmem {
   static constexpr uint32_t total = xch + kSlots * BQ * 4 + 1024;
 };
 
-template <int AD>
+template <int AD, bool EMIT>
 __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFwdArgs a) {
   constexpr int Dp = AD * 32, HC = AD * 16;
   using L = FSmem<AD>;
@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
         if (lo) bulk_g2s(smem + dst_lo, a.k_lo + src, L::kKTile, bar);
       };
       // pass 1: hi planes only, 4-slot ring over the K region
-      for (int j = 0; j < nk; ++j) {
+      for (int j = 0; j < nk && !EMIT; ++j) {
         const int slot = j & 3;
         mbar_wait(&r_empty[slot], ((j >> 2) & 1) ^ 1);
         load_k(L::k_ring + slot * L::kKTile, 0, j, false, &r_full[slot]);
       }
-      for (int slot = 0; slot < 4 && slot < nk; ++slot) {  // all pass-1 MMAs have released their slots
+      for (int slot = 0; slot < 4 && slot < nk && !EMIT; ++slot) {  // all pass-1 MMAs have released their slots
         const int last = ((nk - 1 - slot) / 4) * 4 + slot;
         mbar_wait(&r_empty[slot], (last >> 2) & 1);
       }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
         if (a.x3) bulk_g2s(smem + L::v_ring + 2 * L::kVTile, a.q_lo + qoff, 2 * L::kVTile, stage_full);
         mbar_wait(q_ready, 0);  // every row has been read out of the ring
       }
-      for (int j = 0; j < nk; ++j) {
+      for (int j = 0; j < nk && !EMIT; ++j) {
         const int s = j & 1;
         mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[s], a.x3 ? 2 * L::kVTile : L::kVTile);
@@ -228,16 +228,20 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
 
     mbar_wait(q_ready, 0);
     tc_fence_after();
-    for (int j = 0; j < nk; ++j) {  // pass 1: reference row max from the hi planes
-      const int slot = j & 3;
-      issue_s(kDescK64 | (uint64_t)(kr0 + slot * (L::kKTile >> 4)), 0, false, &r_full[slot], (j >> 2) & 1, &r_empty[slot]);
+    if constexpr (EMIT) {
+      for (int j = 0; j < nk; ++j) issue_s2(j);  // exact scores only
+    } else {
+      for (int j = 0; j < nk; ++j) {  // pass 1: reference row max from the hi planes
+        const int slot = j & 3;
+        issue_s(kDescK64 | (uint64_t)(kr0 + slot * (L::kKTile >> 4)), 0, false, &r_full[slot], (j >> 2) & 1, &r_empty[slot]);
+      }
+      issue_s2(0);
+      for (int j = 0; j + 1 < nk; ++j) {
+        issue_s2(j + 1);  // S(j+1) overlaps softmax(j)
+        issue_pv(j, false);
+      }
+      issue_pv(nk - 1, true);
     }
-    issue_s2(0);
-    for (int j = 0; j + 1 < nk; ++j) {
-      issue_s2(j + 1);  // S(j+1) overlaps softmax(j)
-      issue_pv(j, false);
-    }
-    issue_pv(nk - 1, true);
   } else {
     // ============================== SOFTMAX / EPILOGUE ==============================
     const int quarter = warp & 3, slot = warp >> 2;
@@ -256,6 +260,37 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
       tc_fence_before();
       mbar_arrive(q_ready);
     }
+    if constexpr (EMIT) {
+      // ---- probabilities only: P = exp2(S c - lse) with the lse a forward saved; each warp transposes its 32 x 16 piece
+      // through a private shared-memory tile (the idle K-ring tail is not used: the V ring is, after the Q rows left it)
+      // so that half a warp writes 64 contiguous bytes of one row of the [T, T] matrix
+      const float lse_r = a.lse_in[(int64_t)bh * a.Tp + qi];
+      named_bar_sync(1, kSmThreads);  // every warp has read its Q rows out of the V ring before tiles go there
+      float* tile = reinterpret_cast<float*>(smem + L::v_ring) + warp * (32 * 17);
+      float* prow = a.probs + ((int64_t)bh * a.T + q0 + quarter * 32) * a.T;
+      for (int j = 0; j < nk; ++j) {
+        const uint32_t buf = j & 1;
+        const int jb = j * BKEY + slot * NW;
+        mbar_wait(&s_full[buf], (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[NW];
+        tmem_ld16(tmem_base + lane_off + cS + buf * BKEY + slot * NW, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[buf]);
+#pragma unroll
+        for (int c = 0; c < NW; ++c) tile[lane * 17 + c] = fast_exp2(fmaf(__uint_as_float(v[c]), a.scale_log2, -lse_r));
+        __syncwarp();
+        const int cc = lane & 15, rr = lane >> 4;
+#pragma unroll
+        for (int r2 = 0; r2 < 32; r2 += 2) {
+          const int r = r2 + rr;
+          if (q0 + quarter * 32 + r < a.T && jb + cc < a.T) prow[(int64_t)r * a.T + jb + cc] = tile[r * 17 + cc];
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+    } else {
     uint32_t its = 0;
     float m = -INFINITY;
     // ---- pass 1: row max over this warp's NW of the 64 key columns
@@ -408,6 +443,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     // padded query rows get +inf so that the backward's exp2(S*c - lse) vanishes there without bounds checks
     if (slot == 0 && a.lse) a.lse[(int64_t)bh * a.Tp + qi] = qi < a.T ? m2 + log2f(l) : INFINITY;
     tc_fence_before();
+    }  // !EMIT
   }
 
   __syncthreads();
@@ -418,14 +454,24 @@ template <int AD>
 int launch_fwd2(const AttnFwdArgs& a, cudaStream_t st) {
   using L = FSmem<AD>;
   static_assert(L::total <= 232448, "shared memory budget exceeded");
-  V1T_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
   dim3 grid(cdiv(a.T, BQ), a.B * a.H);
-  attn_fwd2_kernel<AD><<<grid, kThreadsAttn, L::total, st>>>(a);
+  if (a.probs) {
+    V1T_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<AD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    attn_fwd2_kernel<AD, true><<<grid, kThreadsAttn, L::total, st>>>(a);
+  } else {
+    V1T_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<AD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    attn_fwd2_kernel<AD, false><<<grid, kThreadsAttn, L::total, st>>>(a);
+  }
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
 
 }  // namespace
+
+int attn_emit_probs_tc(const AttnFwdArgs& a, cudaStream_t st) {
+  V1T_CHECK_ARG(a.probs && a.lse_in, "attn_emit_probs_tc: probs / lse_in missing");
+  return attn_fwd2_tc(a, st);
+}
 
 int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st) {
   V1T_CHECK_ARG(a.Dp % 32 == 0 && a.Dp >= 32 && a.Dp <= 160 && a.Tp % 128 == 0 && a.Tp >= a.T && a.E <= a.Dp,

@@ -735,6 +735,18 @@ extern "C" int v1t_attention_probs(const v1t_core_shape* shape, const void* save
   V1T_CHECK_ARG(saved_mem && probs && block >= 0 && block < d.blocks, "attention_probs: bad argument");
   Saved sv = carve_saved(d, const_cast<void*>(saved_mem));
   const int chunk = attn_chunk(d);
+  if (d.fused) {
+    // the forward kept Q, K as operand planes and the base-2 log-sum-exp of every row: P = exp2(S c - lse) comes out of
+    // the forward kernel's score pipeline in ONE launch (no fp32 qkv rebuild, no T x T GEMM output + softmax passes)
+    const BlockSaved& S = sv.blk[block];
+    AttnFwdArgs fa{};
+    fa.q_hi = S.qp[0]; fa.q_lo = S.qp[1]; fa.k_hi = S.kp[0]; fa.k_lo = S.kp[1];
+    fa.B = d.B; fa.H = d.heads; fa.T = d.T; fa.Tp = d.Tq; fa.E = d.E; fa.Dp = d.Ep;
+    fa.scale_log2 = (1.0f / sqrtf((float)d.E)) * 1.4426950408889634f;
+    fa.x3 = d.impl == V1T_IMPL_BF16X3;
+    fa.probs = probs; fa.lse_in = S.lse;
+    return attn_emit_probs_tc(fa, (cudaStream_t)stream);
+  }
   if (qkv_to_planes(d))  // the forward kept q, k, v only as bf16 hi/lo planes: rebuild fp32 qkv in its (unused) slot
     V1T_TRY(planes_to_qkv(head_planes(d, sv.blk[block]), d.B, d.E, sv.blk[block].qkv, (cudaStream_t)stream));
   for (int b0 = 0; b0 < d.B; b0 += chunk) {

@@ -157,6 +157,9 @@ struct AttnFwdArgs {
   float scale_log2;  // E^-0.5 * log2(e)
   int x3;
   int prec;          // precision-budget experiment (attn_prec_env): bit 0 = P enters P V as its bf16 hi plane only
+  // EMIT mode (attn_emit_probs_tc): only the normalised probabilities are produced, from the lse a forward saved
+  float* probs;          // [B*H, T, T] fp32, softmax(Q K^T E^-0.5) before dropout
+  const float* lse_in;   // [B*H, Tp] base-2 log-sum-exp of that forward
   DropSpec drop;
 };
 // V1T_ATTN_PREC (default 0 = every contraction with all three bf16x3 terms).  Bits drop ONE cross term of a
@@ -171,6 +174,9 @@ int attn_bwd_group_env();
 // bytes of the keep-bit mask of one attention call (0 rows are never read for padded queries)
 static inline size_t attn_drop_bits_bytes(int B, int H, int Tp) { return (size_t)B * H * Tp * (size_t)(Tp / 8); }
 int attn_fwd2_tc(const AttnFwdArgs& a, cudaStream_t st);  // Q and P in tensor memory (attn_fwd2.cu)
+// softmax(QK^T) [B*H,T,T] alone, for the attention-map hooks: the forward kernel's score pipeline with P = exp2(S c - lse)
+// written out row-coalesced (no P V, no second pass): one launch instead of qkv rebuild + GEMM + softmax pass
+int attn_emit_probs_tc(const AttnFwdArgs& a, cudaStream_t st);
 int attn_fwd_dispatch(const AttnFwdArgs& a, cudaStream_t st);
 struct AttnBwdArgs {
   const uint8_t *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo, *do_hi, *do_lo;  // RM planes (rows = tokens, K = head dim)
