@@ -49,6 +49,10 @@ struct FSmem {
   static constexpr uint32_t bars = v_ring + 4 * kVTile;
   static constexpr uint32_t xch = bars + 256;              // cross-half exchange of row max / row sum
   static constexpr uint32_t total = xch + kSlots * BQ * 4 + 1024;
+  // EMIT instantiation: per-warp 32 x 17 fp32 transpose tiles behind everything else (the rings are too small for them at
+  // small head dims)
+  static constexpr uint32_t emit_tiles = xch + kSlots * BQ * 4;
+  static constexpr uint32_t total_emit = emit_tiles + kSmWarps * 32 * 17 * 4 + 1024;
 };
 
 template <int AD, bool EMIT>
@@ -262,11 +266,9 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_fwd2_kernel(const AttnFw
     }
     if constexpr (EMIT) {
       // ---- probabilities only: P = exp2(S c - lse) with the lse a forward saved; each warp transposes its 32 x 16 piece
-      // through a private shared-memory tile (the idle K-ring tail is not used: the V ring is, after the Q rows left it)
-      // so that half a warp writes 64 contiguous bytes of one row of the [T, T] matrix
+      // through a private shared-memory tile so that half a warp writes 64 contiguous bytes of one row of the [T, T] matrix
       const float lse_r = a.lse_in[(int64_t)bh * a.Tp + qi];
-      named_bar_sync(1, kSmThreads);  // every warp has read its Q rows out of the V ring before tiles go there
-      float* tile = reinterpret_cast<float*>(smem + L::v_ring) + warp * (32 * 17);
+      float* tile = reinterpret_cast<float*>(smem + L::emit_tiles) + warp * (32 * 17);
       float* prow = a.probs + ((int64_t)bh * a.T + q0 + quarter * 32) * a.T;
       for (int j = 0; j < nk; ++j) {
         const uint32_t buf = j & 1;
@@ -456,8 +458,9 @@ int launch_fwd2(const AttnFwdArgs& a, cudaStream_t st) {
   static_assert(L::total <= 232448, "shared memory budget exceeded");
   dim3 grid(cdiv(a.T, BQ), a.B * a.H);
   if (a.probs) {
-    V1T_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<AD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
-    attn_fwd2_kernel<AD, true><<<grid, kThreadsAttn, L::total, st>>>(a);
+    static_assert(L::total_emit <= 232448, "shared memory budget exceeded");
+    V1T_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<AD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total_emit));
+    attn_fwd2_kernel<AD, true><<<grid, kThreadsAttn, L::total_emit, st>>>(a);
   } else {
     V1T_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<AD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     attn_fwd2_kernel<AD, false><<<grid, kThreadsAttn, L::total, st>>>(a);
