@@ -455,13 +455,20 @@ def run_b200(args, cfg):
                 "frac": ach / peaks["bf16_tflops_sustained"], "share_of_step": p["ms_per_step"] / max(phase_sum, 1e-9)}
 
     per_block_fwd = 4 * D["H"] * D["T"] ** 2 * D["E"]
-    kb = kernel_roofline("attn_bwd2_kernel", "attn_bwd_kernel", 2 * per_block_fwd)
+    kb = kernel_roofline("attention backward = attn_bwd_pair_kernel (dV + dK, 2-CTA clusters) + attn_bwd2_kernel (dQ pass)",
+                         "attn_bwd_kernel", 2 * per_block_fwd)
+    if kb:
+        for key, ph in (("pair_us_per_launch", "attn_bwd_pair"), ("dq_us_per_launch", "attn_bwd_dq")):
+            p = phases.get(ph)
+            if p and p["scopes_per_step"] > 0:
+                kb[key] = 1e3 * p["ms_per_step"] / p["scopes_per_step"]
     kf = kernel_roofline("attn_fwd2_kernel", "attn_fwd_kernel", per_block_fwd)
     dom = kb or {"kernel": "attention backward (materialised path)", "achieved": 0.0, "frac": 0.0}
     roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["achieved"],
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": dom["frac"],
-                "traffic": kernel_traffic("attn_bwd2_kernel"),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu, profiles/)",
+                "traffic": (kernel_traffic("attn_bwd_pair_kernel") or 0) + (kernel_traffic("attn_bwd2_kernel") or 0) or None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches (ncu launch list under profiles/; "
+                                "captured at the batch that list names)",
                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "detail": kb, "attn_fwd2_kernel": kf,
                 "flops_note": "algorithmic FLOPs: fwd 4*B*H*T^2*E per launch, bwd 2x that; the bf16x3 mode executes 3 "
                               "MMAs per product and the backward recomputes S, so the tensor pipe does ~8x this"}
@@ -725,7 +732,7 @@ def run_ensemble(args, cfg):
                     "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in hb.values())),
                     "d2h_bytes_per_step": int(out_host.numel() * 4 + heat_host.numel() * 4)},
             "gpu_launches": launches, "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": "emit-P stack write + rollout read (v1t_attention_probs, rollout_step_kernel)",
+            "roofline": {"bound": "hbm", "kernel": "emit-P stack write (attn_fwd2_kernel<EMIT>) + rollout read (rollout_step_kernel)",
                          "achieved": 2 * stack_bytes / (ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": 2 * stack_bytes / (ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
                          "note": "whole step time against the bytes of the [B,L,H,T,T] stack written once and read once; "

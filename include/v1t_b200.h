@@ -110,7 +110,9 @@ int v1t_version(void);
 #define V1T_PHASE_READOUT_BWD 8 /* readout backward (K9) */
 #define V1T_PHASE_ATTN_FWD_KERNEL 9  /* the fused attention forward launch alone (inside V1T_PHASE_ATTN_FWD) */
 #define V1T_PHASE_ATTN_BWD_KERNEL 10 /* the fused attention backward launch alone (inside V1T_PHASE_ATTN_BWD) */
-#define V1T_NUM_PHASES 11
+#define V1T_PHASE_ATTN_BWD_PAIR 11   /* the two-CTA-cluster dV + dK launch alone (inside V1T_PHASE_ATTN_BWD_KERNEL) */
+#define V1T_PHASE_ATTN_BWD_DQ 12     /* the dQ launch alone (inside V1T_PHASE_ATTN_BWD_KERNEL) */
+#define V1T_NUM_PHASES 13
 uint64_t v1t_launch_count(void);
 int v1t_prof_enable(int on);
 int v1t_prof_reset(void);

@@ -12,8 +12,8 @@ import os
 V1T_MAX_BLOCKS = 16
 IMPL_FP32, IMPL_BF16X3, IMPL_BF16 = 0, 1, 2
 PHASES = ["patch", "ln_qkv", "attn_fwd", "proj", "mlp", "attn_bwd", "linear_bwd", "readout_fwd", "readout_bwd",
-          "attn_fwd_kernel", "attn_bwd_kernel"]  # the last two are nested inside attn_fwd / attn_bwd
-NESTED_PHASES = ("attn_fwd_kernel", "attn_bwd_kernel")
+          "attn_fwd_kernel", "attn_bwd_kernel", "attn_bwd_pair", "attn_bwd_dq"]  # the last four are nested scopes
+NESTED_PHASES = ("attn_fwd_kernel", "attn_bwd_kernel", "attn_bwd_pair", "attn_bwd_dq")
 IMPL_NAMES = {"fp32": IMPL_FP32, "bf16x3": IMPL_BF16X3, "exact": IMPL_BF16X3, "bf16": IMPL_BF16, "fast": IMPL_BF16}
 
 _f32p = C.POINTER(C.c_float)

@@ -936,8 +936,12 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    V1T_CUDA(cudaLaunchKernelEx(&cfg, attn_bwd_pair_kernel<AD>, a));
-    V1T_LAUNCH_CHECK();
+    {
+      ProfScope prof(V1T_PHASE_ATTN_BWD_PAIR, st);
+      V1T_CUDA(cudaLaunchKernelEx(&cfg, attn_bwd_pair_kernel<AD>, a));
+      V1T_LAUNCH_CHECK();
+    }
+    ProfScope prof(V1T_PHASE_ATTN_BWD_DQ, st);
     dim3 gq(cdiv(a.T, 128), 1, a.B * a.H);
     attn_bwd2_kernel<AD><<<gq, kThreadsAttn, smem, st>>>(a, 1, cdiv(a.T, 128), 1);
     V1T_LAUNCH_CHECK();

@@ -352,11 +352,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             const uint4 y = lds128(rb + i * (kProdThreads * 32) + 16);
             const float v[8] = {__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w),
                                 __uint_as_float(y.x), __uint_as_float(y.y), __uint_as_float(y.z), __uint_as_float(y.w)};
-            uint4 hi, lo;
-            split8(v, hi, lo);
             const uint32_t dst = (i < 2 ? sa_hi + ca[i].soff : sb_hi + cb[i - 2].soff);
-            sts128(dst, hi);
-            if (a.x3) sts128(dst + (i < 2 ? A_PLANE : B_PLANE), lo);
+            if (a.x3) {
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              sts128(dst, hi);
+              sts128(dst + (i < 2 ? A_PLANE : B_PLANE), lo);
+            } else {  // plain-bf16 mode: four packs instead of the ~30-instruction hi/lo split (the converter warps, not the
+                      // single-pass MMAs, bound these launches: the materialised attention of the scaled core)
+              uint4 hi;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+              hi.x = *reinterpret_cast<uint32_t*>(&h0); hi.y = *reinterpret_cast<uint32_t*>(&h1);
+              hi.z = *reinterpret_cast<uint32_t*>(&h2); hi.w = *reinterpret_cast<uint32_t*>(&h3);
+              sts128(dst, hi);
+            }
           }
         }
         fence_proxy_async();
