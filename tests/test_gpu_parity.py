@@ -168,6 +168,35 @@ def test_scaled_core_dims_match_oracle(impl, tol_fwd, tol_grad):
     assert worst[0] < tol_grad, worst
 
 
+@pytest.mark.parametrize("stride", [4, 2])
+def test_scaled_core_dropout_matches_fp32_path(stride):
+    """Head dim 512 WITH dropout: the plane-operand tensor-core path (softmax + dropout written as bf16x3 operand
+    planes, softmax backward fused with the mask replay) against the library's own fp32 materialised path on the same
+    seed -- the masks are functions of (seed, site, element index), so both paths drop the same elements.  stride 2
+    gives 435 tokens (ragged last 128-row tile, 4 k-atoms of padding)."""
+    rng = np.random.default_rng(33)
+    n, B = 200, 2
+    out = {}
+    for impl in ("fp32", "bf16x3"):
+        r = np.random.default_rng(5)
+        model, crit, cfg, sd = _default_model(n, 2, r, emb_dim=512, num_heads=2, patch_stride=stride, b200_impl=impl,
+                                              p_dropout=0.1, t_dropout=0.2)
+        model.train(True)
+        model.core.dropout_seed = 777
+        r2 = np.random.default_rng(6)
+        images = r2.standard_normal((B, 1, 36, 64)).astype(np.float32)
+        beh, pup = r2.uniform(size=(B, 3)).astype(np.float32), r2.uniform(size=(B, 2)).astype(np.float32)
+        y_true = r2.uniform(0, 2, size=(B, n)).astype(np.float32)
+        noise = r2.standard_normal((B, n, 2)).astype(np.float32)
+        y, _, _ = model(cu(images), mouse_id="A", behaviors=cu(beh), pupil_centers=cu(pup), noise=cu(noise))
+        crit(y_true=cu(y_true), y_pred=y, mouse_id="A", batch_size=B).backward()
+        out[impl] = (y.detach().cpu().numpy(), {k: p.grad.cpu().numpy() for k, p in model.named_parameters()})
+    assert rel_err(out["bf16x3"][0], out["fp32"][0]) < TOL_FWD
+    worst = max((rel_err(g, out["fp32"][1][k]), k) for k, g in out["bf16x3"][1].items())
+    print(f"[scaled dropout stride {stride}] worst grad {worst[0]:.2e} ({worst[1]})")
+    assert worst[0] < TOL_GRAD, worst
+
+
 def test_dropout_masks_replay_exactly_against_oracle():
     """Train mode WITH dropout: fetch the kernels' own masks through v1t_dropout_mask and hand them to the
     oracle -> forward and gradients must still agree (validates in-kernel RNG replay in backward)."""

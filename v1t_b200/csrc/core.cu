@@ -22,6 +22,7 @@ struct Dims {
   int B, C, H, W, p, s, gh, gw, L, T, Tp, Tq, E, Ep, heads, I, M, Mp, pd, hid, bdim, blocks, impl;
   bool fused;  // fused tcgen05 attention (tensor-core impls, head dim <= 160)
   bool drop;   // block dropout active (the fused attention then keeps its keep-bit mask for the backward)
+  bool matpl;  // materialised attention (head dim > 160) on tensor cores: batched GEMMs over bf16 operand planes
   int64_t R;  // B*T rows
 };
 
@@ -58,6 +59,7 @@ int make_dims(const v1t_core_shape* sh, Dims& d) {
   d.Tq = (int)round_up(d.T, 128);  // token padding of the attention operand planes
   d.fused = d.impl != V1T_IMPL_FP32 && d.Ep <= 160 && (int64_t)d.B * d.heads <= 65535;
   d.drop = sh->p_drop_block > 0.f;
+  d.matpl = !d.fused && d.impl != V1T_IMPL_FP32 && d.Tq <= 2048;
   return V1T_OK;
 }
 
@@ -166,6 +168,9 @@ struct Scratch {
   float *h, *dh, *g, *dqkv, *dO, *patches, *P1, *P2, *partials, *dlat, *dz3, *dhid, *dpos;
   uint8_t *dpl[2], *dupl[2];           // operand planes of dropout(dx) and of du (backward)
   uint8_t* dqpl[2];                    // operand planes of the head-padded dqkv (from the attention backward)
+  // materialised attention on plane operands (Dims::matpl), one chunk of samples at a time: per-(sample, head) planes
+  // of Q, K, V, dO [chunk*H][Ep/32][Tq][64 B] and of the T x T matrices Pd, dS [chunk*H][Tq/32][Tq][64 B]
+  uint8_t *bhq[2], *bhk[2], *bhv[2], *bhdo[2], *pdpl[2], *dspl[2];
   AttnPlanes planes;
   int chunk;         // attention batch chunk
   size_t total;
@@ -204,6 +209,15 @@ Scratch carve_scratch(const Dims& d, void* base) {
     s.dpl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.E) / sizeof(float)) : 1);
     s.dupl[i] = (uint8_t*)c.take(tc ? (int64_t)(matrix_plane_bytes(d.R, d.M) / sizeof(float)) : 1);
     s.dqpl[i] = (uint8_t*)c.take(d.fused ? (int64_t)(matrix_plane_bytes(d.R, 3 * d.heads * d.Ep) / sizeof(float)) : 1);
+    const bool need = d.matpl && (i == 0 || d.impl == V1T_IMPL_BF16X3);
+    const int64_t bhf = need ? (int64_t)(bh_plane_bytes(s.chunk, d.heads, d.Tq, d.Ep) / sizeof(float)) : 1;
+    const int64_t ppf = need ? (int64_t)(prob_plane_bytes((int64_t)s.chunk * d.heads, d.Tq) / sizeof(float)) : 1;
+    s.bhq[i] = (uint8_t*)c.take(bhf);
+    s.bhk[i] = (uint8_t*)c.take(bhf);
+    s.bhv[i] = (uint8_t*)c.take(bhf);
+    s.bhdo[i] = (uint8_t*)c.take(bhf);
+    s.pdpl[i] = (uint8_t*)c.take(ppf);
+    s.dspl[i] = (uint8_t*)c.take(ppf);
   }
   s.partials = c.take(kPartialBytes / sizeof(float));
   s.dlat = c.take((int64_t)d.B * d.E);
@@ -218,6 +232,32 @@ v1t_gemm_desc gd(int m, int n, int k) {
   v1t_gemm_desc g{};
   g.m = m; g.n = n; g.k = k; g.batch1 = 1; g.batch2 = 1; g.alpha = 1.f;
   return g;
+}
+
+// ---- materialised attention over plane operands (Dims::matpl) ----
+inline PlaneOp bh_op(const Dims& d, uint8_t* const p[2]) {  // one (sample, head) matrix [T, E] per batch entry
+  return PlaneOp{p[0], d.impl == V1T_IMPL_BF16X3 ? p[1] : nullptr, d.Tq, d.Ep / 32, (int64_t)(d.Ep / 32) * d.Tq * 64};
+}
+inline PlaneOp prob_op(const Dims& d, uint8_t* const p[2]) {  // one T x T matrix per batch entry
+  return PlaneOp{p[0], d.impl == V1T_IMPL_BF16X3 ? p[1] : nullptr, d.Tq, d.Tq / 32, (int64_t)(d.Tq / 32) * d.Tq * 64};
+}
+// batched [bc, heads] problem with both operands from planes; a_mn / b_mn: operand contracted over its plane ROWS
+inline v1t_gemm_desc bh_gemm(const Dims& d, int bc, int m, int n, int k, bool a_mn, bool b_mn) {
+  v1t_gemm_desc g = gd(m, n, k);
+  g.batch1 = bc; g.batch2 = d.heads;
+  g.a_m = a_mn ? 1 : d.Tq; g.a_k = a_mn ? d.Tq : 1;
+  g.b_n = b_mn ? 1 : d.Tq; g.b_k = b_mn ? d.Tq : 1;
+  return g;
+}
+int bh_planes_of(const Dims& d, const float* X, int64_t ld, int col0, int bc, uint8_t* const p[2], cudaStream_t st) {
+  return bh_planes(X, ld, col0, bc, d.heads, d.T, d.Tq, d.E, d.Ep, p[0], d.impl == V1T_IMPL_BF16X3 ? p[1] : nullptr, st);
+}
+// scores S[b,h] = scale * Q K^T for samples [b0, b0+bc) from the Q / K planes of the chunk
+int scores_from_planes(const Dims& d, const Scratch& sc, int bc, float* S, cudaStream_t st) {
+  v1t_gemm_desc g = bh_gemm(d, bc, d.T, d.T, d.E, false, false);
+  g.c_m = d.Tp; g.c_b1 = (int64_t)d.heads * d.T * d.Tp; g.c_b2 = (int64_t)d.T * d.Tp;
+  g.alpha = 1.0f / sqrtf((float)d.E);  // emb_dim ** -0.5 (vit.py:234)
+  return gemm_any(d.impl, g, nullptr, nullptr, S, nullptr, nullptr, st, no_drop(), no_epi(), bh_op(d, sc.bhq), bh_op(d, sc.bhk));
 }
 
 // P[b,h] = softmax(scale * Q K^T) (optionally with dropout) for samples [b0, b0+bc) into P1
@@ -324,7 +364,9 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
       V1T_TRY(matrix_planes_batch(jobs, st));
     }
     // ---- Attention.mha (vit.py:267-275)
-    V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, sc.h, S.st1, d.R, d.E, d.Ep, st, act_plane_out(d, S.h1pl)));
+    // the normalised rows leave as operand planes; the fp32 copy is written only when a consumer reads it
+    V1T_TRY(ln_forward(x, lat, d.T, S.x1, W.ln1_w, W.ln1_b, qkv_to_planes(d) ? nullptr : sc.h, S.st1, d.R, d.E, d.Ep, st,
+                       act_plane_out(d, S.h1pl)));
     V1T_CHECK_ARG(d.R <= INT32_MAX, "core_forward: too many rows");
     if (qkv_to_planes(d)) {
       // q, k, v leave the GEMM epilogue as the attention kernels' operand planes (fp32 qkv is never materialised;
@@ -378,7 +420,24 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
         V1T_TRY(attn_fwd_dispatch(fa, st));
       }
     }
-    for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
+    for (int b0 = 0; d.matpl && b0 < d.B; b0 += sc.chunk) {
+      // head dim > 160: S and P go through HBM, but every GEMM reads ready-made bf16 operand planes (no conversion
+      // work in the GEMMs) and the softmax writes the probabilities as planes
+      ProfScope prof(V1T_PHASE_ATTN_FWD, st);
+      const int bc = std::min(sc.chunk, d.B - b0);
+      const float* q = S.qkv + (int64_t)b0 * d.T * 3 * d.I;
+      V1T_TRY(bh_planes_of(d, q, 3 * d.I, 0, bc, sc.bhq, st));
+      V1T_TRY(bh_planes_of(d, q, 3 * d.I, d.I, bc, sc.bhk, st));
+      V1T_TRY(bh_planes_of(d, q, 3 * d.I, 2 * d.I, bc, sc.bhv, st));
+      V1T_TRY(scores_from_planes(d, sc, bc, sc.P1, st));
+      V1T_TRY(softmax_rows_planes(sc.P1, (int64_t)bc * d.heads, d.T, d.Tq, d.Tp, site_drop(*shape, i, kSiteAttn),
+                                  (int64_t)b0 * d.heads * d.T, sc.pdpl[0], d.impl == V1T_IMPL_BF16X3 ? sc.pdpl[1] : nullptr, st));
+      v1t_gemm_desc g = bh_gemm(d, bc, d.T, d.E, d.T, false, true);  // O = Pd V
+      g.c_m = d.I; g.c_b1 = (int64_t)d.T * d.I; g.c_b2 = d.E;
+      V1T_TRY(gemm_any(d.impl, g, nullptr, nullptr, S.o + (int64_t)b0 * d.T * d.I, nullptr, nullptr, st, no_drop(), no_epi(),
+                       prob_op(d, sc.pdpl), bh_op(d, sc.bhv)));
+    }
+    for (int b0 = 0; !d.fused && !d.matpl && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_FWD, st);
       const int bc = std::min(sc.chunk, d.B - b0);
       V1T_TRY(attention_probs(d, S.qkv, b0, bc, sc.P1, d.Tp, site_drop(*shape, i, kSiteAttn), st));
@@ -408,10 +467,11 @@ extern "C" int v1t_core_forward(const v1t_core_shape* shape, const v1t_core_ptrs
     }
     // ---- MLP (vit.py:143-150)
     ProfScope prof_mlp(V1T_PHASE_MLP, st);
-    V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, sc.h, S.st2, d.R, d.E, d.Ep, st, act_plane_out(d, S.h2pl)));
     {
       v1t_gemm_desc g = gd((int)d.R, d.M, d.E);
       g.a_m = d.Ep; g.a_k = 1; g.b_k = 1; g.b_n = d.E; g.c_m = d.Mp;
+      V1T_TRY(ln_forward(S.x2, nullptr, d.T, nullptr, W.ln2_w, W.ln2_b, gemm_uses_tc(d.impl, g) ? nullptr : sc.h, S.st2, d.R, d.E,
+                         d.Ep, st, act_plane_out(d, S.h2pl)));
       if (gemm_uses_tc(d.impl, g)) {  // u and gelu(u)*dropout from one epilogue
         // gelu(u) * dropout leaves the epilogue as operand planes only (consumers: W2 GEMM and its weight gradient)
         const EpiOp act{kEpiGeluOut, nullptr, nullptr, d.Mp, site_drop(*shape, i, kSiteMlp1), act_plane_out(d, S.gpl)};
@@ -583,7 +643,42 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
         V1T_TRY(attn_bwd_dispatch(ba, st));
       }
     }
-    for (int b0 = 0; !d.fused && b0 < d.B; b0 += sc.chunk) {
+    for (int b0 = 0; d.matpl && b0 < d.B; b0 += sc.chunk) {
+      ProfScope prof(V1T_PHASE_ATTN_BWD, st);
+      const int bc = std::min(sc.chunk, d.B - b0);
+      const float* q = S.qkv + (int64_t)b0 * d.T * ld;
+      float* dq = sc.dqkv + (int64_t)b0 * d.T * ld;
+      const bool x3 = d.impl == V1T_IMPL_BF16X3;
+      V1T_TRY(bh_planes_of(d, q, ld, 0, bc, sc.bhq, st));
+      V1T_TRY(bh_planes_of(d, q, ld, d.I, bc, sc.bhk, st));
+      V1T_TRY(bh_planes_of(d, q, ld, 2 * d.I, bc, sc.bhv, st));
+      V1T_TRY(bh_planes_of(d, sc.dO + (int64_t)b0 * d.T * d.I, d.I, 0, bc, sc.bhdo, st));
+      V1T_TRY(scores_from_planes(d, sc, bc, sc.P1, st));  // recomputed scores
+      {  // dPd = dO V^T
+        v1t_gemm_desc g = bh_gemm(d, bc, d.T, d.T, d.E, false, false);
+        g.c_m = d.Tp; g.c_b1 = (int64_t)d.heads * d.T * d.Tp; g.c_b2 = (int64_t)d.T * d.Tp;
+        V1T_TRY(gemm_any(d.impl, g, nullptr, nullptr, sc.P2, nullptr, nullptr, st, no_drop(), no_epi(), bh_op(d, sc.bhdo),
+                         bh_op(d, sc.bhv)));
+      }
+      // softmax, dropout and the softmax backward in one pass over the rows: Pd and dS leave as operand planes
+      V1T_TRY(softmax_bwd_rows_planes(sc.P1, sc.P2, (int64_t)bc * d.heads, d.T, d.Tq, d.Tp, site_drop(*shape, i, kSiteAttn),
+                                      (int64_t)b0 * d.heads * d.T, sc.pdpl[0], x3 ? sc.pdpl[1] : nullptr, sc.dspl[0],
+                                      x3 ? sc.dspl[1] : nullptr, st));
+      v1t_gemm_desc g = bh_gemm(d, bc, d.T, d.E, d.T, true, true);
+      g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
+      // dV[j,d] = sum_i Pd[i,j] dO[i,d]
+      V1T_TRY(gemm_any(d.impl, g, nullptr, nullptr, dq + 2 * d.I, nullptr, nullptr, st, no_drop(), no_epi(), prob_op(d, sc.pdpl),
+                       bh_op(d, sc.bhdo)));
+      g.alpha = scale;  // dK[j,d] = scale * sum_i dS[i,j] Q[i,d]
+      V1T_TRY(gemm_any(d.impl, g, nullptr, nullptr, dq + d.I, nullptr, nullptr, st, no_drop(), no_epi(), prob_op(d, sc.dspl),
+                       bh_op(d, sc.bhq)));
+      g = bh_gemm(d, bc, d.T, d.E, d.T, false, true);  // dQ[i,d] = scale * sum_j dS[i,j] K[j,d]
+      g.alpha = scale;
+      g.c_m = ld; g.c_b1 = d.T * ld; g.c_b2 = d.E;
+      V1T_TRY(gemm_any(d.impl, g, nullptr, nullptr, dq, nullptr, nullptr, st, no_drop(), no_epi(), prob_op(d, sc.dspl),
+                       bh_op(d, sc.bhk)));
+    }
+    for (int b0 = 0; !d.fused && !d.matpl && b0 < d.B; b0 += sc.chunk) {
       ProfScope prof(V1T_PHASE_ATTN_BWD, st);
       const int bc = std::min(sc.chunk, d.B - b0);
       const float* q = S.qkv + (int64_t)b0 * d.T * ld;

@@ -67,6 +67,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 struct Tile {
   int m0, n0, k_begin, k_end;
   int64_t a_off, b_off, c_off, r_off;
+  int64_t pa_off, pb_off;  // byte offsets of this batch entry's plane operands
 };
 
 __device__ __forceinline__ Tile decode_tile(const TcArgs& a, int t) {
@@ -84,6 +85,8 @@ __device__ __forceinline__ Tile decode_tile(const TcArgs& a, int t) {
   tl.b_off = b1 * g.d.b_b1 + b2 * g.d.b_b2;
   tl.c_off = b1 * g.d.c_b1 + b2 * g.d.c_b2 + (int64_t)split * g.c_split;
   tl.r_off = b1 * g.d.r_b1 + b2 * g.d.r_b2;
+  tl.pa_off = (int64_t)(b1 * g.d.batch2 + b2) * a.pa.batch_bytes;
+  tl.pb_off = (int64_t)(b1 * g.d.batch2 + b2) * a.pb.batch_bytes;
   return tl;
 }
 
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const int plane = idx % np, atom = idx / np;  // atom: MN atom (MN-major) or k atom 0/1 (K-major)
         const bool mn = is_b ? a.mn_b : a.mn_a;
         const PlaneOp& po = is_b ? a.pb : a.pa;
-        const uint8_t* src_base = plane ? po.lo : po.hi;
+        const uint8_t* src_base = (plane ? po.lo : po.hi) + (is_b ? tl.pb_off : tl.pa_off);
         const int row0 = is_b ? tl.n0 : tl.m0;
         const int rows = is_b ? b_rows : a_rows;
         const int pitch_k = (is_b ? a.bn : BM) * 64;  // K-major: bytes between the two k atoms of a stage
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
         const int plane = idx % np, atom = idx / np;
         const bool mn = is_b ? a.mn_b : a.mn_a;
         const PlaneOp& po = is_b ? a.pb : a.pa;
-        const uint8_t* src_base = plane ? po.lo : po.hi;
+        const uint8_t* src_base = (plane ? po.lo : po.hi) + (is_b ? tl.pb_off : tl.pa_off);
         const int row0 = is_b ? tl.n0 : tl.m0;
         const uint32_t dst_off = (is_b ? 2 * A_PLANE : 0) + plane * (is_b ? B_PLANE : A_PLANE) + (mn ? atom * 2048 : 0);
         const uint32_t cbytes = mn ? 2048u : (uint32_t)((is_b ? b_rows : a_rows) * 64);
@@ -696,8 +699,9 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.pa = pa; a.pb = pb;
   a.a_pl = pa.hi != nullptr; a.b_pl = pb.hi != nullptr;
   if (a.a_pl || a.b_pl)
-    V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && (!x3 || ((!a.a_pl || pa.lo) && (!a.b_pl || pb.lo))),
-                  "tc gemm: plane operands need an unbatched problem and, in bf16x3 mode, the lo plane");
+    V1T_CHECK_ARG(((d.batch1 == 1 && d.batch2 == 1) || ((!a.a_pl || pa.batch_bytes > 0) && (!a.b_pl || pb.batch_bytes > 0))) &&
+                      (!x3 || ((!a.a_pl || pa.lo) && (!a.b_pl || pb.lo))),
+                  "tc gemm: plane operands need an unbatched problem (or a batch stride) and, in bf16x3 mode, the lo plane");
   a.bn = pick_bn(d, pb, epi);
   a.tiles_n = cdiv(d.n, a.bn);
   a.tiles_m = cdiv(d.m, BM);

@@ -51,8 +51,9 @@ struct PlaneOp {
   const uint8_t* hi;
   const uint8_t* lo;
   int rows_p, catoms;
+  int64_t batch_bytes;  // batched problems: bytes between the planes of consecutive (batch1, batch2) matrices (0: unbatched)
 };
-static inline PlaneOp no_plane() { return PlaneOp{nullptr, nullptr, 0, 0}; }
+static inline PlaneOp no_plane() { return PlaneOp{nullptr, nullptr, 0, 0, 0}; }
 
 struct GemmArgs {
   v1t_gemm_desc d;
@@ -119,6 +120,20 @@ size_t matrix_plane_bytes(int64_t rows, int64_t cols);
 // per-head blocks of Wqkv (155 rows) padded to 160 so that the QKV GEMM output is head-aligned.
 int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, PlaneOp* out,
                   cudaStream_t st, int row_gin = 0, int row_gout = 0, int col_gin = 0, int col_gout = 0);
+// ---- materialised attention on tensor cores with plane operands (head dim > 160) -------------------
+// per-(sample, head) matrix planes [b*H + h][Dp/32 atoms][Tq rows][64 B] of X[(b*T + t), col0 + h*E + d]
+size_t bh_plane_bytes(int B, int H, int Tq, int Dp);
+int bh_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tq, int E, int Dp, void* hi, void* lo,
+              cudaStream_t st);
+// bytes of one plane of `mats` T x T probability matrices: [mat][Tq/32 atoms][Tq rows][64 B]
+size_t prob_plane_bytes(int64_t mats, int Tq);
+// rows of S [mats*T, ld] (scores * scale already applied by the GEMM) -> P = softmax(row) (dropout) as planes; keeps
+// nothing in fp32.  row_offset = global row index of S's first row (dropout indexing as softmax_rows)
+int softmax_rows_planes(const float* S, int64_t mats, int T, int Tq, int64_t ld, DropSpec dr, int64_t row_offset, void* p_hi,
+                        void* p_lo, cudaStream_t st);
+// backward: S (recomputed scores) and dPd [mats*T, ld] -> planes of Pd = P * mask and of dS = P * (dPd * mask - delta)
+int softmax_bwd_rows_planes(const float* S, const float* dPd, int64_t mats, int T, int Tq, int64_t ld, DropSpec dr,
+                            int64_t row_offset, void* pd_hi, void* pd_lo, void* ds_hi, void* ds_lo, cudaStream_t st);
 int attn_delta_planes(const PlaneOp& o, const void* do_hi, const void* do_lo, float* delta, int B, int H, int T, int Tp,
                       int AD, cudaStream_t st);
 // the same for several matrices in ONE launch (all weights of a block)

@@ -74,6 +74,169 @@ __global__ void __launch_bounds__(256) make_planes_kernel(const float* __restric
   }
 }
 
+// ---- materialised attention on tensor cores with plane operands (head dim > 160) -------------------------------------
+// per-(sample, head) matrix planes [bh][Dp/32 atoms][Tq rows][64 B]: one thread per 16-byte chunk; pad rows / columns zero
+__global__ void bh_planes_kernel(const float* __restrict__ X, int64_t ld, int col0, int H, int T, int Tq, int E, int Dp,
+                                 int64_t chunks, uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= chunks) return;
+  const int c = (int)(idx & 3);
+  int64_t q = idx >> 2;
+  const int r = (int)(q % Tq); q /= Tq;
+  const int atoms = Dp / 32;
+  const int a = (int)(q % atoms);
+  const int64_t bh = q / atoms;
+  const int b = (int)(bh / H), h = (int)(bh % H);
+  const int d0 = a * 32 + c * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    v[e] = (r < T && d0 + e < E) ? __ldg(X + ((int64_t)b * T + r) * ld + col0 + h * E + d0 + e) : 0.f;
+  uint4 hv, lv;
+  split8(v, hv, lv);
+  const int64_t off = ((bh * atoms + a) * Tq + r) * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+  *reinterpret_cast<uint4*>(hi + off) = hv;
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = lv;
+}
+
+// One warp per row of a T x T score matrix; the row lives in registers (kCh chunks of 8 columns per lane).
+constexpr int kRowChunks = 8;  // per lane: Tq <= 32 * 8 * 8 = 2048 columns
+struct RowRegs { float v[kRowChunks][8]; };
+__device__ __forceinline__ void load_row(const float* __restrict__ row, int T, int nch, int lane, RowRegs& x, float fill) {
+#pragma unroll
+  for (int i = 0; i < kRowChunks; ++i) {
+    const int ch = lane + 32 * i, c0 = ch * 8;
+    if (ch < nch && c0 + 8 <= T) {  // rows start 16-byte aligned (ld % 4 == 0)
+      const float4 lo4 = __ldg(reinterpret_cast<const float4*>(row + c0)), hi4 = __ldg(reinterpret_cast<const float4*>(row + c0 + 4));
+      x.v[i][0] = lo4.x; x.v[i][1] = lo4.y; x.v[i][2] = lo4.z; x.v[i][3] = lo4.w;
+      x.v[i][4] = hi4.x; x.v[i][5] = hi4.y; x.v[i][6] = hi4.z; x.v[i][7] = hi4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x.v[i][e] = (ch < nch && c0 + e < T) ? __ldg(row + c0 + e) : fill;
+    }
+  }
+}
+// writes this lane's chunks of row t of matrix `mat` into planes [mat][Tq/32 atoms][Tq rows][64 B]
+__device__ __forceinline__ void store_row_planes(const RowRegs& x, int64_t mat, int t, int Tq, int nch, int lane,
+                                                 uint8_t* __restrict__ hi, uint8_t* __restrict__ lo) {
+  const int atoms = Tq / 32;
+#pragma unroll
+  for (int i = 0; i < kRowChunks; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < nch) {
+      uint4 hv, lv;
+      split8(x.v[i], hv, lv);
+      const int64_t off = ((mat * atoms + (ch >> 2)) * Tq + t) * 64 + (((ch & 3) ^ ((t >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(hi + off) = hv;
+      if (lo) *reinterpret_cast<uint4*>(lo + off) = lv;
+    }
+  }
+}
+__device__ __forceinline__ void softmax_in_regs(RowRegs& x, int T, int nch, int lane) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m = fmaxf(m, x.v[i][e]);  // columns >= T were loaded as -inf
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      x.v[i][e] = __expf(x.v[i][e] - m);
+      s += x.v[i][e];
+    }
+  s = warp_sum(s);
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x.v[i][e] *= inv;
+}
+__device__ __forceinline__ void row_mask(float (&mk)[kRowChunks][8], DropSpec dr, int64_t grow, int T, int nch, int lane) {
+  const float inv_keep = dr.p > 0.f ? 1.f / (1.f - dr.p) : 1.f;
+  const int64_t Tc = drop_stride(T);
+#pragma unroll
+  for (int i = 0; i < kRowChunks; ++i) {
+    const int ch = lane + 32 * i;
+    if (dr.p > 0.f && ch < nch && ch * 8 < T) dropout_mult8(dr.seed, dr.site, (uint64_t)(grow * Tc + ch * 8) >> 3, dr.p, inv_keep, mk[i]);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mk[i][e] = 1.f;
+    }
+  }
+}
+// rows: mats * Tq (pad rows t >= T are written as zero rows so that contractions over the rows see zeros)
+__global__ void __launch_bounds__(256) softmax_rows_planes_kernel(const float* __restrict__ S, int64_t mats, int T, int Tq, int64_t ld,
+                                                                  DropSpec dr, int64_t row_offset, uint8_t* __restrict__ p_hi,
+                                                                  uint8_t* __restrict__ p_lo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= mats * Tq) return;
+  const int64_t mat = w / Tq;
+  const int t = (int)(w % Tq), nch = Tq / 8;
+  RowRegs x;
+  if (t < T) {
+    load_row(S + (mat * T + t) * ld, T, nch, lane, x, -INFINITY);
+    softmax_in_regs(x, T, nch, lane);
+    float mk[kRowChunks][8];
+    row_mask(mk, dr, row_offset + mat * T + t, T, nch, lane);
+#pragma unroll
+    for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x.v[i][e] *= mk[i][e];
+  } else {
+#pragma unroll
+    for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x.v[i][e] = 0.f;
+  }
+  store_row_planes(x, mat, t, Tq, nch, lane, p_hi, p_lo);
+}
+__global__ void __launch_bounds__(256) softmax_bwd_rows_planes_kernel(const float* __restrict__ S, const float* __restrict__ dPd,
+                                                                      int64_t mats, int T, int Tq, int64_t ld, DropSpec dr,
+                                                                      int64_t row_offset, uint8_t* __restrict__ pd_hi,
+                                                                      uint8_t* __restrict__ pd_lo, uint8_t* __restrict__ ds_hi,
+                                                                      uint8_t* __restrict__ ds_lo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= mats * Tq) return;
+  const int64_t mat = w / Tq;
+  const int t = (int)(w % Tq), nch = Tq / 8;
+  RowRegs p, g;
+  if (t < T) {
+    load_row(S + (mat * T + t) * ld, T, nch, lane, p, -INFINITY);
+    softmax_in_regs(p, T, nch, lane);
+    load_row(dPd + (mat * T + t) * ld, T, nch, lane, g, 0.f);
+    float mk[kRowChunks][8];
+    row_mask(mk, dr, row_offset + mat * T + t, T, nch, lane);
+    float delta = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        g.v[i][e] *= mk[i][e];                 // dP = dPd * mask
+        delta = fmaf(p.v[i][e], g.v[i][e], delta);
+      }
+    delta = warp_sum(delta);
+#pragma unroll
+    for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        g.v[i][e] = p.v[i][e] * (g.v[i][e] - delta);  // dS
+        p.v[i][e] *= mk[i][e];                        // Pd
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kRowChunks; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { p.v[i][e] = 0.f; g.v[i][e] = 0.f; }
+  }
+  store_row_planes(p, mat, t, Tq, nch, lane, pd_hi, pd_lo);
+  store_row_planes(g, mat, t, Tq, nch, lane, ds_hi, ds_lo);
+}
+
 // GEMM-operand planes of a row-major matrix X[rows, cols]: one thread per 16-byte chunk (8 columns of one row)
 __device__ __forceinline__ void matrix_planes_chunk(int64_t idx, const float* __restrict__ X, int64_t ld, int64_t rows,
                                                     int64_t cols, int64_t rows_p, uint8_t* __restrict__ hi,
@@ -185,7 +348,7 @@ int matrix_planes(const float* X, int64_t ld, int64_t rows, int64_t cols, void* 
   matrix_planes_kernel<<<(unsigned)cdiv(chunks, 256), 256, 0, st>>>(X, ld, rows, cols, rows_p, chunks, (uint8_t*)hi,
                                                                       (uint8_t*)lo, row_gin, row_gout, col_gin, col_gout);
   V1T_LAUNCH_CHECK();
-  out->hi = (const uint8_t*)hi; out->lo = (const uint8_t*)lo; out->rows_p = (int)rows_p; out->catoms = (int)catoms;
+  out->hi = (const uint8_t*)hi; out->lo = (const uint8_t*)lo; out->rows_p = (int)rows_p; out->catoms = (int)catoms; out->batch_bytes = 0;
   return V1T_OK;
 }
 
@@ -287,6 +450,36 @@ int attn_delta(const float* O, const float* dO, float* delta, int B, int H, int 
   const int64_t warps = (int64_t)B * T * H;
   V1T_CUDA(cudaMemsetAsync(delta, 0, sizeof(float) * (size_t)B * H * Tp, st));  // zero the padded rows
   attn_delta_kernel<<<cdiv(warps, 8), 256, 0, st>>>(O, dO, delta, B, H, T, Tp, E, ld);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+
+
+size_t bh_plane_bytes(int B, int H, int Tq, int Dp) { return (size_t)B * H * (size_t)(Dp / 32) * Tq * 64; }
+int bh_planes(const float* X, int64_t ld, int col0, int B, int H, int T, int Tq, int E, int Dp, void* hi, void* lo,
+              cudaStream_t st) {
+  V1T_CHECK_ARG(X && hi && Dp % 32 == 0 && Tq % 32 == 0 && Tq >= T && E <= Dp, "bh_planes: bad argument");
+  const int64_t chunks = (int64_t)B * H * (Dp / 32) * Tq * 4;
+  bh_planes_kernel<<<cdiv(chunks, 256), 256, 0, st>>>(X, ld, col0, H, T, Tq, E, Dp, chunks, (uint8_t*)hi, (uint8_t*)lo);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+size_t prob_plane_bytes(int64_t mats, int Tq) { return (size_t)mats * (size_t)(Tq / 32) * Tq * 64; }
+int softmax_rows_planes(const float* S, int64_t mats, int T, int Tq, int64_t ld, DropSpec dr, int64_t row_offset, void* p_hi,
+                        void* p_lo, cudaStream_t st) {
+  V1T_CHECK_ARG(S && p_hi && Tq % 32 == 0 && Tq >= T && Tq <= 32 * 8 * kRowChunks && ld % 4 == 0, "softmax_rows_planes: T up to %d",
+                32 * 8 * kRowChunks);
+  softmax_rows_planes_kernel<<<cdiv(mats * Tq, 8), 256, 0, st>>>(S, mats, T, Tq, ld, dr, row_offset, (uint8_t*)p_hi,
+                                                                 (uint8_t*)p_lo);
+  V1T_LAUNCH_CHECK();
+  return V1T_OK;
+}
+int softmax_bwd_rows_planes(const float* S, const float* dPd, int64_t mats, int T, int Tq, int64_t ld, DropSpec dr,
+                            int64_t row_offset, void* pd_hi, void* pd_lo, void* ds_hi, void* ds_lo, cudaStream_t st) {
+  V1T_CHECK_ARG(S && dPd && pd_hi && ds_hi && Tq % 32 == 0 && Tq >= T && Tq <= 32 * 8 * kRowChunks && ld % 4 == 0,
+                "softmax_bwd_rows_planes: T up to %d", 32 * 8 * kRowChunks);
+  softmax_bwd_rows_planes_kernel<<<cdiv(mats * Tq, 8), 256, 0, st>>>(S, dPd, mats, T, Tq, ld, dr, row_offset, (uint8_t*)pd_hi,
+                                                                     (uint8_t*)pd_lo, (uint8_t*)ds_hi, (uint8_t*)ds_lo);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
