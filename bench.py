@@ -463,10 +463,18 @@ def run_b200(args, cfg):
             if p and p["scopes_per_step"] > 0:
                 kb[key] = 1e3 * p["ms_per_step"] / p["scopes_per_step"]
     kf = kernel_roofline("attn_fwd2_kernel", "attn_fwd_kernel", per_block_fwd)
-    dom = kb or {"kernel": "attention backward (materialised path)", "achieved": 0.0, "frac": 0.0}
+    fused_path = kb is not None
+    if kb is None:  # head dim > 160: no fused kernel; the scope holds the batched plane GEMMs + softmax-backward rows kernel
+        kb = kernel_roofline("materialised attention backward (tc_gemm_kernel x6 over operand planes + "
+                             "softmax_bwd_rows_planes_kernel + bh_planes_kernel x4, per chunk of samples)", "attn_bwd",
+                             2 * per_block_fwd)
+        kf = kernel_roofline("materialised attention forward (tc_gemm_kernel x2 + softmax_rows_planes_kernel + "
+                             "bh_planes_kernel x3)", "attn_fwd", per_block_fwd)
+    dom = kb or {"kernel": "attention backward", "achieved": 0.0, "frac": 0.0}
     roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["achieved"],
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": dom["frac"],
-                "traffic": (kernel_traffic("attn_bwd_pair_kernel") or 0) + (kernel_traffic("attn_bwd2_kernel") or 0) or None,
+                "traffic": ((kernel_traffic("attn_bwd_pair_kernel") or 0) + (kernel_traffic("attn_bwd2_kernel") or 0) or None)
+                if fused_path else None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches (ncu launch list under profiles/; "
                                 "captured at the batch that list names)",
                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "detail": kb, "attn_fwd2_kernel": kf,

@@ -30,11 +30,20 @@ if [[ $what == *configs* ]]; then
   done
 fi
 if [[ $what == *sanitize* ]]; then
-  for tool in racecheck memcheck; do
-    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 800 \
-      -k "fused_attention or (gemm and tc) or (golden and tiny_train and bf16x3) or ts_mma" > gpurun_out/sanitizer_$tool.log 2>&1
-    echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/sanitizer_$tool.log | head -4
+  # racecheck: one process per test group (a report in one group must not poison the next, see profiles/r2_sanitizer_summary.txt)
+  : > gpurun_out/sanitizer_summary.txt
+  for grp in "fused_attention" "golden and tiny_train and bf16x3" "dropout_masks or attention_probs or emit"; do
+    tag=$(echo "$grp" | tr -c 'a-zA-Z0-9' '_' | cut -c1-40)
+    timeout 900 compute-sanitizer --tool racecheck --print-limit 10 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 800 \
+      -k "$grp" > gpurun_out/sanitizer_racecheck_$tag.log 2>&1
+    echo "== racecheck -k '$grp' (exit $?)" >> gpurun_out/sanitizer_summary.txt
+    grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/sanitizer_racecheck_$tag.log | head -3 >> gpurun_out/sanitizer_summary.txt
   done
+  timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 800 \
+    -k "fused_attention or (gemm and tc) or (golden and tiny_train and bf16x3) or ts_mma or scaled or emit" > gpurun_out/sanitizer_memcheck.log 2>&1
+  echo "== memcheck (exit $?)" >> gpurun_out/sanitizer_summary.txt
+  grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_memcheck.log | head -3 >> gpurun_out/sanitizer_summary.txt
+  cat gpurun_out/sanitizer_summary.txt
 fi
 if [[ $what == *ncu* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 4000 --csv \

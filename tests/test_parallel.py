@@ -236,11 +236,11 @@ def test_plan_mouse2d_partitions_every_mouse_exactly_once_and_balances_ranks():
     assert parallel.make_plan(mice, 7, 8, "mouse", 16).my_slices == {}
 
 
-def _plan_worker(rank, world, port, mode, out):
+def _plan_worker(rank, world, port, mode, out, n_mice=4):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     parallel.init_from_env(backend="gloo")
-    mice = ["A", "B", "C", "D"]
+    mice = [chr(ord("A") + i) for i in range(n_mice)]
     batch = 3
     torch.manual_seed(3)
     model = _FakeModel(mice)
@@ -261,11 +261,11 @@ def _plan_worker(rank, world, port, mode, out):
     dist.destroy_process_group()
 
 
-def _run_plan_case(world, mode):
+def _run_plan_case(world, mode, n_mice=4):
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    procs = [ctx.Process(target=_plan_worker, args=(r, world, port, mode, q)) for r in range(world)]
+    procs = [ctx.Process(target=_plan_worker, args=(r, world, port, mode, q, n_mice)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get() for _ in range(world)]
@@ -273,7 +273,7 @@ def _run_plan_case(world, mode):
         p.join(120)
         assert p.exitcode == 0
     got.sort(key=lambda t: t[0])
-    mice = ["A", "B", "C", "D"]
+    mice = [chr(ord("A") + i) for i in range(n_mice)]
     gbatch = parallel.make_plan(mice, 0, world, mode, 3).global_batch
     model = _FakeModel(mice)
     model.load_state_dict(got[0][3])
@@ -300,3 +300,10 @@ def test_sweep_mouse2d_three_ranks_gloo_matches_single_process():
 
 def test_sweep_batch_mode_two_ranks_gloo_matches_single_process():
     _run_plan_case(2, "batch")
+
+
+def test_sweep_mouse2d_eight_ranks_seven_mice_gloo_matches_single_process():
+    """The driver's largest case: 7 mice on 8 ranks (every rank holds rows of one or two mice; most readout groups
+    are pairs of neighbouring ranks)."""
+    _run_plan_case(8, "mouse2d", n_mice=7)
+

@@ -177,7 +177,7 @@ struct Scratch {
 };
 int attn_chunk(const Dims& d) {
   const int64_t per = (int64_t)d.heads * d.T * d.Tp * (int64_t)sizeof(float);
-  int64_t c = (1ll << 30) / std::max<int64_t>(per, 1);
+  int64_t c = (2ll << 30) / std::max<int64_t>(per, 1);  // two fp32 T x T buffers of <= 2 GiB each
   c = std::max<int64_t>(1, std::min<int64_t>(c, d.B));
   // keep grid.z = chunk*heads within limits
   while (c * d.heads > 65535) --c;
