@@ -26,7 +26,8 @@ int v1t_bulk_microbench(const void* src, long long span, int bytes, int copies, 
 int v1t_ts_selftest(const float* A, const float* B, float* C, int N, int K, void* stream);
 
 /* hook exported by the PRODUCT library (libv1t_b200.so), not by the diagnostics library: device buffer of
- * 2 ranks x 24 tiles x 8 events (int64 cycles since the cluster's start barrier) that CTAs 0/1 of head 0 of the
+ * 2 items x 2 ranks x 32 tiles x 8 events (int64 cycles since the cluster's start barrier; tile row 31 = the hand-over
+ * between items, see attn_bwd2.cu) that the first cluster of the
  * pair attention-backward kernel fill (events: MMA warp 0 = scores wait begins, 1 = scores issue, 2 = accumulate wait
  * begins, 3 = accumulate issue; softmax warp 0: 4 = scores arrived, 5 = exchange wait passed, 6 = operand slot free,
  * 7 = operand written); NULL switches the trace off.  scripts/pair_trace.py prints the timeline. */

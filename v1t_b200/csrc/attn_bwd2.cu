@@ -472,10 +472,13 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a, const int t
 // =====================================================================================================================
 // optional per-tile timeline of one cluster (diagnostics: include/v1t_b200_diag.h, scripts/pair_trace.py); null = off
 __device__ long long* g_pair_trace = nullptr;
-constexpr int kTraceTiles = 24, kTraceEvents = 8;  // [rank 2][tile][event] cycles since the cluster's start barrier
+// [item 2][rank 2][tile][event] cycles since the cluster's start barrier, for the first two items of cluster 0; row
+// kTraceTiles - 1 holds the hand-over between items: 0 accumulator complete, 1 epilogue done, 2 resident operand stored,
+// 3 (MMA warp) resident operand visible
+constexpr int kTraceTiles = 32, kTraceEvents = 8;
 #define PAIR_TRACE(ev, j)                                                                                       \
   do {                                                                                                          \
-    if (trace && (j) < kTraceTiles) trace[((int)rank * kTraceTiles + (j)) * kTraceEvents + (ev)] = clock64() - t_start; \
+    if (trace && (j) < kTraceTiles - 1) trace[((int)rank * kTraceTiles + (j)) * kTraceEvents + (ev)] = clock64() - t_start; \
   } while (0)
 
 template <int AD>
@@ -519,7 +522,7 @@ __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <int AD>
-__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const AttnBwdArgs a) {
+__global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const AttnBwdArgs a, const int tiles) {
   constexpr int N = 64, Dp = AD * 32, HC = AD * 16, NH = N / kSlots, OPC = N / 2;
   using L = SmemPair<AD>;
   extern __shared__ uint8_t smem_raw[];
@@ -543,8 +546,14 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0: P side (dV), 1: dS side (dK)
-  const int r0 = (blockIdx.x >> 1) * 128, bh = blockIdx.z;
   const int nt = (a.T + N - 1) / N;
+  // PERSISTENT clusters: cluster c works on items c, c + #clusters, ... (item = head * tiles + 128-key tile, so the clusters
+  // running at one time share a few heads' planes in L2).  Tensor memory, barriers and the bulk-copy rings live across
+  // items: every ring / score / exchange barrier is indexed by the running tile count `it` = k * nt + j, the per-item
+  // barriers (stage_full, res_full, o_full) by the item count k.
+  const int ncl = (int)gridDim.x >> 1, cid = (int)blockIdx.x >> 1, total = tiles * a.B * a.H;
+  const int my_items = cid < total ? (total - cid + ncl - 1) / ncl : 0;
+  const int total_its = my_items * nt;
   const uint8_t* R_hi = rank == 0 ? a.k_hi : a.v_hi;  const uint8_t* R_lo = rank == 0 ? a.k_lo : a.v_lo;   // resident
   const uint8_t* s0_hi = rank == 0 ? a.q_hi : a.do_hi; const uint8_t* s0_lo = rank == 0 ? a.q_lo : a.do_lo; // ring 0
   const uint8_t* s1_hi = rank == 0 ? a.do_hi : a.q_hi; const uint8_t* s1_lo = rank == 0 ? a.do_lo : a.q_lo; // ring 1
@@ -573,7 +582,8 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
   tc_fence_after();
   cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   const long long t_start = clock64();
-  long long* trace = (g_pair_trace && blockIdx.x < 2 && blockIdx.z == 0 && (threadIdx.x & 31) == 0) ? g_pair_trace : nullptr;
+  long long* const trace0 = (g_pair_trace && blockIdx.x < 2 && (threadIdx.x & 31) == 0) ? g_pair_trace : nullptr;
+#define PAIR_TRACE_X(ev) do { if (trace) trace[((int)rank * kTraceTiles + kTraceTiles - 1) * kTraceEvents + (ev)] = clock64() - t_start; } while (0)
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t cR_hi = 0, cR_lo = HC, cS = 2 * HC, cPS_hi = cS + 2 * N, cPS_lo = cPS_hi + OPC, cOut = cPS_lo + OPC;
   static_assert(cOut + Dp <= 512, "TMEM budget exceeded");
@@ -587,23 +597,31 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       const uint8_t* src_hi = is0 ? s0_hi : s1_hi;
       const uint8_t* src_lo = is0 ? s0_lo : s1_lo;
       uint8_t* ring = smem + (is0 ? L::ring0 : L::ring1);
-      if (!is0) {
-        // ring 1 is idle until the first accumulating MMA: it first carries the resident operand's 128 rows (two
-        // consecutive 64-row plane tiles = ONE contiguous copy per plane) to the softmax warps, which move them to TMEM
-        const int64_t roff = attn_plane_off(bh, 0, r0, a.Tp, AD);
-        mbar_expect_tx(stage_full, (a.x3 ? 2 : 1) * 2 * L::kTile);
-        bulk_g2s(ring, R_hi + roff, 2 * L::kTile, stage_full);
-        if (a.x3) bulk_g2s(ring + 2 * L::kTile, R_lo + roff, 2 * L::kTile, stage_full);
-        mbar_wait(res_full, 0);  // every row has been read out of the ring
-      }
-      for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        mbar_wait(&emptyb[s], ((j >> 1) & 1) ^ 1);
-        uint8_t* base = ring + s * L::kSlot;
-        mbar_expect_tx(&fullb[s], (a.x3 ? 2 : 1) * L::kTile);
-        const int64_t src = attn_plane_off(bh, 0, j * N, a.Tp, AD);  // a 64-row plane tile is contiguous: one copy per plane
-        bulk_g2s(base, src_hi + src, L::kTile, &fullb[s]);
-        if (a.x3) bulk_g2s(base + L::kTile, src_lo + src, L::kTile, &fullb[s]);
+      for (int k = 0; k < my_items; ++k) {
+        const int item = cid + k * ncl, bh = item / tiles, r0 = (item % tiles) * 128, itb = k * nt;
+        if (!is0) {
+          // ring 1 is idle between the last accumulating MMA of an item and the first one of the next: it first carries
+          // the resident operand's 128 rows (two consecutive 64-row plane tiles = ONE contiguous copy per plane) to the
+          // softmax warps, which move them to TMEM
+          if (k > 0) {  // both slots drained: the producer waits of tiles itb and itb + 1, without producing
+            mbar_wait(&emptyb[itb & 1], ((itb >> 1) & 1) ^ 1);
+            mbar_wait(&emptyb[(itb + 1) & 1], (((itb + 1) >> 1) & 1) ^ 1);
+          }
+          const int64_t roff = attn_plane_off(bh, 0, r0, a.Tp, AD);
+          mbar_expect_tx(stage_full, (a.x3 ? 2 : 1) * 2 * L::kTile);
+          bulk_g2s(ring, R_hi + roff, 2 * L::kTile, stage_full);
+          if (a.x3) bulk_g2s(ring + 2 * L::kTile, R_lo + roff, 2 * L::kTile, stage_full);
+          mbar_wait(res_full, k & 1);  // every row has been read out of the ring
+        }
+        for (int j = 0; j < nt; ++j) {
+          const int it = itb + j, s = it & 1;
+          mbar_wait(&emptyb[s], ((it >> 1) & 1) ^ 1);
+          uint8_t* base = ring + s * L::kSlot;
+          mbar_expect_tx(&fullb[s], (a.x3 ? 2 : 1) * L::kTile);
+          const int64_t src = attn_plane_off(bh, 0, j * N, a.Tp, AD);  // a 64-row plane tile is contiguous: one copy per plane
+          bulk_g2s(base, src_hi + src, L::kTile, &fullb[s]);
+          if (a.x3) bulk_g2s(base + L::kTile, src_lo + src, L::kTile, &fullb[s]);
+        }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -620,12 +638,13 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     const uint32_t tR_hi = tmem_base + cR_hi, tR_lo = tmem_base + cR_lo;
     const uint32_t tPS_hi = tmem_base + cPS_hi, tPS_lo = tmem_base + cPS_lo, tOut = tmem_base + cOut;
 
-    auto issue_scores = [&](int j) {
-      const int s = j & 1;
+    long long* trace = nullptr;
+    auto issue_scores = [&](int it, int j) {
+      const int s = it & 1;
       const uint32_t xb = g0 + s * (L::kSlot >> 4);
       PAIR_TRACE(0, j);
-      mbar_wait(&r0_full[s], (j >> 1) & 1);
-      mbar_wait(&sp_empty[s], ((j >> 1) & 1) ^ 1);
+      mbar_wait(&r0_full[s], (it >> 1) & 1);
+      mbar_wait(&sp_empty[s], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       PAIR_TRACE(1, j);
       const uint64_t xh = kDescK64 | (uint64_t)xb, xl = kDescK64 | (uint64_t)(xb + (L::kTile >> 4));
@@ -647,11 +666,11 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       }
       __syncwarp();
     };
-    auto issue_out = [&](int j, bool last) {
-      const int s = j & 1;
+    auto issue_out = [&](int it, int j, bool last) {
+      const int s = it & 1;
       PAIR_TRACE(2, j);
-      mbar_wait(&r1_full[s], (j >> 1) & 1);
-      mbar_wait(ps_full, j & 1);
+      mbar_wait(&r1_full[s], (it >> 1) & 1);
+      mbar_wait(ps_full, it & 1);
       tc_fence_after();
       PAIR_TRACE(3, j);
       const uint32_t sb = g1 + s * (L::kSlot >> 4);
@@ -674,36 +693,44 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       __syncwarp();
     };
 
-    mbar_wait(res_full, 0);
-    tc_fence_after();
-    issue_scores(0);
-    for (int j = 0; j + 1 < nt; ++j) {
-      issue_scores(j + 1);
-      issue_out(j, false);
+    for (int k = 0; k < my_items; ++k) {
+      const int itb = k * nt;
+      trace = (trace0 && k < 2) ? trace0 + k * (2 * kTraceTiles * kTraceEvents) : nullptr;
+      // the resident operand of item k is in TMEM -- stored by the softmax threads after they drained `out` of item k - 1
+      mbar_wait(res_full, k & 1);
+      tc_fence_after();
+      PAIR_TRACE_X(3);
+      issue_scores(itb, 0);
+      for (int j = 0; j + 1 < nt; ++j) {
+        issue_scores(itb + j + 1, j + 1);
+        issue_out(itb + j, j, false);
+      }
+      issue_out(itb + nt - 1, nt - 1, true);
     }
-    issue_out(nt - 1, true);
   } else {
     // ============================== SOFTMAX-BACKWARD / EPILOGUE ==============================
     const int quarter = warp & 3, slot = warp >> 2;
     const int row = quarter * 32 + lane;
-    const int ri = r0 + row;  // key index
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int b = bh / a.H, h = bh % a.H;
+    long long* trace = nullptr;
 
-    {  // resident operand: staged rows (ring 1) -> TMEM; slot s takes plane (s & 1) and the head-dim atoms of parity (s >> 1)
+    // resident operand of item k: staged rows (ring 1) -> TMEM; slot s takes plane (s & 1) and the head-dim atoms of parity
+    // (s >> 1).  Runs after the accumulator of item k - 1 has been read out, so res_full also tells the MMA warp that
+    // `out` may be overwritten.
+    auto load_resident = [&](int k) {
       const bool lo = (slot & 1) != 0;
-      mbar_wait(stage_full, 0);
+      mbar_wait(stage_full, k & 1);
       if (!lo || a.x3)
         smem_row_to_tmem<AD>(smem_u32(smem + L::ring1) + (lo ? 2 * L::kTile : 0), row, tmem_base + lane_off + (lo ? cR_lo : cR_hi),
                              slot >> 1, 2);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(res_full);
-    }
+      if (warp == 0) PAIR_TRACE_X(2);
+    };
 
     const float inv_keep = a.drop.p > 0.f ? 1.f / (1.f - a.drop.p) : 1.f;
-    const float* lse = a.lse + (int64_t)bh * a.Tp;
-    const float* delta = a.delta + (int64_t)bh * a.Tp;
+    const bool staged = a.dq_pl.hi != nullptr;  // the gradients leave as operand planes of the head-padded dqkv
     // exchange buffer addressing: chunk c (4 floats) of this thread's 16 columns sits at
     //   xch + ((buf * 4 + slot) * 4 + c) * 2048 + row * 16      (8 adjacent lanes = 128 contiguous bytes)
     const uint32_t xch_local = smem_u32(smem + L::xch) + (uint32_t)slot * 8192u + (uint32_t)row * 16u;
@@ -712,12 +739,20 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
     const uint32_t pe_empty_peer = mapa_u32(smem_u32(pe_empty), 0u);            // rank 1 -> rank 0
     constexpr uint32_t kTileBytes = 128 * N * 4;                                // P' of one tile
     if (rank == 1 && threadIdx.x == 0) {  // arm the two exchange buffers for tiles 0 and 1
-      mbar_expect_tx(&pe_full[0], kTileBytes);
-      if (nt > 1) mbar_expect_tx(&pe_full[1], kTileBytes);
+      if (total_its > 0) mbar_expect_tx(&pe_full[0], kTileBytes);
+      if (total_its > 1) mbar_expect_tx(&pe_full[1], kTileBytes);
     }
 
+    for (int k = 0; k < my_items; ++k) {
+    const int item = cid + k * ncl, bh = item / tiles, r0 = (item % tiles) * 128, itb = k * nt;
+    const int ri = r0 + row;  // key index
+    const int b = bh / a.H, h = bh % a.H;
+    const float* lse = a.lse + (int64_t)bh * a.Tp;
+    const float* delta = a.delta + (int64_t)bh * a.Tp;
+    trace = (trace0 && k < 2) ? trace0 + k * (2 * kTraceTiles * kTraceEvents) : nullptr;
+    load_resident(k);
     for (int j = 0; j < nt; ++j) {
-      const int buf = j & 1;
+      const int it = itb + j, buf = it & 1;
       const int c0 = j * N + slot * NH;
       float stat[NH];  // rank 0: lse of this warp's query columns; rank 1: their delta
       {
@@ -742,7 +777,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
 #pragma unroll
           for (int c = 0; c < NH; ++c) mult[c] = (__shfl_sync(0xffffffffu, mine, c) >> lane) & 1u ? inv_keep : 0.f;
         }
-        mbar_wait(&sp_full[buf], (j >> 1) & 1);
+        mbar_wait(&sp_full[buf], (it >> 1) & 1);
         tc_fence_after();
         if (warp == 0) PAIR_TRACE(4, j);
         {
@@ -757,7 +792,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
 #pragma unroll
         for (int c = 0; c < NH; ++c) sv[c] = fast_exp2(fmaf(sv[c], a.scale_log2, -stat[c]));  // P' (0 for padded queries)
         // ---- ship P' to rank 1: fp32, dropped elements carry the sign bit
-        mbar_wait(&pe_empty[buf], ((j >> 1) & 1) ^ 1);  // rank 1 has consumed tile j - 2 (two tiles of slack)
+        mbar_wait(&pe_empty[buf], ((it >> 1) & 1) ^ 1);  // rank 1 has consumed tile it - 2 (two tiles of slack)
         if (warp == 0) PAIR_TRACE(5, j);
 #pragma unroll
         for (int c = 0; c < NH / 4; ++c) {
@@ -771,7 +806,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
 #pragma unroll
         for (int c = 0; c < NH; ++c) sv[c] *= mult[c];  // Pd'
       } else {
-        mbar_wait(&sp_full[buf], (j >> 1) & 1);
+        mbar_wait(&sp_full[buf], (it >> 1) & 1);
         tc_fence_after();
         if (warp == 0) PAIR_TRACE(4, j);
         float dv[NH];
@@ -785,7 +820,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         tc_fence_before();
         mbar_arrive(&sp_empty[buf]);
         // ---- P' from rank 0
-        mbar_wait(&pe_full[buf], (j >> 1) & 1);  // all 32 KB of tile j have landed (st.async transaction bytes)
+        mbar_wait(&pe_full[buf], (it >> 1) & 1);  // all 32 KB of tile it have landed (st.async transaction bytes)
         if (warp == 0) PAIR_TRACE(5, j);
 #pragma unroll
         for (int c = 0; c < NH / 4; ++c) {
@@ -795,7 +830,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         }
         // re-arm this buffer for tile j + 2: its bytes cannot start to arrive before every warp of this CTA has signalled
         // pe_empty below, i.e. not before all of them have passed the wait above
-        if (threadIdx.x == 0 && j + 2 < nt) mbar_expect_tx(&pe_full[buf], kTileBytes);
+        if (threadIdx.x == 0 && it + 2 < total_its) mbar_expect_tx(&pe_full[buf], kTileBytes);
 #pragma unroll
         for (int c = 0; c < NH; ++c) {
           const uint32_t u = __float_as_uint(sv[c]);
@@ -805,7 +840,7 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         }
       }
       // A operand of the accumulating MMA -> TMEM (two bf16 per column), hi and lo planes
-      mbar_wait(ps_empty, (j & 1) ^ 1);
+      mbar_wait(ps_empty, (it & 1) ^ 1);
       tc_fence_after();
       if (warp == 0) PAIR_TRACE(6, j);
 #pragma unroll
@@ -829,55 +864,49 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
       }
     }
     // ---- epilogue: rank 0 -> dV (column block 2I), rank 1 -> dK (column block I, scaled); see attn_bwd2_body
-    mbar_wait(o_full, 0);
+    mbar_wait(o_full, k & 1);
     tc_fence_after();
+    if (warp == 0) PAIR_TRACE_X(0);
     const int I = a.H * a.E;
     const int kSec = rank == 0 ? 2 : 1;
     float* dst = a.dqkv ? a.dqkv + ((int64_t)b * a.T + ri) * (3 * I) + h * a.E + kSec * I : nullptr;
     const float sc = rank == 0 ? 1.f : a.scale;
     const int64_t prow = (int64_t)b * a.T + ri;
     const int atom0 = (kSec * a.H + h) * AD;
-    const uint32_t stage = smem_u32(smem + L::ring0);  // both rings are idle now: 4 x 40 KB >= 2 x AD x 8 KB
+    // Operand planes straight from the registers: one 16-byte chunk per (row, 8 columns) and plane, merged into full
+    // 64-byte plane rows in L2.  The epilogue is bound by getting 80 KB per item out of the SM while every other SM streams
+    // its tiles from L2, not by how the stores are formed -- measured per item with every softmax warp held (cycles from
+    // "accumulator complete" to the end of the epilogue, scripts/pair_trace_model.py): shared-memory stage + bulk stores
+    // with their fence / wait rounds 5.6 k, stage + 512-byte coalesced copy-out by all warps 5.2 k, these stores 5.8 k
+    // (but no barrier, no stage, and the shortest kernel of the three).
+    uint8_t* const phi = staged && ri < a.T ? a.dq_pl.hi : nullptr;  // rows past T belong to the next sample
+    uint8_t* const plo = staged && ri < a.T ? a.dq_pl.lo : nullptr;
 #pragma unroll
     for (int cc = 0; cc < AD; ++cc) {
       const int d0 = slot * (AD * 8) + cc * 8;
       uint32_t v[8];
       tmem_ld8(tmem_base + lane_off + cOut + d0, v);
       tmem_ld_wait();
+      if (cc == 0 && warp == 0) PAIR_TRACE_X(4);
       if (ri < a.T && dst) {
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           if (d0 + c < a.E) dst[d0 + c] = __uint_as_float(v[c]) * sc;
       }
-      if (a.dq_pl.hi) {
+      if (phi) {
         float x[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[e]) * sc;
         uint4 hi, lo;
         split8(x, hi, lo);
-        const uint32_t so = (uint32_t)(d0 >> 5) * (128 * 64) + row * 64 + ((((d0 & 31) >> 3) ^ (int)((prow >> 1) & 3)) << 4);
-        sts128(stage + so, hi);
-        if (a.dq_pl.lo) sts128(stage + AD * 128 * 64 + so, lo);
-      }
-    }
-    if (a.dq_pl.hi) {
-      fence_proxy_async();
-      named_bar_sync(1, kSmThreads);
-      const int rows_valid = min(128, a.T - r0);
-      if (threadIdx.x < AD * 2 && rows_valid > 0) {
-        const int at_i = threadIdx.x >> 1, pln = threadIdx.x & 1;
-        uint8_t* dstp = pln ? a.dq_pl.lo : a.dq_pl.hi;
-        if (dstp) {
-          const int64_t off = ((int64_t)(atom0 + at_i) * a.dq_pl.rows_p + ((int64_t)b * a.T + r0)) * 64;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp + off),
-                       "r"(stage + (uint32_t)(pln * AD + at_i) * (128 * 64)), "r"(rows_valid * 64)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
+        const int64_t off = ((int64_t)(atom0 + (d0 >> 5)) * a.dq_pl.rows_p + prow) * 64 + ((((d0 & 31) >> 3) ^ (int)((prow >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(phi + off) = hi;
+        if (plo) *reinterpret_cast<uint4*>(plo + off) = lo;
       }
     }
     tc_fence_before();
+    if (warp == 0) PAIR_TRACE_X(1);
+    }  // items
   }
 
   __syncthreads();
@@ -925,7 +954,12 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
     static_assert(LP::total <= 232448, "shared memory budget exceeded");
     V1T_CUDA(cudaFuncSetAttribute(attn_bwd_pair_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP::total));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * cdiv(a.T, 128), 1, a.B * a.H);
+    const int tiles_p = cdiv(a.T, 128);
+    const int64_t items = (int64_t)tiles_p * a.B * a.H;
+    V1T_CHECK_ARG(items <= (1 << 30), "attn_bwd2_tc: too many (head, key tile) items");
+    // persistent clusters, one per SM pair (V1T_ATTN_PAIR_PERSIST=0: one cluster per item)
+    static const bool persist = [] { const char* e = getenv("V1T_ATTN_PAIR_PERSIST"); return !(e && e[0] == '0'); }();
+    cfg.gridDim = dim3(2 * (unsigned)(persist ? std::min<int64_t>(items, kNumSMs / 2) : items), 1, 1);
     cfg.blockDim = dim3(kThreadsAttn, 1, 1);
     cfg.dynamicSmemBytes = LP::total;
     cfg.stream = st;
@@ -938,7 +972,7 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
     cfg.numAttrs = 1;
     {
       ProfScope prof(V1T_PHASE_ATTN_BWD_PAIR, st);
-      V1T_CUDA(cudaLaunchKernelEx(&cfg, attn_bwd_pair_kernel<AD>, a));
+      V1T_CUDA(cudaLaunchKernelEx(&cfg, attn_bwd_pair_kernel<AD>, a, tiles_p));
       V1T_LAUNCH_CHECK();
     }
     ProfScope prof(V1T_PHASE_ATTN_BWD_DQ, st);
@@ -957,7 +991,7 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-// diagnostics hook (include/v1t_b200_diag.h): per-tile timeline buffer of the pair kernel, 2 * 24 * 8 int64, or null
+// diagnostics hook (include/v1t_b200_diag.h): per-tile timeline buffer of the pair kernel, 2 * 2 * 32 * 8 int64, or null
 int attn_pair_trace_set(long long* buf) {
   V1T_CUDA(cudaMemcpyToSymbol(g_pair_trace, &buf, sizeof(buf)));
   return V1T_OK;

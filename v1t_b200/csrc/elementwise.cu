@@ -237,12 +237,17 @@ __global__ void __launch_bounds__(256) bmlp_backward_kernel(const float* __restr
     for (int b = 0; b < B; ++b) s += dz3[b * E + e];
     db3[e] = s;
   }
-  for (int i = threadIdx.x; i < B * jn; i += blockDim.x) {
+  // one warp per (sample, hidden unit): the lanes split the E-long dot product (a serial loop per thread was a chain of
+  // E dependent L2 loads of w3 -- most of this kernel's 89 us at 112 samples); fixed butterfly order
+  for (int i = threadIdx.x >> 5; i < B * jn; i += blockDim.x >> 5) {
     const int b = i / jn, j = j0 + i % jn;
     float s = 0.f;
-    for (int e = 0; e < E; ++e) s = fmaf(dz3[b * E + e], __ldg(w3 + e * H + j), s);
-    const float y = hid[b * H + j];
-    dz0[b * jn + (j - j0)] = s * (1.f - y * y);
+    for (int e = threadIdx.x & 31; e < E; e += 32) s = fmaf(dz3[b * E + e], __ldg(w3 + e * H + j), s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) {
+      const float y = hid[b * H + j];
+      dz0[b * jn + (j - j0)] = s * (1.f - y * y);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < jn * bdim && dw0; i += blockDim.x) {
@@ -352,28 +357,48 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
     dg[i] = 0.f;
     db[i] = 0.f;
   }
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-    float xh[NV], dxh[NV];
-    float s1 = 0.f, s2 = 0.f;
+  // U rows per warp and iteration with every load (dh, x, the dx accumulator, the row statistics) issued before the first
+  // use: one row at a time left ~10 loads per warp in flight and the kernel at 2.7 TB/s
+  constexpr int U = NV <= 8 ? 2 : 1;
+  for (int64_t r0 = warp * U; r0 < rows; r0 += nwarps * U) {
+    float d[U][NV], xv[U][NV], acc[U][NV], mean[U], rstd[U];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      const bool in = c < E;
-      const float d = in ? dh[r * ld + c] : 0.f;
-      xh[i] = in ? (x[r * ld + c] - mean) * rstd : 0.f;
-      dxh[i] = d * g[i];
-      dg[i] += d * xh[i];
-      db[i] += d;
-      s1 += dxh[i];
-      s2 += dxh[i] * xh[i];
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u;
+      const bool row_in = r < rows;
+      mean[u] = row_in ? __ldg(stats + 2 * r) : 0.f;
+      rstd[u] = row_in ? __ldg(stats + 2 * r + 1) : 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        const bool in = row_in && c < E;
+        d[u][i] = in ? __ldg(dh + r * ld + c) : 0.f;
+        xv[u][i] = in ? __ldg(x + r * ld + c) : 0.f;
+        acc[u][i] = in ? dx_accum[r * ld + c] : 0.f;
+      }
     }
-    s1 = warp_sum(s1) / (float)E;
-    s2 = warp_sum(s2) / (float)E;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < E) dx_accum[r * ld + c] += rstd * (dxh[i] - s1 - xh[i] * s2);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u;
+      float xh[NV], dxh[NV];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const bool in = r < rows && lane + 32 * i < E;
+        xh[i] = in ? (xv[u][i] - mean[u]) * rstd[u] : 0.f;
+        dxh[i] = d[u][i] * g[i];
+        dg[i] += d[u][i] * xh[i];
+        db[i] += d[u][i];
+        s1 += dxh[i];
+        s2 += dxh[i] * xh[i];
+      }
+      s1 = warp_sum(s1) / (float)E;
+      s2 = warp_sum(s2) / (float)E;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (r < rows && c < E) dx_accum[r * ld + c] = acc[u][i] + rstd[u] * (dxh[i] - s1 - xh[i] * s2);
+      }
     }
   }
 #pragma unroll
@@ -544,22 +569,36 @@ __global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ p
   }
 }
 
-// out[b*out_ld + c] = sum_strip partials[(b*strips+strip)*cols + c].  lane = column (coalesced), the 8 warps of a
-// block take every 8th strip, fixed-order smem reduction.  grid (ceil(cols/32), batch)
-__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partials, float* __restrict__ out,
-                                                            int batch, int cols, int strips, int64_t out_ld) {
-  __shared__ float red[8][33];
+// out[b*out_ld + c] = sum_strip partials[(b*strips+strip)*cols + c].  lane = column (coalesced), the 32 warps of a
+// block take every 32nd strip with 8 independent loads in flight (the kernel is pure load latency: with 8 warps and a
+// serial loop the 5784 strips of the MLP bias gradient took 79 us), fixed-order smem reduction.
+// grid (ceil(cols/32), batch)
+constexpr int kColsumFinishWarps = 32;
+__global__ void __launch_bounds__(kColsumFinishWarps * 32) colsum_finish_kernel(const float* __restrict__ partials,
+                                                                                float* __restrict__ out, int batch, int cols,
+                                                                                int strips, int64_t out_ld) {
+  __shared__ float red[kColsumFinishWarps][33];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane, b = blockIdx.y;
   float s = 0.f;
-  if (c < cols)
-    for (int k = wid; k < strips; k += 8) s += partials[((int64_t)b * strips + k) * cols + c];
+  if (c < cols) {
+    const float* src = partials + (int64_t)b * strips * cols + c;
+    int k = wid;
+    for (; k + 7 * kColsumFinishWarps < strips; k += 8 * kColsumFinishWarps) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (int64_t)(k + u * kColsumFinishWarps) * cols);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; k < strips; k += kColsumFinishWarps) s += __ldg(src + (int64_t)k * cols);
+  }
   red[wid][lane] = s;
   __syncthreads();
   if (wid == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    for (int w = 0; w < kColsumFinishWarps; ++w) t += red[w][lane];
     out[b * out_ld + c] = t;
   }
 }
@@ -615,7 +654,7 @@ int dropout_rows(const float* src, float* dst, int64_t rows, int cols, int64_t l
     dropout_rows8_colsum_kernel<<<grid, 256, sizeof(float) * rpp * chunks * 8, st>>>(src, dst, rows, cols, ld, chunks, dr,
                                                                                      pl, partials);
     V1T_LAUNCH_CHECK();
-    colsum_finish_kernel<<<dim3(cdiv(cols, 32), 1), 256, 0, st>>>(partials, colsum_out, 1, cols, grid, 0);
+    colsum_finish_kernel<<<dim3(cdiv(cols, 32), 1), kColsumFinishWarps * 32, 0, st>>>(partials, colsum_out, 1, cols, grid, 0);
     V1T_LAUNCH_CHECK();
     return V1T_OK;
   }
@@ -735,13 +774,13 @@ int colsum(const float* X, float* out, int batch, int64_t rows, int cols, int64_
   dim3 grid(cdiv(cols, 32), strips, batch), block(32, 8);
   colsum_kernel<<<grid, block, 0, st>>>(X, partials, rows, cols, xb, ld, strips);
   V1T_LAUNCH_CHECK();
-  colsum_finish_kernel<<<dim3(cdiv(cols, 32), batch), 256, 0, st>>>(partials, out, batch, cols, strips, out_ld);
+  colsum_finish_kernel<<<dim3(cdiv(cols, 32), batch), kColsumFinishWarps * 32, 0, st>>>(partials, out, batch, cols, strips, out_ld);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }
 
 int colsum_finish(const float* partials, float* out, int cols, int strips, cudaStream_t st) {
-  colsum_finish_kernel<<<dim3(cdiv(cols, 32), 1), 256, 0, st>>>(partials, out, 1, cols, strips, 0);
+  colsum_finish_kernel<<<dim3(cdiv(cols, 32), 1), kColsumFinishWarps * 32, 0, st>>>(partials, out, 1, cols, strips, 0);
   V1T_LAUNCH_CHECK();
   return V1T_OK;
 }

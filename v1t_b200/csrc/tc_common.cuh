@@ -294,18 +294,16 @@ template <int AD>
 __device__ __forceinline__ void smem_row_to_tmem(uint32_t smem_plane, int row, uint32_t taddr, int at0, int astep) {
   const uint32_t base = smem_plane + (uint32_t)(row >> 6) * (AD * 4096u) + (uint32_t)(row & 63) * 64u;
   const uint32_t sw = (uint32_t)(row >> 1) & 3u;
-  uint4 v[AD][4];
+  // one atom at a time (4 chunks in flight): shared-memory latency is short, and 16 live registers instead of 16 x atoms
+  // keep this out of local memory inside the persistent kernels
 #pragma unroll
   for (int at_i = 0; at_i < AD; ++at_i)
     if (at_i >= at0 && (at_i - at0) % astep == 0) {
+      uint4 v[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[at_i][c] = lds128(base + at_i * 4096u + ((c ^ sw) << 4));
-    }
+      for (int c = 0; c < 4; ++c) v[c] = lds128(base + at_i * 4096u + ((c ^ sw) << 4));
 #pragma unroll
-  for (int at_i = 0; at_i < AD; ++at_i)
-    if (at_i >= at0 && (at_i - at0) % astep == 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_st4(taddr + at_i * 16 + c * 4, v[at_i][c].x, v[at_i][c].y, v[at_i][c].z, v[at_i][c].w);
+      for (int c = 0; c < 4; ++c) tmem_st4(taddr + at_i * 16 + c * 4, v[c].x, v[c].y, v[c].z, v[c].w);
     }
 }
 // byte offset of 16-byte chunk `chunk` of row `row` in column atom `atom` of a matrix plane ([atoms][rows_p][64 B])
