@@ -215,15 +215,28 @@ __global__ void __launch_bounds__(256) bmlp_backward_kernel(const float* __restr
                                                             const float* __restrict__ w3, float* __restrict__ dw0,
                                                             float* __restrict__ db0, float* __restrict__ dw3,
                                                             float* __restrict__ db3, int B, int bdim, int H, int E) {
-  extern __shared__ float sh[];
+  extern __shared__ __align__(16) float sh[];
   float* dz3 = sh;            // [B][E]
   float* dz0 = sh + B * E;    // [B][jn] (this CTA's hidden units)
   const int G = gridDim.x, g = blockIdx.x;
   const int e0 = (int)((int64_t)E * g / G), e1 = (int)((int64_t)E * (g + 1) / G);
   const int j0 = (int)((int64_t)H * g / G), j1 = (int)((int64_t)H * (g + 1) / G), jn = j1 - j0;
-  for (int i = threadIdx.x; i < B * E; i += blockDim.x) {
-    const float y = lat[i];
-    dz3[i] = dlat[i] * (1.f - y * y);
+  {  // every CTA recomputes dz3: 128-bit loads, four of them in flight per thread
+    const int n = B * E;
+    const bool vec = ((reinterpret_cast<uintptr_t>(lat) | reinterpret_cast<uintptr_t>(dlat)) & 15) == 0;
+    const int n4 = vec ? n / 4 : 0;
+    const float4* l4 = reinterpret_cast<const float4*>(lat);
+    const float4* d4 = reinterpret_cast<const float4*>(dlat);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 y = __ldg(l4 + i), g4 = __ldg(d4 + i);
+      reinterpret_cast<float4*>(dz3)[i] = make_float4(g4.x * (1.f - y.x * y.x), g4.y * (1.f - y.y * y.y), g4.z * (1.f - y.z * y.z),
+                                                      g4.w * (1.f - y.w * y.w));
+    }
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float y = lat[i];
+      dz3[i] = dlat[i] * (1.f - y * y);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < (e1 - e0) * H && dw3; i += blockDim.x) {
@@ -239,14 +252,25 @@ __global__ void __launch_bounds__(256) bmlp_backward_kernel(const float* __restr
   }
   // one warp per (sample, hidden unit): the lanes split the E-long dot product (a serial loop per thread was a chain of
   // E dependent L2 loads of w3 -- most of this kernel's 89 us at 112 samples); fixed butterfly order
-  for (int i = threadIdx.x >> 5; i < B * jn; i += blockDim.x >> 5) {
-    const int b = i / jn, j = j0 + i % jn;
-    float s = 0.f;
-    for (int e = threadIdx.x & 31; e < E; e += 32) s = fmaf(dz3[b * E + e], __ldg(w3 + e * H + j), s);
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) {
-      const float y = hid[b * H + j];
-      dz0[b * jn + (j - j0)] = s * (1.f - y * y);
+  // (four items per warp and pass, so that their loads overlap)
+  for (int i0 = (threadIdx.x >> 5) * 4; i0 < B * jn; i0 += (blockDim.x >> 5) * 4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = threadIdx.x & 31; e < E; e += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = min(i0 + u, B * jn - 1);
+        s[u] = fmaf(dz3[(i / jn) * E + e], __ldg(w3 + e * H + j0 + i % jn), s[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_sum(s[u]);
+      const int i = i0 + u;
+      if ((threadIdx.x & 31) == 0 && i < B * jn) {
+        const int b = i / jn, j = j0 + i % jn;
+        const float y = hid[b * H + j];
+        dz0[b * jn + (j - j0)] = t * (1.f - y * y);
+      }
     }
   }
   __syncthreads();
@@ -292,48 +316,61 @@ __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict
       }
     }
   }
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    float v[NV];
-    const float* xr = x_in + r * ld;
-    const float* ar = add ? add + (r / rows_per_batch) * E : nullptr;
-    float s = 0.f;
+  // U rows per warp and iteration, all loads issued before the first reduction
+  constexpr int U = NV <= 8 ? 2 : 1;
+  for (int64_t r0 = warp * U; r0 < rows; r0 += nwarps * U) {
+    float v[U][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      float t = c < E ? xr[c] : 0.f;
-      if (ar && c < E) t += ar[c];
-      v[i] = t;
-      s += t;
-    }
-    const float mean = warp_sum(s) / (float)E;
-    float q = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u;
+      const float* xr = x_in + r * ld;
+      const float* ar = add ? add + (r / rows_per_batch) * E : nullptr;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      const float d = c < E ? v[i] - mean : 0.f;
-      q += d * d;
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)E + kLnEps);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane + 32 * i;
-      if (c < ld) {
-        const bool in = c < E;
-        if (x_out) x_out[r * ld + c] = in ? v[i] : 0.f;
-        if (h) h[r * ld + c] = in ? (v[i] - mean) * rstd * g[i] + bt[i] : 0.f;
-      }
-      // GEMM-operand planes of the normalised row: lane = column within atom i, 8 lanes per 16-byte chunk
-      if (pl.hi && c < 32 * ((E + 31) / 32)) {
-        const float y = c < E ? (v[i] - mean) * rstd * g[i] + bt[i] : 0.f;
-        const __nv_bfloat16 hb = __float2bfloat16_rn(y);
-        const int64_t off = tc::plane_chunk_off(i, pl.rows_p, r, lane >> 3) + (lane & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(pl.hi + off) = hb;
-        if (pl.lo) *reinterpret_cast<__nv_bfloat16*>(pl.lo + off) = __float2bfloat16_rn(y - __bfloat162float(hb));
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        const bool in = r < rows && c < E;
+        float t = in ? __ldg(xr + c) : 0.f;
+        if (ar && in) t += __ldg(ar + c);
+        v[u][i] = t;
       }
     }
-    if (lane == 0 && stats) {
-      stats[2 * r] = mean;
-      stats[2 * r + 1] = rstd;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u;
+      if (r >= rows) break;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += v[u][i];
+      const float mean = warp_sum(s) / (float)E;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        const float d = c < E ? v[u][i] - mean : 0.f;
+        q += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(q) / (float)E + kLnEps);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < ld) {
+          const bool in = c < E;
+          if (x_out) x_out[r * ld + c] = in ? v[u][i] : 0.f;
+          if (h) h[r * ld + c] = in ? (v[u][i] - mean) * rstd * g[i] + bt[i] : 0.f;
+        }
+        // GEMM-operand planes of the normalised row: lane = column within atom i, 8 lanes per 16-byte chunk
+        if (pl.hi && c < 32 * ((E + 31) / 32)) {
+          const float y = c < E ? (v[u][i] - mean) * rstd * g[i] + bt[i] : 0.f;
+          const __nv_bfloat16 hb = __float2bfloat16_rn(y);
+          const int64_t off = tc::plane_chunk_off(i, pl.rows_p, r, lane >> 3) + (lane & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(pl.hi + off) = hb;
+          if (pl.lo) *reinterpret_cast<__nv_bfloat16*>(pl.lo + off) = __float2bfloat16_rn(y - __bfloat162float(hb));
+        }
+      }
+      if (lane == 0 && stats) {
+        stats[2 * r] = mean;
+        stats[2 * r + 1] = rstd;
+      }
     }
   }
 }
