@@ -617,13 +617,17 @@ def test_fused_attention_forward_dropout_replay():
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 3e-5
 
 
+# the last three cases give the persistent pair kernel (74 clusters) several items per cluster: 80 items of ONE query tile
+# (T = 64), 80 items of 7 tiles (odd tile count: ring slots and barrier phases continue across items), 160 items of 4
 @pytest.mark.parametrize("B,H,T,E,p", [(1, 1, 64, 32, 0.0), (2, 2, 200, 24, 0.0), (1, 2, 1654, 155, 0.0),
-                                       (2, 3, 333, 155, 0.25)])
+                                       (2, 3, 333, 155, 0.25), (20, 4, 64, 32, 0.1), (5, 4, 435, 40, 0.25),
+                                       (10, 8, 200, 24, 0.1)])
 @pytest.mark.parametrize("impl,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
 @pytest.mark.parametrize("variant", ["three", "pair"])
 def test_fused_attention_backward(B, H, T, E, p, impl, tol, variant, monkeypatch):
     """dQ, dK, dV of the fused tcgen05 attention vs fp64 autograd of softmax(QK^T)V (same dropout mask).  Both
-    backward organisations: three atomic-free passes, and dV + dK by two-CTA clusters sharing P' (V1T_ATTN_BWD=pair)."""
+    backward organisations: three atomic-free passes, and dV + dK by persistent two-CTA clusters sharing P'
+    (V1T_ATTN_BWD=pair)."""
     from v1t_b200 import _lib
     lib = _lib.load()
     monkeypatch.setenv("V1T_ATTN_BWD", variant)
