@@ -469,16 +469,24 @@ __device__ __forceinline__ void attn_bwd2_body(const AttnBwdArgs& a, const int t
 // SIGN bit (P' >= 0), so rank 1 neither draws nor transposes the mask.  MMA units per (key tile, query tile):
 // 3 + 3 (rank 0) and 3 + 3 (rank 1) instead of 6 (dV pass) + 9 (dK pass); dQ stays the query-stationary pass above.
 // TMEM columns (both ranks): R_hi | R_lo | scores[2][64] | A_hi[32] | A_lo[32] | out[Dp] = 2 HC + 192 + Dp (512 @ Dp = 160).
+// The clusters are PERSISTENT (one per SM pair): each loops over (head, key tile) items with tensor memory, barriers and the
+// rings kept alive; ring 0 prefetches the next item's first tiles during the current item's tail, ring 1 carries the next
+// resident operand as soon as its last accumulating MMA has completed (hand-over measured by scripts/pair_trace_model.py).
 // =====================================================================================================================
 // optional per-tile timeline of one cluster (diagnostics: include/v1t_b200_diag.h, scripts/pair_trace.py); null = off
 __device__ long long* g_pair_trace = nullptr;
 // [item 2][rank 2][tile][event] cycles since the cluster's start barrier, for the first two items of cluster 0; row
 // kTraceTiles - 1 holds the hand-over between items: 0 accumulator complete, 1 epilogue done, 2 resident operand stored,
-// 3 (MMA warp) resident operand visible
+// 3 (MMA warp) resident operand visible, 4 first accumulator chunk read
 constexpr int kTraceTiles = 32, kTraceEvents = 8;
 #define PAIR_TRACE(ev, j)                                                                                       \
   do {                                                                                                          \
     if (trace && (j) < kTraceTiles - 1) trace[((int)rank * kTraceTiles + (j)) * kTraceEvents + (ev)] = clock64() - t_start; \
+  } while (0)
+// hand-over events of an item (row kTraceTiles - 1)
+#define PAIR_TRACE_X(ev)                                                                                         \
+  do {                                                                                                           \
+    if (trace) trace[((int)rank * kTraceTiles + kTraceTiles - 1) * kTraceEvents + (ev)] = clock64() - t_start; \
   } while (0)
 
 template <int AD>
@@ -583,7 +591,6 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
   cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   const long long t_start = clock64();
   long long* const trace0 = (g_pair_trace && blockIdx.x < 2 && (threadIdx.x & 31) == 0) ? g_pair_trace : nullptr;
-#define PAIR_TRACE_X(ev) do { if (trace) trace[((int)rank * kTraceTiles + kTraceTiles - 1) * kTraceEvents + (ev)] = clock64() - t_start; } while (0)
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t cR_hi = 0, cR_lo = HC, cS = 2 * HC, cPS_hi = cS + 2 * N, cPS_lo = cPS_hi + OPC, cOut = cPS_lo + OPC;
   static_assert(cOut + Dp <= 512, "TMEM budget exceeded");
