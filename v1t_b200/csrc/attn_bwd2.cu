@@ -529,6 +529,12 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, float a, float b, flo
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// one 256-bit global store (sm_100: STG.256), 32-byte aligned
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 template <int AD>
 __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const AttnBwdArgs a, const int tiles) {
   constexpr int N = 64, Dp = AD * 32, HC = AD * 16, NH = N / kSlots, OPC = N / 2;
@@ -846,6 +852,12 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
           sv[c] = p * (dv[c] * m - stat[c]);  // dS'
         }
       }
+      // rank 1 also leaves dS' as GEMM operand planes [bh][query atom][key row][64 B] for the dQ GEMM (bwd2_all): this
+      // thread's 16 queries of key row `ri` are half a plane row, i.e. one full 32-byte sector per plane
+      uint32_t ds_h[NH / 8][4], ds_l[NH / 8][4];
+      uint8_t* const ds_row = (rank == 1 && a.ds_hi)
+                                  ? a.ds_hi + (((int64_t)bh * (a.Tp >> 5) + (j * 2 + (slot >> 1))) * a.Tp + ri) * 64
+                                  : nullptr;
       // A operand of the accumulating MMA -> TMEM (two bf16 per column), hi and lo planes
       mbar_wait(ps_empty, (it & 1) ^ 1);
       tc_fence_after();
@@ -860,6 +872,36 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
         const uint32_t col = (slot * NH + ch * 8) / 2;
         tmem_st4(tmem_base + lane_off + cPS_hi + col, hw[0], hw[1], hw[2], hw[3]);
         if (a.x3) tmem_st4(tmem_base + lane_off + cPS_lo + col, lw[0], lw[1], lw[2], lw[3]);
+        if (ds_row) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ds_h[ch][i] = hw[i];
+            ds_l[ch][i] = lw[i];
+          }
+        }
+      }
+      if (ds_row) {
+        // the two 16-byte chunks of this thread are the two halves of one aligned 32-byte sector of the swizzled plane row
+        // (their order swaps with the row's swizzle bit 0): ONE 256-bit store per plane -- 16-byte stores at a 64-byte
+        // stride cost an LSU pass per half sector and slowed the kernel by a third
+        const int sw = (ri >> 1) & 3;
+        const int64_t co = (int64_t)(((((slot & 1) * 2) ^ sw) & ~1) << 4);
+        const bool swap = (sw & 1) != 0;
+        uint32_t f[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f[i] = swap ? ds_h[1][i] : ds_h[0][i];
+          f[4 + i] = swap ? ds_h[0][i] : ds_h[1][i];
+        }
+        stg256(ds_row + co, f);
+        if (a.ds_lo) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[i] = swap ? ds_l[1][i] : ds_l[0][i];
+            f[4 + i] = swap ? ds_l[0][i] : ds_l[1][i];
+          }
+          stg256(a.ds_lo + (ds_row - a.ds_hi) + co, f);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -951,12 +993,16 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
 }
 
 template <int AD>
-int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
+int bwd2_all(const AttnBwdArgs& a_in, cudaStream_t st) {
+  const AttnBwdArgs& a = a_in;
   constexpr uint32_t smem = std::max({Smem2<MODE_V, 64, AD>::total, Smem2<MODE_S, 32, AD>::total});
   static_assert(smem <= 232448, "shared memory budget exceeded");
   V1T_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (attn_bwd_pair_env()) {
     // dV + dK by clusters of two CTAs that share one recomputation of P' (see attn_bwd_pair_kernel), then dQ alone
+    AttnBwdArgs aa = a_in;
+    if (!attn_dq_gemm_env()) aa.ds_hi = aa.ds_lo = nullptr;
+    const AttnBwdArgs& a = aa;
     using LP = SmemPair<AD>;
     static_assert(LP::total <= 232448, "shared memory budget exceeded");
     V1T_CUDA(cudaFuncSetAttribute(attn_bwd_pair_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP::total));
@@ -983,6 +1029,28 @@ int bwd2_all(const AttnBwdArgs& a, cudaStream_t st) {
       V1T_LAUNCH_CHECK();
     }
     ProfScope prof(V1T_PHASE_ATTN_BWD_DQ, st);
+    if (a.ds_hi) {
+      // dQ = scale * dS K as ONE batched tcgen05 GEMM over the dS' planes the pair kernel has just written (A, MN-major:
+      // the contraction runs over the plane rows = keys) and the K attention planes (B, MN-major, tile-major layout):
+      // 3 MMA units per (query tile, key tile) instead of the 9 of the query-stationary pass, which recomputes S and dP
+      v1t_gemm_desc g{};
+      g.m = a.T; g.k = a.T; g.n = a.dq_pl.hi ? AD * 32 : a.E;
+      g.batch1 = a.B; g.batch2 = a.H; g.alpha = a.scale;
+      g.a_m = 1; g.a_k = a.Tp; g.b_n = 1; g.b_k = a.Tp;
+      const PlaneOp pa{a.ds_hi, a.x3 ? a.ds_lo : nullptr, a.Tp, a.Tp / 32, (int64_t)(a.Tp / 32) * a.Tp * 64, 0};
+      const PlaneOp pb{a.k_hi, a.x3 ? a.k_lo : nullptr, a.Tp, AD, (int64_t)a.Tp * AD * 64, 1};
+      EpiOp epi = no_epi();
+      float* C = nullptr;
+      if (a.dq_pl.hi) {  // dQ of (sample b, head h): rows b * T + t, column atoms h * AD + d / 32 of the gradient planes
+        epi.kind = kEpiPlanesOut;
+        epi.pl = PlaneOut{a.dq_pl.hi, a.x3 ? a.dq_pl.lo : nullptr, a.dq_pl.rows_p, a.T, AD};
+      } else {
+        const int64_t I3 = 3ll * a.H * a.E;
+        C = a.dqkv;
+        g.c_m = I3; g.c_b1 = (int64_t)a.T * I3; g.c_b2 = a.E;
+      }
+      return gemm_tc(g, nullptr, nullptr, C, nullptr, nullptr, st, no_drop(), a.x3, epi, pa, pb);
+    }
     dim3 gq(cdiv(a.T, 128), 1, a.B * a.H);
     attn_bwd2_kernel<AD><<<gq, kThreadsAttn, smem, st>>>(a, 1, cdiv(a.T, 128), 1);
     V1T_LAUNCH_CHECK();

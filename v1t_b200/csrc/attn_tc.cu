@@ -31,6 +31,11 @@ AttnPlanes carve_attn_planes(void* base, int B, int H, int Tp, int Dp, bool with
   for (int i = 0; i < 2; ++i) { p.q[i] = take(); p.k[i] = take(); p.v[i] = take(); }
   if (with_backward) {
     for (int i = 0; i < 2; ++i) p.dO[i] = take();
+    const size_t sb = (size_t)round_up((int64_t)B * H * (Tp / 32) * (int64_t)Tp * 64, 1024);
+    for (int i = 0; i < 2; ++i) {
+      p.dS[i] = c ? (uint8_t*)(c + off) : nullptr;
+      off += sb;
+    }
   }
   p.lse = (float*)(c ? c + off : nullptr);
   off += (size_t)round_up((int64_t)B * H * Tp * 4, 1024);
@@ -51,6 +56,10 @@ int attn_prec_env() {
 int attn_bwd_pair_env() {  // default: pair; V1T_ATTN_BWD=three selects the three-pass organisation
   const char* e = getenv("V1T_ATTN_BWD");
   return !(e && e[0] == 't');
+}
+int attn_dq_gemm_env() {  // default: dQ as a batched GEMM over the dS' planes of the pair kernel; V1T_ATTN_DQ=pass: dQ pass
+  const char* e = getenv("V1T_ATTN_DQ");
+  return !(e && e[0] == 'p');
 }
 int attn_bwd_group_env() {
   const char* e = getenv("V1T_ATTN_BWD_GROUP");
@@ -118,6 +127,7 @@ extern "C" int v1t_attn_backward(const float* qkv, const float* out, const float
   a.q_hi = p.q[0]; a.q_lo = p.q[1]; a.k_hi = p.k[0]; a.k_lo = p.k[1]; a.v_hi = p.v[0]; a.v_lo = p.v[1];
   a.do_hi = p.dO[0]; a.do_lo = p.dO[1];
   a.lse = lse; a.delta = p.delta; a.dqkv = d_qkv;
+  a.ds_hi = p.dS[0]; a.ds_lo = x3 ? p.dS[1] : nullptr;
   a.drop_bits = p_drop > 0.f ? p.drop_bits : nullptr;  // written by v1t_attn_forward into the same scratch
   a.B = B; a.H = H; a.T = T; a.Tp = Tp; a.E = E; a.Dp = Dp;
   a.scale = 1.0f / sqrtf((float)E);

@@ -624,6 +624,7 @@ extern "C" int v1t_core_backward(const v1t_core_shape* shape, const v1t_core_ptr
       ba.q_hi = S.qp[0]; ba.q_lo = S.qp[1]; ba.k_hi = S.kp[0]; ba.k_lo = S.kp[1]; ba.v_hi = S.vp[0]; ba.v_lo = S.vp[1];
       ba.do_hi = pl.dO[0]; ba.do_lo = pl.dO[1];
       ba.lse = S.lse; ba.delta = pl.delta;
+      ba.ds_hi = pl.dS[0]; ba.ds_lo = x3 ? pl.dS[1] : nullptr;
       ba.drop_bits = d.drop ? S.dbits : nullptr;
       if (qkv_to_planes(d)) {  // dQ | dK | dV leave the kernels as operand planes of the head-padded gradient only
         ba.dqkv = nullptr;

@@ -68,6 +68,7 @@ struct Tile {
   int m0, n0, k_begin, k_end;
   int64_t a_off, b_off, c_off, r_off;
   int64_t pa_off, pb_off;  // byte offsets of this batch entry's plane operands
+  int pl_row0, pl_atom0;   // kEpiPlanesOut: first row / column atom of this batch entry in the output planes
 };
 
 __device__ __forceinline__ Tile decode_tile(const TcArgs& a, int t) {
@@ -87,6 +88,8 @@ __device__ __forceinline__ Tile decode_tile(const TcArgs& a, int t) {
   tl.r_off = b1 * g.d.r_b1 + b2 * g.d.r_b2;
   tl.pa_off = (int64_t)(b1 * g.d.batch2 + b2) * a.pa.batch_bytes;
   tl.pb_off = (int64_t)(b1 * g.d.batch2 + b2) * a.pb.batch_bytes;
+  tl.pl_row0 = b1 * g.epi.pl.b1_rows;
+  tl.pl_atom0 = b2 * g.epi.pl.b2_atoms;
   return tl;
 }
 
@@ -179,8 +182,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           }
           __syncwarp();
           if (mine && (mn || atom * 32 < klen)) {
-            const int64_t src = mn ? ((int64_t)(row0 / 32 + atom) * po.rows_p + k0) * 64
-                                   : ((int64_t)((k0 >> 5) + atom) * po.rows_p + row0) * 64;
+            const int64_t src = !mn             ? ((int64_t)((k0 >> 5) + atom) * po.rows_p + row0) * 64
+                                : po.tile_major ? ((int64_t)((k0 >> 6) * po.catoms + row0 / 32 + atom) * 64 + (k0 & 63)) * 64
+                                                : ((int64_t)(row0 / 32 + atom) * po.rows_p + k0) * 64;
             bulk_g2s(smem + stage * W_STAGE + dst_off, src_base + src, mn ? klen * 64 : rows * 64, &pfull[stage]);
           }
         }
@@ -555,7 +559,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           const float4 uv = u_nx, rv = r_nx;
           if (i + 1 < 8) prefetch(i + 1);
           if (mm >= g.d.m || nv <= 0) {  // past the last row / column: only the zero padding of the emitted planes
-            if (kKind != kEpiNone && g.epi.pl.hi && mm < g.epi.pl.rows_p && n4 < 32 * ((g.d.n + 31) / 32)) {
+            if (kKind != kEpiNone && kKind != kEpiPlanesOut && g.epi.pl.hi && mm < g.epi.pl.rows_p &&
+                n4 < 32 * ((g.d.n + 31) / 32)) {
               const int64_t off = plane_chunk_off(n4 >> 5, g.epi.pl.rows_p, mm, cq >> 1) + (cq & 1) * 8;
               *reinterpret_cast<uint2*>(g.epi.pl.hi + off) = make_uint2(0u, 0u);
               if (g.epi.pl.lo) *reinterpret_cast<uint2*>(g.epi.pl.lo + off) = make_uint2(0u, 0u);
@@ -640,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
             const float pv[4] = {o[0], nv > 1 ? o[1] : 0.f, nv > 2 ? o[2] : 0.f, nv > 3 ? o[3] : 0.f};
             uint2 ph, plo;
             split4(pv, ph, plo);
-            const int64_t off = plane_chunk_off(n4 >> 5, g.epi.pl.rows_p, mm, cq >> 1) + (cq & 1) * 8;
+            const int64_t off = plane_chunk_off(tl.pl_atom0 + (n4 >> 5), g.epi.pl.rows_p, tl.pl_row0 + mm, cq >> 1) + (cq & 1) * 8;
             *reinterpret_cast<uint2*>(g.epi.pl.hi + off) = ph;
             if (g.epi.pl.lo) *reinterpret_cast<uint2*>(g.epi.pl.lo + off) = plo;
           }
@@ -707,6 +712,8 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.tiles_m = cdiv(d.m, BM);
   a.x3 = x3;
   a.wide = (a.a_pl && a.b_pl && a.bn <= W_BN) ? 1 : 0;
+  V1T_CHECK_ARG(!pa.tile_major && (!pb.tile_major || (a.wide && d.b_k != 1)),
+                "tc gemm: attention-plane (tile-major) operands are supported as the MN-major B operand of all-plane launches");
   // plane operands cannot be transposed while staging: their orientation follows the problem
   a.mn_a = a.a_pl ? (d.a_k != 1) : (g_use_mn_major && d.a_k != 1 && d.a_m == 1);
   a.mn_b = a.b_pl ? (d.b_k != 1) : (g_use_mn_major && d.b_k != 1 && d.b_n == 1 && a.bn % 32 == 0);
@@ -722,12 +729,14 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   using Kern = void (*)(const TcArgs);
 #define V1T_TC_ROW(E) {{tc_gemm_kernel<E, false, false>, tc_gemm_kernel<E, false, true>}, \
                        {tc_gemm_kernel<E, true, false>, tc_gemm_kernel<E, true, true>}}
-  static const Kern table[5][2][2] = {V1T_TC_ROW(0), V1T_TC_ROW(1), V1T_TC_ROW(kEpiGeluOut << 1),
-                                      V1T_TC_ROW(kEpiGeluGrad << 1), V1T_TC_ROW(kEpiHeadPlanes << 1)};
+  static const Kern table[6][2][2] = {V1T_TC_ROW(0), V1T_TC_ROW(1), V1T_TC_ROW(kEpiGeluOut << 1),
+                                      V1T_TC_ROW(kEpiGeluGrad << 1), V1T_TC_ROW(kEpiHeadPlanes << 1),
+                                      V1T_TC_ROW(kEpiPlanesOut << 1)};
 #undef V1T_TC_ROW
-  static bool attr_set[5][2][2] = {};
+  static bool attr_set[6][2][2] = {};
   V1T_CHECK_ARG(epi.kind == kEpiNone || drop.p <= 0.f, "tc gemm: a fused activation excludes dropout on the main output");
-  const int ev = epi.kind == kEpiGeluOut ? 2 : epi.kind == kEpiGeluGrad ? 3 : epi.kind == kEpiHeadPlanes ? 4 : (drop.p > 0.f ? 1 : 0);
+  const int ev = epi.kind == kEpiGeluOut ? 2 : epi.kind == kEpiGeluGrad ? 3 : epi.kind == kEpiHeadPlanes ? 4 :
+                 epi.kind == kEpiPlanesOut ? 5 : (drop.p > 0.f ? 1 : 0);
   const int ac = a.a_pl ? 0 : 1, bc = a.b_pl ? 0 : 1;
   Kern kern = table[ev][ac][bc];
   if (!attr_set[ev][ac][bc]) {
@@ -757,6 +766,10 @@ int gemm_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, co
                       (d.n == per || (d.n == 3 * per && hp.p[1][0] && hp.p[2][0])) && hp.T > 0 && d.m % hp.T == 0 &&
                       hp.Tq >= hp.T,
                   "gemm_tc: head-plane output does not match the problem");
+  } else if (epi.kind == kEpiPlanesOut) {
+    V1T_CHECK_ARG(epi.pl.hi && !C && !bias && !R && !d.accumulate && d.n % 32 == 0 && d.n <= BN_MAX &&
+                      ((d.batch1 == 1 && d.batch2 == 1) || (epi.pl.b1_rows >= d.m && epi.pl.b2_atoms >= d.n / 32)),
+                  "gemm_tc: plane-only output needs whole 32-column atoms in one N tile and per-batch row / atom offsets");
   } else if (epi.kind != kEpiNone) {
     V1T_CHECK_ARG(d.batch1 == 1 && d.batch2 == 1 && epi.ld % 4 == 0 && aligned16(epi.kind == kEpiGeluOut ? (const void*)epi.aux : (const void*)epi.u),
                   "gemm_tc: fused activation needs an unbatched problem and 16-byte aligned rows");

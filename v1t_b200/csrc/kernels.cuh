@@ -12,15 +12,18 @@ struct DropSpec {  // inverted dropout; p == 0 -> disabled
 static inline DropSpec no_drop() { return DropSpec{0, 0, 0.f}; }
 
 // optional fused element-wise stage of the tensor-core GEMM epilogue (MLP of the ViT block, vit.py:144-148)
-enum { kEpiNone = 0, kEpiGeluOut = 1, kEpiGeluGrad = 2, kEpiHeadPlanes = 3 };
+enum { kEpiNone = 0, kEpiGeluOut = 1, kEpiGeluGrad = 2, kEpiHeadPlanes = 3, kEpiPlanesOut = 4 };
 // Destination for operand planes (see PlaneOp below) emitted by the kernel that PRODUCES an activation, so that the
 // GEMMs consuming it never convert: hi/lo plane base pointers and the padded row count of the [rows, cols] matrix.
 struct PlaneOut {
   uint8_t* hi;
   uint8_t* lo;
   int rows_p;
+  // kEpiPlanesOut of a batched problem: batch entry (b1, b2) writes rows b1 * b1_rows + m of column atoms
+  // b2 * b2_atoms + n / 32 (e.g. dQ of sample b1, head b2 inside the planes of the head-padded [B*T, 3*H*Dp] gradient)
+  int b1_rows, b2_atoms;
 };
-static inline PlaneOut no_plane_out() { return PlaneOut{nullptr, nullptr, 0}; }
+static inline PlaneOut no_plane_out() { return PlaneOut{nullptr, nullptr, 0, 0, 0}; }
 
 // Destination of kEpiHeadPlanes: the GEMM output [B*T, S * H * AD*32] (S = 3: q | k | v, S = 1: dO; every head padded to AD*32
 // columns) leaves the epilogue as the per-(sample, head) attention operand planes of planes.cu
@@ -33,6 +36,7 @@ struct HeadPlanes {
 struct EpiOp {
   int kind;           // kEpiGeluOut: aux = gelu(C) * dropout ;  kEpiGeluGrad: C *= gelu'(u) * dropout
                       // kEpiHeadPlanes: alpha * acc -> attention planes `hp` (C may be null)
+                      // kEpiPlanesOut: alpha * acc -> matrix planes `pl` only (C null; batched problems allowed)
   float* aux;         // [m, ld] second output (kEpiGeluOut)
   const float* u;     // [m, ld] pre-activation (kEpiGeluGrad)
   int64_t ld;
@@ -52,8 +56,9 @@ struct PlaneOp {
   const uint8_t* lo;
   int rows_p, catoms;
   int64_t batch_bytes;  // batched problems: bytes between the planes of consecutive (batch1, batch2) matrices (0: unbatched)
+  int tile_major;       // MN-major operand stored as ATTENTION planes ([64-row tile][catoms atoms][64 rows][64 B], planes.cu)
 };
-static inline PlaneOp no_plane() { return PlaneOp{nullptr, nullptr, 0, 0, 0}; }
+static inline PlaneOp no_plane() { return PlaneOp{nullptr, nullptr, 0, 0, 0, 0}; }
 
 struct GemmArgs {
   v1t_gemm_desc d;
@@ -199,6 +204,8 @@ struct AttnBwdArgs {
   const float* delta;  // [B*H, Tp] rowsum(dO * O)
   const uint8_t* drop_bits;  // keep bits written by the forward (required when drop.p > 0)
   float* dqkv;         // [B, T, 3*H*E] packed like to_qkv's output: dQ | dK | dV (may be null when dq_pl is given)
+  uint8_t *ds_hi, *ds_lo;  // optional scratch: dS' as GEMM operand planes [b*H + h][Tp/32 query atoms][Tp key rows][64 B],
+                           // written by the pair kernel; dQ = scale * dS K is then ONE batched plane GEMM (attn_bwd2.cu)
   PlaneOut dq_pl;      // optional: GEMM-operand planes of the head-padded [B*T, 3*H*Dp] gradient (dQ | dK | dV)
   int B, H, T, Tp, E, Dp;
   float scale_log2, scale;
@@ -207,10 +214,12 @@ struct AttnBwdArgs {
   DropSpec drop;
 };
 int attn_bwd2_tc(const AttnBwdArgs& a, cudaStream_t st);  // resident operands in tensor memory (attn_bwd2.cu)
+int attn_dq_gemm_env();
 int attn_bwd_dispatch(const AttnBwdArgs& a, cudaStream_t st);
 struct AttnPlanes {  // [0] = hi, [1] = lo
   uint8_t *q[2], *k[2], *v[2];    // RM planes (rows = tokens, K = head dim)
   uint8_t *dO[2];                 // backward
+  uint8_t *dS[2];                 // backward: dS' planes for the dQ GEMM, [B*H][Tp/32][Tp][64 B] each
   float *lse, *delta;                                 // [B*H, Tp]
   uint8_t* drop_bits;                                 // [B*H, Tp, Tp/8] (standalone entry points)
   size_t total;
