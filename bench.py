@@ -455,7 +455,10 @@ def run_b200(args, cfg):
                 "frac": ach / peaks["bf16_tflops_sustained"], "share_of_step": p["ms_per_step"] / max(phase_sum, 1e-9)}
 
     per_block_fwd = 4 * D["H"] * D["T"] ** 2 * D["E"]
-    kb = kernel_roofline("attention backward = attn_bwd_pair_kernel (dV + dK, 2-CTA clusters) + attn_bwd2_kernel (dQ pass)",
+    dq_gemm = os.environ.get("V1T_ATTN_DQ", "gemm")[:1] != "p" and os.environ.get("V1T_ATTN_BWD", "pair")[:1] != "t"
+    dq_kernel = "tc_gemm_kernel<8," if dq_gemm else "attn_bwd2_kernel"
+    kb = kernel_roofline("attention backward = attn_bwd_pair_kernel (dV + dK + dS' planes, persistent 2-CTA clusters) + " +
+                         ("tc_gemm_kernel<8,0,0> (dQ = dS K, batched plane GEMM)" if dq_gemm else "attn_bwd2_kernel (dQ pass)"),
                          "attn_bwd_kernel", 2 * per_block_fwd)
     if kb:
         for key, ph in (("pair_us_per_launch", "attn_bwd_pair"), ("dq_us_per_launch", "attn_bwd_dq")):
@@ -473,7 +476,7 @@ def run_b200(args, cfg):
     dom = kb or {"kernel": "attention backward", "achieved": 0.0, "frac": 0.0}
     roofline = {"bound": "tensor", "kernel": dom["kernel"], "achieved": dom["achieved"],
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": dom["frac"],
-                "traffic": ((kernel_traffic("attn_bwd_pair_kernel") or 0) + (kernel_traffic("attn_bwd2_kernel") or 0) or None)
+                "traffic": ((kernel_traffic("attn_bwd_pair_kernel") or 0) + (kernel_traffic(dq_kernel) or 0) or None)
                 if fused_path else None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches (ncu launch list under profiles/; "
                                 "captured at the batch that list names)",
