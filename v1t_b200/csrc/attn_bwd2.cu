@@ -880,6 +880,15 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
           }
         }
       }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ps_full);
+      if (warp == 0) PAIR_TRACE(7, j);
+      if (rank == 1) {  // P' of tile j is consumed (its values went through the dS' -> TMEM chain above): one signal per warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_relaxed(pe_empty_peer + (uint32_t)buf * 8u);
+      }
+      // (after the arrivals above: the accumulating MMA and rank 0 do not wait for these stores)
       if (ds_row) {
         // the two 16-byte chunks of this thread are the two halves of one aligned 32-byte sector of the swizzled plane row
         // (their order swaps with the row's swizzle bit 0): ONE 256-bit store per plane -- 16-byte stores at a 64-byte
@@ -902,14 +911,6 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
           }
           stg256(a.ds_lo + (ds_row - a.ds_hi) + co, f);
         }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(ps_full);
-      if (warp == 0) PAIR_TRACE(7, j);
-      if (rank == 1) {  // P' of tile j is consumed (its values went through the dS' -> TMEM chain above): one signal per warp
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote_relaxed(pe_empty_peer + (uint32_t)buf * 8u);
       }
     }
     // ---- epilogue: rank 0 -> dV (column block 2I), rank 1 -> dK (column block I, scaled); see attn_bwd2_body
