@@ -623,14 +623,16 @@ def test_fused_attention_forward_dropout_replay():
                                        (2, 3, 333, 155, 0.25), (20, 4, 64, 32, 0.1), (5, 4, 435, 40, 0.25),
                                        (10, 8, 200, 24, 0.1)])
 @pytest.mark.parametrize("impl,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
-@pytest.mark.parametrize("variant", ["three", "pair"])
+@pytest.mark.parametrize("variant", ["three", "pair", "pair+dqpass"])
 def test_fused_attention_backward(B, H, T, E, p, impl, tol, variant, monkeypatch):
     """dQ, dK, dV of the fused tcgen05 attention vs fp64 autograd of softmax(QK^T)V (same dropout mask).  Both
     backward organisations: three atomic-free passes, and dV + dK by persistent two-CTA clusters sharing P'
-    (V1T_ATTN_BWD=pair)."""
+    (V1T_ATTN_BWD=pair) with dQ either as the batched plane GEMM over the dS' planes the clusters write (default) or as the
+    query-stationary pass (V1T_ATTN_DQ=pass)."""
     from v1t_b200 import _lib
     lib = _lib.load()
-    monkeypatch.setenv("V1T_ATTN_BWD", variant)
+    monkeypatch.setenv("V1T_ATTN_BWD", variant.split("+")[0])
+    monkeypatch.setenv("V1T_ATTN_DQ", "pass" if variant.endswith("dqpass") else "gemm")
     g = torch.Generator(device=DEV).manual_seed(B * 1000 + T + 1)
     qkv = torch.randn(B, T, 3 * H * E, device=DEV, generator=g)
     d_out = torch.randn(B, T, H * E, device=DEV, generator=g)
