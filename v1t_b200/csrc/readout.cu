@@ -20,7 +20,7 @@ namespace v1t {
 namespace {
 
 constexpr int kNeuronsPerCta = 32;
-constexpr int kWarps = 16;     // backward: 2 neurons per warp (96-107 registers per thread: one 512-thread CTA per SM)
+constexpr int kWarps = 32;     // backward: 1 neuron per warp, one 1024-thread CTA per SM (64 registers per thread)
 constexpr int kFwdWarps = 32;  // forward: 1 neuron per warp, 54 warps/SM at N=8000 (58 registers per thread)
 constexpr int kBatchTile = 32;  // samples staged per output tile
 constexpr float kEpsF32 = 1.1920928955078125e-07f;  // torch.finfo(float32).eps (losses.py:22)
@@ -509,6 +509,210 @@ __global__ void __launch_bounds__(kWarps * 32) readout_backward_v4_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// d_fmap without atomics, bitwise reproducible (pixel-major): d_fmap[b, pix, :] += sum over the (neuron, corner) pairs that
+// touch pixel `pix` of sample b of  dz[b,n] * w_corner * features[:, n].
+//   1. readout_sort_kernel (one CTA per sample): a counting sort of the sample's <= 4 N (neuron, corner) entries by pixel
+//      with a FIXED placement order -- warp w owns a contiguous range of neurons and its own row of per-pixel counters, so
+//      the slot of an entry is  offset[pix] + (entries of warps < w on pix) + (earlier entries of warp w on pix), all of
+//      which are independent of scheduling;
+//   2. transpose_features_kernel: features [C, N] -> [N, Cq] so that a neuron's feature vector is one contiguous row;
+//   3. readout_gather_kernel: one warp per (sample, pixel) walks its segment in order and adds coef * featT[n, :].
+// The red.global.add scatter of the neuron-major kernel (B N 4 C reductions, serialised on the few pixels all neurons sit on
+// at the start of training) is not issued then (its d_fmap argument is NULL).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSortWarps = 32;
+
+// gradient of the loss w.r.t. the pre-activation z[b, n]: given, or the fused ELU1 + Poisson gradient
+__device__ __forceinline__ float readout_dz(const float* __restrict__ dz_in, const float* __restrict__ z_in,
+                                            const float* __restrict__ y_true, float gscale, int64_t o) {
+  if (dz_in) return __ldg(dz_in + o);
+  const float z = __ldg(z_in + o);
+  const float y = elu1(z);
+  return gscale * (1.f - (__ldg(y_true + o) + kEpsF32) / (y + kEpsF32)) * (z > 0.f ? 1.f : expf(z));
+}
+
+// pixel index (y * gw + x) and bilinear weight of the 4 corners of (b, n); pix = -1 for corners outside the map
+__device__ __forceinline__ void corner_pixels(const v1t_readout_shape& s, const float* __restrict__ mu,
+                                              const float* __restrict__ sigma, const float* __restrict__ noise,
+                                              const float* __restrict__ shifts, int b, int n, int (&pix)[4], float (&w)[4]) {
+  const GridPos g = grid_position(mu, sigma, noise, shifts, b, n, s.neurons, s.gh, s.gw);
+  const float ixc = fminf(fmaxf(g.ix, -2.f), (float)s.gw + 1.f);
+  const float iyc = fminf(fmaxf(g.iy, -2.f), (float)s.gh + 1.f);
+  const int x0 = (int)floorf(ixc), y0 = (int)floorf(iyc);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int xc = x0 + (k & 1), yc = y0 + (k >> 1);
+    const bool ok = (xc >= 0) && (xc <= s.gw - 1) && (yc >= 0) && (yc <= s.gh - 1);
+    pix[k] = ok ? yc * s.gw + xc : -1;
+    w[k] = (1.f - fabsf(g.ix - (float)xc)) * (1.f - fabsf(g.iy - (float)yc));
+  }
+}
+
+// smem: cnt [kSortWarps][ceil(L/2)] packed 16-bit counters per (warp, pixel) | off [L + 1]
+__global__ void __launch_bounds__(kSortWarps * 32) readout_sort_kernel(
+    v1t_readout_shape s, const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ noise,
+    const float* __restrict__ shifts, const float* __restrict__ z_in, const float* __restrict__ dz_in,
+    const float* __restrict__ y_true, float gscale, int* __restrict__ seg_off, int* __restrict__ sorted_n,
+    float* __restrict__ sorted_coef) {
+  extern __shared__ uint32_t sm_sort[];
+  const int L = s.gh * s.gw, Lw = (L + 1) / 2, N = s.neurons, b = blockIdx.x;
+  uint32_t* cnt = sm_sort;                                   // [kSortWarps][Lw]
+  int* off = reinterpret_cast<int*>(sm_sort + kSortWarps * Lw);  // [L + 1]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int npw = ((N + kSortWarps - 1) / kSortWarps + 31) & ~31;  // neurons per warp: whole 32-neuron steps
+  const int n_begin = wid * npw, n_end = min(N, n_begin + npw);
+  for (int i = threadIdx.x; i < kSortWarps * Lw; i += blockDim.x) cnt[i] = 0u;
+  __syncthreads();
+  uint32_t* mine = cnt + wid * Lw;
+  // ---- pass A: entries of this warp's neurons per pixel
+  for (int n = n_begin + lane; n < n_end; n += 32) {
+    int pix[4];
+    float w[4];
+    corner_pixels(s, mu, sigma, noise, shifts, b, n, pix, w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pix[k] >= 0) atomicAdd(&mine[pix[k] >> 1], (pix[k] & 1) ? 65536u : 1u);
+  }
+  __syncthreads();
+  // ---- per pixel: exclusive prefix over the warps (in place), total -> off, then an exclusive scan over the pixels
+  for (int wd = threadIdx.x; wd < Lw; wd += blockDim.x) {  // one thread per counter word = pixels 2 wd, 2 wd + 1
+    uint32_t run0 = 0, run1 = 0;
+    for (int w2 = 0; w2 < kSortWarps; ++w2) {
+      uint32_t* word = cnt + w2 * Lw + wd;
+      const uint32_t c = *word;
+      *word = run0 | (run1 << 16);
+      run0 += c & 0xffffu;
+      run1 += c >> 16;
+    }
+    off[2 * wd] = (int)run0;
+    if (2 * wd + 1 < L) off[2 * wd + 1] = (int)run1;
+  }
+  __syncthreads();
+  {  // block-wide exclusive scan of off[0..L) (L is a few thousand at most: serial per thread, then over the threads)
+    __shared__ int part[kSortWarps * 32];
+    const int per = (L + blockDim.x - 1) / blockDim.x;
+    const int lo = threadIdx.x * per, hi = min(L, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += off[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int i = 0; i < (int)blockDim.x; ++i) {
+        const int v = part[i];
+        part[i] = run;
+        run += v;
+      }
+      off[L] = run;
+    }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (int i = lo; i < hi; ++i) {
+      const int v = off[i];
+      off[i] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= L; i += blockDim.x) seg_off[(int64_t)b * (L + 1) + i] = off[i];
+  // ---- pass B: placement.  Within the warp: neuron steps in order, corner 0..3, lanes in order.
+  int* out_n = sorted_n + (int64_t)b * 4 * N;
+  float* out_c = sorted_coef + (int64_t)b * 4 * N;
+  for (int n0 = n_begin; n0 < n_end; n0 += 32) {
+    const int n = n0 + lane;
+    int pix[4] = {-1, -1, -1, -1};
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    float g = 0.f;
+    if (n < n_end) {
+      corner_pixels(s, mu, sigma, noise, shifts, b, n, pix, w);
+      g = readout_dz(dz_in, z_in, y_true, gscale, (int64_t)b * N + n);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool valid = pix[k] >= 0;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const uint32_t same = __match_any_sync(vmask, pix[k]);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        const int leader = __ffs(same) - 1;
+        const int sh = (pix[k] & 1) * 16;
+        uint32_t cur = 0;
+        if (lane == leader) cur = atomicAdd(&mine[pix[k] >> 1], (uint32_t)__popc(same) << sh);  // returns the old word
+        cur = (__shfl_sync(same, cur, leader) >> sh) & 0xffffu;
+        const int slot = off[pix[k]] + (int)cur + rank;
+        out_n[slot] = n;
+        out_c[slot] = g * w[k];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// features [C, N] -> featT [N, Cq]  (32 x 32 tiles through shared memory); pad columns are zero
+__global__ void transpose_features_kernel(const float* __restrict__ f, float* __restrict__ ft, int C, int N, int Cq) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, n = n0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && n < N) ? __ldg(f + (int64_t)c * N + n) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int n = n0 + r, c = c0 + threadIdx.x;
+    if (n < N && c < Cq) ft[(int64_t)n * Cq + c] = tile[threadIdx.x][r];
+  }
+}
+
+// one warp per (sample, pixel): d_fmap[b, pix, c] += sum_e coef[e] * featT[n[e], c], entries in segment order
+template <int NV>
+__global__ void __launch_bounds__(256) readout_gather_kernel(v1t_readout_shape s, const int* __restrict__ seg_off,
+                                                             const int* __restrict__ sorted_n,
+                                                             const float* __restrict__ sorted_coef,
+                                                             const float* __restrict__ ft, int Cq, float* __restrict__ d_fmap) {
+  const int L = s.gh * s.gw, C = s.channels, N = s.neurons;
+  const int lane = threadIdx.x & 31;
+  const int64_t wg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wg >= (int64_t)s.batch * L) return;
+  const int b = (int)(wg / L), pix = (int)(wg % L);
+  const int beg = seg_off[(int64_t)b * (L + 1) + pix], end = seg_off[(int64_t)b * (L + 1) + pix + 1];
+  const int* en = sorted_n + (int64_t)b * 4 * N;
+  const float* ec = sorted_coef + (int64_t)b * 4 * N;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+  int e = beg;
+  for (; e + 4 <= end; e += 4) {  // four entries in flight
+    int n4[4];
+    float c4[4], v[4][NV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      n4[u] = __ldg(en + e + u);
+      c4[u] = __ldg(ec + e + u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[u][i] = (lane + 32 * i < C) ? __ldg(ft + (int64_t)n4[u] * Cq + lane + 32 * i) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = fmaf(c4[u], v[u][i], acc[i]);
+  }
+  for (; e < end; ++e) {
+    const int n = __ldg(en + e);
+    const float c = __ldg(ec + e);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < C) acc[i] = fmaf(c, __ldg(ft + (int64_t)n * Cq + lane + 32 * i), acc[i]);
+  }
+  if (beg == end) return;  // nothing lands here: the caller's buffer keeps its value
+  float* dst = d_fmap + (int64_t)b * s.fs_b + (int64_t)(pix / s.gw) * s.fs_y + (int64_t)(pix % s.gw) * s.fs_x;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + 32 * i < C) dst[lane + 32 * i] += acc[i];
+}
+
 // out[i] = sum_p part[p*n + i]
 __global__ void sum_parts_kernel(const float* __restrict__ part, int parts, int64_t n, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -572,6 +776,10 @@ struct ReadoutScratch {
   float* feat_part;      // [tiles][C][N]
   float* small_part;     // [tiles][N][7]
   float* shift_part;     // [ctas_x][B][2]
+  int* seg_off;          // [B][L + 1] segment starts of the pixel-major d_fmap pass
+  int* sorted_n;         // [B][4 N] neuron of every (neuron, corner) entry, sorted by pixel
+  float* sorted_coef;    // [B][4 N] dz * bilinear weight of the entry
+  float* feat_t;         // [N][Cq] transposed features
   size_t total;
 };
 
@@ -589,6 +797,10 @@ ReadoutScratch carve(const v1t_readout_shape& s, void* base) {
   r.feat_part = take(sizeof(float) * tiles * (size_t)s.channels * s.neurons);
   r.small_part = take(sizeof(float) * tiles * (size_t)s.neurons * 7);
   r.shift_part = take(sizeof(float) * ctas_x * (size_t)s.batch * 2);
+  r.seg_off = (int*)take(sizeof(int) * (size_t)s.batch * ((size_t)s.gh * s.gw + 1));
+  r.sorted_n = (int*)take(sizeof(int) * (size_t)s.batch * 4 * s.neurons);
+  r.sorted_coef = take(sizeof(float) * (size_t)s.batch * 4 * s.neurons);
+  r.feat_t = take(sizeof(float) * (size_t)s.neurons * round_up(s.channels, 4));
   r.total = off;
   return r;
 }
@@ -610,6 +822,20 @@ bool vec4_ok(const v1t_readout_shape& s, const float* fmap, const float* d_fmap)
          s.channels >= 4;
 }
 
+size_t sort_smem(const v1t_readout_shape& s) {
+  const size_t L = (size_t)s.gh * s.gw;
+  return sizeof(uint32_t) * kSortWarps * ((L + 1) / 2) + sizeof(int) * (L + 1);
+}
+// V1T_READOUT_DFMAP=sorted selects the pixel-major, atomic-free (bitwise reproducible) d_fmap pass when the per-(warp, pixel)
+// counters of one sample fit shared memory; the default is the red.global.add scatter of the neuron-major kernel, which is
+// faster: measured at B = 16, N = 8000 the scatter adds 30-45 us to that kernel, the three extra launches cost 190 us
+// (positions spread over the map) to 670 us (all neurons on a few pixels, one warp walking ~1000 entries per pixel)
+bool dfmap_sorted(const v1t_readout_shape& s) {
+  const char* e = getenv("V1T_READOUT_DFMAP");  // read on every call: tests switch it between launches
+  const bool atomic = !(e && e[0] == 's');
+  // 16-bit counters: a pixel holds at most 4 N entries of one sample
+  return !atomic && sort_smem(s) <= 200 * 1024 && (int64_t)4 * s.neurons < 65536 && (int64_t)s.batch * 4 * s.neurons < (1ll << 31);
+}
 size_t fwd_smem(const v1t_readout_shape& s) { return sizeof(float) * ((size_t)s.channels * 33 + kBatchTile * 33); }
 size_t bwd_smem(const v1t_readout_shape& s) { return sizeof(float) * ((size_t)s.channels * 33 + kBatchTile * 64); }
 
@@ -686,6 +912,9 @@ extern "C" int v1t_readout_backward(const v1t_readout_shape* s, const float* fma
   const size_t smem = bwd_smem(*s);
   const int nv = cdiv(s->channels, 32);
   const bool want_small = d_bias || d_mu || d_sigma;
+  float* const d_fmap_out = d_fmap;
+  const bool sorted = d_fmap && dfmap_sorted(*s);
+  if (sorted) d_fmap = nullptr;  // the neuron-major kernel skips its scatter; the pixel-major pass below writes d_fmap
   // with a single batch tile the per-tile slabs ARE the outputs: write d_features straight to its destination
   float* feat_dst = d_features ? (tiles == 1 ? d_features : ws.feat_part) : nullptr;
 #define CALL(NVV)                                                                                               \
@@ -727,6 +956,26 @@ extern "C" int v1t_readout_backward(const v1t_readout_shape* s, const float* fma
   if (d_shifts) {
     const int64_t n = (int64_t)s->batch * 2;
     sum_parts_kernel<<<cdiv(n, 256), 256, 0, st>>>(ws.shift_part, (int)grid.x, n, d_shifts);
+    V1T_LAUNCH_CHECK();
+  }
+  if (sorted) {
+    const int Cq = (int)round_up(s->channels, 4);
+    const size_t ssm = sort_smem(*s);
+    static size_t configured = 0;
+    if (ssm > 48 * 1024 && ssm > configured) {
+      V1T_CUDA(cudaFuncSetAttribute(readout_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+      configured = ssm;
+    }
+    readout_sort_kernel<<<s->batch, kSortWarps * 32, ssm, st>>>(*s, mu, sigma, noise, shifts, z, dz, y_true, loss_scale * dloss,
+                                                                ws.seg_off, ws.sorted_n, ws.sorted_coef);
+    V1T_LAUNCH_CHECK();
+    transpose_features_kernel<<<dim3(cdiv(s->neurons, 32), cdiv(Cq, 32)), dim3(32, 8), 0, st>>>(features, ws.feat_t, s->channels,
+                                                                                                 s->neurons, Cq);
+    V1T_LAUNCH_CHECK();
+    const int64_t warps = (int64_t)s->batch * s->gh * s->gw;
+#define CALLG(NVV) readout_gather_kernel<NVV><<<(unsigned)cdiv(warps, 8), 256, 0, st>>>(*s, ws.seg_off, ws.sorted_n, ws.sorted_coef, ws.feat_t, Cq, d_fmap_out)
+    V1T_NV_DISPATCH(nv, CALLG)
+#undef CALLG
     V1T_LAUNCH_CHECK();
   }
   return V1T_OK;
