@@ -177,7 +177,8 @@ int v1t_readout_forward(const v1t_readout_shape* s, const float* fmap, const flo
                         void* scratch, void* stream);
 
 /* backward.  dz [B,N] = dL/dz, or NULL with y_true given: then dz = dloss * loss_scale * dPoisson/dz (fused).
- * Outputs (any may be NULL): d_fmap (same strides as fmap, ACCUMULATED into: caller zero-fills),
+ * Outputs (any may be NULL): d_fmap (same strides as fmap, ACCUMULATED into: caller zero-fills; V1T_READOUT_DFMAP=sorted
+ * selects the pixel-major atomic-free pass, bitwise reproducible),
  * d_mu [N,2], d_sigma [N,2,2], d_shifts [B,2], d_features [C,N], d_bias [N]. */
 int v1t_readout_backward(const v1t_readout_shape* s, const float* fmap, const float* mu, const float* sigma,
                          const float* noise, const float* shifts, const float* features, const float* z,
