@@ -3,11 +3,35 @@ all-reduce give the same result as a single process summing both shards."""
 import os
 import socket
 
+import numpy as np
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from v1t_b200 import parallel
+
+
+
+def _to_np(x):
+    """Queue payloads travel by value: a tensor put on a multiprocessing queue is shared through a file descriptor that
+    dies with the sending process (the parent then fails with ConnectionResetError if the worker has already exited)."""
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy().copy()
+    if isinstance(x, dict):
+        return {k: _to_np(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(_to_np(v) for v in x)
+    return x
+
+
+def _to_t(x):
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(x)
+    if isinstance(x, dict):
+        return {k: _to_t(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(_to_t(v) for v in x)
+    return x
 
 
 def _free_port():
@@ -49,7 +73,7 @@ def _worker(rank, world, port, out):
     sync2.all_reduce(sinks=[sink])
     views_ok = all(p.grad.data_ptr() == sink.view_of(p, sink.flat).data_ptr() for p in shared)
     if rank == 0:
-        out.put(([p.grad.clone() for p in params], [p.grad.clone() for p in shared + own], views_ok))
+        out.put(_to_np(([p.grad.clone() for p in params], [p.grad.clone() for p in shared + own], views_ok)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,7 +85,7 @@ def test_gradsync_two_ranks_gloo():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got, got2, views_ok = q.get()
+    got, got2, views_ok = _to_t(q.get())
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
@@ -174,7 +198,7 @@ def _sweep_worker(rank, world, port, out):
         results.append(({k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_parameters()},
                         float(total)))
     if rank == 0:
-        out.put((results, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+        out.put(_to_np((results, {k: v.detach().clone() for k, v in model.state_dict().items()})))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -186,7 +210,7 @@ def test_sweep_two_ranks_fused_accumulation_matches_plain_and_single_process():
     procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results, sd = q.get()
+    results, sd = _to_t(q.get())
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
@@ -256,7 +280,7 @@ def _plan_worker(rank, world, port, mode, out, n_mice=4):
         model.zero_grad(set_to_none=True)
         parallel.sweep(model, crit, mine, plan.global_batch, sync, fused_accumulate=True, micro_batch=2)
     grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_parameters()}
-    out.put((rank, grads, dict(plan.my_slices), {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    out.put(_to_np((rank, grads, dict(plan.my_slices), {k: v.detach().clone() for k, v in model.state_dict().items()})))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -268,7 +292,7 @@ def _run_plan_case(world, mode, n_mice=4):
     procs = [ctx.Process(target=_plan_worker, args=(r, world, port, mode, q, n_mice)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get() for _ in range(world)]
+    got = [_to_t(q.get()) for _ in range(world)]
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
