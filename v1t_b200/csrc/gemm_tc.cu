@@ -12,6 +12,11 @@
 // TMEM alloc + MMA issue, warps 9-16 converting producers, warp 17 bulk-copy loader for operands that arrive as
 // pre-swizzled bf16 planes (PlaneOp: weights converted once per step, see planes.cu).  Pipelines: full/empty mbarriers per smem stage (4 stages x 48 KB), tmem_full/tmem_empty
 // per accumulator buffer.
+//
+// Plane operands may be batched (PlaneOp::batch_bytes: the T x T problems of the materialised attention, core.cu) and the
+// MN-major B operand may come straight from the attention planes (PlaneOp::tile_major).  Epilogue kinds (EpiOp): bias /
+// dropout / residual, GELU forward (+ planes), GELU gradient (+ planes + column sums), head planes (q | k | v or dO as
+// attention planes), and planes-only output with per-batch row / atom offsets (kEpiPlanesOut: dQ = dS K of attn_bwd2.cu).
 #include <algorithm>
 
 #include "common.cuh"
