@@ -852,12 +852,16 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd_pair_kernel(const At
           sv[c] = p * (dv[c] * m - stat[c]);  // dS'
         }
       }
-      // rank 1 also leaves dS' as GEMM operand planes [bh][query atom][key row][64 B] for the dQ GEMM (bwd2_all): this
-      // thread's 16 queries of key row `ri` are half a plane row, i.e. one full 32-byte sector per plane
+      // rank 1 also leaves dS' as GEMM operand planes for the dQ GEMM (bwd2_all): this thread's 16 queries of key row `ri`
+      // are half a 64-byte plane row, i.e. one full 32-byte sector per plane
       uint32_t ds_h[NH / 8][4], ds_l[NH / 8][4];
-      uint8_t* const ds_row = (rank == 1 && a.ds_hi)
-                                  ? a.ds_hi + (((int64_t)bh * (a.Tp >> 5) + (j * 2 + (slot >> 1))) * a.Tp + ri) * 64
-                                  : nullptr;
+      // layout [bh][128-query tile][64-key tile][4 query atoms][64 key rows][64 B]: a (128 queries x 64 keys) block -- one
+      // k-block of the GEMM's A operand -- is 16 contiguous KB
+      const int qa = j * 2 + (slot >> 1);  // 32-query atom of this thread's columns
+      uint8_t* const ds_row =
+          (rank == 1 && a.ds_hi)
+              ? a.ds_hi + ((((((int64_t)bh * (a.Tp >> 7) + (qa >> 2)) * (a.Tp >> 6) + (ri >> 6)) * 4 + (qa & 3)) * 64 + (ri & 63)) << 6)
+              : nullptr;
       // A operand of the accumulating MMA -> TMEM (two bf16 per column), hi and lo planes
       mbar_wait(ps_empty, (it & 1) ^ 1);
       tc_fence_after();
@@ -1038,7 +1042,7 @@ int bwd2_all(const AttnBwdArgs& a_in, cudaStream_t st) {
       g.m = a.T; g.k = a.T; g.n = a.dq_pl.hi ? AD * 32 : a.E;
       g.batch1 = a.B; g.batch2 = a.H; g.alpha = a.scale;
       g.a_m = 1; g.a_k = a.Tp; g.b_n = 1; g.b_k = a.Tp;
-      const PlaneOp pa{a.ds_hi, a.x3 ? a.ds_lo : nullptr, a.Tp, a.Tp / 32, (int64_t)(a.Tp / 32) * a.Tp * 64, 0};
+      const PlaneOp pa{a.ds_hi, a.x3 ? a.ds_lo : nullptr, a.Tp, a.Tp / 32, (int64_t)(a.Tp / 32) * a.Tp * 64, 2};
       const PlaneOp pb{a.k_hi, a.x3 ? a.k_lo : nullptr, a.Tp, AD, (int64_t)a.Tp * AD * 64, 1};
       EpiOp epi = no_epi();
       float* C = nullptr;

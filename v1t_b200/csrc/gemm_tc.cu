@@ -187,10 +187,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs a) {
           }
           __syncwarp();
           if (mine && (mn || atom * 32 < klen)) {
-            const int64_t src = !mn             ? ((int64_t)((k0 >> 5) + atom) * po.rows_p + row0) * 64
-                                : po.tile_major ? ((int64_t)((k0 >> 6) * po.catoms + row0 / 32 + atom) * 64 + (k0 & 63)) * 64
-                                                : ((int64_t)(row0 / 32 + atom) * po.rows_p + k0) * 64;
-            bulk_g2s(smem + stage * W_STAGE + dst_off, src_base + src, mn ? klen * 64 : rows * 64, &pfull[stage]);
+            const int64_t src =
+                !mn                  ? ((int64_t)((k0 >> 5) + atom) * po.rows_p + row0) * 64
+                : po.tile_major == 1 ? ((int64_t)((k0 >> 6) * po.catoms + row0 / 32 + atom) * 64 + (k0 & 63)) * 64
+                : po.tile_major == 2 ? ((((int64_t)(row0 >> 7) * (po.rows_p >> 6) + (k0 >> 6)) * 4 + atom) * 64 + (k0 & 63)) * 64
+                                     : ((int64_t)(row0 / 32 + atom) * po.rows_p + k0) * 64;
+            // a full 64-row k-block of a tile-major operand is contiguous over its atoms, in global memory as in the
+            // stage: ONE copy per plane instead of one per atom (a bulk copy costs ~90 cycles on top of its bytes)
+            const bool whole = mn && po.tile_major && klen == WBK;
+            if (!whole) bulk_g2s(smem + stage * W_STAGE + dst_off, src_base + src, mn ? klen * 64 : rows * 64, &pfull[stage]);
+            else if (atom == 0)
+              bulk_g2s(smem + stage * W_STAGE + dst_off, src_base + src, (is_b ? b_atoms : a_atoms) * (WBK * 64), &pfull[stage]);
           }
         }
       }
@@ -717,8 +724,9 @@ int launch_tc(const v1t_gemm_desc& d, const float* A, const float* B, float* C, 
   a.tiles_m = cdiv(d.m, BM);
   a.x3 = x3;
   a.wide = (a.a_pl && a.b_pl && a.bn <= W_BN) ? 1 : 0;
-  V1T_CHECK_ARG(!pa.tile_major && (!pb.tile_major || (a.wide && d.b_k != 1)),
-                "tc gemm: attention-plane (tile-major) operands are supported as the MN-major B operand of all-plane launches");
+  V1T_CHECK_ARG((!pa.tile_major || (pa.tile_major == 2 && a.wide && d.a_k != 1 && pa.rows_p % 64 == 0 && pa.catoms % 4 == 0)) &&
+                    (!pb.tile_major || (pb.tile_major == 1 && a.wide && d.b_k != 1)),
+                "tc gemm: tile-major operands are supported as MN-major operands of all-plane launches (A: layout 2, B: layout 1)");
   // plane operands cannot be transposed while staging: their orientation follows the problem
   a.mn_a = a.a_pl ? (d.a_k != 1) : (g_use_mn_major && d.a_k != 1 && d.a_m == 1);
   a.mn_b = a.b_pl ? (d.b_k != 1) : (g_use_mn_major && d.b_k != 1 && d.b_n == 1 && a.bn % 32 == 0);

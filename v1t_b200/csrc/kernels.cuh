@@ -56,7 +56,9 @@ struct PlaneOp {
   const uint8_t* lo;
   int rows_p, catoms;
   int64_t batch_bytes;  // batched problems: bytes between the planes of consecutive (batch1, batch2) matrices (0: unbatched)
-  int tile_major;       // MN-major operand stored as ATTENTION planes ([64-row tile][catoms atoms][64 rows][64 B], planes.cu)
+  int tile_major;       // MN-major operand whose 64-row k-blocks are contiguous over the atoms (ONE bulk copy per k-block):
+                        // 1 = attention planes [64-row tile][catoms atoms][64 rows][64 B] (planes.cu), B operand;
+                        // 2 = [128-column M tile][64-row tile][4 atoms][64 rows][64 B], A operand (dS' of attn_bwd2.cu)
 };
 static inline PlaneOp no_plane() { return PlaneOp{nullptr, nullptr, 0, 0, 0, 0}; }
 
@@ -204,7 +206,7 @@ struct AttnBwdArgs {
   const float* delta;  // [B*H, Tp] rowsum(dO * O)
   const uint8_t* drop_bits;  // keep bits written by the forward (required when drop.p > 0)
   float* dqkv;         // [B, T, 3*H*E] packed like to_qkv's output: dQ | dK | dV (may be null when dq_pl is given)
-  uint8_t *ds_hi, *ds_lo;  // optional scratch: dS' as GEMM operand planes [b*H + h][Tp/32 query atoms][Tp key rows][64 B],
+  uint8_t *ds_hi, *ds_lo;  // optional scratch: dS' as GEMM operand planes [b*H + h][Tp/128 query tiles][Tp/64 key tiles][4 atoms][64][64 B],
                            // written by the pair kernel; dQ = scale * dS K is then ONE batched plane GEMM (attn_bwd2.cu)
   PlaneOut dq_pl;      // optional: GEMM-operand planes of the head-padded [B*T, 3*H*Dp] gradient (dQ | dK | dV)
   int B, H, T, Tp, E, Dp;
