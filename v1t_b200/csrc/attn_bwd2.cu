@@ -999,15 +999,14 @@ __global__ void __launch_bounds__(kThreadsAttn, 1) attn_bwd2_kernel(const AttnBw
 
 template <int AD>
 int bwd2_all(const AttnBwdArgs& a_in, cudaStream_t st) {
-  const AttnBwdArgs& a = a_in;
+  AttnBwdArgs a = a_in;
+  const bool pair = attn_bwd_pair_env() != 0;
+  if (!pair || !attn_dq_gemm_env()) a.ds_hi = a.ds_lo = nullptr;  // no dS' planes: the dQ pass recomputes what it needs
   constexpr uint32_t smem = std::max({Smem2<MODE_V, 64, AD>::total, Smem2<MODE_S, 32, AD>::total});
   static_assert(smem <= 232448, "shared memory budget exceeded");
   V1T_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (attn_bwd_pair_env()) {
+  if (pair) {
     // dV + dK by clusters of two CTAs that share one recomputation of P' (see attn_bwd_pair_kernel), then dQ alone
-    AttnBwdArgs aa = a_in;
-    if (!attn_dq_gemm_env()) aa.ds_hi = aa.ds_lo = nullptr;
-    const AttnBwdArgs& a = aa;
     using LP = SmemPair<AD>;
     static_assert(LP::total <= 232448, "shared memory budget exceeded");
     V1T_CUDA(cudaFuncSetAttribute(attn_bwd_pair_kernel<AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LP::total));
