@@ -529,9 +529,10 @@ __device__ __forceinline__ void st_async_v4(uint32_t addr, float a, float b, flo
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// one 256-bit global store (sm_100: STG.256), 32-byte aligned
+// one 256-bit global store (sm_100: STG.256), 32-byte aligned; L2 evict-first: the dS' planes are written once and read
+// by the next launch, they should not push the Q / dO planes that 13 clusters per head re-read out of L2
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+  asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
